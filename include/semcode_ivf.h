@@ -1,0 +1,166 @@
+/*
+ * semcode_ivf.h -- C ABI of the B200-native IVF_FLAT engine (libsemcode_ivf.so).
+ *
+ * The reference has no FFI for this path: its "FFI" is pymilvus -> gRPC -> Milvus.  Each entry
+ * point below cites the reference call (path:line under /root/reference) whose work it replaces;
+ * INTEGRATION.md shows the ctypes binding a semcode maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 (sc_status) on failure; sc_last_error() gives the
+ *     thread-local message of the last failure on this thread.
+ *   - plain pointers + sizes only.  Bulk array pointers may be HOST or DEVICE (same GPU) pointers;
+ *     the library detects which (cudaPointerGetAttributes).  Device arrays must be 16-byte aligned,
+ *     C-contiguous, row stride = dim floats.
+ *   - `stream` is a cudaStream_t (void* here so that C callers need no CUDA headers); NULL = the
+ *     legacy default stream.  All work of a call is ordered on that stream.
+ *   - DEVICE outputs are valid once the caller synchronises `stream` (no hidden sync);
+ *     HOST outputs are valid on return (the call synchronises `stream`).
+ *   - the caller owns every input/output buffer; the library owns index storage and scratch.
+ *   - a handle may be used from several threads: calls on one handle are serialised internally.
+ *   - there is NO CPU fallback: every call fails with SC_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef SEMCODE_IVF_H
+#define SEMCODE_IVF_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SC_ABI_VERSION 1
+
+typedef enum sc_status {
+    SC_OK = 0,
+    SC_ERR_INVALID = -1, /* bad argument */
+    SC_ERR_CUDA = -2,    /* CUDA runtime / launch failure, or no usable device */
+    SC_ERR_STATE = -3,   /* e.g. search/add before centroids exist */
+    SC_ERR_OOM = -4      /* device allocation failed */
+} sc_status;
+
+typedef enum sc_metric {
+    SC_METRIC_IP = 0, /* inner product, larger is better  (milvus_store.py:79 "metric_type": "IP") */
+    SC_METRIC_L2 = 1  /* squared L2, smaller is better    (FAISS METRIC_L2, no sqrt)               */
+} sc_metric;
+
+typedef struct sc_index sc_index_t; /* opaque */
+
+/* Scalar filter pushed into the list scan (replaces the client-side post-filter of
+ * src/semcode/frontend/app.py:100-116 / gradio_app.py:79-94; Milvus would take it as `expr`).
+ * HOST arrays.  n_repos == 0 -> any repo; n_langs == 0 -> any language. A row passes when its
+ * repo tag is in repo_tags[] AND its language tag is in lang_tags[]. Removed rows never pass. */
+typedef struct sc_filter {
+    const uint32_t *repo_tags;
+    int32_t n_repos;
+    const uint8_t *lang_tags;
+    int32_t n_langs;
+} sc_filter_t;
+
+typedef struct sc_stats {
+    int32_t dim, dim_padded, metric, nlist, device, trained;
+    int64_t ntotal;        /* live rows (added - removed) */
+    int64_t nremoved;      /* tombstoned rows still occupying list slots */
+    int64_t npages;        /* allocated 32-row list pages */
+    int64_t bytes_lists;   /* device bytes held by list slabs (vectors + ids + tags) */
+    int64_t bytes_scratch; /* device bytes held by scratch */
+    int32_t max_list_len, min_list_len;
+    /* device-side timing of the last sc_index_search call (valid after the stream has been
+       synchronised and sc_index_last_search_times() has been called) */
+} sc_stats_t;
+
+/* per-phase device times (ms) of the most recent sc_index_search on this handle, measured with
+ * CUDA events on the caller's stream when profiling is enabled with sc_index_set_profiling(). */
+typedef struct sc_search_times {
+    float coarse_ms, probe_select_ms, plan_ms, scan_ms, topk_ms, total_ms;
+    int64_t scanned_rows;  /* rows whose distance was evaluated (sum over queries) */
+    int64_t scanned_pages; /* 32-row pages visited (sum over queries) */
+    int32_t scan_launches; /* launches of the list-scan kernel */
+    int32_t total_launches;
+} sc_search_times_t;
+
+const char *sc_last_error(void);
+int sc_abi_version(void);
+/* number of visible CUDA devices with compute capability 10.x (0 => nothing will work) */
+int sc_device_count(void);
+
+/* -- lifecycle.  Replaces Collection(...)+create_index(IVF_FLAT, metric, nlist) at
+ *    src/semcode/storage/milvus_store.py:75-84 ------------------------------------------------- */
+int sc_index_create(int32_t dim, int32_t metric, int32_t nlist, int32_t device, sc_index_t **out);
+int sc_index_destroy(sc_index_t *idx);
+/* drop all rows (keeps centroids) */
+int sc_index_reset(sc_index_t *idx);
+
+/* -- coarse quantizer.  Replaces the server-side k-means that Milvus runs when a segment is
+ *    sealed after Collection.upsert (milvus_store.py:128-130) [FAISS IndexIVFFlat::train] ------- */
+/* Lloyd k-means on x[n,dim]; niter iterations; init rows / subsample drawn from `seed` exactly as
+ * oracle/ivf_numpy.py does when init_rows/sub_rows are given by the host wrapper:
+ *   init_rows [nlist] : rows (of the *subsampled* training set) that seed the centroids
+ *   objective_out     : HOST array [niter] or NULL, objective entering each iteration */
+int sc_index_train(sc_index_t *idx, const float *x, int64_t n, int32_t niter, const int64_t *init_rows,
+                   double *objective_out, void *stream);
+/* The three building blocks of sc_index_train, exposed so that data-parallel training (one process
+ * per GPU, rows sharded) can all-reduce between them -- SURVEY.md section 8e:
+ *   kmeans_init   centroids <- x[init_rows]  (every rank passes the same rows of the same x, or calls
+ *                 sc_index_set_centroids with broadcast centroids instead)
+ *   kmeans_step   one assignment pass over this rank's rows; ACCUMULATES into caller-owned DEVICE buffers
+ *                 sums [nlist, dim_padded] fp64, counts [nlist] int32, objective [1] fp64
+ *   kmeans_update centroids <- sums / counts, empty clusters split FAISS-style; nsplit_out host, nullable */
+int sc_index_kmeans_init(sc_index_t *idx, const float *x, int64_t n, const int64_t *init_rows, void *stream);
+int sc_index_kmeans_step(sc_index_t *idx, const float *x, int64_t n, double *sums, int32_t *counts,
+                         double *objective, void *stream);
+int sc_index_kmeans_update(sc_index_t *idx, const double *sums, const int32_t *counts, int32_t *nsplit_out,
+                           void *stream);
+int sc_index_set_centroids(sc_index_t *idx, const float *centroids, int32_t nlist, void *stream);
+int sc_index_get_centroids(sc_index_t *idx, float *out /* [nlist,dim] host or device */, void *stream);
+
+/* list id of the best centroid per row (FAISS quantizer->assign); out_list host or device [n] */
+int sc_index_assign(sc_index_t *idx, const float *x, int64_t n, int32_t *out_list, void *stream);
+/* coarse pass only: the nprobe best lists per query, best first (out host or device [nq,nprobe]) */
+int sc_index_probe(sc_index_t *idx, const float *q, int64_t nq, int32_t nprobe, int32_t *out_lists,
+                   float *out_scores /* nullable */, void *stream);
+
+/* -- insert.  Replaces Collection.upsert([...,vectors,...]) at milvus_store.py:128-130
+ *    [FAISS IndexIVFFlat::add_with_ids].  repo_tags / lang_tags may be NULL (all zero). -------- */
+int sc_index_add(sc_index_t *idx, const float *x, const int64_t *ids, const uint32_t *repo_tags,
+                 const uint8_t *lang_tags, int64_t n, void *stream);
+/* same, with the list of every row supplied by the caller (parity runs / sharded insert) */
+int sc_index_add_preassigned(sc_index_t *idx, const float *x, const int64_t *ids, const uint32_t *repo_tags,
+                             const uint8_t *lang_tags, const int32_t *lists, int64_t n, void *stream);
+/* tombstone rows by id (upsert = remove + add; Collection.upsert replaces by primary key,
+ * milvus_store.py:128).  n_removed_out (host, nullable) receives how many rows matched. */
+int sc_index_remove_ids(sc_index_t *idx, const int64_t *ids, int64_t n, int64_t *n_removed_out, void *stream);
+
+/* -- search.  Replaces Collection.search(data=[vector], param={"metric_type":"IP","params":
+ *    {"nprobe":16}}, limit=top_k) at milvus_store.py:141-147 [FAISS IndexIVFFlat::search].
+ *    out_dist [nq,k] raw inner product or squared L2, best first; out_ids [nq,k], -1 = no result
+ *    (then dist = -FLT_MAX for IP, +FLT_MAX for L2).  filter may be NULL.  k <= 2048,
+ *    nprobe is clamped to nlist. -------------------------------------------------------------- */
+int sc_index_search(sc_index_t *idx, const float *q, int64_t nq, int32_t k, int32_t nprobe,
+                    const sc_filter_t *filter, float *out_dist, int64_t *out_ids, void *stream);
+/* same, probing caller-supplied lists (host or device [nq,nprobe]; -1 entries are skipped) */
+int sc_index_search_preassigned(sc_index_t *idx, const float *q, int64_t nq, int32_t k, int32_t nprobe,
+                                const int32_t *lists, const sc_filter_t *filter, float *out_dist,
+                                int64_t *out_ids, void *stream);
+
+/* -- cross-shard reduce.  Replaces the Milvus proxy's reduce over segments/shards [EXT]:
+ *    part_dist/part_ids [parts,nq,kin] (device) -> out [nq,k] best first; ids < 0 are ignored. -- */
+int sc_merge_topk(const float *part_dist, const int64_t *part_ids, int32_t parts, int64_t nq, int32_t kin,
+                  int32_t k, int32_t metric, float *out_dist, int64_t *out_ids, int32_t device, void *stream);
+
+/* -- introspection / export (persistence, CPU baseline, tests) -------------------------------- */
+int sc_index_stats(sc_index_t *idx, sc_stats_t *out);
+int sc_index_list_sizes(sc_index_t *idx, int32_t *out_host /* [nlist], slots incl. tombstones */);
+/* copy one list out (host or device buffers, each nullable): vectors [len,dim], ids, tags, where
+ * tags = (removed<<31)|(repo<<8)|lang.  len_out (host) receives the slot count. cap = rows the
+ * buffers can hold. */
+int sc_index_export_list(sc_index_t *idx, int32_t list, int64_t cap, float *vecs, int64_t *ids, uint32_t *tags,
+                         int64_t *len_out, void *stream);
+int sc_index_set_profiling(sc_index_t *idx, int32_t enabled);
+int sc_index_last_search_times(sc_index_t *idx, sc_search_times_t *out);
+/* tuning knobs (tests/bench): scratch budget in bytes for candidate distances; scan variant */
+int sc_index_set_param(sc_index_t *idx, const char *name, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEMCODE_IVF_H */

@@ -1,0 +1,144 @@
+// Shared declarations for libsemcode_ivf (sm_100a only).
+//
+// HBM layout of one index (see DESIGN.md "Data layout"):
+//   centroids   [nlist, ds] fp32, ds = dim rounded up to 4 floats (16-byte rows)
+//   list pages  fixed 32-row pages drawn from slabs; slab s holds `pages_per_slab` pages:
+//                 vec  [pages_per_slab*32, ds] fp32
+//                 ids  [pages_per_slab*32]     int64
+//                 tags [pages_per_slab*32]     uint32 = removed<<31 | repo<<8 | lang
+//               unused slots keep tags = 0xFFFFFFFF (removed bit set) so they never match.
+//   page table  CSR: pt_off[nlist+1] (int32), pt[total_pages] (int32 page ids), list_len[nlist]
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sc {
+
+constexpr int kPageRows = 32;
+constexpr int kMaxSlabs = 1024;
+constexpr uint32_t kTagRemoved = 0x80000000u;
+constexpr uint32_t kTagRepoMax = (1u << 23) - 1;
+constexpr int kMaxK = 2048;
+
+struct SlabTable {
+    float *vec[kMaxSlabs];
+    int64_t *ids[kMaxSlabs];
+    uint32_t *tags[kMaxSlabs];
+};
+
+__host__ __device__ __forceinline__ uint32_t make_tag(uint32_t repo, uint32_t lang) {
+    return ((repo & kTagRepoMax) << 8) | (lang & 0xffu);
+}
+
+// ---- device helpers -----------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// streaming 128-bit load: read-only path, do not allocate in L1 (list rows are read once)
+__device__ __forceinline__ float4 ld_stream_f4(const float4 *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// order-preserving float -> uint key (larger float => larger key). NaN -> 0 (below -inf).
+constexpr uint32_t kKeyNegInf = 0x007fffffu;  // key of -inf; keys <= this are "no result"
+__device__ __forceinline__ uint32_t f2key(float f) {
+    uint32_t u = __float_as_uint(f);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return 0u;
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(u);
+}
+
+#endif  // __CUDACC__
+
+// ---- kernel launchers (host API, defined in the .cu files) ---------------------------------
+
+// C[M,N] = A[M,K] . B[N,K]^T ; if bnorm != nullptr: C = 2*C - bnorm[n]   (all fp32, K % 4 == 0)
+cudaError_t launch_gemm_nt(const float *A, int64_t M, const float *B, int N, int K, const float *bnorm, float *C,
+                           cudaStream_t st);
+// out[r] = sum_k x[r,k]^2
+cudaError_t launch_row_norms(const float *x, int64_t rows, int ds, float *out, cudaStream_t st);
+// per row: index of the largest score (ties -> lowest index) and the score
+cudaError_t launch_argmax_rows(const float *scores, int64_t M, int N, int32_t *out_idx, float *out_val,
+                               cudaStream_t st);
+// out[n,ds] = zero-padded copy of in[n,d]
+cudaError_t launch_pad_rows(const float *in, int64_t n, int d, int ds, float *out, cudaStream_t st);
+
+// top-k of each row of scores[M,N] (largest first) -> idx [M,k] int32, val [M,k] (nullable)
+cudaError_t launch_select_rows(const float *scores, int64_t M, int N, int k, int32_t *out_idx, float *out_val,
+                               cudaStream_t st);
+
+struct FilterDev {
+    uint32_t flags;  // bit0: language filter, bit1: repo filter
+    uint32_t lang_bits[8];
+    const uint32_t *repo_bits;
+    uint32_t n_repo_bits;
+};
+
+struct ScanArgs {
+    const float *q;  // [nq, ds]
+    int ds;
+    int metric;
+    int nprobe;
+    int64_t npairs;           // nq * nprobe
+    const int32_t *probe;     // [npairs] list ids (-1 = skip)
+    const int64_t *page_off;  // [npairs+1] exclusive prefix of pages per pair
+    const int32_t *list_len;  // [nlist]
+    const int32_t *pt_off;    // [nlist+1]
+    const int32_t *pt;        // page ids
+    const SlabTable *slabs;
+    int slab_shift;
+    float *cand;  // [page_off[npairs]*32] similarity to maximise, -inf for dead slots
+    FilterDev filt;
+};
+
+cudaError_t launch_plan_pairs(const int32_t *probe, int64_t npairs, const int32_t *list_len, int32_t nlist,
+                              int64_t *pair_pages, unsigned long long *rows_total, cudaStream_t st);
+// exclusive prefix sum of int64 in[n] -> out[n+1] (out[n] = total); single launch
+cudaError_t launch_exclusive_scan_i64(const int64_t *in, int64_t n, int64_t *out, cudaStream_t st);
+cudaError_t launch_exclusive_scan_i32(const int32_t *in, int64_t n, int32_t *out, cudaStream_t st);
+cudaError_t launch_scan_pages(const ScanArgs &a, int variant, int num_sms, int *launches, cudaStream_t st);
+// final top-k over the candidates of each query + id translation
+cudaError_t launch_select_candidates(const ScanArgs &a, int64_t nq, int k, float *out_dist, int64_t *out_ids,
+                                     cudaStream_t st);
+cudaError_t launch_merge_topk(const float *part_dist, const int64_t *part_ids, int parts, int64_t nq, int kin, int k,
+                              int metric, float *out_dist, int64_t *out_ids, cudaStream_t st);
+
+// list maintenance
+cudaError_t launch_count_positions(const int32_t *assign, int64_t n, int32_t nlist, int32_t *list_len, int32_t *pos,
+                                   int32_t *bad, cudaStream_t st);
+cudaError_t launch_page_need(const int32_t *len_old, const int32_t *len_new, int32_t nlist, int32_t *need,
+                             int32_t *npg_new, cudaStream_t st);
+cudaError_t launch_rebuild_pt(const int32_t *pt_off_old, const int32_t *pt_old, const int32_t *pt_off_new,
+                              int32_t *pt_new, const int32_t *need_off, int32_t pool_top, int32_t nlist,
+                              cudaStream_t st);
+cudaError_t launch_scatter_rows(const float *x, const int64_t *ids, const uint32_t *repo, const uint8_t *lang,
+                                const int32_t *assign, const int32_t *pos, int64_t n, int ds, const int32_t *pt_off,
+                                const int32_t *pt, const SlabTable *slabs, int slab_shift, cudaStream_t st);
+cudaError_t launch_remove_ids(const int64_t *sorted_ids, int64_t nrm, const SlabTable *slabs, int slab_shift,
+                              int64_t npages, unsigned long long *count, cudaStream_t st);
+cudaError_t launch_export_list(const int32_t *pt, int32_t pt_begin, int32_t len, int ds, int d_out,
+                               const SlabTable *slabs, int slab_shift, float *vecs, int64_t *ids, uint32_t *tags,
+                               cudaStream_t st);
+
+// k-means
+cudaError_t launch_kmeans_accumulate(const float *x, int64_t n, int ds, const int32_t *assign, const float *best,
+                                     int metric, double *sums, int32_t *counts, double *objective, cudaStream_t st);
+cudaError_t launch_kmeans_finalize(const double *sums, const int32_t *counts, int32_t nlist, int ds, float *centroids,
+                                   cudaStream_t st);
+cudaError_t launch_split_centroid(float *centroids, int ds, int32_t ci, int32_t cj, cudaStream_t st);
+cudaError_t launch_gather_rows(const float *x, const int64_t *rows, int64_t n, int ds, float *out, cudaStream_t st);
+
+}  // namespace sc

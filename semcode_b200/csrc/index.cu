@@ -1,0 +1,1161 @@
+// Host side of libsemcode_ivf.so: the C ABI declared in include/semcode_ivf.h.
+//
+// One sc_index = one IVF_FLAT index resident on one B200: replicated centroids, paged inverted
+// lists (common.cuh), and stream-ordered scratch.  It replaces what Milvus does server-side behind
+// reference src/semcode/storage/milvus_store.py:75-84 (create_index), :128-130 (upsert -> train /
+// add) and :141-147 (search).  There is no CPU path in here: every entry point launches the
+// sm_100a kernels of this directory or fails.
+#include <float.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/semcode_ivf.h"
+#include "common.cuh"
+
+using namespace sc;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            cudaGetLastError();                                                                      \
+            return fail(e_ == cudaErrorMemoryAllocation ? SC_ERR_OOM : SC_ERR_CUDA, "%s: %s (%s:%d)", \
+                        #call, cudaGetErrorString(e_), __FILE__, __LINE__);                          \
+        }                                                                                            \
+    } while (0)
+
+#define SC(call)               \
+    do {                       \
+        int r_ = (call);       \
+        if (r_ != SC_OK) return r_; \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// small utilities
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes == 0) bytes = 256;
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);  // cudaFree waits for in-flight work that may still use the buffer
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8;
+        want = (want + 255) & ~(size_t)255;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            want = (bytes + 255) & ~(size_t)255;
+            e = cudaMalloc(&p, want);
+        }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T *as() const {
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+struct Slab {
+    float *vec;
+    int64_t *ids;
+    uint32_t *tags;
+};
+
+// is `p` a device (or managed) pointer usable on `device`?  host otherwise
+bool is_device_ptr(const void *p, int device) {
+    if (p == nullptr) return false;
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    if (at.type == cudaMemoryTypeDevice) return at.device == device;
+    return at.type == cudaMemoryTypeManaged;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            cudaGetLastError();
+            prev = -1;
+        }
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+__global__ void fill_u32_kernel(uint32_t *p, int64_t n, uint32_t v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// the index object
+// ------------------------------------------------------------------------------------------------
+struct sc_index {
+    int dim = 0, ds = 0, metric = 0, nlist = 0, device = 0, num_sms = 148;
+    bool trained = false;
+    float *centroids = nullptr;  // [nlist, ds]
+    float *cnorm = nullptr;      // [nlist]  |c|^2 (L2 only)
+
+    // paged lists
+    int slab_shift = 0;
+    std::vector<Slab> slabs;
+    SlabTable *h_tab = nullptr;  // host mirror
+    SlabTable *d_tab = nullptr;
+    int32_t pool_top = 0;          // pages handed out
+    int32_t *list_len = nullptr;   // [nlist] slots used (incl. tombstones)
+    int32_t *pt_off = nullptr;     // [nlist+1]
+    int32_t *pt_off_alt = nullptr; // double buffer
+    int32_t *pt = nullptr;
+    int32_t *pt_alt = nullptr;
+    int64_t pt_cap = 0, pt_alt_cap = 0;
+    std::vector<int32_t> h_len;          // host mirror of list_len
+    std::vector<int64_t> h_bound_prefix; // [nlist+1] pages of the j largest lists
+    int32_t h_max_pages = 0;
+    int64_t ntotal = 0, nremoved = 0;
+
+    // scratch (stream ordered; ev_done chains calls made on different streams)
+    DevBuf s_q, s_scores, s_probe, s_pairpages, s_pageoff, s_cand, s_outd, s_outi, s_repobits;
+    DevBuf s_x, s_xpad, s_ids, s_repo, s_lang, s_assign, s_best, s_pos, s_lenold, s_need, s_npg, s_needoff, s_bad;
+    DevBuf s_sums, s_counts, s_obj, s_rows, s_rm, s_cnt;
+    int64_t scratch_budget = (int64_t)2 << 30;
+    int scan_variant = 0;
+    cudaEvent_t ev_done = nullptr;
+
+    // profiling of the last search
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_ev;  // 6 events per chunk: t0 coarse | select | plan | scan | topk t5
+    unsigned long long *prof_rows = nullptr;  // device counter
+    int64_t prof_pages = 0;
+    int prof_scan_launches = 0, prof_total_launches = 0;
+
+    std::mutex mu;
+};
+
+namespace {
+
+size_t page_bytes(const sc_index *ix) { return (size_t)kPageRows * ix->ds * sizeof(float); }
+
+int ensure_slabs(sc_index *ix, int64_t pages_needed, cudaStream_t st) {
+    const int64_t pps = (int64_t)1 << ix->slab_shift;
+    bool grew = false;
+    while ((int64_t)ix->slabs.size() * pps < pages_needed) {
+        if ((int)ix->slabs.size() >= kMaxSlabs) return fail(SC_ERR_OOM, "slab table full (%d slabs)", kMaxSlabs);
+        Slab s{nullptr, nullptr, nullptr};
+        const int64_t rows = pps * kPageRows;
+        cudaError_t e = cudaMalloc(&s.vec, (size_t)rows * ix->ds * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&s.ids, (size_t)rows * sizeof(int64_t));
+        if (e == cudaSuccess) e = cudaMalloc(&s.tags, (size_t)rows * sizeof(uint32_t));
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            if (s.vec) cudaFree(s.vec);
+            if (s.ids) cudaFree(s.ids);
+            if (s.tags) cudaFree(s.tags);
+            return fail(SC_ERR_OOM, "cannot allocate list slab %zu (%lld rows x %d floats): %s", ix->slabs.size(),
+                        (long long)rows, ix->ds, cudaGetErrorString(e));
+        }
+        // unused slots never match any predicate
+        fill_u32_kernel<<<ix->num_sms * 4, 256, 0, st>>>(s.tags, rows, 0xFFFFFFFFu);
+        CU(cudaGetLastError());
+        const int i = (int)ix->slabs.size();
+        ix->h_tab->vec[i] = s.vec;
+        ix->h_tab->ids[i] = s.ids;
+        ix->h_tab->tags[i] = s.tags;
+        ix->slabs.push_back(s);
+        grew = true;
+    }
+    if (grew) CU(cudaMemcpyAsync(ix->d_tab, ix->h_tab, sizeof(SlabTable), cudaMemcpyHostToDevice, st));
+    return SC_OK;
+}
+
+void free_lists(sc_index *ix) {
+    for (auto &s : ix->slabs) {
+        cudaFree(s.vec);
+        cudaFree(s.ids);
+        cudaFree(s.tags);
+    }
+    ix->slabs.clear();
+    ix->pool_top = 0;
+    ix->ntotal = 0;
+    ix->nremoved = 0;
+}
+
+void refresh_bounds(sc_index *ix) {
+    std::vector<int32_t> pages(ix->nlist);
+    int32_t mx = 0;
+    for (int i = 0; i < ix->nlist; ++i) {
+        pages[i] = (ix->h_len[i] + kPageRows - 1) / kPageRows;
+        mx = std::max(mx, pages[i]);
+    }
+    std::sort(pages.begin(), pages.end(), [](int32_t a, int32_t b) { return a > b; });
+    ix->h_bound_prefix.assign(ix->nlist + 1, 0);
+    for (int i = 0; i < ix->nlist; ++i) ix->h_bound_prefix[i + 1] = ix->h_bound_prefix[i] + pages[i];
+    ix->h_max_pages = mx;
+}
+
+// device pointer to `count` elements of T: `p` itself when it already lives on the device,
+// otherwise a stream-ordered copy in `buf`
+template <typename T>
+int stage(sc_index *ix, const T *p, size_t count, DevBuf &buf, cudaStream_t st, const T **out) {
+    if (p == nullptr) {
+        *out = nullptr;
+        return SC_OK;
+    }
+    if (is_device_ptr(p, ix->device)) {
+        *out = p;
+        return SC_OK;
+    }
+    CU(buf.reserve(count * sizeof(T)));
+    CU(cudaMemcpyAsync(buf.p, p, count * sizeof(T), cudaMemcpyHostToDevice, st));
+    *out = buf.as<T>();
+    return SC_OK;
+}
+
+// rows [n, dim] (host or device) -> device rows [n, ds], 16-byte aligned
+int stage_rows(sc_index *ix, const float *x, int64_t n, DevBuf &raw, DevBuf &padded, cudaStream_t st,
+               const float **out) {
+    const float *xd = nullptr;
+    SC(stage(ix, x, (size_t)n * ix->dim, raw, st, &xd));
+    if (ix->ds == ix->dim && ((uintptr_t)xd & 15) == 0) {
+        *out = xd;
+        return SC_OK;
+    }
+    CU(padded.reserve((size_t)n * ix->ds * sizeof(float)));
+    CU(launch_pad_rows(xd, n, ix->dim, ix->ds, padded.as<float>(), st));
+    *out = padded.as<float>();
+    return SC_OK;
+}
+
+int copy_out(sc_index *ix, void *dst, const void *src_dev, size_t bytes, cudaStream_t st) {
+    if (dst == src_dev || bytes == 0) return SC_OK;
+    const bool dev = is_device_ptr(dst, ix->device);
+    CU(cudaMemcpyAsync(dst, src_dev, bytes, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    return SC_OK;
+}
+
+int begin_call(sc_index *ix, cudaStream_t st) {
+    // scratch is shared by all calls on the handle: order this call after the previous one even
+    // when the caller switched streams
+    CU(cudaStreamWaitEvent(st, ix->ev_done, 0));
+    return SC_OK;
+}
+
+int end_call(sc_index *ix, cudaStream_t st) {
+    CU(cudaEventRecord(ix->ev_done, st));
+    return SC_OK;
+}
+
+int require_trained(const sc_index *ix) {
+    if (!ix->trained) return fail(SC_ERR_STATE, "index has no centroids: call sc_index_train or sc_index_set_centroids first");
+    return SC_OK;
+}
+
+int update_cnorm(sc_index *ix, cudaStream_t st) {
+    CU(launch_row_norms(ix->centroids, ix->nlist, ix->ds, ix->cnorm, st));
+    return SC_OK;
+}
+
+// rows per coarse chunk so that the [rows, nlist] similarity tile stays within ~1/4 of the budget
+int64_t coarse_chunk_rows(const sc_index *ix, int64_t n) {
+    const int64_t budget = std::max<int64_t>(ix->scratch_budget / 4, (int64_t)64 << 20);
+    int64_t rows = budget / ((int64_t)ix->nlist * 4);
+    rows = std::max<int64_t>(128, (rows / 128) * 128);
+    return std::min<int64_t>(rows, std::max<int64_t>(n, 1));
+}
+
+// assign[i] = argbest centroid of xd[i] (device rows [n, ds]); best[i] = its similarity
+int coarse_assign(sc_index *ix, const float *xd, int64_t n, int32_t *assign, float *best, cudaStream_t st) {
+    const int64_t ch = coarse_chunk_rows(ix, n);
+    CU(ix->s_scores.reserve((size_t)ch * ix->nlist * sizeof(float)));
+    for (int64_t s = 0; s < n; s += ch) {
+        const int64_t m = std::min(ch, n - s);
+        CU(launch_gemm_nt(xd + s * ix->ds, m, ix->centroids, ix->nlist, ix->ds,
+                          ix->metric == SC_METRIC_L2 ? ix->cnorm : nullptr, ix->s_scores.as<float>(), st));
+        CU(launch_argmax_rows(ix->s_scores.as<float>(), m, ix->nlist, assign + s, best ? best + s : nullptr, st));
+    }
+    return SC_OK;
+}
+
+// append rows that already sit on the device ([n, ds] rows, device ids/tags/lists)
+int add_device_rows(sc_index *ix, const float *xd, const int64_t *ids_d, const uint32_t *repo_d,
+                    const uint8_t *lang_d, const int32_t *lists_d, int64_t n, cudaStream_t st) {
+    const int nlist = ix->nlist;
+    CU(ix->s_pos.reserve((size_t)n * 4));
+    CU(ix->s_lenold.reserve((size_t)nlist * 4));
+    CU(ix->s_need.reserve((size_t)nlist * 4));
+    CU(ix->s_npg.reserve((size_t)nlist * 4));
+    CU(ix->s_needoff.reserve((size_t)(nlist + 1) * 4));
+    CU(ix->s_bad.reserve(16));
+    CU(cudaMemcpyAsync(ix->s_lenold.p, ix->list_len, (size_t)nlist * 4, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemsetAsync(ix->s_bad.p, 0, 16, st));
+    CU(launch_count_positions(lists_d, n, nlist, ix->list_len, ix->s_pos.as<int32_t>(), ix->s_bad.as<int32_t>(), st));
+    CU(launch_page_need(ix->s_lenold.as<int32_t>(), ix->list_len, nlist, ix->s_need.as<int32_t>(),
+                        ix->s_npg.as<int32_t>(), st));
+    CU(launch_exclusive_scan_i32(ix->s_need.as<int32_t>(), nlist, ix->s_needoff.as<int32_t>(), st));
+    CU(launch_exclusive_scan_i32(ix->s_npg.as<int32_t>(), nlist, ix->pt_off_alt, st));
+    int32_t h_new = 0, h_total = 0, h_bad = 0;
+    CU(cudaMemcpyAsync(&h_new, ix->s_needoff.as<int32_t>() + nlist, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&h_total, ix->pt_off_alt + nlist, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&h_bad, ix->s_bad.p, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (h_bad != 0) {
+        // undo the length bumps of the valid rows so that the index stays consistent
+        CU(cudaMemcpyAsync(ix->list_len, ix->s_lenold.p, (size_t)nlist * 4, cudaMemcpyDeviceToDevice, st));
+        CU(cudaStreamSynchronize(st));
+        return fail(SC_ERR_INVALID, "%d rows carry a list id outside [0, %d)", h_bad, nlist);
+    }
+    if ((int64_t)ix->pool_top + h_new > (int64_t)INT32_MAX / 2) return fail(SC_ERR_OOM, "page id space exhausted");
+    SC(ensure_slabs(ix, (int64_t)ix->pool_top + h_new, st));
+    if (h_total > ix->pt_alt_cap) {
+        const int64_t want = std::max<int64_t>((int64_t)h_total + h_total / 2, 1024);
+        if (ix->pt_alt) cudaFree(ix->pt_alt);
+        ix->pt_alt = nullptr;
+        ix->pt_alt_cap = 0;
+        CU(cudaMalloc(&ix->pt_alt, (size_t)want * 4));
+        ix->pt_alt_cap = want;
+    }
+    CU(launch_rebuild_pt(ix->pt_off, ix->pt, ix->pt_off_alt, ix->pt_alt, ix->s_needoff.as<int32_t>(), ix->pool_top,
+                         nlist, st));
+    std::swap(ix->pt, ix->pt_alt);
+    std::swap(ix->pt_cap, ix->pt_alt_cap);
+    std::swap(ix->pt_off, ix->pt_off_alt);
+    ix->pool_top += h_new;
+    CU(launch_scatter_rows(xd, ids_d, repo_d, lang_d, lists_d, ix->s_pos.as<int32_t>(), n, ix->ds, ix->pt_off, ix->pt,
+                           ix->d_tab, ix->slab_shift, st));
+    ix->ntotal += n;
+    return SC_OK;
+}
+
+int sync_host_lengths(sc_index *ix, cudaStream_t st) {
+    CU(cudaMemcpyAsync(ix->h_len.data(), ix->list_len, (size_t)ix->nlist * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    refresh_bounds(ix);
+    return SC_OK;
+}
+
+int add_impl(sc_index *ix, const float *x, const int64_t *ids, const uint32_t *repo, const uint8_t *lang,
+             const int32_t *lists, int64_t n, cudaStream_t st) {
+    if (n < 0) return fail(SC_ERR_INVALID, "n < 0");
+    if (n == 0) return SC_OK;
+    if (x == nullptr || ids == nullptr) return fail(SC_ERR_INVALID, "x and ids must not be NULL");
+    SC(require_trained(ix));
+    CU(cudaDeviceSynchronize());  // no search may still be reading the page table we are about to swap
+    // bounded staging: ~256 MB of rows per pass
+    int64_t chunk = std::max<int64_t>(1024, ((int64_t)256 << 20) / ((int64_t)ix->ds * 4));
+    chunk = std::min(chunk, n);
+    for (int64_t s = 0; s < n; s += chunk) {
+        const int64_t m = std::min(chunk, n - s);
+        const float *xd = nullptr;
+        const int64_t *ids_d = nullptr;
+        const uint32_t *repo_d = nullptr;
+        const uint8_t *lang_d = nullptr;
+        const int32_t *lists_d = nullptr;
+        SC(stage_rows(ix, x + s * ix->dim, m, ix->s_x, ix->s_xpad, st, &xd));
+        SC(stage(ix, ids + s, (size_t)m, ix->s_ids, st, &ids_d));
+        SC(stage(ix, repo ? repo + s : nullptr, (size_t)m, ix->s_repo, st, &repo_d));
+        SC(stage(ix, lang ? lang + s : nullptr, (size_t)m, ix->s_lang, st, &lang_d));
+        if (lists) {
+            SC(stage(ix, lists + s, (size_t)m, ix->s_assign, st, &lists_d));
+        } else {
+            CU(ix->s_assign.reserve((size_t)m * 4));
+            SC(coarse_assign(ix, xd, m, ix->s_assign.as<int32_t>(), nullptr, st));
+            lists_d = ix->s_assign.as<int32_t>();
+        }
+        SC(add_device_rows(ix, xd, ids_d, repo_d, lang_d, lists_d, m, st));
+    }
+    SC(sync_host_lengths(ix, st));
+    return SC_OK;
+}
+
+int build_filter(sc_index *ix, const sc_filter_t *filt, cudaStream_t st, FilterDev *out) {
+    FilterDev f;
+    memset(&f, 0, sizeof(f));
+    if (filt != nullptr) {
+        if (filt->n_langs < 0 || filt->n_repos < 0) return fail(SC_ERR_INVALID, "negative filter length");
+        if (filt->n_langs > 0) {
+            if (!filt->lang_tags) return fail(SC_ERR_INVALID, "filter lang_tags is NULL");
+            f.flags |= 1u;
+            for (int i = 0; i < filt->n_langs; ++i) f.lang_bits[filt->lang_tags[i] >> 5] |= 1u << (filt->lang_tags[i] & 31);
+        }
+        if (filt->n_repos > 0) {
+            if (!filt->repo_tags) return fail(SC_ERR_INVALID, "filter repo_tags is NULL");
+            f.flags |= 2u;
+            uint32_t mx = 0;
+            for (int i = 0; i < filt->n_repos; ++i) {
+                if (filt->repo_tags[i] > kTagRepoMax) return fail(SC_ERR_INVALID, "repo tag %u exceeds %u", filt->repo_tags[i], kTagRepoMax);
+                mx = std::max(mx, filt->repo_tags[i]);
+            }
+            const uint32_t nbits = mx + 1;
+            std::vector<uint32_t> bits((nbits + 31) / 32, 0u);
+            for (int i = 0; i < filt->n_repos; ++i) bits[filt->repo_tags[i] >> 5] |= 1u << (filt->repo_tags[i] & 31);
+            CU(ix->s_repobits.reserve(bits.size() * 4));
+            CU(cudaMemcpyAsync(ix->s_repobits.p, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, st));
+            CU(cudaStreamSynchronize(st));  // `bits` dies at scope exit
+            f.repo_bits = ix->s_repobits.as<uint32_t>();
+            f.n_repo_bits = nbits;
+        }
+    }
+    *out = f;
+    return SC_OK;
+}
+
+void clear_prof(sc_index *ix) {
+    for (auto e : ix->prof_ev) cudaEventDestroy(e);
+    ix->prof_ev.clear();
+    ix->prof_scan_launches = 0;
+    ix->prof_total_launches = 0;
+}
+
+int prof_mark(sc_index *ix, cudaStream_t st) {
+    if (!ix->profiling) return SC_OK;
+    cudaEvent_t e;
+    CU(cudaEventCreate(&e));
+    CU(cudaEventRecord(e, st));
+    ix->prof_ev.push_back(e);
+    return SC_OK;
+}
+
+int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, const int32_t *lists,
+                const sc_filter_t *filt, float *out_dist, int64_t *out_ids, cudaStream_t st) {
+    if (nq < 0) return fail(SC_ERR_INVALID, "nq < 0");
+    if (k < 1 || k > kMaxK) return fail(SC_ERR_INVALID, "k must be in [1, %d]", kMaxK);
+    if (nprobe < 1) return fail(SC_ERR_INVALID, "nprobe must be >= 1");
+    SC(require_trained(ix));
+    if (nq == 0) return SC_OK;
+    if (!q || !out_dist || !out_ids) return fail(SC_ERR_INVALID, "q / out_dist / out_ids must not be NULL");
+    const int np = lists ? nprobe : std::min(nprobe, ix->nlist);
+    const bool outd_dev = is_device_ptr(out_dist, ix->device), outi_dev = is_device_ptr(out_ids, ix->device);
+
+    SC(begin_call(ix, st));
+    FilterDev fdev;
+    SC(build_filter(ix, filt, st, &fdev));
+    if (ix->profiling) {
+        clear_prof(ix);
+        if (!ix->prof_rows) CU(cudaMalloc(&ix->prof_rows, 8));
+        CU(cudaMemsetAsync(ix->prof_rows, 0, 8, st));
+    }
+
+    // worst-case pages one query can touch -> candidate scratch per query
+    int64_t pb = lists ? (int64_t)np * ix->h_max_pages : ix->h_bound_prefix[std::min(np, ix->nlist)];
+    pb = std::max<int64_t>(pb, 1);
+    const int64_t per_query = (lists ? 0 : (int64_t)ix->nlist * 4) + (int64_t)np * 20 + pb * kPageRows * 4 +
+                              (int64_t)ix->ds * 4 + (int64_t)k * 12;
+    int64_t nqc = std::max<int64_t>(1, ix->scratch_budget / per_query);
+    nqc = std::min(nqc, nq);
+    if (!lists && nqc >= 128) nqc = (nqc / 128) * 128;  // whole GEMM tiles
+    nqc = std::min(nqc, nq);
+
+    const int64_t npairs_max = nqc * np;
+    if (!lists) CU(ix->s_scores.reserve((size_t)nqc * ix->nlist * 4));
+    if (!lists) CU(ix->s_probe.reserve((size_t)npairs_max * 4));
+    CU(ix->s_pairpages.reserve((size_t)npairs_max * 8));
+    CU(ix->s_pageoff.reserve((size_t)(npairs_max + 1) * 8));
+    CU(ix->s_cand.reserve((size_t)nqc * pb * kPageRows * 4));
+    if (!outd_dev) CU(ix->s_outd.reserve((size_t)nqc * k * 4));
+    if (!outi_dev) CU(ix->s_outi.reserve((size_t)nqc * k * 8));
+
+    for (int64_t s = 0; s < nq; s += nqc) {
+        const int64_t m = std::min(nqc, nq - s);
+        const int64_t npairs = m * np;
+        const float *qd = nullptr;
+        SC(stage_rows(ix, q + s * ix->dim, m, ix->s_q, ix->s_xpad, st, &qd));
+        const int32_t *probe = nullptr;
+        SC(prof_mark(ix, st));
+        if (lists) {
+            SC(stage(ix, lists + s * np, (size_t)npairs, ix->s_probe, st, &probe));
+            SC(prof_mark(ix, st));
+        } else {
+            CU(launch_gemm_nt(qd, m, ix->centroids, ix->nlist, ix->ds,
+                              ix->metric == SC_METRIC_L2 ? ix->cnorm : nullptr, ix->s_scores.as<float>(), st));
+            SC(prof_mark(ix, st));
+            CU(launch_select_rows(ix->s_scores.as<float>(), m, ix->nlist, np, ix->s_probe.as<int32_t>(), nullptr, st));
+            probe = ix->s_probe.as<int32_t>();
+            ix->prof_total_launches += 2;
+        }
+        SC(prof_mark(ix, st));
+        CU(launch_plan_pairs(probe, npairs, ix->list_len, ix->nlist, ix->s_pairpages.as<int64_t>(),
+                             ix->profiling ? ix->prof_rows : nullptr, st));
+        CU(launch_exclusive_scan_i64(ix->s_pairpages.as<int64_t>(), npairs, ix->s_pageoff.as<int64_t>(), st));
+        SC(prof_mark(ix, st));
+        ScanArgs a;
+        memset(&a, 0, sizeof(a));
+        a.q = qd;
+        a.ds = ix->ds;
+        a.metric = ix->metric;
+        a.nprobe = np;
+        a.npairs = npairs;
+        a.probe = probe;
+        a.page_off = ix->s_pageoff.as<int64_t>();
+        a.list_len = ix->list_len;
+        a.pt_off = ix->pt_off;
+        a.pt = ix->pt;
+        a.slabs = ix->d_tab;
+        a.slab_shift = ix->slab_shift;
+        a.cand = ix->s_cand.as<float>();
+        a.filt = fdev;
+        CU(launch_scan_pages(a, ix->scan_variant, ix->num_sms, &ix->prof_scan_launches, st));
+        SC(prof_mark(ix, st));
+        float *od = outd_dev ? out_dist + s * k : ix->s_outd.as<float>();
+        int64_t *oi = outi_dev ? out_ids + s * k : ix->s_outi.as<int64_t>();
+        CU(launch_select_candidates(a, m, k, od, oi, st));
+        SC(prof_mark(ix, st));
+        ix->prof_total_launches += 4;
+        if (!outd_dev) CU(cudaMemcpyAsync(out_dist + s * k, od, (size_t)m * k * 4, cudaMemcpyDeviceToHost, st));
+        if (!outi_dev) CU(cudaMemcpyAsync(out_ids + s * k, oi, (size_t)m * k * 8, cudaMemcpyDeviceToHost, st));
+    }
+    SC(end_call(ix, st));
+    if (!outd_dev || !outi_dev) CU(cudaStreamSynchronize(st));
+    return SC_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *sc_last_error(void) { return g_err.c_str(); }
+
+int sc_abi_version(void) { return SC_ABI_VERSION; }
+
+int sc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ++ok;
+    }
+    return ok;
+}
+
+int sc_index_create(int32_t dim, int32_t metric, int32_t nlist, int32_t device, sc_index_t **out) {
+    if (!out) return fail(SC_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (dim < 1 || dim > 65536) return fail(SC_ERR_INVALID, "dim must be in [1, 65536]");
+    if (metric != SC_METRIC_IP && metric != SC_METRIC_L2) return fail(SC_ERR_INVALID, "unknown metric %d", metric);
+    if (nlist < 1 || nlist > (1 << 24)) return fail(SC_ERR_INVALID, "nlist must be in [1, 2^24]");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(SC_ERR_CUDA, "no CUDA device visible: this library has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(SC_ERR_INVALID, "device %d out of range (%d visible)", device, ndev);
+    int major = 0, sms = 0;
+    CU(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    if (major != 10) return fail(SC_ERR_CUDA, "device %d has compute capability %d.x; kernels are built for sm_100a only", device, major);
+    DeviceGuard g(device);
+    if (!g.ok) return fail(SC_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+
+    sc_index *ix = new sc_index();
+    ix->dim = dim;
+    ix->ds = (dim + 3) & ~3;
+    ix->metric = metric;
+    ix->nlist = nlist;
+    ix->device = device;
+    ix->num_sms = sms;
+    // slab = ~256 MB of vectors, at least 64 pages, at most 2^16 pages
+    int shift = 6;
+    while (shift < 16 && ((size_t)2 << shift) * page_bytes(ix) <= ((size_t)256 << 20)) ++shift;
+    ix->slab_shift = shift;
+    ix->h_tab = new SlabTable();
+    memset(ix->h_tab, 0, sizeof(SlabTable));
+    ix->h_len.assign(nlist, 0);
+    ix->h_bound_prefix.assign(nlist + 1, 0);
+    auto cleanup = [&](int code) {
+        sc_index_destroy(ix);
+        return code;
+    };
+    cudaError_t e = cudaMalloc(&ix->centroids, (size_t)nlist * ix->ds * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&ix->cnorm, (size_t)nlist * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&ix->d_tab, sizeof(SlabTable));
+    if (e == cudaSuccess) e = cudaMalloc(&ix->list_len, (size_t)nlist * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&ix->pt_off, (size_t)(nlist + 1) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&ix->pt_off_alt, (size_t)(nlist + 1) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&ix->pt, 1024 * 4);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->ev_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMemset(ix->list_len, 0, (size_t)nlist * 4);
+    if (e == cudaSuccess) e = cudaMemset(ix->pt_off, 0, (size_t)(nlist + 1) * 4);
+    if (e == cudaSuccess) e = cudaMemset(ix->d_tab, 0, sizeof(SlabTable));
+    if (e == cudaSuccess) e = cudaMemset(ix->centroids, 0, (size_t)nlist * ix->ds * 4);
+    if (e == cudaSuccess) e = cudaEventRecord(ix->ev_done, 0);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return cleanup(fail(e == cudaErrorMemoryAllocation ? SC_ERR_OOM : SC_ERR_CUDA, "index allocation failed: %s",
+                            cudaGetErrorString(e)));
+    }
+    ix->pt_cap = 1024;
+    *out = ix;
+    return SC_OK;
+}
+
+int sc_index_destroy(sc_index_t *ix) {
+    if (!ix) return SC_OK;
+    DeviceGuard g(ix->device);
+    cudaDeviceSynchronize();
+    free_lists(ix);
+    clear_prof(ix);
+    for (DevBuf *b : {&ix->s_q, &ix->s_scores, &ix->s_probe, &ix->s_pairpages, &ix->s_pageoff, &ix->s_cand, &ix->s_outd,
+                      &ix->s_outi, &ix->s_repobits, &ix->s_x, &ix->s_xpad, &ix->s_ids, &ix->s_repo, &ix->s_lang,
+                      &ix->s_assign, &ix->s_best, &ix->s_pos, &ix->s_lenold, &ix->s_need, &ix->s_npg, &ix->s_needoff,
+                      &ix->s_bad, &ix->s_sums, &ix->s_counts, &ix->s_obj, &ix->s_rows, &ix->s_rm, &ix->s_cnt})
+        b->release();
+    for (void *p : {(void *)ix->centroids, (void *)ix->cnorm, (void *)ix->d_tab, (void *)ix->list_len, (void *)ix->pt_off,
+                    (void *)ix->pt_off_alt, (void *)ix->pt, (void *)ix->pt_alt, (void *)ix->prof_rows})
+        if (p) cudaFree(p);
+    if (ix->ev_done) cudaEventDestroy(ix->ev_done);
+    delete ix->h_tab;
+    cudaGetLastError();
+    delete ix;
+    return SC_OK;
+}
+
+int sc_index_reset(sc_index_t *ix) {
+    if (!ix) return fail(SC_ERR_INVALID, "idx is NULL");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    CU(cudaDeviceSynchronize());
+    free_lists(ix);
+    memset(ix->h_tab, 0, sizeof(SlabTable));
+    CU(cudaMemset(ix->list_len, 0, (size_t)ix->nlist * 4));
+    CU(cudaMemset(ix->pt_off, 0, (size_t)(ix->nlist + 1) * 4));
+    std::fill(ix->h_len.begin(), ix->h_len.end(), 0);
+    refresh_bounds(ix);
+    return SC_OK;
+}
+
+int sc_index_set_centroids(sc_index_t *ix, const float *centroids, int32_t nlist, void *stream) {
+    if (!ix || !centroids) return fail(SC_ERR_INVALID, "NULL argument");
+    if (nlist != ix->nlist) return fail(SC_ERR_INVALID, "nlist %d does not match the index (%d)", nlist, ix->nlist);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ix->ntotal > 0) return fail(SC_ERR_STATE, "cannot replace centroids of a non-empty index (reset it first)");
+    CU(cudaDeviceSynchronize());
+    const float *cd = nullptr;
+    SC(stage(ix, centroids, (size_t)nlist * ix->dim, ix->s_x, st, &cd));
+    CU(launch_pad_rows(cd, nlist, ix->dim, ix->ds, ix->centroids, st));
+    SC(update_cnorm(ix, st));
+    CU(cudaStreamSynchronize(st));
+    ix->trained = true;
+    return SC_OK;
+}
+
+int sc_index_get_centroids(sc_index_t *ix, float *out, void *stream) {
+    if (!ix || !out) return fail(SC_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    SC(require_trained(ix));
+    SC(begin_call(ix, st));
+    const bool dev = is_device_ptr(out, ix->device);
+    CU(cudaMemcpy2DAsync(out, (size_t)ix->dim * 4, ix->centroids, (size_t)ix->ds * 4, (size_t)ix->dim * 4, ix->nlist,
+                         dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    SC(end_call(ix, st));
+    if (!dev) CU(cudaStreamSynchronize(st));
+    return SC_OK;
+}
+
+// ---- k-means ------------------------------------------------------------------------------------
+int sc_index_kmeans_init(sc_index_t *ix, const float *x, int64_t n, const int64_t *init_rows, void *stream) {
+    if (!ix || !x || !init_rows) return fail(SC_ERR_INVALID, "NULL argument");
+    if (n < ix->nlist) return fail(SC_ERR_INVALID, "need at least nlist=%d training rows, got %lld", ix->nlist, (long long)n);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ix->ntotal > 0) return fail(SC_ERR_STATE, "cannot retrain a non-empty index (reset it first)");
+    CU(cudaDeviceSynchronize());
+    std::vector<int64_t> rows(ix->nlist);
+    if (is_device_ptr(init_rows, ix->device)) {
+        CU(cudaMemcpy(rows.data(), init_rows, (size_t)ix->nlist * 8, cudaMemcpyDeviceToHost));
+    } else {
+        memcpy(rows.data(), init_rows, (size_t)ix->nlist * 8);
+    }
+    for (int i = 0; i < ix->nlist; ++i)
+        if (rows[i] < 0 || rows[i] >= n) return fail(SC_ERR_INVALID, "init_rows[%d]=%lld outside [0,%lld)", i, (long long)rows[i], (long long)n);
+    if (is_device_ptr(x, ix->device)) {
+        if (ix->ds == ix->dim && ((uintptr_t)x & 15) == 0) {
+            CU(ix->s_rows.reserve((size_t)ix->nlist * 8));
+            CU(cudaMemcpyAsync(ix->s_rows.p, rows.data(), (size_t)ix->nlist * 8, cudaMemcpyHostToDevice, st));
+            CU(launch_gather_rows(x, ix->s_rows.as<int64_t>(), ix->nlist, ix->ds, ix->centroids, st));
+        } else {
+            for (int i = 0; i < ix->nlist; ++i)
+                CU(launch_pad_rows(x + rows[i] * ix->dim, 1, ix->dim, ix->ds, ix->centroids + (int64_t)i * ix->ds, st));
+        }
+    } else {
+        std::vector<float> c((size_t)ix->nlist * ix->ds, 0.f);
+        for (int i = 0; i < ix->nlist; ++i) memcpy(&c[(size_t)i * ix->ds], x + rows[i] * ix->dim, (size_t)ix->dim * 4);
+        CU(cudaMemcpyAsync(ix->centroids, c.data(), c.size() * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    SC(update_cnorm(ix, st));
+    CU(cudaStreamSynchronize(st));
+    ix->trained = true;
+    return SC_OK;
+}
+
+// one assignment pass over x[n, dim]: sums[nlist, ds] (fp64), counts[nlist], objective[1] are
+// ACCUMULATED into (device buffers owned by the caller, so that ranks can all-reduce them)
+int sc_index_kmeans_step(sc_index_t *ix, const float *x, int64_t n, double *sums, int32_t *counts, double *objective,
+                         void *stream) {
+    if (!ix || !sums || !counts || !objective) return fail(SC_ERR_INVALID, "NULL argument");
+    if (n < 0) return fail(SC_ERR_INVALID, "n < 0");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    SC(require_trained(ix));
+    if (!is_device_ptr(sums, ix->device) || !is_device_ptr(counts, ix->device) || !is_device_ptr(objective, ix->device))
+        return fail(SC_ERR_INVALID, "sums / counts / objective must be device buffers");
+    if (n == 0) return SC_OK;
+    if (!x) return fail(SC_ERR_INVALID, "x is NULL");
+    SC(begin_call(ix, st));
+    int64_t chunk = std::max<int64_t>(1024, ((int64_t)256 << 20) / ((int64_t)ix->ds * 4));
+    chunk = std::min(chunk, n);
+    CU(ix->s_assign.reserve((size_t)chunk * 4));
+    CU(ix->s_best.reserve((size_t)chunk * 4));
+    for (int64_t s = 0; s < n; s += chunk) {
+        const int64_t m = std::min(chunk, n - s);
+        const float *xd = nullptr;
+        SC(stage_rows(ix, x + s * ix->dim, m, ix->s_x, ix->s_xpad, st, &xd));
+        SC(coarse_assign(ix, xd, m, ix->s_assign.as<int32_t>(), ix->s_best.as<float>(), st));
+        CU(launch_kmeans_accumulate(xd, m, ix->ds, ix->s_assign.as<int32_t>(), ix->s_best.as<float>(), ix->metric, sums,
+                                    counts, objective, st));
+    }
+    SC(end_call(ix, st));
+    return SC_OK;
+}
+
+// centroids <- sums / counts, then FAISS-style split of empty clusters (largest donor first,
+// ties to the lowest index, +-1/1024 perturbation).  nsplit_out (host, nullable).
+int sc_index_kmeans_update(sc_index_t *ix, const double *sums, const int32_t *counts, int32_t *nsplit_out,
+                           void *stream) {
+    if (!ix || !sums || !counts) return fail(SC_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    SC(require_trained(ix));
+    if (!is_device_ptr(sums, ix->device) || !is_device_ptr(counts, ix->device))
+        return fail(SC_ERR_INVALID, "sums / counts must be device buffers");
+    SC(begin_call(ix, st));
+    CU(launch_kmeans_finalize(sums, counts, ix->nlist, ix->ds, ix->centroids, st));
+    std::vector<int32_t> hc(ix->nlist);
+    CU(cudaMemcpyAsync(hc.data(), counts, (size_t)ix->nlist * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    int nsplit = 0;
+    std::vector<int64_t> c64(hc.begin(), hc.end());
+    for (int ci = 0; ci < ix->nlist; ++ci) {
+        if (c64[ci] != 0) continue;
+        int cj = 0;
+        for (int j = 1; j < ix->nlist; ++j)
+            if (c64[j] > c64[cj]) cj = j;
+        if (c64[cj] < 2) break;
+        CU(launch_split_centroid(ix->centroids, ix->ds, ci, cj, st));
+        c64[ci] = c64[cj] / 2;
+        c64[cj] -= c64[ci];
+        ++nsplit;
+    }
+    SC(update_cnorm(ix, st));
+    SC(end_call(ix, st));
+    CU(cudaStreamSynchronize(st));
+    if (nsplit_out) *nsplit_out = nsplit;
+    return SC_OK;
+}
+
+int sc_index_train(sc_index_t *ix, const float *x, int64_t n, int32_t niter, const int64_t *init_rows,
+                   double *objective_out, void *stream) {
+    if (!ix || !x || !init_rows) return fail(SC_ERR_INVALID, "NULL argument");
+    if (niter < 0) return fail(SC_ERR_INVALID, "niter < 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    const float *xd = x;
+    float *owned = nullptr;
+    {
+        DeviceGuard g(ix->device);
+        if (!is_device_ptr(x, ix->device)) {
+            // keep the training set resident for all iterations
+            cudaError_t e = cudaMalloc(&owned, (size_t)n * ix->dim * 4);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return fail(SC_ERR_OOM, "cannot stage %lld training rows on the device: %s", (long long)n, cudaGetErrorString(e));
+            }
+            e = cudaMemcpyAsync(owned, x, (size_t)n * ix->dim * 4, cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) {
+                cudaFree(owned);
+                return fail(SC_ERR_CUDA, "H2D copy of the training set failed: %s", cudaGetErrorString(e));
+            }
+            xd = owned;
+        }
+    }
+    int rc = sc_index_kmeans_init(ix, xd, n, init_rows, stream);
+    double *sums = nullptr;
+    int32_t *counts = nullptr;
+    double *obj = nullptr;
+    {
+        DeviceGuard g(ix->device);
+        if (rc == SC_OK) {
+            cudaError_t e = cudaMalloc(&sums, (size_t)ix->nlist * ix->ds * 8);
+            if (e == cudaSuccess) e = cudaMalloc(&counts, (size_t)ix->nlist * 4);
+            if (e == cudaSuccess) e = cudaMalloc(&obj, 8);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                rc = fail(SC_ERR_OOM, "k-means accumulators: %s", cudaGetErrorString(e));
+            }
+        }
+        for (int it = 0; rc == SC_OK && it < niter; ++it) {
+            cudaMemsetAsync(sums, 0, (size_t)ix->nlist * ix->ds * 8, st);
+            cudaMemsetAsync(counts, 0, (size_t)ix->nlist * 4, st);
+            cudaMemsetAsync(obj, 0, 8, st);
+            rc = sc_index_kmeans_step(ix, xd, n, sums, counts, obj, stream);
+            if (rc != SC_OK) break;
+            if (objective_out) {
+                cudaError_t e = cudaMemcpyAsync(objective_out + it, obj, 8, cudaMemcpyDeviceToHost, st);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+                if (e != cudaSuccess) {
+                    rc = fail(SC_ERR_CUDA, "objective readback: %s", cudaGetErrorString(e));
+                    break;
+                }
+            }
+            rc = sc_index_kmeans_update(ix, sums, counts, nullptr, stream);
+        }
+        cudaStreamSynchronize(st);
+        if (sums) cudaFree(sums);
+        if (counts) cudaFree(counts);
+        if (obj) cudaFree(obj);
+        if (owned) cudaFree(owned);
+    }
+    return rc;
+}
+
+// ---- coarse quantizer -----------------------------------------------------------------------------
+int sc_index_assign(sc_index_t *ix, const float *x, int64_t n, int32_t *out_list, void *stream) {
+    if (!ix || !out_list) return fail(SC_ERR_INVALID, "NULL argument");
+    if (n < 0) return fail(SC_ERR_INVALID, "n < 0");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    SC(require_trained(ix));
+    if (n == 0) return SC_OK;
+    if (!x) return fail(SC_ERR_INVALID, "x is NULL");
+    SC(begin_call(ix, st));
+    const bool dev = is_device_ptr(out_list, ix->device);
+    int64_t chunk = std::max<int64_t>(1024, ((int64_t)256 << 20) / ((int64_t)ix->ds * 4));
+    chunk = std::min(chunk, n);
+    if (!dev) CU(ix->s_assign.reserve((size_t)chunk * 4));
+    for (int64_t s = 0; s < n; s += chunk) {
+        const int64_t m = std::min(chunk, n - s);
+        const float *xd = nullptr;
+        SC(stage_rows(ix, x + s * ix->dim, m, ix->s_x, ix->s_xpad, st, &xd));
+        int32_t *dst = dev ? out_list + s : ix->s_assign.as<int32_t>();
+        SC(coarse_assign(ix, xd, m, dst, nullptr, st));
+        if (!dev) CU(cudaMemcpyAsync(out_list + s, dst, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    }
+    SC(end_call(ix, st));
+    if (!dev) CU(cudaStreamSynchronize(st));
+    return SC_OK;
+}
+
+int sc_index_probe(sc_index_t *ix, const float *q, int64_t nq, int32_t nprobe, int32_t *out_lists, float *out_scores,
+                   void *stream) {
+    if (!ix || !out_lists) return fail(SC_ERR_INVALID, "NULL argument");
+    if (nq < 0 || nprobe < 1) return fail(SC_ERR_INVALID, "bad nq / nprobe");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    SC(require_trained(ix));
+    if (nprobe > ix->nlist) return fail(SC_ERR_INVALID, "nprobe %d exceeds nlist %d (outputs are [nq, nprobe])", nprobe, ix->nlist);
+    if (nq == 0) return SC_OK;
+    if (!q) return fail(SC_ERR_INVALID, "q is NULL");
+    SC(begin_call(ix, st));
+    const bool ldev = is_device_ptr(out_lists, ix->device);
+    const bool sdev = out_scores ? is_device_ptr(out_scores, ix->device) : true;
+    const int64_t ch = coarse_chunk_rows(ix, nq);
+    CU(ix->s_scores.reserve((size_t)ch * ix->nlist * 4));
+    if (!ldev) CU(ix->s_probe.reserve((size_t)ch * nprobe * 4));
+    if (out_scores && !sdev) CU(ix->s_best.reserve((size_t)ch * nprobe * 4));
+    for (int64_t s = 0; s < nq; s += ch) {
+        const int64_t m = std::min(ch, nq - s);
+        const float *qd = nullptr;
+        SC(stage_rows(ix, q + s * ix->dim, m, ix->s_q, ix->s_xpad, st, &qd));
+        CU(launch_gemm_nt(qd, m, ix->centroids, ix->nlist, ix->ds, ix->metric == SC_METRIC_L2 ? ix->cnorm : nullptr,
+                          ix->s_scores.as<float>(), st));
+        int32_t *ol = ldev ? out_lists + s * nprobe : ix->s_probe.as<int32_t>();
+        float *os = out_scores ? (sdev ? out_scores + s * nprobe : ix->s_best.as<float>()) : nullptr;
+        CU(launch_select_rows(ix->s_scores.as<float>(), m, ix->nlist, nprobe, ol, os, st));
+        if (!ldev) CU(cudaMemcpyAsync(out_lists + s * nprobe, ol, (size_t)m * nprobe * 4, cudaMemcpyDeviceToHost, st));
+        if (out_scores && !sdev)
+            CU(cudaMemcpyAsync(out_scores + s * nprobe, os, (size_t)m * nprobe * 4, cudaMemcpyDeviceToHost, st));
+    }
+    SC(end_call(ix, st));
+    if (!ldev || !sdev) CU(cudaStreamSynchronize(st));
+    return SC_OK;
+}
+
+// ---- insert / remove ------------------------------------------------------------------------------
+int sc_index_add(sc_index_t *ix, const float *x, const int64_t *ids, const uint32_t *repo_tags,
+                 const uint8_t *lang_tags, int64_t n, void *stream) {
+    if (!ix) return fail(SC_ERR_INVALID, "idx is NULL");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    return add_impl(ix, x, ids, repo_tags, lang_tags, nullptr, n, (cudaStream_t)stream);
+}
+
+int sc_index_add_preassigned(sc_index_t *ix, const float *x, const int64_t *ids, const uint32_t *repo_tags,
+                             const uint8_t *lang_tags, const int32_t *lists, int64_t n, void *stream) {
+    if (!ix) return fail(SC_ERR_INVALID, "idx is NULL");
+    if (!lists && n > 0) return fail(SC_ERR_INVALID, "lists is NULL");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    return add_impl(ix, x, ids, repo_tags, lang_tags, lists, n, (cudaStream_t)stream);
+}
+
+int sc_index_remove_ids(sc_index_t *ix, const int64_t *ids, int64_t n, int64_t *n_removed_out, void *stream) {
+    if (!ix) return fail(SC_ERR_INVALID, "idx is NULL");
+    if (n < 0) return fail(SC_ERR_INVALID, "n < 0");
+    if (n_removed_out) *n_removed_out = 0;
+    if (n == 0) return SC_OK;
+    if (!ids) return fail(SC_ERR_INVALID, "ids is NULL");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaDeviceSynchronize());
+    std::vector<int64_t> h((size_t)n);
+    if (is_device_ptr(ids, ix->device)) {
+        CU(cudaMemcpy(h.data(), ids, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    } else {
+        memcpy(h.data(), ids, (size_t)n * 8);
+    }
+    std::sort(h.begin(), h.end());
+    h.erase(std::unique(h.begin(), h.end()), h.end());
+    CU(ix->s_rm.reserve(h.size() * 8));
+    CU(ix->s_cnt.reserve(8));
+    CU(cudaMemcpyAsync(ix->s_rm.p, h.data(), h.size() * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(ix->s_cnt.p, 0, 8, st));
+    CU(launch_remove_ids(ix->s_rm.as<int64_t>(), (int64_t)h.size(), ix->d_tab, ix->slab_shift, ix->pool_top,
+                         ix->s_cnt.as<unsigned long long>(), st));
+    unsigned long long cnt = 0;
+    CU(cudaMemcpyAsync(&cnt, ix->s_cnt.p, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    ix->ntotal -= (int64_t)cnt;
+    ix->nremoved += (int64_t)cnt;
+    if (n_removed_out) *n_removed_out = (int64_t)cnt;
+    return SC_OK;
+}
+
+// ---- search ---------------------------------------------------------------------------------------
+int sc_index_search(sc_index_t *ix, const float *q, int64_t nq, int32_t k, int32_t nprobe, const sc_filter_t *filter,
+                    float *out_dist, int64_t *out_ids, void *stream) {
+    if (!ix) return fail(SC_ERR_INVALID, "idx is NULL");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    return search_impl(ix, q, nq, k, nprobe, nullptr, filter, out_dist, out_ids, (cudaStream_t)stream);
+}
+
+int sc_index_search_preassigned(sc_index_t *ix, const float *q, int64_t nq, int32_t k, int32_t nprobe,
+                                const int32_t *lists, const sc_filter_t *filter, float *out_dist, int64_t *out_ids,
+                                void *stream) {
+    if (!ix) return fail(SC_ERR_INVALID, "idx is NULL");
+    if (!lists && nq > 0) return fail(SC_ERR_INVALID, "lists is NULL");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    return search_impl(ix, q, nq, k, nprobe, lists, filter, out_dist, out_ids, (cudaStream_t)stream);
+}
+
+int sc_merge_topk(const float *part_dist, const int64_t *part_ids, int32_t parts, int64_t nq, int32_t kin, int32_t k,
+                  int32_t metric, float *out_dist, int64_t *out_ids, int32_t device, void *stream) {
+    if (!part_dist || !part_ids || !out_dist || !out_ids) return fail(SC_ERR_INVALID, "NULL argument");
+    if (parts < 1 || kin < 1 || k < 1 || k > kMaxK || nq < 0) return fail(SC_ERR_INVALID, "bad parts / kin / k / nq");
+    if (metric != SC_METRIC_IP && metric != SC_METRIC_L2) return fail(SC_ERR_INVALID, "unknown metric %d", metric);
+    DeviceGuard g(device);
+    if (!g.ok) return fail(SC_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    if (!is_device_ptr(part_dist, device) || !is_device_ptr(part_ids, device) || !is_device_ptr(out_dist, device) ||
+        !is_device_ptr(out_ids, device))
+        return fail(SC_ERR_INVALID, "sc_merge_topk works on device buffers only");
+    CU(launch_merge_topk(part_dist, part_ids, parts, nq, kin, k, metric, out_dist, out_ids, (cudaStream_t)stream));
+    return SC_OK;
+}
+
+// ---- introspection ----------------------------------------------------------------------------------
+int sc_index_stats(sc_index_t *ix, sc_stats_t *out) {
+    if (!ix || !out) return fail(SC_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    memset(out, 0, sizeof(*out));
+    out->dim = ix->dim;
+    out->dim_padded = ix->ds;
+    out->metric = ix->metric;
+    out->nlist = ix->nlist;
+    out->device = ix->device;
+    out->trained = ix->trained ? 1 : 0;
+    out->ntotal = ix->ntotal;
+    out->nremoved = ix->nremoved;
+    out->npages = ix->pool_top;
+    const int64_t rows = ((int64_t)ix->slabs.size() << ix->slab_shift) * kPageRows;
+    out->bytes_lists = rows * ((int64_t)ix->ds * 4 + 12);
+    int64_t sb = 0;
+    for (const DevBuf *b : {&ix->s_q, &ix->s_scores, &ix->s_probe, &ix->s_pairpages, &ix->s_pageoff, &ix->s_cand,
+                            &ix->s_outd, &ix->s_outi, &ix->s_repobits, &ix->s_x, &ix->s_xpad, &ix->s_ids, &ix->s_repo,
+                            &ix->s_lang, &ix->s_assign, &ix->s_best, &ix->s_pos, &ix->s_lenold, &ix->s_need, &ix->s_npg,
+                            &ix->s_needoff, &ix->s_bad, &ix->s_sums, &ix->s_counts, &ix->s_obj, &ix->s_rows, &ix->s_rm,
+                            &ix->s_cnt})
+        sb += (int64_t)b->cap;
+    out->bytes_scratch = sb;
+    int32_t mx = 0, mn = ix->nlist > 0 ? INT32_MAX : 0;
+    for (int32_t v : ix->h_len) {
+        mx = std::max(mx, v);
+        mn = std::min(mn, v);
+    }
+    out->max_list_len = mx;
+    out->min_list_len = mn;
+    return SC_OK;
+}
+
+int sc_index_list_sizes(sc_index_t *ix, int32_t *out_host) {
+    if (!ix || !out_host) return fail(SC_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    memcpy(out_host, ix->h_len.data(), (size_t)ix->nlist * 4);
+    return SC_OK;
+}
+
+int sc_index_export_list(sc_index_t *ix, int32_t list, int64_t cap, float *vecs, int64_t *ids, uint32_t *tags,
+                         int64_t *len_out, void *stream) {
+    if (!ix) return fail(SC_ERR_INVALID, "idx is NULL");
+    if (list < 0 || list >= ix->nlist) return fail(SC_ERR_INVALID, "list %d outside [0,%d)", list, ix->nlist);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int32_t len = ix->h_len[list];
+    if (len_out) *len_out = len;
+    if (len == 0 || (!vecs && !ids && !tags)) return SC_OK;
+    if (cap < len) return fail(SC_ERR_INVALID, "list %d holds %d rows, buffers hold %lld", list, len, (long long)cap);
+    SC(begin_call(ix, st));
+    int32_t pt_begin = 0;
+    CU(cudaMemcpyAsync(&pt_begin, ix->pt_off + list, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const bool vdev = vecs ? is_device_ptr(vecs, ix->device) : true;
+    const bool idev = ids ? is_device_ptr(ids, ix->device) : true;
+    const bool tdev = tags ? is_device_ptr(tags, ix->device) : true;
+    float *vd = vecs;
+    int64_t *idd = ids;
+    uint32_t *td = tags;
+    if (vecs && !vdev) {
+        CU(ix->s_x.reserve((size_t)len * ix->dim * 4));
+        vd = ix->s_x.as<float>();
+    }
+    if (ids && !idev) {
+        CU(ix->s_ids.reserve((size_t)len * 8));
+        idd = ix->s_ids.as<int64_t>();
+    }
+    if (tags && !tdev) {
+        CU(ix->s_repo.reserve((size_t)len * 4));
+        td = ix->s_repo.as<uint32_t>();
+    }
+    CU(launch_export_list(ix->pt, pt_begin, len, ix->ds, ix->dim, ix->d_tab, ix->slab_shift, vd, idd, td, st));
+    if (vecs && !vdev) CU(cudaMemcpyAsync(vecs, vd, (size_t)len * ix->dim * 4, cudaMemcpyDeviceToHost, st));
+    if (ids && !idev) CU(cudaMemcpyAsync(ids, idd, (size_t)len * 8, cudaMemcpyDeviceToHost, st));
+    if (tags && !tdev) CU(cudaMemcpyAsync(tags, td, (size_t)len * 4, cudaMemcpyDeviceToHost, st));
+    SC(end_call(ix, st));
+    CU(cudaStreamSynchronize(st));
+    return SC_OK;
+}
+
+int sc_index_set_profiling(sc_index_t *ix, int32_t enabled) {
+    if (!ix) return fail(SC_ERR_INVALID, "idx is NULL");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ix->profiling = enabled != 0;
+    if (!ix->profiling) {
+        DeviceGuard g(ix->device);
+        clear_prof(ix);
+    }
+    return SC_OK;
+}
+
+int sc_index_last_search_times(sc_index_t *ix, sc_search_times_t *out) {
+    if (!ix || !out) return fail(SC_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    memset(out, 0, sizeof(*out));
+    if (!ix->profiling || ix->prof_ev.empty()) return fail(SC_ERR_STATE, "profiling is off or no search has run");
+    if (ix->prof_ev.size() % 6 != 0) return fail(SC_ERR_STATE, "incomplete profile (a search failed midway)");
+    CU(cudaEventSynchronize(ix->prof_ev.back()));
+    for (size_t c = 0; c < ix->prof_ev.size(); c += 6) {
+        float ms[5];
+        for (int i = 0; i < 5; ++i) CU(cudaEventElapsedTime(&ms[i], ix->prof_ev[c + i], ix->prof_ev[c + i + 1]));
+        out->coarse_ms += ms[0];
+        out->probe_select_ms += ms[1];
+        out->plan_ms += ms[2];
+        out->scan_ms += ms[3];
+        out->topk_ms += ms[4];
+    }
+    float tot = 0.f;
+    CU(cudaEventElapsedTime(&tot, ix->prof_ev.front(), ix->prof_ev.back()));
+    out->total_ms = tot;
+    unsigned long long rows = 0;
+    if (ix->prof_rows) CU(cudaMemcpy(&rows, ix->prof_rows, 8, cudaMemcpyDeviceToHost));
+    out->scanned_rows = (int64_t)rows;
+    out->scanned_pages = 0;
+    out->scan_launches = ix->prof_scan_launches;
+    out->total_launches = ix->prof_total_launches;
+    return SC_OK;
+}
+
+int sc_index_set_param(sc_index_t *ix, const char *name, int64_t value) {
+    if (!ix || !name) return fail(SC_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (strcmp(name, "scratch_bytes") == 0) {
+        if (value < ((int64_t)1 << 20)) return fail(SC_ERR_INVALID, "scratch_bytes must be >= 1 MiB");
+        ix->scratch_budget = value;
+        return SC_OK;
+    }
+    if (strcmp(name, "scan_variant") == 0) {
+        if (value < 0 || value > 4) return fail(SC_ERR_INVALID, "scan_variant must be in [0,4]");
+        ix->scan_variant = (int)value;
+        return SC_OK;
+    }
+    return fail(SC_ERR_INVALID, "unknown parameter '%s'", name);
+}
+
+}  // extern "C"

@@ -1,0 +1,236 @@
+// K5: the nprobe inverted-list scan -- the HBM-bound hot kernel.
+//
+// Replaces FAISS IVFFlatScanner::scan_codes (+ knowhere BitsetView filtering) behind
+// Collection.search(data=[vector], param={"metric_type":"IP","params":{"nprobe":16}}, ...)
+// at reference src/semcode/storage/milvus_store.py:141-147.
+//
+// Work decomposition: the (query, probed list) pairs are flattened into 32-row *pages*
+// (page_off = exclusive prefix of pages per pair).  The kernel is persistent: every warp owns a
+// contiguous, equally sized range of pages, so each warp streams the same number of bytes no
+// matter how skewed the list lengths are.  Per page a warp
+//   1. reads the 32 row tags with one coalesced 128-byte load and evaluates the fused predicate
+//      (tombstone | language bitmap | repo bitmap) -> ballot of live rows;
+//   2. streams the live rows with 128-bit ld.global.nc.L1::no_allocate loads, R rows x U float4
+//      per lane in flight (all independent), against the query slice staged in shared memory;
+//   3. butterfly-reduces the R partial sums and writes one similarity per row into the candidate
+//      array (dead slots get -inf).  Top-k selection is a separate kernel (select.cu).
+// Algorithmic bytes per live row: 4*ds (vector) + 4 (tag); the 4-byte candidate write and the
+// winners' 8-byte ids are the only other traffic.  Roofline: HBM bandwidth.
+#include "common.cuh"
+
+namespace sc {
+
+namespace {
+
+__global__ void plan_pairs_kernel(const int32_t *__restrict__ probe, int64_t npairs,
+                                  const int32_t *__restrict__ list_len, int32_t nlist,
+                                  int64_t *__restrict__ pair_pages, unsigned long long *__restrict__ rows_total) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npairs) return;
+    const int32_t l = probe[i];
+    int64_t pages = 0;
+    if (l >= 0 && l < nlist) {
+        const int32_t len = list_len[l];
+        pages = (len + kPageRows - 1) / kPageRows;
+        if (rows_total != nullptr && len > 0) atomicAdd(rows_total, (unsigned long long)len);
+    }
+    pair_pages[i] = pages;
+}
+
+__device__ __forceinline__ bool filter_pass(const FilterDev &f, uint32_t tag) {
+    if (tag & kTagRemoved) return false;
+    if (f.flags & 1u) {
+        const uint32_t lang = tag & 0xffu;
+        if (!((f.lang_bits[lang >> 5] >> (lang & 31u)) & 1u)) return false;
+    }
+    if (f.flags & 2u) {
+        const uint32_t repo = (tag >> 8) & kTagRepoMax;
+        if (repo >= f.n_repo_bits) return false;
+        if (!((__ldg(f.repo_bits + (repo >> 5)) >> (repo & 31u)) & 1u)) return false;
+    }
+    return true;
+}
+
+template <bool L2>
+__device__ __forceinline__ float accum4(float acc, const float4 &x, const float4 &q) {
+    if (L2) {
+        const float a = x.x - q.x, b = x.y - q.y, c = x.z - q.z, d = x.w - q.w;
+        acc = fmaf(a, a, acc);
+        acc = fmaf(b, b, acc);
+        acc = fmaf(c, c, acc);
+        acc = fmaf(d, d, acc);
+    } else {
+        acc = fmaf(x.x, q.x, acc);
+        acc = fmaf(x.y, q.y, acc);
+        acc = fmaf(x.z, q.z, acc);
+        acc = fmaf(x.w, q.w, acc);
+    }
+    return acc;
+}
+
+// R rows in flight per warp, U float4 per lane per row per chunk. EXACT: ds4 % (32*U) == 0.
+template <int R, int U, bool L2, bool EXACT, int MINB>
+__global__ void __launch_bounds__(256, MINB) scan_pages_kernel(const ScanArgs a) {
+    extern __shared__ __align__(16) float4 qsmem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int wpb = blockDim.x >> 5;
+    const int ds4 = a.ds >> 2;
+    float4 *qs = qsmem + (size_t)warp * ds4;
+
+    const int64_t W = a.page_off[a.npairs];
+    const int64_t nwarps = (int64_t)gridDim.x * wpb;
+    const int64_t gw = (int64_t)blockIdx.x * wpb + warp;
+    const int64_t per = (W + nwarps - 1) / nwarps;
+    const int64_t w0 = gw * per;
+    const int64_t w1 = (w0 + per < W) ? (w0 + per) : W;
+    if (w0 >= w1) return;
+
+    // pair that owns page w0: last i with page_off[i] <= w0 (pairs with no pages are skipped)
+    int64_t lo = 0, hi = a.npairs;
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (a.page_off[mid] <= w0)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    int64_t pair = lo;
+    int64_t pair_start = a.page_off[pair];
+    int64_t pair_end = a.page_off[pair + 1];
+    int64_t cur_q = -1;
+    int32_t len = 0, ptbase = 0;
+    bool fresh = true;
+    const int slab_mask = (1 << a.slab_shift) - 1;
+
+    for (int64_t w = w0; w < w1; ++w) {
+        while (w >= pair_end) {
+            ++pair;
+            pair_start = pair_end;
+            pair_end = a.page_off[pair + 1];
+            fresh = true;
+        }
+        if (fresh) {
+            fresh = false;
+            const int32_t l = a.probe[pair];
+            len = a.list_len[l];
+            ptbase = a.pt_off[l];
+            const int64_t qi = pair / a.nprobe;
+            if (qi != cur_q) {
+                cur_q = qi;
+                __syncwarp();
+                const float4 *qg = reinterpret_cast<const float4 *>(a.q + qi * (int64_t)a.ds);
+                for (int c = lane; c < ds4; c += 32) qs[c] = __ldg(qg + c);
+                __syncwarp();
+            }
+        }
+        const int32_t j = (int32_t)(w - pair_start);
+        const int32_t page = __ldg(a.pt + ptbase + j);
+        const int slab = page >> a.slab_shift;
+        const int64_t slot0 = (int64_t)(page & slab_mask) * kPageRows;
+        const int rows = min(kPageRows, len - j * kPageRows);
+        const uint32_t tag = __ldg(a.slabs->tags[slab] + slot0 + lane);
+        const bool live = lane < rows && filter_pass(a.filt, tag);
+        uint32_t m = __ballot_sync(0xffffffffu, live);
+        float *cpage = a.cand + w * kPageRows;
+        if (!live) cpage[lane] = -INFINITY;
+        const float4 *vbase = reinterpret_cast<const float4 *>(a.slabs->vec[slab]) + slot0 * ds4;
+
+        while (m) {
+            int row[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                row[r] = m ? (__ffs(m) - 1) : -1;
+                m &= m - 1;  // 0 & (0-1) == 0
+            }
+            float acc[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r] = 0.f;
+            for (int c0 = 0; c0 < ds4; c0 += 32 * U) {
+                float4 x[R][U];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const float4 *rp = vbase + (int64_t)(row[r] < 0 ? row[0] : row[r]) * ds4 + c0 + lane;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (row[r] >= 0 && (EXACT || c0 + lane + 32 * u < ds4))
+                            x[r][u] = ld_stream_f4(rp + 32 * u);
+                        else
+                            x[r][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (EXACT || c0 + lane + 32 * u < ds4) qv = qs[c0 + lane + 32 * u];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) acc[r] = accum4<L2>(acc[r], x[r][u], qv);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float s = warp_sum(acc[r]);
+                if (lane == 0 && row[r] >= 0) cpage[row[r]] = L2 ? -s : s;
+            }
+        }
+    }
+}
+
+template <int R, int U, bool L2, bool EXACT, int MINB>
+cudaError_t launch_variant(const ScanArgs &a, int num_sms, cudaStream_t st) {
+    auto kern = scan_pages_kernel<R, U, L2, EXACT, MINB>;
+    // shared memory: one query copy per warp; shrink the CTA when the query is large
+    const size_t per_warp = (size_t)a.ds * sizeof(float);
+    int wpb = 8;
+    const size_t budget = (size_t)(200 * 1024) / MINB;
+    while (wpb > 1 && per_warp * wpb > budget) wpb >>= 1;
+    const size_t smem = per_warp * wpb;
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int grid = num_sms * MINB;
+    kern<<<grid, wpb * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int R, int U, int MINB>
+cudaError_t launch_rum(const ScanArgs &a, int num_sms, cudaStream_t st) {
+    const bool exact = ((a.ds >> 2) % (32 * U)) == 0;
+    if (a.metric == 1)
+        return exact ? launch_variant<R, U, true, true, MINB>(a, num_sms, st)
+                     : launch_variant<R, U, true, false, MINB>(a, num_sms, st);
+    return exact ? launch_variant<R, U, false, true, MINB>(a, num_sms, st)
+                 : launch_variant<R, U, false, false, MINB>(a, num_sms, st);
+}
+
+}  // namespace
+
+cudaError_t launch_plan_pairs(const int32_t *probe, int64_t npairs, const int32_t *list_len, int32_t nlist,
+                              int64_t *pair_pages, unsigned long long *rows_total, cudaStream_t st) {
+    if (npairs <= 0) return cudaSuccess;
+    plan_pairs_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(probe, npairs, list_len, nlist, pair_pages,
+                                                                         rows_total);
+    return cudaGetLastError();
+}
+
+// variant: 0 = auto, 1 = R2/U6 x2 CTAs, 2 = R4/U6 x1 CTA, 3 = R2/U4 x2 CTAs, 4 = R4/U4 x2 CTAs
+cudaError_t launch_scan_pages(const ScanArgs &a, int variant, int num_sms, int *launches, cudaStream_t st) {
+    if (a.npairs <= 0) return cudaSuccess;
+    if (launches) *launches += 1;
+    const int ds4 = a.ds >> 2;
+    if (variant == 0) variant = (ds4 % 192 == 0) ? 1 : 3;
+    switch (variant) {
+        case 1:
+            return launch_rum<2, 6, 2>(a, num_sms, st);
+        case 2:
+            return launch_rum<4, 6, 1>(a, num_sms, st);
+        case 3:
+            return launch_rum<2, 4, 2>(a, num_sms, st);
+        case 4:
+            return launch_rum<4, 4, 2>(a, num_sms, st);
+        default:
+            return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace sc

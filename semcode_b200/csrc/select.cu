@@ -1,0 +1,353 @@
+// K6: per-query top-k selection.  One CTA per query: 3-pass radix select (11/11/10 bits) over an
+// order-preserving key finds the k-th best similarity exactly, the winners are compacted into
+// shared memory and bitonic-sorted (key descending, candidate index ascending), then translated
+// to ids.  Replaces FAISS HeapResultHandler / the Milvus segment reduce behind
+// Collection.search(..., limit=top_k)  (reference src/semcode/storage/milvus_store.py:141-147).
+//
+// The same kernel serves three candidate sources:
+//   RowsSrc   coarse similarities [nq, nlist]        -> the nprobe best lists per query (K1 tail)
+//   CandSrc   candidate similarities written by K5   -> final (dist, id) per query
+//   MergeSrc  partial results of several shards      -> merged (dist, id) (K7 tail)
+#include <float.h>
+
+#include "common.cuh"
+
+namespace sc {
+
+namespace {
+
+constexpr int SEL_T = 512;
+constexpr int SEL_BINS = 2048;
+
+struct SelShared {
+    uint32_t hist[SEL_BINS];
+    unsigned long long pairs[kMaxK];
+    uint32_t warp_tot[SEL_T / 32];
+    uint32_t sel_bin, need, eq_total, cnt_gt, cnt_eq, base;
+};
+
+__device__ __forceinline__ unsigned long long pack_pair(uint32_t key, uint32_t idx) {
+    return ((unsigned long long)key << 32) | (unsigned long long)(0xffffffffu - idx);
+}
+
+// ---- candidate sources ----------------------------------------------------------------------
+struct RowsSrc {
+    const float *s;
+    int N;
+    int k;
+    int32_t *out_idx;
+    float *out_val;
+    struct View {
+        const float *p;
+        uint32_t n;
+        __device__ __forceinline__ float load(uint32_t i) const { return __ldg(p + i); }
+    };
+    __device__ __forceinline__ View view(int64_t q) const { return View{s + q * (int64_t)N, (uint32_t)N}; }
+    __device__ __forceinline__ void emit(int64_t q, int j, bool valid, float score, uint32_t idx) const {
+        out_idx[q * k + j] = valid ? (int32_t)idx : -1;
+        if (out_val) out_val[q * k + j] = valid ? score : -INFINITY;
+    }
+};
+
+struct CandSrc {
+    ScanArgs a;
+    int k;
+    float *out_dist;
+    int64_t *out_ids;
+    struct View {
+        const float *p;
+        uint32_t n;
+        __device__ __forceinline__ float load(uint32_t i) const { return __ldg(p + i); }
+    };
+    __device__ __forceinline__ View view(int64_t q) const {
+        const int64_t b = a.page_off[q * a.nprobe], e = a.page_off[(q + 1) * a.nprobe];
+        return View{a.cand + b * kPageRows, (uint32_t)((e - b) * kPageRows)};
+    }
+    __device__ __forceinline__ void emit(int64_t q, int j, bool valid, float score, uint32_t idx) const {
+        const bool ip = a.metric == 0;
+        if (!valid) {
+            out_dist[q * k + j] = ip ? -FLT_MAX : FLT_MAX;
+            out_ids[q * k + j] = -1;
+            return;
+        }
+        const int64_t w = a.page_off[q * a.nprobe] + (idx >> 5);
+        const int r = idx & 31;
+        // last pair i in [q*nprobe, (q+1)*nprobe) with page_off[i] <= w
+        int64_t lo = q * a.nprobe, hi = (q + 1) * a.nprobe;  // invariant: page_off[lo] <= w < page_off[hi]
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (a.page_off[mid] <= w)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const int32_t l = a.probe[lo];
+        const int32_t page = a.pt[a.pt_off[l] + (int32_t)(w - a.page_off[lo])];
+        const int slab = page >> a.slab_shift;
+        const int64_t slot = (int64_t)(page & ((1 << a.slab_shift) - 1)) * kPageRows + r;
+        out_ids[q * k + j] = a.slabs->ids[slab][slot];
+        out_dist[q * k + j] = ip ? score : -score;
+    }
+};
+
+struct MergeSrc {
+    const float *pd;
+    const int64_t *pi;
+    int parts;
+    int64_t nq;
+    int kin;
+    int k;
+    int metric;
+    float *out_dist;
+    int64_t *out_ids;
+    __device__ __forceinline__ int64_t off(int64_t q, uint32_t i) const {
+        const int p = i / kin, j = i - p * kin;
+        return ((int64_t)p * nq + q) * kin + j;
+    }
+    struct View {
+        const MergeSrc *m;
+        int64_t q;
+        uint32_t n;
+        __device__ __forceinline__ float load(uint32_t i) const {
+            const int64_t o = m->off(q, i);
+            if (m->pi[o] < 0) return -INFINITY;
+            const float d = m->pd[o];
+            return m->metric == 0 ? d : -d;
+        }
+    };
+    __device__ __forceinline__ View view(int64_t q) const { return View{this, q, (uint32_t)(parts * kin)}; }
+    __device__ __forceinline__ void emit(int64_t q, int j, bool valid, float, uint32_t idx) const {
+        if (!valid) {
+            out_dist[q * k + j] = metric == 0 ? -FLT_MAX : FLT_MAX;
+            out_ids[q * k + j] = -1;
+            return;
+        }
+        const int64_t o = off(q, idx);
+        out_dist[q * k + j] = pd[o];
+        out_ids[q * k + j] = pi[o];
+    }
+};
+
+// inclusive warp scan
+template <typename T>
+__device__ __forceinline__ T warp_incl_scan(T v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const T t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+template <class Src>
+__global__ void __launch_bounds__(SEL_T) select_topk_kernel(Src src, int k) {
+    __shared__ SelShared sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t q = blockIdx.x;
+    const typename Src::View view = src.view(q);
+    const uint32_t n = view.n;
+    const uint32_t kk = (uint32_t)k < n ? (uint32_t)k : n;
+
+    if (kk == 0) {
+        for (int j = tid; j < k; j += SEL_T) src.emit(q, j, false, 0.f, 0);
+        return;
+    }
+
+    uint32_t prefix = 0, mask = 0, need = kk;
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+        const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+        const uint32_t nb = pass == 2 ? 1024u : 2048u;
+        for (int b = tid; b < SEL_BINS; b += SEL_T) sh.hist[b] = 0;
+        __syncthreads();
+        for (uint32_t i = tid; i < n; i += SEL_T) {
+            const uint32_t key = f2key(view.load(i));
+            if ((key & mask) == prefix) atomicAdd(&sh.hist[(key >> shift) & (nb - 1)], 1u);
+        }
+        __syncthreads();
+        // thread t owns bins 4t..4t+3; find the bin (from the top) that holds the need-th element
+        uint32_t c[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) c[b] = sh.hist[4 * tid + b];
+        const uint32_t local = c[0] + c[1] + c[2] + c[3];
+        const uint32_t incl = warp_incl_scan(local, lane);
+        if (lane == 31) sh.warp_tot[warp] = incl;
+        __syncthreads();
+        uint32_t wprefix = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < SEL_T / 32; ++w) {
+            const uint32_t t = sh.warp_tot[w];
+            if (w < warp) wprefix += t;
+            total += t;
+        }
+        uint32_t running = total - (wprefix + incl);  // elements in bins above this thread's bins
+#pragma unroll
+        for (int b = 3; b >= 0; --b) {
+            if (running < need && running + c[b] >= need) {
+                sh.sel_bin = 4 * tid + b;
+                sh.need = need - running;
+                sh.eq_total = c[b];
+            }
+            running += c[b];
+        }
+        __syncthreads();
+        prefix |= sh.sel_bin << shift;
+        mask |= (nb - 1) << shift;
+        need = sh.need;
+        __syncthreads();
+    }
+
+    const uint32_t T = prefix;           // key of the kk-th best candidate
+    const uint32_t n_gt = kk - need;     // candidates strictly better than T
+    const uint32_t eq_total = sh.eq_total;
+    const bool take_eq = T > kKeyNegInf;  // keys <= key(-inf) are "no result"
+    const bool ordered = take_eq && eq_total > need;
+    if (tid == 0) {
+        sh.cnt_gt = 0;
+        sh.cnt_eq = 0;
+        sh.base = 0;
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += SEL_T) {
+        const uint32_t key = f2key(view.load(i));
+        if (key > T) {
+            const uint32_t s = atomicAdd(&sh.cnt_gt, 1u);
+            sh.pairs[s] = pack_pair(key, i);
+        } else if (key == T && take_eq && !ordered) {
+            const uint32_t s = atomicAdd(&sh.cnt_eq, 1u);
+            if (s < need) sh.pairs[n_gt + s] = pack_pair(key, i);
+        }
+    }
+    __syncthreads();
+    if (ordered) {
+        // more candidates tie with the k-th than there is room for: keep the lowest indices
+        for (uint32_t c0 = 0; c0 < n; c0 += SEL_T) {
+            const uint32_t base = sh.base;
+            if (base >= need) break;
+            const uint32_t i = c0 + tid;
+            const bool flag = i < n && f2key(view.load(i)) == T;
+            const uint32_t bal = __ballot_sync(0xffffffffu, flag);
+            if (lane == 0) sh.warp_tot[warp] = __popc(bal);
+            __syncthreads();
+            uint32_t wprefix = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < SEL_T / 32; ++w) {
+                const uint32_t t = sh.warp_tot[w];
+                if (w < warp) wprefix += t;
+                total += t;
+            }
+            const uint32_t rank = base + wprefix + __popc(bal & ((1u << lane) - 1u));
+            if (flag && rank < need) sh.pairs[n_gt + rank] = pack_pair(T, i);
+            __syncthreads();
+            if (tid == 0) sh.base = base + total;
+            __syncthreads();
+        }
+    }
+    const uint32_t n_valid = n_gt + (take_eq ? need : 0u);
+
+    // bitonic sort (descending) of the winners
+    uint32_t P = 1;
+    while (P < n_valid) P <<= 1;
+    for (uint32_t i = n_valid + tid; i < P; i += SEL_T) sh.pairs[i] = 0ull;
+    __syncthreads();
+    for (uint32_t size = 2; size <= P; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = tid; t < (P >> 1); t += SEL_T) {
+                const uint32_t lo = 2 * t - (t & (stride - 1));
+                const uint32_t hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const unsigned long long x = sh.pairs[lo], y = sh.pairs[hi];
+                if ((x < y) == desc) {
+                    sh.pairs[lo] = y;
+                    sh.pairs[hi] = x;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int j = tid; j < k; j += SEL_T) {
+        if ((uint32_t)j < n_valid) {
+            const unsigned long long p = sh.pairs[j];
+            src.emit(q, j, true, key2f((uint32_t)(p >> 32)), 0xffffffffu - (uint32_t)p);
+        } else {
+            src.emit(q, j, false, 0.f, 0);
+        }
+    }
+}
+
+// ---- exclusive prefix sums (single CTA; inputs are at most nq*nprobe or nlist long) -----------
+template <typename T>
+__global__ void __launch_bounds__(1024) exclusive_scan_kernel(const T *__restrict__ in, int64_t n, T *__restrict__ out) {
+    __shared__ T warp_tot[32];
+    __shared__ T blk_total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    T carry = 0;
+    constexpr int IPT = 4;
+    for (int64_t base = 0; base < n; base += 1024 * IPT) {
+        const int64_t i0 = base + (int64_t)tid * IPT;
+        T v[IPT];
+        T local = 0;
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+            v[j] = (i0 + j < n) ? in[i0 + j] : (T)0;
+            local += v[j];
+        }
+        const T incl = warp_incl_scan(local, lane);
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const T t = warp_tot[lane];
+            const T ti = warp_incl_scan(t, lane);
+            warp_tot[lane] = ti - t;
+            if (lane == 31) blk_total = ti;
+        }
+        __syncthreads();
+        T run = carry + warp_tot[warp] + incl - local;
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+            if (i0 + j < n) out[i0 + j] = run;
+            run += v[j];
+        }
+        carry += blk_total;
+        __syncthreads();
+    }
+    if (tid == 0) out[n] = carry;
+}
+
+}  // namespace
+
+cudaError_t launch_select_rows(const float *scores, int64_t M, int N, int k, int32_t *out_idx, float *out_val,
+                               cudaStream_t st) {
+    if (M <= 0) return cudaSuccess;
+    RowsSrc src{scores, N, k, out_idx, out_val};
+    select_topk_kernel<RowsSrc><<<(unsigned)M, SEL_T, 0, st>>>(src, k);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_select_candidates(const ScanArgs &a, int64_t nq, int k, float *out_dist, int64_t *out_ids,
+                                     cudaStream_t st) {
+    if (nq <= 0) return cudaSuccess;
+    CandSrc src{a, k, out_dist, out_ids};
+    select_topk_kernel<CandSrc><<<(unsigned)nq, SEL_T, 0, st>>>(src, k);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_merge_topk(const float *part_dist, const int64_t *part_ids, int parts, int64_t nq, int kin, int k,
+                              int metric, float *out_dist, int64_t *out_ids, cudaStream_t st) {
+    if (nq <= 0) return cudaSuccess;
+    MergeSrc src{part_dist, part_ids, parts, nq, kin, k, metric, out_dist, out_ids};
+    select_topk_kernel<MergeSrc><<<(unsigned)nq, SEL_T, 0, st>>>(src, k);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_exclusive_scan_i64(const int64_t *in, int64_t n, int64_t *out, cudaStream_t st) {
+    exclusive_scan_kernel<int64_t><<<1, 1024, 0, st>>>(in, n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_exclusive_scan_i32(const int32_t *in, int64_t n, int32_t *out, cudaStream_t st) {
+    exclusive_scan_kernel<int32_t><<<1, 1024, 0, st>>>(in, n, out);
+    return cudaGetLastError();
+}
+
+}  // namespace sc

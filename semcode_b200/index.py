@@ -1,0 +1,444 @@
+"""IVFFlatIndex -- Python host mirror of one sc_index (one B200).
+
+This is the object the drop-in ``MilvusVectorStore`` (storage/milvus_store.py) drives in place of
+the Milvus collection index declared at reference src/semcode/storage/milvus_store.py:76-83
+(``IVF_FLAT``, ``metric_type`` IP, ``nlist``) and searched at :141-147 (``nprobe``).  All arithmetic
+happens in libsemcode_ivf.so; torch is used for device buffers and streams only.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Iterable, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _capi
+from ._capi import METRIC_IP, METRIC_L2, torch
+
+Array = Union[np.ndarray, "torch.Tensor"]
+
+# FAISS ClusteringParameters defaults the reference engine would use [EXT]
+KMEANS_NITER = 25
+KMEANS_SEED = 1234
+KMEANS_MAX_POINTS_PER_CENTROID = 256
+KMEANS_MIN_POINTS_PER_CENTROID = 39
+
+
+def metric_code(metric) -> int:
+    if metric in (METRIC_IP, "IP", "ip"):
+        return METRIC_IP
+    if metric in (METRIC_L2, "L2", "l2"):
+        return METRIC_L2
+    raise ValueError(f"unknown metric {metric!r} (expected 'IP' or 'L2')")
+
+
+def kmeans_init_rows(n: int, nlist: int, seed: int) -> np.ndarray:
+    """Rows that seed the centroids: a seeded random sample without replacement, sorted."""
+    return np.sort(np.random.default_rng(seed).permutation(n)[:nlist]).astype(np.int64)
+
+
+def kmeans_subsample_rows(n: int, nlist: int, max_points_per_centroid: int, seed: int) -> Optional[np.ndarray]:
+    """FAISS trains on at most max_points_per_centroid*nlist rows [EXT]; None = use every row."""
+    if max_points_per_centroid <= 0 or n <= max_points_per_centroid * nlist:
+        return None
+    rows = np.random.default_rng(seed + 1).permutation(n)[: max_points_per_centroid * nlist]
+    return np.sort(rows).astype(np.int64)
+
+
+def _is_tensor(x) -> bool:
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+def _as_rows(x: Array, dim: int, name: str) -> Array:
+    """float32, C-contiguous [n, dim] without changing where the data lives."""
+    if _is_tensor(x):
+        if x.dim() == 1:
+            x = x.unsqueeze(0)
+        if x.dim() != 2 or x.shape[1] != dim:
+            raise ValueError(f"{name}: expected shape [n, {dim}], got {tuple(x.shape)}")
+        return x.to(torch.float32).contiguous()
+    a = np.asarray(x, dtype=np.float32)
+    if a.ndim == 1:
+        a = a[None, :]
+    if a.ndim != 2 or a.shape[1] != dim:
+        raise ValueError(f"{name}: expected shape [n, {dim}], got {a.shape}")
+    return np.ascontiguousarray(a)
+
+
+def _as_vec(x, kind: str, n: int, name: str) -> Optional[Array]:
+    if x is None:
+        return None
+    if _is_tensor(x):
+        want = _capi._torch_dtype(kind)
+        x = x.to(want).contiguous().reshape(-1)
+    else:
+        x = np.ascontiguousarray(np.asarray(x, dtype=_capi._NP[kind]).reshape(-1))
+    if x.shape[0] != n:
+        raise ValueError(f"{name}: expected {n} entries, got {x.shape[0]}")
+    return x
+
+
+@dataclass
+class SearchTimes:
+    coarse_ms: float
+    probe_select_ms: float
+    plan_ms: float
+    scan_ms: float
+    topk_ms: float
+    total_ms: float
+    scanned_rows: int
+    scan_launches: int
+    total_launches: int
+
+
+class IVFFlatIndex:
+    """One IVF_FLAT index on one GPU (device ordinal ``device``)."""
+
+    def __init__(self, dim: int, nlist: int = 128, metric="IP", device: int = 0):
+        self._h = None
+        L = _capi.lib()
+        self.dim = int(dim)
+        self.nlist = int(nlist)
+        self.metric = metric_code(metric)
+        self.device = int(device)
+        h = C.c_void_p()
+        _capi.check(L.sc_index_create(self.dim, self.metric, self.nlist, self.device, C.byref(h)))
+        self._h = h
+        self._L = L
+
+    # -- lifecycle ------------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None:
+            self._L.sc_index_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self) -> None:
+        _capi.check(self._L.sc_index_reset(self._h))
+
+    def _stream(self) -> int:
+        return _capi.current_stream(self.device)
+
+    def _dev(self):
+        return torch.device("cuda", self.device)
+
+    # -- coarse quantizer -------------------------------------------------------------------------
+    @property
+    def is_trained(self) -> bool:
+        return bool(self.stats().trained)
+
+    def set_centroids(self, centroids: Array) -> None:
+        c = _as_rows(centroids, self.dim, "centroids")
+        if c.shape[0] != self.nlist:
+            raise ValueError(f"centroids: expected {self.nlist} rows, got {c.shape[0]}")
+        _capi.check(self._L.sc_index_set_centroids(self._h, _capi.ptr(c, "f32"), self.nlist, self._stream()))
+
+    def get_centroids(self) -> np.ndarray:
+        out = np.empty((self.nlist, self.dim), dtype=np.float32)
+        _capi.check(self._L.sc_index_get_centroids(self._h, _capi.ptr(out, "f32"), self._stream()))
+        return out
+
+    def train(
+        self,
+        x: Array,
+        niter: int = KMEANS_NITER,
+        seed: int = KMEANS_SEED,
+        max_points_per_centroid: int = KMEANS_MAX_POINTS_PER_CENTROID,
+        init_centroids: Optional[Array] = None,
+    ) -> List[float]:
+        """Lloyd k-means on x (FAISS Clustering::train restated); returns the objective entering
+        each iteration.  Subsampling and init rows follow oracle/ivf_numpy.py exactly."""
+        x = _as_rows(x, self.dim, "x")
+        n = x.shape[0]
+        if n < self.nlist:
+            raise ValueError(f"need at least nlist={self.nlist} training rows, got {n}")
+        rows = kmeans_subsample_rows(n, self.nlist, max_points_per_centroid, seed)
+        if rows is not None:
+            if _is_tensor(x):
+                x = x.index_select(0, torch.from_numpy(rows).to(x.device))
+            else:
+                x = np.ascontiguousarray(x[rows])
+            n = x.shape[0]
+        obj = np.zeros(max(niter, 1), dtype=np.float64)
+        if init_centroids is not None:
+            self.set_centroids(init_centroids)
+            return self._lloyd(x, niter)
+        init = kmeans_init_rows(n, self.nlist, seed)
+        _capi.check(
+            self._L.sc_index_train(
+                self._h, _capi.ptr(x, "f32"), n, int(niter), _capi.ptr(init, "i64"), _capi.ptr(obj, "f64"),
+                self._stream(),
+            )
+        )
+        return [float(v) for v in obj[:niter]]
+
+    def _lloyd(self, x: Array, niter: int) -> List[float]:
+        """Lloyd iterations from the current centroids, driven from Python through the
+        kmeans_step / kmeans_update building blocks (the same ones the sharded trainer uses)."""
+        dev = self._dev()
+        ds = self.stats().dim_padded
+        sums = torch.zeros(self.nlist * ds, dtype=torch.float64, device=dev)
+        counts = torch.zeros(self.nlist, dtype=torch.int32, device=dev)
+        obj = torch.zeros(1, dtype=torch.float64, device=dev)
+        out = []
+        for _ in range(niter):
+            sums.zero_()
+            counts.zero_()
+            obj.zero_()
+            self.kmeans_step(x, sums, counts, obj)
+            out.append(float(obj.item()))
+            self.kmeans_update(sums, counts)
+        return out
+
+    def kmeans_step(self, x: Array, sums, counts, obj) -> None:
+        x = _as_rows(x, self.dim, "x")
+        _capi.check(
+            self._L.sc_index_kmeans_step(
+                self._h, _capi.ptr(x, "f32"), x.shape[0], _capi.ptr(sums, "f64"), _capi.ptr(counts, "i32"),
+                _capi.ptr(obj, "f64"), self._stream(),
+            )
+        )
+
+    def kmeans_update(self, sums, counts) -> int:
+        ns = C.c_int32(0)
+        _capi.check(
+            self._L.sc_index_kmeans_update(
+                self._h, _capi.ptr(sums, "f64"), _capi.ptr(counts, "i32"), C.addressof(ns), self._stream()
+            )
+        )
+        return int(ns.value)
+
+    def assign(self, x: Array) -> Array:
+        x = _as_rows(x, self.dim, "x")
+        n = x.shape[0]
+        if _is_tensor(x) and x.is_cuda:
+            out = torch.empty(n, dtype=torch.int32, device=x.device)
+        else:
+            out = np.empty(n, dtype=np.int32)
+        _capi.check(self._L.sc_index_assign(self._h, _capi.ptr(x, "f32"), n, _capi.ptr(out, "i32"), self._stream()))
+        return out
+
+    def probe(self, q: Array, nprobe: int, with_scores: bool = False):
+        q = _as_rows(q, self.dim, "q")
+        nq = q.shape[0]
+        nprobe = min(int(nprobe), self.nlist)
+        if _is_tensor(q) and q.is_cuda:
+            lists = torch.empty((nq, nprobe), dtype=torch.int32, device=q.device)
+            scores = torch.empty((nq, nprobe), dtype=torch.float32, device=q.device) if with_scores else None
+        else:
+            lists = np.empty((nq, nprobe), dtype=np.int32)
+            scores = np.empty((nq, nprobe), dtype=np.float32) if with_scores else None
+        _capi.check(
+            self._L.sc_index_probe(
+                self._h, _capi.ptr(q, "f32"), nq, nprobe, _capi.ptr(lists, "i32"), _capi.ptr(scores, "f32"),
+                self._stream(),
+            )
+        )
+        return (lists, scores) if with_scores else lists
+
+    # -- insert / remove ----------------------------------------------------------------------------
+    def add(
+        self,
+        x: Array,
+        ids: Array,
+        repo_tags: Optional[Array] = None,
+        lang_tags: Optional[Array] = None,
+        lists: Optional[Array] = None,
+    ) -> None:
+        """Append rows (FAISS add_with_ids).  ``lists`` pre-assigns the inverted list of every row."""
+        x = _as_rows(x, self.dim, "x")
+        n = x.shape[0]
+        ids = _as_vec(ids, "i64", n, "ids")
+        repo_tags = _as_vec(repo_tags, "u32", n, "repo_tags")
+        lang_tags = _as_vec(lang_tags, "u8", n, "lang_tags")
+        lists = _as_vec(lists, "i32", n, "lists")
+        args = [self._h, _capi.ptr(x, "f32"), _capi.ptr(ids, "i64"), _capi.ptr(repo_tags, "u32"),
+                _capi.ptr(lang_tags, "u8")]
+        if lists is None:
+            _capi.check(self._L.sc_index_add(*args, n, self._stream()))
+        else:
+            _capi.check(self._L.sc_index_add_preassigned(*args, _capi.ptr(lists, "i32"), n, self._stream()))
+
+    def remove_ids(self, ids: Array) -> int:
+        ids = _as_vec(ids, "i64", len(ids), "ids")
+        out = C.c_int64(0)
+        _capi.check(
+            self._L.sc_index_remove_ids(self._h, _capi.ptr(ids, "i64"), ids.shape[0], C.addressof(out), self._stream())
+        )
+        return int(out.value)
+
+    # -- search ---------------------------------------------------------------------------------------
+    @staticmethod
+    def _filter(repos: Optional[Iterable[int]], langs: Optional[Iterable[int]]):
+        if repos is None and langs is None:
+            return None, ()
+        f = _capi.ScFilter()
+        keep = []
+        if repos is not None:
+            r = np.ascontiguousarray(np.asarray(list(repos), dtype=np.uint32))
+            if r.size == 0:
+                raise ValueError("repos filter is empty: pass None for 'any repo'")
+            f.repo_tags = r.ctypes.data_as(C.POINTER(C.c_uint32))
+            f.n_repos = r.size
+            keep.append(r)
+        if langs is not None:
+            l = np.ascontiguousarray(np.asarray(list(langs), dtype=np.uint8))
+            if l.size == 0:
+                raise ValueError("langs filter is empty: pass None for 'any language'")
+            f.lang_tags = l.ctypes.data_as(C.POINTER(C.c_uint8))
+            f.n_langs = l.size
+            keep.append(l)
+        return f, keep
+
+    def search(
+        self,
+        q: Array,
+        k: int,
+        nprobe: int = 16,
+        repos: Optional[Iterable[int]] = None,
+        langs: Optional[Iterable[int]] = None,
+        lists: Optional[Array] = None,
+        out: Optional[Tuple[Array, Array]] = None,
+    ) -> Tuple[Array, Array]:
+        """Top-k per query: (dist [nq,k] fp32, ids [nq,k] int64), best first, id -1 = no result.
+
+        CUDA-tensor queries give CUDA-tensor results without synchronising the stream; numpy / CPU
+        queries give numpy results (synchronous)."""
+        q = _as_rows(q, self.dim, "q")
+        nq = q.shape[0]
+        k = int(k)
+        on_dev = _is_tensor(q) and q.is_cuda
+        if out is not None:
+            dist, ids = out
+        elif on_dev:
+            dist = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+            ids = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+        else:
+            dist = np.empty((nq, k), dtype=np.float32)
+            ids = np.empty((nq, k), dtype=np.int64)
+        f, keep = self._filter(repos, langs)
+        fp = C.byref(f) if f is not None else None
+        if lists is None:
+            _capi.check(
+                self._L.sc_index_search(
+                    self._h, _capi.ptr(q, "f32"), nq, k, int(nprobe), fp, _capi.ptr(dist, "f32"),
+                    _capi.ptr(ids, "i64"), self._stream(),
+                )
+            )
+        else:
+            if _is_tensor(lists):
+                lists = lists.to(torch.int32).contiguous()
+            else:
+                lists = np.ascontiguousarray(np.asarray(lists, dtype=np.int32))
+            if lists.shape[0] != nq:
+                raise ValueError("lists: one row of probes per query expected")
+            _capi.check(
+                self._L.sc_index_search_preassigned(
+                    self._h, _capi.ptr(q, "f32"), nq, k, int(lists.shape[1]), _capi.ptr(lists, "i32"), fp,
+                    _capi.ptr(dist, "f32"), _capi.ptr(ids, "i64"), self._stream(),
+                )
+            )
+        del keep
+        return dist, ids
+
+    # -- introspection ------------------------------------------------------------------------------
+    def stats(self) -> _capi.ScStats:
+        s = _capi.ScStats()
+        _capi.check(self._L.sc_index_stats(self._h, C.byref(s)))
+        return s
+
+    @property
+    def ntotal(self) -> int:
+        return int(self.stats().ntotal)
+
+    def list_sizes(self) -> np.ndarray:
+        out = np.empty(self.nlist, dtype=np.int32)
+        _capi.check(self._L.sc_index_list_sizes(self._h, _capi.ptr(out, "i32")))
+        return out
+
+    def export_list(self, l: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """(vectors [len,dim], ids [len], tags [len]) of one inverted list, slot order."""
+        n = int(self.list_sizes()[l])
+        vec = np.empty((n, self.dim), dtype=np.float32)
+        ids = np.empty(n, dtype=np.int64)
+        tags = np.empty(n, dtype=np.uint32)
+        ln = C.c_int64(0)
+        _capi.check(
+            self._L.sc_index_export_list(
+                self._h, int(l), n, _capi.ptr(vec, "f32"), _capi.ptr(ids, "i64"), _capi.ptr(tags, "u32"),
+                C.addressof(ln), self._stream(),
+            )
+        )
+        return vec, ids, tags
+
+    def export_csr(self, live_only: bool = True):
+        """Whole index as CSR on the host: (list_off [nlist+1], vecs [n,dim], ids [n], tags [n]).
+        Used by persistence and to hand the same lists to the CPU baseline."""
+        sizes = self.list_sizes().astype(np.int64)
+        total = int(sizes.sum())
+        vecs = np.empty((total, self.dim), dtype=np.float32)
+        ids = np.empty(total, dtype=np.int64)
+        tags = np.empty(total, dtype=np.uint32)
+        off = np.zeros(self.nlist + 1, dtype=np.int64)
+        np.cumsum(sizes, out=off[1:])
+        ln = C.c_int64(0)
+        st = self._stream()
+        for l in range(self.nlist):
+            n = int(sizes[l])
+            if n == 0:
+                continue
+            lo = int(off[l])
+            _capi.check(
+                self._L.sc_index_export_list(
+                    self._h, l, n, vecs[lo:].ctypes.data, ids[lo:].ctypes.data, tags[lo:].ctypes.data,
+                    C.addressof(ln), st,
+                )
+            )
+        if live_only and total:
+            live = (tags & np.uint32(0x80000000)) == 0
+            if not live.all():
+                row_list = np.repeat(np.arange(self.nlist), sizes)
+                new_sizes = np.bincount(row_list[live], minlength=self.nlist).astype(np.int64)
+                vecs, ids, tags = vecs[live], ids[live], tags[live]
+                off = np.zeros(self.nlist + 1, dtype=np.int64)
+                np.cumsum(new_sizes, out=off[1:])
+        return off, vecs, ids, tags
+
+    # -- profiling / tuning -------------------------------------------------------------------------
+    def set_profiling(self, enabled: bool) -> None:
+        _capi.check(self._L.sc_index_set_profiling(self._h, 1 if enabled else 0))
+
+    def last_search_times(self) -> SearchTimes:
+        t = _capi.ScSearchTimes()
+        _capi.check(self._L.sc_index_last_search_times(self._h, C.byref(t)))
+        return SearchTimes(t.coarse_ms, t.probe_select_ms, t.plan_ms, t.scan_ms, t.topk_ms, t.total_ms,
+                           int(t.scanned_rows), int(t.scan_launches), int(t.total_launches))
+
+    def set_param(self, name: str, value: int) -> None:
+        _capi.check(self._L.sc_index_set_param(self._h, name.encode(), int(value)))
+
+
+def merge_topk(part_dist, part_ids, k: int, metric, device: Optional[int] = None):
+    """Device merge of partial results [parts, nq, kin] -> ([nq,k], [nq,k]) (cross-shard reduce)."""
+    if not (_is_tensor(part_dist) and part_dist.is_cuda):
+        raise TypeError("merge_topk works on CUDA tensors")
+    parts, nq, kin = part_dist.shape
+    part_dist = part_dist.to(torch.float32).contiguous()
+    part_ids = part_ids.to(torch.int64).contiguous()
+    dev = part_dist.device.index if device is None else device
+    out_d = torch.empty((nq, k), dtype=torch.float32, device=part_dist.device)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=part_dist.device)
+    _capi.check(
+        _capi.lib().sc_merge_topk(
+            _capi.ptr(part_dist, "f32"), _capi.ptr(part_ids, "i64"), parts, nq, kin, int(k), metric_code(metric),
+            _capi.ptr(out_d, "f32"), _capi.ptr(out_i, "i64"), dev, _capi.current_stream(dev),
+        )
+    )
+    return out_d, out_i

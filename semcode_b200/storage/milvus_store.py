@@ -1,0 +1,559 @@
+"""Drop-in replacement for reference src/semcode/storage/milvus_store.py.
+
+Same class name, constructor, methods, error strings and log events as the reference wrapper
+(milvus_store.py:29-148), but the Milvus server behind it is replaced by an in-process collection
+whose IVF_FLAT index lives on a B200 (semcode_b200.IVFFlatIndex -> libsemcode_ivf.so):
+
+  reference call (milvus_store.py)                         here
+  ------------------------------------------------------   -----------------------------------------
+  connections.connect + utility.has_collection (:42-54)    process-wide collection registry (+ optional
+                                                           on-disk snapshot under SEMCODE_IVF_PERSIST_DIR)
+  CollectionSchema(7 fields) + create_index(IVF_FLAT, IP,  GpuCollection(dim, nlist=128, metric="IP")
+    nlist=128) + load()  (:59-84)
+  Collection.upsert([7 columns])  (:128-130)               GpuCollection.upsert -> remove_ids + add
+  Collection.search(data=[vector], nprobe=16, limit)       GpuCollection.search -> sc_index_search
+    (:141-147)
+
+Rows not yet covered by a trained index sit in a *growing segment* that is searched exactly (a
+one-list index), as Milvus does for unsealed data [EXT]; once `seal_rows` rows exist (default
+39 x nlist, FAISS' min_points_per_centroid) k-means runs and later rows are added straight to
+the inverted lists (FAISS add).  Scalar columns (id, repo, path, language, text, metadata) stay on
+the host; repo and language are additionally encoded as integer tags next to each vector so that
+`repos=` / `languages=` filters are evaluated inside the list scan.
+
+Keyword-only extensions (absent from the reference, defaults reproduce it): nprobe, repos,
+languages on search(); search_batch(); search_arrays(); upsert_arrays(); build_index().
+"""
+
+from __future__ import annotations
+
+import json
+import os
+import threading
+from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence
+
+import numpy as np
+
+from ..index import KMEANS_MIN_POINTS_PER_CENTROID, IVFFlatIndex, merge_topk, metric_code
+from .._capi import METRIC_IP, torch
+
+try:  # the reference's own settings / logger when the drop-in runs inside semcode
+    from semcode.settings import settings  # type: ignore
+except Exception:  # pragma: no cover - exercised when semcode is not importable
+
+    class _EnvSettings:
+        """Minimal stand-in for semcode.settings.AppSettings (settings.py:30-82): SEMCODE_* env."""
+
+        def __getattr__(self, name: str):
+            env = os.environ.get("SEMCODE_" + name.upper())
+            defaults = {
+                "embedding_dimension": 3072,  # settings.py:47
+                "milvus_uri": "http://localhost:19530",  # settings.py:40
+                "milvus_upsert_batch_size": 128,  # settings.py:76
+            }
+            if env is None:
+                if name in defaults:
+                    return defaults[name]
+                raise AttributeError(name)
+            d = defaults.get(name)
+            return type(d)(env) if d is not None else env
+
+    settings = _EnvSettings()
+
+try:
+    from semcode.logger import get_logger  # type: ignore
+except Exception:  # pragma: no cover
+    import logging
+
+    class _KVLogger:
+        def __init__(self, name: str):
+            self._l = logging.getLogger(name)
+
+        def _fmt(self, event: str, kw: Dict[str, Any]) -> str:
+            return event + "".join(f" {k}={v}" for k, v in kw.items())
+
+        def info(self, event: str, **kw):
+            self._l.info(self._fmt(event, kw))
+
+        def warning(self, event: str, **kw):
+            self._l.warning(self._fmt(event, kw))
+
+        def error(self, event: str, **kw):
+            self._l.error(self._fmt(event, kw))
+
+    def get_logger(name: str):
+        return _KVLogger(name)
+
+
+log = get_logger(__name__)
+
+OUTPUT_FIELDS = ("repo", "path", "language", "text", "metadata")  # milvus_store.py:146
+
+
+def _setting(name: str, default):
+    """Optional knob: settings.<name> if present (AppSettings has extra='allow', settings.py:36)."""
+    try:
+        v = getattr(settings, name)
+    except Exception:
+        return default
+    if v is None:
+        return default
+    try:
+        return type(default)(v) if default is not None else v
+    except Exception:
+        return default
+
+
+# --------------------------------------------------------------------------------------------------
+# result objects: the shape SemanticSearchPipeline._hit_to_document reads (rag/pipeline.py:133-169)
+# --------------------------------------------------------------------------------------------------
+class Entity:
+    __slots__ = ("_fields",)
+
+    def __init__(self, fields: Dict[str, Any]):
+        self._fields = fields
+
+    def get(self, name: str, default=None):
+        return self._fields.get(name, default)
+
+    def __getitem__(self, name: str):
+        return self._fields[name]
+
+    def to_dict(self) -> Dict[str, Any]:
+        return dict(self._fields)
+
+    def __repr__(self) -> str:
+        return f"Entity({self._fields!r})"
+
+
+class Hit:
+    __slots__ = ("id", "distance", "entity")
+
+    def __init__(self, pk: str, distance: float, fields: Dict[str, Any]):
+        self.id = pk
+        self.distance = float(distance)
+        self.entity = Entity(fields)
+
+    @property
+    def score(self) -> float:
+        return self.distance
+
+    def get(self, name: str, default=None):
+        return self.entity.get(name, default)
+
+    def to_dict(self) -> Dict[str, Any]:
+        return {"id": self.id, "distance": self.distance, "entity": self.entity.to_dict()}
+
+    def __repr__(self) -> str:
+        return f"Hit(id={self.id!r}, distance={self.distance:.6g})"
+
+
+class Hits(list):
+    @property
+    def ids(self) -> List[str]:
+        return [h.id for h in self]
+
+    @property
+    def distances(self) -> List[float]:
+        return [h.distance for h in self]
+
+
+class SearchResult(list):
+    """list of Hits, one per query vector (pymilvus SearchResult shape)."""
+
+
+# --------------------------------------------------------------------------------------------------
+# the in-process collection
+# --------------------------------------------------------------------------------------------------
+class GpuCollection:
+    """What `Collection(name)` is to the reference wrapper: schema + index + rows."""
+
+    def __init__(self, name: str, dim: int, nlist: int = 128, metric: str = "IP", device: int = 0,
+                 seal_rows: Optional[int] = None, train_niter: int = 25):
+        self.name = name
+        self.dim = int(dim)
+        self.nlist = int(nlist)
+        self.metric = metric_code(metric)
+        self.device = int(device)
+        self.seal_rows = int(seal_rows) if seal_rows else KMEANS_MIN_POINTS_PER_CENTROID * self.nlist
+        self.train_niter = int(train_niter)
+        self._lock = threading.RLock()
+        # host scalar columns, indexed by row number (== the int64 id stored next to the vector)
+        self._pk: List[Optional[str]] = []
+        self._repo: List[str] = []
+        self._path: List[str] = []
+        self._language: List[str] = []
+        self._text: List[str] = []
+        self._metadata: List[Any] = []
+        self._row_of: Dict[str, int] = {}
+        self._repo_vocab: Dict[str, int] = {}
+        self._lang_vocab: Dict[str, int] = {}
+        # growing segment: a one-list index == exact search
+        self._growing = IVFFlatIndex(self.dim, nlist=1, metric=self.metric, device=self.device)
+        self._growing.set_centroids(np.zeros((1, self.dim), dtype=np.float32))
+        self._growing_rows = 0
+        self._ivf: Optional[IVFFlatIndex] = None
+
+    # -- pymilvus-compatible no-ops --------------------------------------------------------------
+    def load(self) -> None:
+        return None
+
+    def flush(self) -> None:
+        return None
+
+    @property
+    def num_entities(self) -> int:
+        with self._lock:
+            return len(self._row_of)
+
+    @property
+    def index(self) -> Optional[IVFFlatIndex]:
+        return self._ivf
+
+    def close(self) -> None:
+        with self._lock:
+            self._growing.close()
+            if self._ivf is not None:
+                self._ivf.close()
+                self._ivf = None
+
+    # -- tags ---------------------------------------------------------------------------------------
+    def _tag(self, vocab: Dict[str, int], value: str, limit: int) -> int:
+        t = vocab.get(value)
+        if t is None:
+            t = len(vocab)
+            if t > limit:
+                raise ValueError(f"too many distinct values for a tag column (limit {limit + 1})")
+            vocab[value] = t
+        return t
+
+    def repo_tags(self, repos: Iterable[str]) -> List[int]:
+        return [self._repo_vocab[r] for r in repos if r in self._repo_vocab]
+
+    def language_tags(self, languages: Iterable[str]) -> List[int]:
+        return [self._lang_vocab[l] for l in languages if l in self._lang_vocab]
+
+    # -- insert -------------------------------------------------------------------------------------
+    def upsert(self, data: Sequence[Sequence[Any]]) -> int:
+        """Collection.upsert([ids, repos, paths, languages, texts, vectors, metadata])
+        (milvus_store.py:128-130): replace by primary key, then insert."""
+        ids, repos, paths, languages, texts, vectors, metadata = data
+        return self.upsert_columns(ids, vectors, repos, paths, languages, texts, metadata)
+
+    def upsert_columns(self, ids: Sequence[str], vectors, repos=None, paths=None, languages=None, texts=None,
+                       metadata=None) -> int:
+        n = len(ids)
+        if n == 0:
+            return 0
+        if torch is not None and isinstance(vectors, torch.Tensor):
+            vec = vectors.to(torch.float32)
+            if vec.dim() != 2 or vec.shape[0] != n or vec.shape[1] != self.dim:
+                raise ValueError(f"vectors: expected shape [{n}, {self.dim}], got {tuple(vec.shape)}")
+        else:
+            vec = np.asarray(vectors, dtype=np.float32)
+            if vec.ndim != 2 or vec.shape[0] != n or vec.shape[1] != self.dim:
+                raise ValueError(f"vectors: expected shape [{n}, {self.dim}], got {vec.shape}")
+
+        def col(c, default):
+            return list(c) if c is not None else [default] * n
+
+        repos, paths, languages, texts = col(repos, ""), col(paths, ""), col(languages, ""), col(texts, "")
+        metadata = col(metadata, None)
+        with self._lock:
+            # last occurrence of a primary key inside the batch wins
+            last: Dict[str, int] = {}
+            for i, pk in enumerate(ids):
+                last[str(pk)] = i
+            keep = sorted(last.values())
+            stale = [self._row_of[pk] for pk in last if pk in self._row_of]
+            if stale:
+                self._remove_rows(stale)
+            base = len(self._pk)
+            row_ids = np.arange(base, base + len(keep), dtype=np.int64)
+            rtags = np.empty(len(keep), dtype=np.uint32)
+            ltags = np.empty(len(keep), dtype=np.uint8)
+            for j, i in enumerate(keep):
+                pk = str(ids[i])
+                r, l = str(repos[i] or ""), str(languages[i] or "")
+                self._pk.append(pk)
+                self._repo.append(r)
+                self._path.append(str(paths[i] or ""))
+                self._language.append(l)
+                self._text.append(texts[i])
+                self._metadata.append(metadata[i])
+                self._row_of[pk] = base + j
+                rtags[j] = self._tag(self._repo_vocab, r, (1 << 23) - 1)
+                ltags[j] = self._tag(self._lang_vocab, l, 255)
+            if len(keep) != n:
+                vec = vec[torch.as_tensor(keep, device=vec.device)] if not isinstance(vec, np.ndarray) else vec[keep]
+            if self._ivf is not None:
+                self._ivf.add(vec, row_ids, rtags, ltags)
+            else:
+                self._growing.add(vec, row_ids, rtags, ltags, lists=np.zeros(len(keep), dtype=np.int32))
+                self._growing_rows += len(keep)
+                if self._growing_rows >= self.seal_rows:
+                    self.build_index()
+            return len(keep)
+
+    def _remove_rows(self, rows: List[int]) -> None:
+        arr = np.asarray(rows, dtype=np.int64)
+        removed = self._growing.remove_ids(arr)
+        self._growing_rows -= removed
+        if self._ivf is not None and removed < len(rows):
+            self._ivf.remove_ids(arr)
+        for r in rows:
+            pk = self._pk[r]
+            if pk is not None:
+                self._row_of.pop(pk, None)
+            self._pk[r] = None
+            self._text[r] = ""
+            self._metadata[r] = None
+
+    def delete(self, ids: Sequence[str]) -> int:
+        with self._lock:
+            rows = [self._row_of[str(pk)] for pk in ids if str(pk) in self._row_of]
+            if rows:
+                self._remove_rows(rows)
+            return len(rows)
+
+    # -- index build ----------------------------------------------------------------------------------
+    def build_index(self, niter: Optional[int] = None, centroids=None) -> Optional[IVFFlatIndex]:
+        """Seal the growing segment: k-means (or the supplied centroids), then move its rows into
+        the inverted lists.  With fewer than 39 rows per list nlist shrinks as knowhere does [EXT]."""
+        with self._lock:
+            if self._growing_rows == 0:
+                return self._ivf
+            vec, rid, tags = self._growing.export_list(0)
+            live = (tags & np.uint32(0x80000000)) == 0
+            vec, rid, tags = vec[live], rid[live], tags[live]
+            n = vec.shape[0]
+            if self._ivf is None:
+                if centroids is not None:
+                    nlist = int(np.asarray(centroids).shape[0])
+                else:
+                    nlist = self.nlist
+                    if nlist * KMEANS_MIN_POINTS_PER_CENTROID > n:
+                        nlist = max(1, n // KMEANS_MIN_POINTS_PER_CENTROID)
+                ivf = IVFFlatIndex(self.dim, nlist=nlist, metric=self.metric, device=self.device)
+                if centroids is not None:
+                    ivf.set_centroids(centroids)
+                else:
+                    ivf.train(vec, niter=self.train_niter if niter is None else niter)
+                log.info("index_trained", collection=self.name, nlist=nlist, rows=n)
+                self._ivf = ivf
+            self._ivf.add(vec, rid, (tags >> np.uint32(8)) & np.uint32((1 << 23) - 1), (tags & np.uint32(0xFF)).astype(np.uint8))
+            self._growing.reset()
+            self._growing_rows = 0
+            return self._ivf
+
+    # -- search ---------------------------------------------------------------------------------------
+    def search_arrays(self, vectors, top_k: int, nprobe: int = 16, repos: Optional[Iterable[str]] = None,
+                      languages: Optional[Iterable[str]] = None):
+        """Raw tensor path: (dist [nq,k] fp32, row ids [nq,k] int64, -1 = none).  CUDA in -> CUDA out."""
+        with self._lock:
+            rt = lt = None
+            if repos is not None:
+                rt = self.repo_tags(repos)
+                if not rt:
+                    return self._empty(vectors, top_k)
+            if languages is not None:
+                lt = self.language_tags(languages)
+                if not lt:
+                    return self._empty(vectors, top_k)
+            parts = []
+            if self._ivf is not None and self._ivf.ntotal > 0:
+                parts.append(self._ivf.search(vectors, top_k, nprobe=nprobe, repos=rt, langs=lt))
+            if self._growing_rows > 0 or not parts:
+                parts.append(self._growing.search(vectors, top_k, nprobe=1, repos=rt, langs=lt))
+            if len(parts) == 1:
+                return parts[0]
+            (d0, i0), (d1, i1) = parts
+            if isinstance(d0, np.ndarray):
+                dev = torch.device("cuda", self.device)
+                pd = torch.stack([torch.from_numpy(d0), torch.from_numpy(d1)]).to(dev)
+                pi = torch.stack([torch.from_numpy(i0), torch.from_numpy(i1)]).to(dev)
+                d, i = merge_topk(pd, pi, top_k, self.metric, self.device)
+                return d.cpu().numpy(), i.cpu().numpy()
+            return merge_topk(torch.stack([d0, d1]), torch.stack([i0, i1]), top_k, self.metric, self.device)
+
+    def _empty(self, vectors, top_k: int):
+        nq = len(vectors) if not hasattr(vectors, "shape") else (1 if len(vectors.shape) == 1 else vectors.shape[0])
+        pad = -np.finfo(np.float32).max if self.metric == METRIC_IP else np.finfo(np.float32).max
+        return np.full((nq, top_k), pad, dtype=np.float32), np.full((nq, top_k), -1, dtype=np.int64)
+
+    def search(self, data, anns_field: str = "embedding", param: Optional[dict] = None, limit: int = 10,
+               expr: Optional[str] = None, output_fields: Optional[Sequence[str]] = None, *,
+               repos: Optional[Iterable[str]] = None, languages: Optional[Iterable[str]] = None, **_) -> SearchResult:
+        """Collection.search(...) with the keyword set the reference passes (milvus_store.py:141-147)."""
+        if anns_field != "embedding":
+            raise ValueError(f"unknown vector field {anns_field!r}")
+        if expr:
+            raise NotImplementedError("boolean expressions are not parsed; use repos= / languages=")
+        param = param or {}
+        want = param.get("metric_type")
+        if want is not None and metric_code(want) != self.metric:
+            raise ValueError(f"metric_type {want!r} does not match the index metric")
+        nprobe = int((param.get("params") or {}).get("nprobe", 16))
+        q = np.asarray(data, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"vector dimension mismatch: expected {self.dim}, got {q.shape[-1]}")
+        fields = tuple(output_fields) if output_fields is not None else ()
+        with self._lock:
+            dist, rows = self.search_arrays(q, int(limit), nprobe=nprobe, repos=repos, languages=languages)
+            if not isinstance(dist, np.ndarray):
+                dist, rows = dist.cpu().numpy(), rows.cpu().numpy()
+            out = SearchResult()
+            for qi in range(q.shape[0]):
+                hits = Hits()
+                for d, r in zip(dist[qi], rows[qi]):
+                    if r < 0:
+                        continue  # Milvus returns short result lists rather than padding
+                    r = int(r)
+                    f = {}
+                    for name in fields:
+                        if name == "repo":
+                            f[name] = self._repo[r]
+                        elif name == "path":
+                            f[name] = self._path[r]
+                        elif name == "language":
+                            f[name] = self._language[r]
+                        elif name == "text":
+                            f[name] = self._text[r]
+                        elif name == "metadata":
+                            f[name] = self._metadata[r]
+                        elif name == "id":
+                            f[name] = self._pk[r]
+                        else:
+                            raise ValueError(f"unknown output field {name!r}")
+                    hits.append(Hit(self._pk[r], float(d), f))
+                out.append(hits)
+            return out
+
+
+_REGISTRY: Dict[str, GpuCollection] = {}
+_REGISTRY_LOCK = threading.Lock()
+
+
+def has_collection(name: str) -> bool:
+    """utility.has_collection (milvus_store.py:51)."""
+    with _REGISTRY_LOCK:
+        return name in _REGISTRY
+
+
+def drop_collection(name: str) -> None:
+    with _REGISTRY_LOCK:
+        c = _REGISTRY.pop(name, None)
+    if c is not None:
+        c.close()
+
+
+# --------------------------------------------------------------------------------------------------
+# the drop-in wrapper
+# --------------------------------------------------------------------------------------------------
+class MilvusVectorStore:
+    """Same surface as the reference wrapper (milvus_store.py:29-148), GPU-backed."""
+
+    def __init__(self, collection_name: str = "semcode_chunks", dim: Optional[int] = None) -> None:
+        self.collection_name = collection_name
+        self.dim = dim or settings.embedding_dimension
+        self._collection: Optional[GpuCollection] = None
+
+    def connect(self) -> None:
+        """Attach to the process-wide collection (creating it on first use)."""
+        log.info("connecting_milvus", uri=_setting("milvus_uri", "gpu://in-process"))
+        self._collection = self._ensure_collection()
+
+    def _ensure_collection(self) -> GpuCollection:
+        with _REGISTRY_LOCK:
+            existing = _REGISTRY.get(self.collection_name)
+            if existing is not None:
+                if existing.dim != self.dim:
+                    raise ValueError(
+                        f"collection {self.collection_name!r} exists with dim {existing.dim}, requested {self.dim}"
+                    )
+                existing.load()
+                return existing
+            log.info("creating_milvus_collection", collection=self.collection_name, dim=self.dim)
+            collection = GpuCollection(
+                self.collection_name,
+                self.dim,
+                nlist=_setting("ivf_nlist", 128),  # milvus_store.py:81
+                metric=_setting("ivf_metric", "IP"),  # milvus_store.py:79
+                device=_setting("ivf_device", 0),
+                seal_rows=_setting("ivf_seal_rows", 0) or None,
+                train_niter=_setting("ivf_train_niter", 25),
+            )
+            collection.load()
+            _REGISTRY[self.collection_name] = collection
+            return collection
+
+    def _require(self) -> GpuCollection:
+        if self._collection is None:
+            raise RuntimeError("Milvus collection is not initialized. Call connect() first.")
+        return self._collection
+
+    def upsert_embeddings(self, payloads: Sequence[Any], progress: Optional[Callable[[int, int], None]] = None) -> None:
+        """Insert or update embeddings (same batching and progress protocol as milvus_store.py:87-133)."""
+        collection = self._require()
+        payload_list = list(payloads)
+        total = len(payload_list)
+        log.info("upserting_embeddings", count=total)
+        if progress:
+            progress(0, total)
+        if total == 0:
+            return
+        batch_size = max(1, _setting("milvus_upsert_batch_size", 128))
+        inserted = 0
+        for start in range(0, total, batch_size):
+            batch = payload_list[start : start + batch_size]
+            ids, repos, paths, languages, texts, vectors, metadata = [], [], [], [], [], [], []
+            for payload in batch:
+                ids.append(payload.id)
+                repos.append(payload.metadata.get("repo", ""))
+                paths.append(payload.metadata.get("path", ""))
+                languages.append(payload.metadata.get("language", ""))
+                texts.append(payload.text)
+                vectors.append(payload.vector)
+                metadata.append(payload.metadata)
+            collection.upsert([ids, repos, paths, languages, texts, vectors, metadata])
+            inserted += len(batch)
+            if progress:
+                progress(inserted, total)
+
+    def search(self, vector: "list[float]", top_k: int = 10, *, nprobe: int = 16,
+               repos: Optional[Iterable[str]] = None, languages: Optional[Iterable[str]] = None) -> list:
+        """Run a raw vector search (milvus_store.py:135-148); returns [Hits] for the one query."""
+        collection = self._require()
+        return collection.search(
+            data=[vector],
+            anns_field="embedding",
+            param={"metric_type": "IP" if collection.metric == METRIC_IP else "L2", "params": {"nprobe": nprobe}},
+            limit=top_k,
+            output_fields=list(OUTPUT_FIELDS),
+            repos=repos,
+            languages=languages,
+        )
+
+    # ---- extensions (BASELINE.json configs need batches, raw arrays and bulk insert) ---------------
+    def search_batch(self, vectors, top_k: int = 10, *, nprobe: int = 16, repos: Optional[Iterable[str]] = None,
+                     languages: Optional[Iterable[str]] = None) -> list:
+        collection = self._require()
+        return collection.search(
+            data=vectors, param={"params": {"nprobe": nprobe}}, limit=top_k, output_fields=list(OUTPUT_FIELDS),
+            repos=repos, languages=languages,
+        )
+
+    def search_arrays(self, vectors, top_k: int = 10, *, nprobe: int = 16, repos: Optional[Iterable[str]] = None,
+                      languages: Optional[Iterable[str]] = None):
+        """(dist [nq,k], row ids [nq,k]) without materialising Python hit objects."""
+        return self._require().search_arrays(vectors, top_k, nprobe=nprobe, repos=repos, languages=languages)
+
+    def upsert_arrays(self, ids: Sequence[str], vectors, repos=None, paths=None, languages=None, texts=None,
+                      metadata=None) -> int:
+        """Bulk insert: `vectors` is one [n, dim] numpy array or torch tensor (CPU or CUDA)."""
+        return self._require().upsert_columns(ids, vectors, repos, paths, languages, texts, metadata)
+
+    def build_index(self, niter: Optional[int] = None, centroids=None):
+        return self._require().build_index(niter=niter, centroids=centroids)

@@ -1,0 +1,396 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bar (north_star): identical ids except exact-distance ties, distances within 1e-5 relative
+(tests/helpers.py states the tolerance).  Everything here runs on cuda:0 of the GPU box.
+"""
+
+import numpy as np
+import pytest
+
+from helpers import assert_sorted, assert_topk_parity, close, unit_rows
+
+pytestmark = pytest.mark.gpu
+
+FMAX = np.finfo(np.float32).max
+
+
+@pytest.fixture(scope="module")
+def sb(native_lib):
+    import semcode_b200
+
+    return semcode_b200
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import ivf_numpy
+
+    return ivf_numpy
+
+
+@pytest.fixture(scope="module")
+def orc_c():
+    from oracle import ivf_c
+
+    ivf_c.build()
+    return ivf_c
+
+
+def make_case(orc, n, d, nlist, nq, metric, seed=0, normalise=True):
+    rng = np.random.default_rng(seed)
+    x = unit_rows(rng, n, d) if normalise else rng.standard_normal((n, d)).astype(np.float32)
+    q = unit_rows(rng, nq, d) if normalise else rng.standard_normal((nq, d)).astype(np.float32)
+    cent = x[orc.kmeans_init_rows(n, nlist, seed)].copy()
+    ids = (np.arange(n, dtype=np.int64) * 7 + 3)  # ids are not row numbers
+    return x, q, cent, ids
+
+
+def build_pair(sb, orc, x, ids, cent, metric, repo=None, lang=None):
+    """Same rows, same centroids, same assignment in the oracle index and the GPU index."""
+    assign = orc.assign(x, cent, metric)
+    oidx = orc.build_index(x, ids, cent, metric, repo, lang, assignment=assign)
+    g = sb.IVFFlatIndex(x.shape[1], nlist=cent.shape[0], metric=metric)
+    g.set_centroids(cent)
+    g.add(x, ids, repo, lang, lists=assign)
+    return g, oidx, assign
+
+
+# ---- KAT-1: tiny, hand-checkable ---------------------------------------------------------------
+def test_tiny_known_answer(sb):
+    # 8 points on the axes of R^4, two lists; query = e0 + 0.5 e1
+    x = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1],
+                  [2, 0, 0, 0], [0, 2, 0, 0], [0, 0, 2, 0], [0, 0, 0, 2]], dtype=np.float32)
+    ids = np.arange(10, 18, dtype=np.int64)
+    cent = np.array([[1, 1, 0, 0], [0, 0, 1, 1]], dtype=np.float32)
+    q = np.array([[1, 0.5, 0, 0]], dtype=np.float32)
+    lists = np.array([0, 0, 1, 1, 0, 0, 1, 1], dtype=np.int32)
+    # inner product: list 0 holds ids 10,11,14,15 with q.x = 1, .5, 2, 1
+    g = sb.IVFFlatIndex(4, nlist=2, metric="IP")
+    g.set_centroids(cent)
+    g.add(x, ids, lists=lists)
+    assert g.probe(q, 1).tolist() == [[0]]
+    d, i = g.search(q, 3, nprobe=1)
+    assert i.tolist()[0][0] == 14 and d.tolist()[0] == [2.0, 1.0, 1.0]
+    assert sorted(i.tolist()[0][1:]) == [10, 15]
+    d, i = g.search(q, 8, nprobe=2)
+    assert i.tolist()[0][0] == 14 and set(i.tolist()[0]) == set(range(10, 18))
+    # k larger than the probed list: padded with -1 / -FLT_MAX
+    d, i = g.search(q, 6, nprobe=1)
+    assert i.tolist()[0][4:] == [-1, -1] and d[0, 4] == -FMAX
+    # squared L2 (no sqrt): list 0 distances to q: 10 -> .25, 11 -> 1.25, 14 -> 1.25, 15 -> 3.25
+    g2 = sb.IVFFlatIndex(4, nlist=2, metric="L2")
+    g2.set_centroids(cent)
+    g2.add(x, ids, lists=lists)
+    d, i = g2.search(q, 4, nprobe=1)
+    assert i.tolist()[0][0] == 10 and i.tolist()[0][3] == 15
+    np.testing.assert_allclose(d[0], [0.25, 1.25, 1.25, 3.25], rtol=1e-6)
+    d, i = g2.search(q, 5, nprobe=1)
+    assert i[0, 4] == -1 and d[0, 4] == FMAX
+
+
+# ---- coarse quantizer ---------------------------------------------------------------------------
+@pytest.mark.parametrize("metric", ["IP", "L2"])
+@pytest.mark.parametrize("d", [768, 100, 30])
+def test_probe_and_assign_match_oracle(sb, orc, metric, d):
+    x, q, cent, ids = make_case(orc, 3000, d, 200, 150, metric, seed=d)
+    g = sb.IVFFlatIndex(d, nlist=200, metric=metric)
+    g.set_centroids(cent)
+    np.testing.assert_array_equal(g.get_centroids(), cent)
+    sim = orc.coarse_similarity(q, cent, metric, dtype=np.float64)
+    want = orc.top_desc(sim, 17)
+    got, sc = g.probe(q, 17, with_scores=True)
+    for r in range(q.shape[0]):
+        if not np.array_equal(got[r], want[r]):
+            # only near-ties (fp32 rounding of the contraction) may reorder
+            assert sorted(got[r]) == sorted(want[r]) or np.allclose(
+                np.sort(sim[r][got[r]]), np.sort(sim[r][want[r]]), rtol=1e-5, atol=1e-6
+            ), f"query {r}: probes differ beyond rounding"
+        assert close(sc[r], sim[r][got[r]].astype(np.float32)).all()
+    a = g.assign(x)
+    a_ref = np.argmax(orc.coarse_similarity(x, cent, metric, dtype=np.float64), axis=1)
+    diff = np.flatnonzero(a != a_ref)
+    simx = orc.coarse_similarity(x[diff], cent, metric, dtype=np.float64)
+    for j, r in enumerate(diff):
+        assert abs(simx[j, a[r]] - simx[j, a_ref[r]]) <= 1e-5 * abs(simx[j, a_ref[r]]) + 1e-6
+
+
+# ---- the list scan + top-k against the oracle, same probes --------------------------------------
+@pytest.mark.parametrize("metric", ["IP", "L2"])
+@pytest.mark.parametrize("d,k", [(768, 10), (768, 50), (100, 10), (30, 7), (2048, 50), (3072, 10), (64, 200)])
+def test_scan_parity_same_probes(sb, orc, orc_c, metric, d, k):
+    n, nlist, nq, nprobe = 6000, 64, 37, 9
+    x, q, cent, ids = make_case(orc, n, d, nlist, nq, metric, seed=d + k)
+    g, oidx, _ = build_pair(sb, orc, x, ids, cent, metric)
+    probes = orc.coarse_probe(q, cent, metric, nprobe)
+    rd, ri = orc.search(oidx, q, k, nprobe, probes=probes)
+    gd, gi = g.search(q, k, lists=probes)
+    assert_topk_parity(gd, gi, rd, ri, f"numpy oracle {metric} d={d} k={k}")
+    assert_sorted(gd, gi, metric == "IP")
+    # second, independent checker: the C restatement
+    cd, ci = orc_c.scan_search(q, oidx.metric, probes, oidx.list_off, oidx.vecs, oidx.ids, k)
+    assert_topk_parity(gd, gi, cd, ci, f"C oracle {metric} d={d} k={k}")
+
+
+@pytest.mark.parametrize("metric", ["IP", "L2"])
+def test_full_search_matches_oracle(sb, orc, metric):
+    """coarse + scan + top-k end to end; the GPU must choose the oracle's probes."""
+    x, q, cent, ids = make_case(orc, 20000, 128, 256, 200, metric, seed=5)
+    g, oidx, _ = build_pair(sb, orc, x, ids, cent, metric)
+    rd, ri = orc.search(oidx, q, 10, 16)
+    gd, gi = g.search(q, 10, nprobe=16)
+    same_probes = np.array([sorted(a) == sorted(b) for a, b in zip(g.probe(q, 16), orc.coarse_probe(q, cent, metric, 16))])
+    assert same_probes.mean() > 0.97  # a near-tied 16th/17th centroid may flip
+    assert_topk_parity(gd[same_probes], gi[same_probes], rd[same_probes], ri[same_probes], f"full {metric}")
+
+
+@pytest.mark.parametrize("metric", ["IP", "L2"])
+def test_nprobe_equals_nlist_is_brute_force(sb, orc, metric):
+    x, q, cent, ids = make_case(orc, 5000, 96, 32, 64, metric, seed=9, normalise=False)
+    g, _, _ = build_pair(sb, orc, x, ids, cent, metric)
+    bd, bi = orc.brute_force(x, ids, q, 10, metric)  # fp64 ground truth
+    for nprobe in (32, 1000):  # nprobe is clamped to nlist
+        gd, gi = g.search(q, 10, nprobe=nprobe)
+        assert_topk_parity(gd, gi, bd.astype(np.float32), bi, f"brute {metric} nprobe={nprobe}")
+
+
+def test_device_tensors_in_and_out(sb, orc):
+    import torch
+
+    x, q, cent, ids = make_case(orc, 4000, 768, 32, 50, "IP", seed=2)
+    g, oidx, _ = build_pair(sb, orc, x, ids, cent, "IP")
+    rd, ri = orc.search(oidx, q, 10, 8)
+    qd = torch.from_numpy(q).cuda()
+    gd, gi = g.search(qd, 10, nprobe=8)
+    assert gd.is_cuda and gi.is_cuda and gi.dtype == torch.int64
+    torch.cuda.synchronize()
+    hd, hi = g.search(q, 10, nprobe=8)
+    np.testing.assert_array_equal(gi.cpu().numpy(), hi)
+    np.testing.assert_array_equal(gd.cpu().numpy(), hd)
+    # device-side add: same index when the rows come from a CUDA tensor
+    g2 = sb.IVFFlatIndex(768, nlist=32, metric="IP")
+    g2.set_centroids(torch.from_numpy(cent).cuda())
+    g2.add(torch.from_numpy(x).cuda(), torch.from_numpy(ids).cuda())
+    d2, i2 = g2.search(q, 10, nprobe=8)
+    assert_topk_parity(d2, i2, hd, hi, "device add")
+    # non-default stream
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        sd, si = g.search(qd, 10, nprobe=8)
+    s.synchronize()
+    np.testing.assert_array_equal(si.cpu().numpy(), hi)
+
+
+# ---- filters, tombstones, upsert ----------------------------------------------------------------
+@pytest.mark.parametrize("metric", ["IP", "L2"])
+def test_filtered_search_parity(sb, orc, orc_c, metric):
+    n, d, nlist = 30000, 256, 64
+    x, q, cent, ids = make_case(orc, n, d, nlist, 60, metric, seed=11)
+    rng = np.random.default_rng(3)
+    repo = rng.zipf(1.3, n).clip(max=199).astype(np.uint32)
+    lang = rng.integers(0, 2, n).astype(np.uint8)
+    g, oidx, _ = build_pair(sb, orc, x, ids, cent, metric, repo, lang)
+    probes = orc.coarse_probe(q, cent, metric, 24)
+    # ~5 % selectivity: a handful of mid-frequency repos, one language
+    repos = [5, 6, 7, 8, 9, 10, 11]
+    mask = orc.row_mask(oidx, repos=repos, langs=[1])
+    sel = 1.0 - mask.mean()
+    assert 0.005 < sel < 0.2
+    rd, ri = orc.search(oidx, q, 50, 24, mask=mask, probes=probes)
+    gd, gi = g.search(q, 50, repos=repos, langs=[1], lists=probes)
+    assert_topk_parity(gd, gi, rd, ri, f"filter {metric}")
+    cd, ci = orc_c.scan_search(q, oidx.metric, probes, oidx.list_off, oidx.vecs, oidx.ids, 50, skip=mask)
+    assert_topk_parity(gd, gi, cd, ci, f"filter C {metric}")
+    # language only / repo only / unknown repo tag -> nothing
+    m2 = orc.row_mask(oidx, langs=[0])
+    rd, ri = orc.search(oidx, q, 10, 24, mask=m2, probes=probes)
+    gd, gi = g.search(q, 10, langs=[0], lists=probes)
+    assert_topk_parity(gd, gi, rd, ri, "lang only")
+    gd, gi = g.search(q, 10, repos=[100000], lists=probes)
+    assert (gi == -1).all()
+
+
+def test_remove_and_reinsert(sb, orc):
+    x, q, cent, ids = make_case(orc, 8000, 64, 16, 40, "IP", seed=21)
+    g, oidx, assign = build_pair(sb, orc, x, ids, cent, "IP")
+    probes = orc.coarse_probe(q, cent, "IP", 16)
+    rd, ri = orc.search(oidx, q, 10, 16, probes=probes)
+    victims = np.unique(ri[:, :3].ravel())
+    victims = victims[victims >= 0]
+    assert g.remove_ids(victims) == victims.size
+    assert g.remove_ids(victims) == 0  # already gone
+    assert g.ntotal == 8000 - victims.size
+    mask = orc.row_mask(oidx, removed_ids=victims)
+    rd2, ri2 = orc.search(oidx, q, 10, 16, mask=mask, probes=probes)
+    gd, gi = g.search(q, 10, lists=probes)
+    assert_topk_parity(gd, gi, rd2, ri2, "after remove")
+    assert not np.isin(gi, victims).any()
+    # upsert = remove + add under the same id with a new vector
+    row = int(np.flatnonzero(ids == victims[0])[0])
+    newv = q[:1].copy()
+    g.add(newv, victims[:1], lists=assign[row : row + 1])
+    gd, gi = g.search(q[:1], 1, nprobe=16)
+    assert gi[0, 0] == victims[0] and abs(gd[0, 0] - float(newv[0] @ q[0])) < 1e-5
+
+
+def test_incremental_add_equals_bulk(sb, orc):
+    x, q, cent, ids = make_case(orc, 9000, 48, 40, 64, "L2", seed=31)
+    g, oidx, assign = build_pair(sb, orc, x, ids, cent, "L2")
+    g2 = sb.IVFFlatIndex(48, nlist=40, metric="L2")
+    g2.set_centroids(cent)
+    cuts = [0, 1, 33, 34, 2000, 2001, 7777, 9000]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        g2.add(x[a:b], ids[a:b])  # GPU picks the lists itself
+    np.testing.assert_array_equal(np.sort(g2.list_sizes()), np.sort(np.bincount(assign, minlength=40)))
+    d1, i1 = g.search(q, 10, nprobe=40)
+    d2, i2 = g2.search(q, 10, nprobe=40)
+    assert_topk_parity(d2, i2, d1, i1, "incremental")
+    off, vecs, eids, tags = g2.export_csr()
+    assert off[-1] == 9000 and sorted(eids.tolist()) == sorted(ids.tolist())
+    pos = {int(v): j for j, v in enumerate(ids)}
+    np.testing.assert_array_equal(vecs[:50], x[[pos[int(v)] for v in eids[:50]]])
+
+
+def test_empty_ragged_and_edge_cases(sb, orc):
+    g = sb.IVFFlatIndex(20, nlist=8, metric="IP")
+    with pytest.raises(sb.NativeError):
+        g.search(np.zeros((1, 20), np.float32), 5)  # no centroids yet
+    cent = np.eye(8, 20, dtype=np.float32)
+    g.set_centroids(cent)
+    d, i = g.search(np.ones((3, 20), np.float32), 5, nprobe=4)  # empty index
+    assert (i == -1).all() and (d == -FMAX).all()
+    d, i = g.search(np.zeros((0, 20), np.float32), 5)
+    assert d.shape == (0, 5)
+    # all rows in one list, the others empty; k above the row count
+    x = np.tile(cent[2], (5, 1)) * np.arange(1, 6, dtype=np.float32)[:, None]
+    g.add(x, np.arange(5, dtype=np.int64))
+    assert g.list_sizes().tolist() == [0, 0, 5, 0, 0, 0, 0, 0]
+    d, i = g.search(cent[2:3], 8, nprobe=8)
+    assert i[0].tolist() == [4, 3, 2, 1, 0, -1, -1, -1]
+    d, i = g.search(cent[5:6], 3, nprobe=1)  # probes an empty list only
+    assert (i == -1).all()
+    with pytest.raises(sb.NativeError):
+        g.search(cent[:1], 0)
+    with pytest.raises(sb.NativeError):
+        g.search(cent[:1], 4096)
+    with pytest.raises(sb.NativeError):
+        g.add(x, np.arange(5, dtype=np.int64), lists=np.full(5, 8, np.int32))  # list id out of range
+    assert g.ntotal == 5
+    with pytest.raises(ValueError):
+        g.search(np.zeros((1, 21), np.float32), 5)
+    g.reset()
+    assert g.ntotal == 0 and g.list_sizes().sum() == 0
+
+
+def test_exact_ties_keep_both(sb):
+    d = 32
+    rng = np.random.default_rng(0)
+    base = unit_rows(rng, 100, d)
+    x = np.concatenate([base, base[:10]])  # ten exact duplicates under other ids
+    ids = np.arange(110, dtype=np.int64)
+    g = sb.IVFFlatIndex(d, nlist=1, metric="IP")
+    g.set_centroids(np.zeros((1, d), np.float32))
+    g.add(x, ids)
+    dd, ii = g.search(base[:10], 2, nprobe=1)
+    for r in range(10):
+        assert sorted(ii[r].tolist()) == [r, 100 + r] and dd[r, 0] == dd[r, 1]
+
+
+def test_chunked_search_equals_single_pass(sb, orc):
+    x, q, cent, ids = make_case(orc, 20000, 64, 128, 700, "IP", seed=41)
+    g, _, _ = build_pair(sb, orc, x, ids, cent, "IP")
+    d1, i1 = g.search(q, 10, nprobe=12)
+    g.set_param("scratch_bytes", 1 << 20)  # forces many query chunks
+    d2, i2 = g.search(q, 10, nprobe=12)
+    np.testing.assert_array_equal(i1, i2)
+    np.testing.assert_array_equal(d1, d2)
+    for v in (1, 2, 3, 4):
+        g.set_param("scan_variant", v)
+        d3, i3 = g.search(q, 10, nprobe=12)
+        assert_topk_parity(d3, i3, d1, i1, f"scan variant {v}")
+
+
+def test_merge_topk(sb, orc):
+    import torch
+
+    rng = np.random.default_rng(1)
+    for metric in ("IP", "L2"):
+        pd = rng.standard_normal((4, 33, 10)).astype(np.float32)
+        pd = -np.sort(-pd, axis=2) if metric == "IP" else np.sort(pd, axis=2)
+        pi = rng.permutation(4 * 33 * 10).reshape(4, 33, 10).astype(np.int64)
+        pi[1, :, 7:] = -1  # a shard with short results
+        rd, ri = orc.merge_topk(pd, pi, 10, metric)
+        gd, gi = sb.merge_topk(torch.from_numpy(pd).cuda(), torch.from_numpy(pi).cuda(), 10, metric)
+        assert_topk_parity(gd.cpu().numpy(), gi.cpu().numpy(), rd, ri, f"merge {metric}")
+
+
+# ---- k-means --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("metric", ["IP", "L2"])
+def test_kmeans_tracks_oracle(sb, orc, metric):
+    rng = np.random.default_rng(17)
+    centres = rng.standard_normal((24, 40)).astype(np.float32) * 3
+    x = (centres[rng.integers(0, 24, 6000)] + rng.standard_normal((6000, 40)).astype(np.float32)).astype(np.float32)
+    if metric == "IP":
+        x /= np.linalg.norm(x, axis=1, keepdims=True)  # embeddings are ~unit norm; keeps IP clusters non-empty
+    c_ref, obj_ref = orc.kmeans_train(x, 24, metric, niter=8, seed=5, max_points_per_centroid=0)
+    g = sb.IVFFlatIndex(40, nlist=24, metric=metric)
+    obj = g.train(x, niter=8, seed=5, max_points_per_centroid=0)
+    # a point whose two best centroids tie within fp32 rounding may be assigned differently, which
+    # moves two centroids by ~|x-c|/count: tolerances are set for a handful of such flips
+    np.testing.assert_allclose(obj, obj_ref, rtol=1e-3)
+    if metric == "L2":
+        assert all(b <= a * (1 + 1e-6) for a, b in zip(obj[:-1], obj[1:])), "L2 objective must not increase"
+    np.testing.assert_allclose(g.get_centroids(), c_ref, rtol=1e-2, atol=2e-2)
+    # Python-driven Lloyd (the building blocks the sharded trainer uses) gives the same result
+    g2 = sb.IVFFlatIndex(40, nlist=24, metric=metric)
+    obj2 = g2.train(x, niter=8, init_centroids=x[orc.kmeans_init_rows(6000, 24, 5)])
+    np.testing.assert_allclose(obj2, obj, rtol=1e-6)
+    np.testing.assert_allclose(g2.get_centroids(), g.get_centroids(), rtol=1e-5, atol=1e-6)
+
+
+def test_kmeans_empty_cluster_split(sb, orc):
+    # two tight blobs but four centroids, two of them initialised far away -> empty -> split
+    rng = np.random.default_rng(2)
+    x = np.concatenate([rng.standard_normal((500, 8)) * 0.01 + 5, rng.standard_normal((300, 8)) * 0.01 - 5]).astype(np.float32)
+    init = np.stack([x[0], x[600], np.full(8, 100, np.float32), np.full(8, -100, np.float32)])
+    c_ref, obj_ref = orc.kmeans_train(x, 4, "L2", niter=3, init_centroids=init, max_points_per_centroid=0)
+    g = sb.IVFFlatIndex(8, nlist=4, metric="L2")
+    obj = g.train(x, niter=3, init_centroids=init)
+    np.testing.assert_allclose(obj, obj_ref, rtol=5e-2)  # |x|^2 - best cancels: fp32 noise dominates tiny objectives
+    np.testing.assert_allclose(g.get_centroids(), c_ref, rtol=1e-3, atol=1e-3)
+    g.add(x, np.arange(800, dtype=np.int64))
+    assert (g.list_sizes() > 0).all()
+
+
+# ---- size-independent properties at a larger size -----------------------------------------------
+def test_properties_at_scale(sb, orc):
+    import torch
+
+    n, d, nlist, nq = 400_000, 768, 1024, 512
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    x = torch.randn((n, d), generator=gen, device="cuda")
+    x = torch.nn.functional.normalize(x, dim=1)
+    g = sb.IVFFlatIndex(d, nlist=nlist, metric="IP")
+    g.train(x, niter=2, max_points_per_centroid=64)
+    ids = torch.arange(n, device="cuda", dtype=torch.int64)
+    g.add(x, ids)
+    assert g.ntotal == n and int(g.list_sizes().sum()) == n
+    q = x[:nq].clone()
+    prev_hit = None
+    for nprobe in (1, 8, 64):
+        dd, ii = g.search(q, 10, nprobe=nprobe)
+        dd, ii = dd.cpu().numpy(), ii.cpu().numpy()
+        assert_sorted(dd, ii, True)
+        # a stored vector queried with itself comes back first, with inner product 1
+        assert (ii[:, 0] == np.arange(nq)).all()
+        np.testing.assert_allclose(dd[:, 0], 1.0, rtol=1e-5)
+        if prev_hit is not None:
+            # probing more lists can only improve the k-th best similarity
+            assert (dd[:, 9] >= prev_hit - 1e-6).all()
+        prev_hit = dd[:, 9]
+    # exhaustive probing == exact search (fp64 check on a sample)
+    dd, ii = g.search(q[:32], 10, nprobe=nlist)
+    exact = (q[:32].double() @ x.double().T).topk(10, dim=1)
+    np.testing.assert_array_equal(ii.cpu().numpy(), exact.indices.cpu().numpy())
+    np.testing.assert_allclose(dd.cpu().numpy(), exact.values.cpu().numpy(), rtol=1e-5)
+    t = g.stats()
+    assert t.npages >= n // 32 and t.bytes_lists >= n * d * 4
