@@ -182,11 +182,7 @@ class IVFFlatIndex:
     def _lloyd(self, x: Array, niter: int) -> List[float]:
         """Lloyd iterations from the current centroids, driven from Python through the
         kmeans_step / kmeans_update building blocks (the same ones the sharded trainer uses)."""
-        dev = self._dev()
-        ds = self.stats().dim_padded
-        sums = torch.zeros(self.nlist * ds, dtype=torch.float64, device=dev)
-        counts = torch.zeros(self.nlist, dtype=torch.int32, device=dev)
-        obj = torch.zeros(1, dtype=torch.float64, device=dev)
+        sums, counts, obj = self.kmeans_buffers()
         out = []
         for _ in range(niter):
             sums.zero_()
@@ -196,6 +192,18 @@ class IVFFlatIndex:
             out.append(float(obj.item()))
             self.kmeans_update(sums, counts)
         return out
+
+    def tensor_device(self):
+        """Where this engine wants its tensors (ShardedIVFFlat asks the engine, not torch.cuda)."""
+        return self._dev()
+
+    def kmeans_buffers(self):
+        """Zeroed accumulators for kmeans_step: sums [nlist*dim_padded] fp64, counts [nlist] int32, objective [1]."""
+        dev = self._dev()
+        ds = self.stats().dim_padded
+        return (torch.zeros(self.nlist * ds, dtype=torch.float64, device=dev),
+                torch.zeros(self.nlist, dtype=torch.int32, device=dev),
+                torch.zeros(1, dtype=torch.float64, device=dev))
 
     def kmeans_step(self, x: Array, sums, counts, obj) -> None:
         x = _as_rows(x, self.dim, "x")

@@ -1,0 +1,133 @@
+"""ShardedIVFFlat -- one IVF_FLAT index row-sharded over the GPUs of a box, one process per GPU.
+
+SURVEY.md section 8e: the centroids are replicated, every inverted list's rows are dealt
+round-robin to the ranks (global int64 ids), every rank runs the identical coarse pass and scans
+its 1/G slice, and the partial top-k are exchanged with ONE small all-gather (12*nq*k bytes per
+rank over NVLink) and merged on the device.  Because the union of the slices equals the single
+index's lists, the merged result equals the 1-GPU result (tie order aside) -- unlike Milvus'
+per-segment indexes [EXT].  k-means is data-parallel Lloyd: local assignment pass, all-reduce of
+the per-centroid sums / counts / objective, identical update everywhere.
+
+torch.distributed is the plumbing (NCCL on GPUs; the host logic is also exercised with gloo and a
+CPU test double in tests/test_sharded_gloo.py).  All arithmetic is in the per-rank engine.
+"""
+
+from __future__ import annotations
+
+from typing import Callable, List, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .index import KMEANS_NITER, KMEANS_SEED, metric_code
+
+
+class ShardedIVFFlat:
+    def __init__(self, dim: int, nlist: int, metric="IP", device: Optional[int] = None, group=None,
+                 engine=None, merge: Optional[Callable] = None):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed must be initialised (one process per GPU)")
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.dim, self.nlist, self.metric = int(dim), int(nlist), metric_code(metric)
+        if engine is None:
+            from .index import IVFFlatIndex, merge_topk
+
+            if device is None:
+                device = torch.cuda.current_device()
+            engine = IVFFlatIndex(dim, nlist=nlist, metric=metric, device=device)
+            merge = merge or (lambda pd, pi, k: merge_topk(pd, pi, k, self.metric, device))
+        if merge is None:
+            raise ValueError("a custom engine needs a merge function")
+        self.local = engine
+        self._merge = merge
+        self._next_row = 0  # global round-robin cursor, identical on every rank
+
+    # -- coarse quantizer -------------------------------------------------------------------------
+    def set_centroids(self, centroids=None, src: int = 0) -> None:
+        """Broadcast `centroids` (given on rank `src`) and install them on every rank."""
+        dev = self.local.tensor_device()
+        if self.rank == src:
+            c = torch.as_tensor(np.asarray(centroids, dtype=np.float32) if not torch.is_tensor(centroids) else centroids)
+            c = c.to(dev, torch.float32).contiguous()
+        else:
+            c = torch.empty((self.nlist, self.dim), dtype=torch.float32, device=dev)
+        dist.broadcast(c, src, group=self.group)
+        self.local.set_centroids(c)
+
+    def train(self, x_local, niter: int = KMEANS_NITER, seed: int = KMEANS_SEED, init_centroids=None) -> List[float]:
+        """Data-parallel Lloyd over the ranks' local rows.  Initial centroids: `init_centroids` on
+        rank 0, else `nlist` seeded random rows of rank 0's shard.  Returns the global objective
+        entering each iteration (identical on every rank)."""
+        from .index import kmeans_init_rows
+
+        if self.rank == 0 and init_centroids is None:
+            n0 = x_local.shape[0]
+            if n0 < self.nlist:
+                raise ValueError(f"rank 0 holds {n0} rows, fewer than nlist={self.nlist}")
+            rows = kmeans_init_rows(n0, self.nlist, seed)
+            init_centroids = x_local[torch.from_numpy(rows).to(x_local.device)] if torch.is_tensor(x_local) else x_local[rows]
+        self.set_centroids(init_centroids, src=0)
+        sums, counts, obj = self.local.kmeans_buffers()
+        out = []
+        for _ in range(niter):
+            sums.zero_()
+            counts.zero_()
+            obj.zero_()
+            self.local.kmeans_step(x_local, sums, counts, obj)
+            # the one exchange of an iteration: nlist*(8*ds + 4) + 8 bytes per rank
+            dist.all_reduce(sums, group=self.group)
+            dist.all_reduce(counts, group=self.group)
+            dist.all_reduce(obj, group=self.group)
+            out.append(float(obj.item()))
+            self.local.kmeans_update(sums, counts)
+        return out
+
+    # -- insert -------------------------------------------------------------------------------------
+    def add(self, x, ids, repo_tags=None, lang_tags=None) -> None:
+        """Every rank passes the SAME global batch; rank r keeps the rows whose global arrival
+        number is congruent to r (round-robin deal), so each list is spread evenly."""
+        n = x.shape[0]
+        first = (self.rank - self._next_row) % self.world
+        sl = slice(first, n, self.world)
+        self._next_row = (self._next_row + n) % self.world
+        if len(range(n)[sl]) == 0:
+            return
+
+        def take(a):
+            if a is None:
+                return None
+            a = a[sl]
+            return a.contiguous() if torch.is_tensor(a) else np.ascontiguousarray(a)
+
+        self.local.add(take(x), take(ids), take(repo_tags), take(lang_tags))
+
+    def add_local(self, x_local, ids_local, repo_tags=None, lang_tags=None) -> None:
+        """The caller has already partitioned the rows (ids must be globally unique)."""
+        self.local.add(x_local, ids_local, repo_tags, lang_tags)
+
+    @property
+    def ntotal(self) -> int:
+        t = torch.tensor([self.local.ntotal], dtype=torch.int64, device=self.local.tensor_device())
+        dist.all_reduce(t, group=self.group)
+        return int(t.item())
+
+    # -- search ---------------------------------------------------------------------------------------
+    def search(self, q, k: int, nprobe: int = 16, repos=None, langs=None):
+        """Every rank passes the same queries and receives the same merged (dist, ids) tensors."""
+        dev = self.local.tensor_device()
+        if not torch.is_tensor(q):
+            q = torch.from_numpy(np.ascontiguousarray(q, dtype=np.float32))
+        q = q.to(dev, torch.float32)
+        d, i = self.local.search(q, k, nprobe=nprobe, repos=repos, langs=langs)
+        if self.world == 1:
+            return d, i
+        nq = d.shape[0]
+        # concatenated layout [world*nq, k] (accepted by every backend), viewed as [world, nq, k]
+        gd = torch.empty((self.world * nq, k), dtype=d.dtype, device=d.device)
+        gi = torch.empty((self.world * nq, k), dtype=i.dtype, device=i.device)
+        dist.all_gather_into_tensor(gd, d.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(gi, i.contiguous(), group=self.group)
+        return self._merge(gd.view(self.world, nq, k), gi.view(self.world, nq, k), k)

@@ -1,0 +1,145 @@
+"""CPU tests of the oracle itself: known answers, brute-force equivalence, NumPy-vs-C agreement and
+the committed golden fixtures.  (The reference has no golden vectors for this path -- parity is
+unpinned at the reference boundary; these tests pin the oracle the GPU path is checked against.)"""
+
+import os
+
+import numpy as np
+import pytest
+
+from helpers import assert_sorted, assert_topk_parity, unit_rows
+from oracle import ivf_c, ivf_numpy as orc
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+FMAX = np.finfo(np.float32).max
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    ivf_c.build()
+
+
+def test_tiny_known_answer():
+    x = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1],
+                  [2, 0, 0, 0], [0, 2, 0, 0], [0, 0, 2, 0], [0, 0, 0, 2]], dtype=np.float32)
+    ids = np.arange(10, 18, dtype=np.int64)
+    cent = np.array([[1, 1, 0, 0], [0, 0, 1, 1]], dtype=np.float32)
+    q = np.array([[1, 0.5, 0, 0]], dtype=np.float32)
+    idx = orc.build_index(x, ids, cent, "IP")
+    assert np.diff(idx.list_off).tolist() == [4, 4]
+    assert orc.coarse_probe(q, cent, "IP", 1).tolist() == [[0]]
+    d, i = orc.search(idx, q, 3, 1)
+    assert i.tolist() == [[14, 10, 15]] and d.tolist() == [[2.0, 1.0, 1.0]]  # tie -> lower id first
+    d, i = orc.search(idx, q, 6, 1)
+    assert i.tolist()[0][4:] == [-1, -1] and d[0, 5] == -FMAX
+    idx2 = orc.build_index(x, ids, cent, "L2")
+    d, i = orc.search(idx2, q, 4, 1)
+    assert i.tolist() == [[10, 11, 14, 15]]
+    np.testing.assert_allclose(d[0], [0.25, 1.25, 1.25, 3.25])
+    cd, ci = ivf_c.scan_search(q, 1, np.array([[0]], np.int32), idx2.list_off, idx2.vecs, idx2.ids, 5)
+    assert ci.tolist() == [[10, 11, 14, 15, -1]] and cd[0, 4] == FMAX
+
+
+@pytest.mark.parametrize("metric", ["IP", "L2"])
+def test_exhaustive_probe_is_brute_force(metric):
+    rng = np.random.default_rng(1)
+    x, q = rng.standard_normal((3000, 40)).astype(np.float32), rng.standard_normal((25, 40)).astype(np.float32)
+    ids = rng.permutation(100000)[:3000].astype(np.int64)
+    cent = x[orc.kmeans_init_rows(3000, 20, 1)]
+    idx = orc.build_index(x, ids, cent, metric)
+    bd, bi = orc.brute_force(x, ids, q, 10, metric)
+    d, i = orc.search(idx, q, 10, 20)
+    assert_topk_parity(d, i, bd.astype(np.float32), bi, "numpy")
+    d2, i2 = orc.search(idx, q, 10, 999)  # nprobe clamps to nlist
+    np.testing.assert_array_equal(i, i2)
+    cd, ci = ivf_c.search(q, idx.metric, cent, 20, idx.list_off, idx.vecs, idx.ids, 10)
+    assert_topk_parity(cd, ci, bd.astype(np.float32), bi, "C")
+    assert_sorted(cd, ci, metric == "IP")
+
+
+@pytest.mark.parametrize("metric", ["IP", "L2"])
+@pytest.mark.parametrize("d", [768, 100, 7])
+def test_c_port_agrees_with_numpy(metric, d):
+    rng = np.random.default_rng(d)
+    x, q = unit_rows(rng, 4000, d), unit_rows(rng, 30, d)
+    ids = np.arange(4000, dtype=np.int64) + 5
+    cent = x[orc.kmeans_init_rows(4000, 50, 3)]
+    idx = orc.build_index(x, ids, cent, metric)
+    s_np = orc.coarse_similarity(q, cent, metric)
+    s_c = ivf_c.coarse_scores(q, cent, idx.metric)
+    np.testing.assert_allclose(s_c, s_np, rtol=1e-5, atol=1e-6)
+    np.testing.assert_array_equal(ivf_c.top_probes(s_np, 9), orc.top_desc(s_np, 9))
+    a_np, a_c = orc.assign(x, cent, metric), ivf_c.assign(x, cent, idx.metric)
+    assert (a_np != a_c).mean() < 0.002  # fp32 near-ties only
+    probes = orc.top_desc(s_np, 9)
+    rng2 = np.random.default_rng(0)
+    mask = rng2.random(4000) < 0.9
+    for m in (None, mask):
+        d1, i1 = orc.search(idx, q, 10, 9, mask=m, probes=probes)
+        d2, i2 = ivf_c.scan_search(q, idx.metric, probes, idx.list_off, idx.vecs, idx.ids, 10, skip=m)
+        assert_topk_parity(d2, i2, d1, i1, f"{metric} d={d}")
+
+
+def test_filter_and_removed_rows_are_skipped_before_ranking():
+    rng = np.random.default_rng(4)
+    x, q = unit_rows(rng, 2000, 16), unit_rows(rng, 10, 16)
+    ids = np.arange(2000, dtype=np.int64)
+    repo = (ids % 10).astype(np.uint32)
+    lang = (ids % 2).astype(np.uint8)
+    cent = x[:8].copy()
+    idx = orc.build_index(x, ids, cent, "IP", repo, lang)
+    mask = orc.row_mask(idx, repos=[3], langs=[1], removed_ids=[3, 13, 23])
+    d, i = orc.search(idx, q, 20, 8, mask=mask)
+    kept = i[i >= 0]
+    assert kept.size == 20 * 10 and (kept % 10 == 3).all() and not np.isin(kept, [3, 13, 23]).any()
+    # filter-then-rank (FAISS/knowhere) is not rank-then-filter (the UIs' post-filter, app.py:100-116)
+    d_all, i_all = orc.search(idx, q, 20, 8)
+    post = [(r % 10 == 3).sum() for r in i_all]
+    assert max(post) < 20
+
+
+def test_merge_topk_equals_single_index():
+    rng = np.random.default_rng(5)
+    x, q = unit_rows(rng, 4000, 32), unit_rows(rng, 20, 32)
+    ids = np.arange(4000, dtype=np.int64)
+    cent = x[orc.kmeans_init_rows(4000, 16, 1)]
+    a = orc.assign(x, cent, "L2")
+    full = orc.build_index(x, ids, cent, "L2", assignment=a)
+    parts = [orc.build_index(x[r::3], ids[r::3], cent, "L2", assignment=a[r::3]) for r in range(3)]
+    probes = orc.coarse_probe(q, cent, "L2", 5)
+    pd, pi = zip(*[orc.search(p, q, 10, 5, probes=probes) for p in parts])
+    md, mi = orc.merge_topk(np.stack(pd), np.stack(pi), 10, "L2")
+    fd, fi = orc.search(full, q, 10, 5, probes=probes)
+    np.testing.assert_array_equal(mi, fi)
+    np.testing.assert_array_equal(md, fd)
+
+
+def test_kmeans_objective_and_split():
+    rng = np.random.default_rng(6)
+    centres = rng.standard_normal((10, 12)).astype(np.float32) * 4
+    x = (centres[rng.integers(0, 10, 3000)] + rng.standard_normal((3000, 12))).astype(np.float32)
+    c, obj = orc.kmeans_train(x, 10, "L2", niter=10, seed=3, max_points_per_centroid=0)
+    assert all(b <= a * (1 + 1e-6) for a, b in zip(obj[:-1], obj[1:]))
+    assert obj[-1] < 0.6 * obj[0]
+    cc = np.array([[1.0, 2.0, 3.0], [0, 0, 0], [5, 5, 5]], dtype=np.float32)
+    n = orc.split_empty_clusters(cc, np.array([10, 0, 3]))
+    assert n == 1
+    np.testing.assert_allclose(cc[1], [1 * (1 + 1 / 1024), 2 * (1 - 1 / 1024), 3 * (1 + 1 / 1024)], rtol=1e-6)
+    np.testing.assert_allclose(cc[0], [1 * (1 - 1 / 1024), 2 * (1 + 1 / 1024), 3 * (1 - 1 / 1024)], rtol=1e-6)
+    assert orc.kmeans_subsample_rows(1000, 10, 256, 1) is None
+    rows = orc.kmeans_subsample_rows(10000, 10, 256, 1)
+    assert rows.size == 2560 and np.all(np.diff(rows) > 0)
+
+
+@pytest.mark.parametrize("metric", ["IP", "L2"])
+def test_golden_small(metric):
+    z = np.load(os.path.join(GOLD, "kat_small.npz"))
+    idx = orc.build_index(z["x"], z["ids"], z[f"cent_{metric}"], metric, z["repo"], z["lang"])
+    np.testing.assert_array_equal(orc.coarse_probe(z["q"], z[f"cent_{metric}"], metric, 4), z[f"probes_{metric}"])
+    mask = orc.row_mask(idx, repos=[1, 2, 3], langs=[1])
+    for m, dk, ik in ((None, "dist", "ids"), (mask, "fdist", "fids")):
+        d, i = orc.search(idx, z["q"], 10, 4, mask=m, probes=z[f"probes_{metric}"])
+        np.testing.assert_array_equal(i, z[f"{ik}_{metric}"])
+        np.testing.assert_allclose(d, z[f"{dk}_{metric}"], rtol=1e-6)
+        cd, ci = ivf_c.scan_search(z["q"], idx.metric, z[f"probes_{metric}"], idx.list_off, idx.vecs, idx.ids, 10, skip=m)
+        assert_topk_parity(cd, ci, z[f"{dk}_{metric}"], z[f"{ik}_{metric}"], f"C vs golden {metric}")
