@@ -122,6 +122,13 @@ struct DeviceGuard {
     }
 };
 
+// probe[q, j] = j : "every list", used when nprobe >= nlist (exhaustive search needs no ranking)
+__global__ void iota_rows_kernel(int32_t *p, int64_t rows, int32_t n) {
+    const int64_t total = rows * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = (int32_t)(i % n);
+}
+
 __global__ void fill_u32_kernel(uint32_t *p, int64_t n, uint32_t v) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         p[i] = v;
@@ -465,6 +472,9 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
     if (nq == 0) return SC_OK;
     if (!q || !out_dist || !out_ids) return fail(SC_ERR_INVALID, "q / out_dist / out_ids must not be NULL");
     const int np = lists ? nprobe : std::min(nprobe, ix->nlist);
+    const bool all_lists = !lists && np == ix->nlist;
+    if (!lists && !all_lists && np > kMaxK)
+        return fail(SC_ERR_INVALID, "nprobe %d: values above %d are supported only as nprobe >= nlist (exhaustive)", np, kMaxK);
     const bool outd_dev = is_device_ptr(out_dist, ix->device), outi_dev = is_device_ptr(out_ids, ix->device);
 
     SC(begin_call(ix, st));
@@ -479,7 +489,7 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
     // worst-case pages one query can touch -> candidate scratch per query
     int64_t pb = lists ? (int64_t)np * ix->h_max_pages : ix->h_bound_prefix[std::min(np, ix->nlist)];
     pb = std::max<int64_t>(pb, 1);
-    const int64_t per_query = (lists ? 0 : (int64_t)ix->nlist * 4) + (int64_t)np * 20 + pb * kPageRows * 4 +
+    const int64_t per_query = ((lists || all_lists) ? 0 : (int64_t)ix->nlist * 4) + (int64_t)np * 20 + pb * kPageRows * 4 +
                               (int64_t)ix->ds * 4 + (int64_t)k * 12;
     int64_t nqc = std::max<int64_t>(1, ix->scratch_budget / per_query);
     nqc = std::min(nqc, nq);
@@ -487,7 +497,7 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
     nqc = std::min(nqc, nq);
 
     const int64_t npairs_max = nqc * np;
-    if (!lists) CU(ix->s_scores.reserve((size_t)nqc * ix->nlist * 4));
+    if (!lists && !all_lists) CU(ix->s_scores.reserve((size_t)nqc * ix->nlist * 4));
     if (!lists) CU(ix->s_probe.reserve((size_t)npairs_max * 4));
     CU(ix->s_pairpages.reserve((size_t)npairs_max * 8));
     CU(ix->s_pageoff.reserve((size_t)(npairs_max + 1) * 8));
@@ -505,6 +515,12 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
         if (lists) {
             SC(stage(ix, lists + s * np, (size_t)npairs, ix->s_probe, st, &probe));
             SC(prof_mark(ix, st));
+        } else if (all_lists) {
+            SC(prof_mark(ix, st));
+            iota_rows_kernel<<<ix->num_sms * 4, 256, 0, st>>>(ix->s_probe.as<int32_t>(), m, np);
+            CU(cudaGetLastError());
+            probe = ix->s_probe.as<int32_t>();
+            ix->prof_total_launches += 1;
         } else {
             CU(launch_gemm_nt(qd, m, ix->centroids, ix->nlist, ix->ds,
                               ix->metric == SC_METRIC_L2 ? ix->cnorm : nullptr, ix->s_scores.as<float>(), st));
@@ -908,6 +924,7 @@ int sc_index_probe(sc_index_t *ix, const float *q, int64_t nq, int32_t nprobe, i
     cudaStream_t st = (cudaStream_t)stream;
     SC(require_trained(ix));
     if (nprobe > ix->nlist) return fail(SC_ERR_INVALID, "nprobe %d exceeds nlist %d (outputs are [nq, nprobe])", nprobe, ix->nlist);
+    if (nprobe > kMaxK) return fail(SC_ERR_INVALID, "sc_index_probe ranks at most %d lists per query", kMaxK);
     if (nq == 0) return SC_OK;
     if (!q) return fail(SC_ERR_INVALID, "q is NULL");
     SC(begin_call(ix, st));

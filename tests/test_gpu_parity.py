@@ -394,3 +394,18 @@ def test_properties_at_scale(sb, orc):
     np.testing.assert_allclose(dd.cpu().numpy(), exact.values.cpu().numpy(), rtol=1e-5)
     t = g.stats()
     assert t.npages >= n // 32 and t.bytes_lists >= n * d * 4
+
+
+def test_exhaustive_probe_beyond_select_limit(sb, orc):
+    """nprobe >= nlist needs no ranking, so it is not bound by the 2048-wide selection kernel."""
+    x, q, cent, ids = make_case(orc, 9000, 32, 3000, 20, "IP", seed=51)
+    g, _, _ = build_pair(sb, orc, x, ids, cent, "IP")
+    bd, bi = orc.brute_force(x, ids, q, 10, "IP")
+    gd, gi = g.search(q, 10, nprobe=3000)
+    assert_topk_parity(gd, gi, bd.astype(np.float32), bi, "exhaustive nlist=3000")
+    gd, gi = g.search(q, 10, nprobe=100000)
+    assert_topk_parity(gd, gi, bd.astype(np.float32), bi, "exhaustive clamp")
+    with pytest.raises(sb.NativeError):
+        g.search(q, 10, nprobe=2500)
+    with pytest.raises(sb.NativeError):
+        g.probe(q, 2500)
