@@ -64,22 +64,42 @@ def parse_args():
     p.add_argument("--cpu-queries", type=int, default=96, help="queries in the CPU baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--scan-variant", type=int, default=0)
+    p.add_argument("--dataset", default="iid", choices=["iid", "clustered"],
+                   help="synthetic set of SURVEY.md 8d: A (iid Gaussian) or B (Zipf-clustered)")
+    p.add_argument("--coarse-impl", type=int, default=0, help="0 = tcgen05 3xTF32, 1 = fp32 SIMT")
     return p.parse_args()
 
 
 # ------------------------------------------------------------------------------------------------
 # synthetic data (set A): unit-norm Gaussian rows, generated on the device
 # ------------------------------------------------------------------------------------------------
-def gen_rows(torch, n0, n1, dim, seed, device):
-    """Rows [n0, n1) of the synthetic matrix: each 65536-row block has its own seeded generator,
-    so any rank can produce any block without materialising the rest."""
+_LATENT = {}
+
+
+def gen_rows(torch, n0, n1, dim, seed, device, dataset="iid"):
+    """Rows [n0, n1) of the synthetic matrix.  Each 65536-row block has its own
+    seeded generator, so any rank can produce any block without materialising the rest.
+      iid        set A: x ~ N(0, I_d), L2-normalised (balanced lists, worst case for recall)
+      clustered  set B: 4096 latent centres ~ N(0, I_d), Zipf(1.1) cluster sizes, within-cluster noise
+                 sigma = 0.3, L2-normalised (skewed lists, like real code embeddings)"""
     blk = 65536
     out = torch.empty((n1 - n0, dim), dtype=torch.float32, device=device)
+    if dataset == "clustered":
+        key = (dim, str(device))
+        if key not in _LATENT:
+            g0 = torch.Generator(device=device).manual_seed(555)
+            centres = torch.randn((4096, dim), generator=g0, device=device, dtype=torch.float32)
+            w = 1.0 / torch.arange(1, 4097, device=device, dtype=torch.float64) ** 1.1
+            _LATENT[key] = (centres, (w / w.sum()).to(torch.float32))
+        centres, w = _LATENT[key]
     b = n0 // blk
     while b * blk < n1:
         lo, hi = max(n0, b * blk), min(n1, (b + 1) * blk)
         g = torch.Generator(device=device).manual_seed(seed * 1_000_003 + b)
         full = torch.randn((blk, dim), generator=g, device=device, dtype=torch.float32)
+        if dataset == "clustered":
+            c = torch.multinomial(w, blk, replacement=True, generator=g)
+            full = centres[c] + 0.3 * full
         out[lo - n0 : hi - n0] = full[lo - b * blk : hi - b * blk]
         b += 1
     return torch.nn.functional.normalize(out, dim=1)
@@ -264,9 +284,10 @@ def run_reference(args):
 def workload_config(args, nq_override=None):
     return {
         "workload": f"IVF_FLAT {args.n}x{args.dim} fp32, nlist={args.nlist}, nprobe={args.nprobe}, "
-                    f"nq={nq_override or args.nq}/step, top-{args.k}, metric={args.metric} (BASELINE.json configs[1])",
+                    f"nq={nq_override or args.nq}/step, top-{args.k}, metric={args.metric}, {args.dataset} synthetic set "
+                    f"(BASELINE.json configs[1])",
         "n": args.n, "dim": args.dim, "nlist": args.nlist, "nprobe": args.nprobe, "nq": nq_override or args.nq,
-        "k": args.k, "metric": args.metric,
+        "k": args.k, "metric": args.metric, "dataset": args.dataset,
         "l2_policy": "inputs larger than L2: every step streams nq*nprobe lists (>> 126 MB) and rotates query batches",
     }
 
@@ -296,9 +317,11 @@ def run_ours(args):
     g = sb.IVFFlatIndex(d, nlist=nlist, metric=args.metric, device=local)
     if args.scan_variant:
         g.set_param("scan_variant", args.scan_variant)
+    if args.coarse_impl:
+        g.set_param("coarse_impl", args.coarse_impl)
     cent = torch.empty((nlist, d), dtype=torch.float32, device=dev)
     if rank == 0:
-        tr = gen_rows(torch, 0, min(args.train_rows, n), d, 1234, dev)
+        tr = gen_rows(torch, 0, min(args.train_rows, n), d, 1234, dev, args.dataset)
         g.train(tr, niter=args.train_iters, max_points_per_centroid=0)
         cent.copy_(torch.from_numpy(g.get_centroids()))
         del tr
@@ -310,7 +333,7 @@ def run_ours(args):
     chunk = 1 << 20
     for s in range(0, n, chunk):
         e = min(n, s + chunk)
-        x = gen_rows(torch, s, e, d, 1234, dev)
+        x = gen_rows(torch, s, e, d, 1234, dev, args.dataset)
         ids = torch.arange(s, e, device=dev, dtype=torch.int64)
         if world > 1:  # deal rows round-robin: rank r keeps global rows i with i % world == r
             x, ids = x[rank::world].contiguous(), ids[rank::world].contiguous()
@@ -321,7 +344,7 @@ def run_ours(args):
 
     # ---- queries: a few rotating batches ----------------------------------------------------------
     nb = 4
-    qall = gen_rows(torch, 0, nb * nq, d, 4321, dev)
+    qall = gen_rows(torch, 0, nb * nq, d, 4321, dev, args.dataset)
     qb = [qall[i * nq : (i + 1) * nq].contiguous() for i in range(nb)]
     qhost = [t.cpu().pin_memory() for t in qb]
     out_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
@@ -446,6 +469,16 @@ def run_ours(args):
         return
 
     peaks, peak_src = measured_peaks()
+    traffic = None
+    try:  # DRAM bytes of the scan kernel from the committed ncu --set full capture of this workload
+        with open(os.path.join(ROOT, "profiles", "scan_traffic.json")) as f:
+            for ent in json.load(f)["captures"]:
+                mm = ent["match"]
+                if all(mm[key] == val for key, val in (("n", n), ("dim", d), ("nlist", nlist), ("nprobe", nprobe),
+                                                       ("nq", nq), ("dataset", args.dataset))):
+                    traffic = ent["dram_bytes_per_launch"]
+    except Exception:
+        traffic = None
     bytes_per_step = statistics.mean(scanned_rows) * 4 * d  # this rank's slice
     scan_s = statistics.mean(scan_ms) / 1e3
     achieved = bytes_per_step / scan_s / 1e9
@@ -462,7 +495,7 @@ def run_ours(args):
         "roofline": {
             "bound": "hbm", "kernel": "scan_pages_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": achieved / peaks["hbm_gbs"], "frac_of_8TBps_nominal": achieved / 8000.0, "peak_source": peak_src,
-            "traffic": None, "algorithmic_bytes_per_launch": bytes_per_step, "kernel_ms": scan_s * 1e3,
+            "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_step, "kernel_ms": scan_s * 1e3,
             "kernel_share_of_step": (phase["scan"] / nprof) / (ms_total / args.steps),
         },
         "phases_ms": {kname: v / nprof for kname, v in phase.items()},
@@ -473,9 +506,13 @@ def run_ours(args):
     # ---- optional nprobe x nq sweep --------------------------------------------------------------------
     if args.sweep and world == 1:
         sweep = []
-        for np_ in (8, 16, 32, 64, 128):
-            for nq_ in (1, 16, 256, 4096):
-                qs = gen_rows(torch, 0, nq_, d, 777 + nq_, dev)
+        for nq_ in (1, 16, 256, 4096):
+            qs = gen_rows(torch, 0, nq_, d, 777 + nq_, dev, args.dataset)
+            exact_ids = None
+            if nq_ == 256:  # recall@10 per nprobe on this batch (exact = exhaustive probe)
+                _, ei = g.search(qs, k, nprobe=nlist)
+                exact_ids = ei.cpu().numpy()
+            for np_ in (8, 16, 32, 64, 128):
                 for _ in range(2):
                     g.search(qs, k, nprobe=np_)
                 torch.cuda.synchronize()
@@ -483,7 +520,7 @@ def run_ours(args):
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
                 for _ in range(reps):
-                    g.search(qs, k, nprobe=np_)
+                    _, ii = g.search(qs, k, nprobe=np_)
                 b.record()
                 torch.cuda.synchronize()
                 ms = a.elapsed_time(b) / reps
@@ -492,9 +529,14 @@ def run_ours(args):
                 torch.cuda.synchronize()
                 tt = g.last_search_times()
                 g.set_profiling(False)
-                sweep.append({"nprobe": np_, "nq": nq_, "ms": ms, "qps": nq_ / ms * 1e3,
-                              "logical_GBps": tt.scanned_rows * 4 * d / ms / 1e6,
-                              "scan_GBps": tt.scanned_rows * 4 * d / max(tt.scan_ms, 1e-6) / 1e6})
+                row = {"nprobe": np_, "nq": nq_, "ms": ms, "qps": nq_ / ms * 1e3,
+                       "logical_GBps": tt.scanned_rows * 4 * d / ms / 1e6,
+                       "scan_GBps": tt.scanned_rows * 4 * d / max(tt.scan_ms, 1e-6) / 1e6}
+                if exact_ids is not None:
+                    ia_ = ii.cpu().numpy()
+                    row["recall_at_10"] = float(np.mean([len(np.intersect1d(ia_[r][ia_[r] >= 0], exact_ids[r])) / k
+                                                         for r in range(nq_)]))
+                sweep.append(row)
         line["sweep"] = sweep
 
     # ---- CPU baseline on the same lists (bounded sample) ----------------------------------------------

@@ -68,6 +68,18 @@ __device__ __forceinline__ float key2f(uint32_t k) {
 // C[M,N] = A[M,K] . B[N,K]^T ; if bnorm != nullptr: C = 2*C - bnorm[n]   (all fp32, K % 4 == 0)
 cudaError_t launch_gemm_nt(const float *A, int64_t M, const float *B, int N, int K, const float *bnorm, float *C,
                            cudaStream_t st);
+// ---- tensor-core contraction (gemm_tc.cu): tcgen05 kind::tf32, 3xTF32 split, TMA-fed -----------------
+// hi = tf32(x), lo = tf32(x - hi); n = number of floats (multiple of 4)
+cudaError_t launch_split_tf32(const float *x, int64_t n, float *hi, float *lo, cudaStream_t st);
+// C[M,N] = alpha * A.B^T - bias[n]   (A, B given as hi/lo pairs, row stride K floats, K % 4 == 0)
+cudaError_t launch_gemm_tc_scores(const float *ahi, const float *alo, int64_t M, const float *bhi, const float *blo, int N,
+                                  int K, float alpha, const float *bias, float *C, int num_sms, cudaStream_t st);
+// per row of A: best_idx = n_base + argmax_n (alpha * A.B^T - bias), best_val = that maximum; merge != 0 folds the
+// values already stored in best_val / best_idx in (for centroid slabs); ties -> lowest index
+cudaError_t launch_gemm_tc_argmax(const float *ahi, const float *alo, int64_t M, const float *bhi, const float *blo, int N,
+                                  int K, float alpha, const float *bias, float *best_val, int32_t *best_idx, int n_base,
+                                  int merge, int num_sms, cudaStream_t st);
+
 // out[r] = sum_k x[r,k]^2
 cudaError_t launch_row_norms(const float *x, int64_t rows, int ds, float *out, cudaStream_t st);
 // per row: index of the largest score (ties -> lowest index) and the score

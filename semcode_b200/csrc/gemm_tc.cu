@@ -21,6 +21,7 @@
 // never materialises the M x N matrix (k-means assignment, bulk add).
 // Roofline: tensor pipe (kind::tf32 dense, 3 MMAs per logical product), operands stream from L2.
 #include <cuda.h>
+#include <string.h>
 
 #include "common.cuh"
 

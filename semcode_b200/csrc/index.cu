@@ -144,6 +144,9 @@ struct sc_index {
     bool trained = false;
     float *centroids = nullptr;  // [nlist, ds]
     float *cnorm = nullptr;      // [nlist]  |c|^2 (L2 only)
+    float *cent_hi = nullptr;    // [nlist, ds] tf32(c)           } 3xTF32 operands of the tcgen05
+    float *cent_lo = nullptr;    // [nlist, ds] tf32(c - cent_hi) } coarse contraction (gemm_tc.cu)
+    int coarse_impl = 0;         // 0 = tcgen05 3xTF32, 1 = fp32 SIMT (exact-fp32 reference kernel)
 
     // paged lists
     int slab_shift = 0;
@@ -165,7 +168,7 @@ struct sc_index {
     // scratch (stream ordered; ev_done chains calls made on different streams)
     DevBuf s_q, s_scores, s_probe, s_pairpages, s_pageoff, s_cand, s_outd, s_outi, s_repobits;
     DevBuf s_x, s_xpad, s_ids, s_repo, s_lang, s_assign, s_best, s_pos, s_lenold, s_need, s_npg, s_needoff, s_bad;
-    DevBuf s_sums, s_counts, s_obj, s_rows, s_rm, s_cnt;
+    DevBuf s_sums, s_counts, s_obj, s_rows, s_rm, s_cnt, s_ahi, s_alo;
     int64_t scratch_budget = (int64_t)2 << 30;
     int scan_variant = 0;
     cudaEvent_t ev_done = nullptr;
@@ -298,8 +301,27 @@ int require_trained(const sc_index *ix) {
     return SC_OK;
 }
 
+// everything derived from the centroids: |c|^2 and the tf32 hi/lo split
 int update_cnorm(sc_index *ix, cudaStream_t st) {
     CU(launch_row_norms(ix->centroids, ix->nlist, ix->ds, ix->cnorm, st));
+    CU(launch_split_tf32(ix->centroids, (int64_t)ix->nlist * ix->ds, ix->cent_hi, ix->cent_lo, st));
+    return SC_OK;
+}
+
+bool use_tc(const sc_index *ix) { return ix->coarse_impl == 0 && ix->ds >= 32; }
+
+// scores[m, nlist] = similarity to maximise (IP: x.c ; L2: 2 x.c - |c|^2) of device rows xd[m, ds]
+int coarse_scores(sc_index *ix, const float *xd, int64_t m, float *scores, cudaStream_t st) {
+    const bool l2 = ix->metric == SC_METRIC_L2;
+    if (!use_tc(ix)) {
+        CU(launch_gemm_nt(xd, m, ix->centroids, ix->nlist, ix->ds, l2 ? ix->cnorm : nullptr, scores, st));
+        return SC_OK;
+    }
+    CU(ix->s_ahi.reserve((size_t)m * ix->ds * 4));
+    CU(ix->s_alo.reserve((size_t)m * ix->ds * 4));
+    CU(launch_split_tf32(xd, m * ix->ds, ix->s_ahi.as<float>(), ix->s_alo.as<float>(), st));
+    CU(launch_gemm_tc_scores(ix->s_ahi.as<float>(), ix->s_alo.as<float>(), m, ix->cent_hi, ix->cent_lo, ix->nlist, ix->ds,
+                             l2 ? 2.f : 1.f, l2 ? ix->cnorm : nullptr, scores, ix->num_sms, st));
     return SC_OK;
 }
 
@@ -313,12 +335,34 @@ int64_t coarse_chunk_rows(const sc_index *ix, int64_t n) {
 
 // assign[i] = argbest centroid of xd[i] (device rows [n, ds]); best[i] = its similarity
 int coarse_assign(sc_index *ix, const float *xd, int64_t n, int32_t *assign, float *best, cudaStream_t st) {
+    if (use_tc(ix) && n >= 4096) {
+        // fused contraction + argmax on the tensor cores: the [n, nlist] matrix is never written.
+        // Centroids are swept in slabs whose hi/lo copies (~48 MB) stay L2-resident while every row
+        // tile passes; the running best is carried across slabs in best/assign.
+        const bool l2 = ix->metric == SC_METRIC_L2;
+        CU(ix->s_ahi.reserve((size_t)n * ix->ds * 4));
+        CU(ix->s_alo.reserve((size_t)n * ix->ds * 4));
+        CU(launch_split_tf32(xd, n * ix->ds, ix->s_ahi.as<float>(), ix->s_alo.as<float>(), st));
+        float *bv = best;
+        if (!bv) {
+            CU(ix->s_best.reserve((size_t)n * 4));
+            bv = ix->s_best.as<float>();
+        }
+        int64_t slab = (((int64_t)48 << 20) / ((int64_t)ix->ds * 8)) / 256 * 256;
+        slab = std::max<int64_t>(256, std::min<int64_t>(slab, ix->nlist));
+        for (int64_t c0 = 0; c0 < ix->nlist; c0 += slab) {
+            const int nc = (int)std::min<int64_t>(slab, ix->nlist - c0);
+            CU(launch_gemm_tc_argmax(ix->s_ahi.as<float>(), ix->s_alo.as<float>(), n, ix->cent_hi + c0 * ix->ds,
+                                     ix->cent_lo + c0 * ix->ds, nc, ix->ds, l2 ? 2.f : 1.f, l2 ? ix->cnorm + c0 : nullptr, bv,
+                                     assign, (int)c0, c0 > 0 ? 1 : 0, ix->num_sms, st));
+        }
+        return SC_OK;
+    }
     const int64_t ch = coarse_chunk_rows(ix, n);
     CU(ix->s_scores.reserve((size_t)ch * ix->nlist * sizeof(float)));
     for (int64_t s = 0; s < n; s += ch) {
         const int64_t m = std::min(ch, n - s);
-        CU(launch_gemm_nt(xd + s * ix->ds, m, ix->centroids, ix->nlist, ix->ds,
-                          ix->metric == SC_METRIC_L2 ? ix->cnorm : nullptr, ix->s_scores.as<float>(), st));
+        SC(coarse_scores(ix, xd + s * ix->ds, m, ix->s_scores.as<float>(), st));
         CU(launch_argmax_rows(ix->s_scores.as<float>(), m, ix->nlist, assign + s, best ? best + s : nullptr, st));
     }
     return SC_OK;
@@ -390,6 +434,7 @@ int add_impl(sc_index *ix, const float *x, const int64_t *ids, const uint32_t *r
     CU(cudaDeviceSynchronize());  // no search may still be reading the page table we are about to swap
     // bounded staging: ~256 MB of rows per pass
     int64_t chunk = std::max<int64_t>(1024, ((int64_t)256 << 20) / ((int64_t)ix->ds * 4));
+    if (is_device_ptr(x, ix->device)) chunk = std::max<int64_t>(chunk, (int64_t)1 << 18);
     chunk = std::min(chunk, n);
     for (int64_t s = 0; s < n; s += chunk) {
         const int64_t m = std::min(chunk, n - s);
@@ -522,12 +567,11 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
             probe = ix->s_probe.as<int32_t>();
             ix->prof_total_launches += 1;
         } else {
-            CU(launch_gemm_nt(qd, m, ix->centroids, ix->nlist, ix->ds,
-                              ix->metric == SC_METRIC_L2 ? ix->cnorm : nullptr, ix->s_scores.as<float>(), st));
+            SC(coarse_scores(ix, qd, m, ix->s_scores.as<float>(), st));
             SC(prof_mark(ix, st));
             CU(launch_select_rows(ix->s_scores.as<float>(), m, ix->nlist, np, ix->s_probe.as<int32_t>(), nullptr, st));
             probe = ix->s_probe.as<int32_t>();
-            ix->prof_total_launches += 2;
+            ix->prof_total_launches += use_tc(ix) ? 3 : 2;
         }
         SC(prof_mark(ix, st));
         CU(launch_plan_pairs(probe, npairs, ix->list_len, ix->nlist, ix->s_pairpages.as<int64_t>(),
@@ -630,6 +674,8 @@ int sc_index_create(int32_t dim, int32_t metric, int32_t nlist, int32_t device, 
     };
     cudaError_t e = cudaMalloc(&ix->centroids, (size_t)nlist * ix->ds * 4);
     if (e == cudaSuccess) e = cudaMalloc(&ix->cnorm, (size_t)nlist * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&ix->cent_hi, (size_t)nlist * ix->ds * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&ix->cent_lo, (size_t)nlist * ix->ds * 4);
     if (e == cudaSuccess) e = cudaMalloc(&ix->d_tab, sizeof(SlabTable));
     if (e == cudaSuccess) e = cudaMalloc(&ix->list_len, (size_t)nlist * 4);
     if (e == cudaSuccess) e = cudaMalloc(&ix->pt_off, (size_t)(nlist + 1) * 4);
@@ -660,9 +706,9 @@ int sc_index_destroy(sc_index_t *ix) {
     for (DevBuf *b : {&ix->s_q, &ix->s_scores, &ix->s_probe, &ix->s_pairpages, &ix->s_pageoff, &ix->s_cand, &ix->s_outd,
                       &ix->s_outi, &ix->s_repobits, &ix->s_x, &ix->s_xpad, &ix->s_ids, &ix->s_repo, &ix->s_lang,
                       &ix->s_assign, &ix->s_best, &ix->s_pos, &ix->s_lenold, &ix->s_need, &ix->s_npg, &ix->s_needoff,
-                      &ix->s_bad, &ix->s_sums, &ix->s_counts, &ix->s_obj, &ix->s_rows, &ix->s_rm, &ix->s_cnt})
+                      &ix->s_bad, &ix->s_sums, &ix->s_counts, &ix->s_obj, &ix->s_rows, &ix->s_rm, &ix->s_cnt, &ix->s_ahi, &ix->s_alo})
         b->release();
-    for (void *p : {(void *)ix->centroids, (void *)ix->cnorm, (void *)ix->d_tab, (void *)ix->list_len, (void *)ix->pt_off,
+    for (void *p : {(void *)ix->centroids, (void *)ix->cnorm, (void *)ix->cent_hi, (void *)ix->cent_lo, (void *)ix->d_tab, (void *)ix->list_len, (void *)ix->pt_off,
                     (void *)ix->pt_off_alt, (void *)ix->pt, (void *)ix->pt_alt, (void *)ix->prof_rows})
         if (p) cudaFree(p);
     if (ix->ev_done) cudaEventDestroy(ix->ev_done);
@@ -771,7 +817,10 @@ int sc_index_kmeans_step(sc_index_t *ix, const float *x, int64_t n, double *sums
     if (n == 0) return SC_OK;
     if (!x) return fail(SC_ERR_INVALID, "x is NULL");
     SC(begin_call(ix, st));
+    // host rows are staged 256 MB at a time; device-resident rows are used in place, in larger chunks
+    // (2048 row tiles = ~14 waves of the persistent tensor-core kernel, so the tail wave is small)
     int64_t chunk = std::max<int64_t>(1024, ((int64_t)256 << 20) / ((int64_t)ix->ds * 4));
+    if (is_device_ptr(x, ix->device)) chunk = std::max<int64_t>(chunk, (int64_t)1 << 18);
     chunk = std::min(chunk, n);
     CU(ix->s_assign.reserve((size_t)chunk * 4));
     CU(ix->s_best.reserve((size_t)chunk * 4));
@@ -938,8 +987,7 @@ int sc_index_probe(sc_index_t *ix, const float *q, int64_t nq, int32_t nprobe, i
         const int64_t m = std::min(ch, nq - s);
         const float *qd = nullptr;
         SC(stage_rows(ix, q + s * ix->dim, m, ix->s_q, ix->s_xpad, st, &qd));
-        CU(launch_gemm_nt(qd, m, ix->centroids, ix->nlist, ix->ds, ix->metric == SC_METRIC_L2 ? ix->cnorm : nullptr,
-                          ix->s_scores.as<float>(), st));
+        SC(coarse_scores(ix, qd, m, ix->s_scores.as<float>(), st));
         int32_t *ol = ldev ? out_lists + s * nprobe : ix->s_probe.as<int32_t>();
         float *os = out_scores ? (sdev ? out_scores + s * nprobe : ix->s_best.as<float>()) : nullptr;
         CU(launch_select_rows(ix->s_scores.as<float>(), m, ix->nlist, nprobe, ol, os, st));
@@ -1057,7 +1105,7 @@ int sc_index_stats(sc_index_t *ix, sc_stats_t *out) {
                             &ix->s_outd, &ix->s_outi, &ix->s_repobits, &ix->s_x, &ix->s_xpad, &ix->s_ids, &ix->s_repo,
                             &ix->s_lang, &ix->s_assign, &ix->s_best, &ix->s_pos, &ix->s_lenold, &ix->s_need, &ix->s_npg,
                             &ix->s_needoff, &ix->s_bad, &ix->s_sums, &ix->s_counts, &ix->s_obj, &ix->s_rows, &ix->s_rm,
-                            &ix->s_cnt})
+                            &ix->s_cnt, &ix->s_ahi, &ix->s_alo})
         sb += (int64_t)b->cap;
     out->bytes_scratch = sb;
     int32_t mx = 0, mn = ix->nlist > 0 ? INT32_MAX : 0;
@@ -1170,6 +1218,11 @@ int sc_index_set_param(sc_index_t *ix, const char *name, int64_t value) {
     if (strcmp(name, "scan_variant") == 0) {
         if (value < 0 || value > 4) return fail(SC_ERR_INVALID, "scan_variant must be in [0,4]");
         ix->scan_variant = (int)value;
+        return SC_OK;
+    }
+    if (strcmp(name, "coarse_impl") == 0) {
+        if (value != 0 && value != 1) return fail(SC_ERR_INVALID, "coarse_impl: 0 = tcgen05 3xTF32, 1 = fp32 SIMT");
+        ix->coarse_impl = (int)value;
         return SC_OK;
     }
     return fail(SC_ERR_INVALID, "unknown parameter '%s'", name);

@@ -409,3 +409,54 @@ def test_exhaustive_probe_beyond_select_limit(sb, orc):
         g.search(q, 10, nprobe=2500)
     with pytest.raises(sb.NativeError):
         g.probe(q, 2500)
+
+
+# ---- tcgen05 3xTF32 contraction (gemm_tc.cu) vs exact arithmetic -----------------------------------
+@pytest.mark.parametrize("metric", ["IP", "L2"])
+@pytest.mark.parametrize("d,nlist,nq", [(768, 1000, 300), (96, 257, 129), (3072, 512, 5), (100, 64, 1)])
+def test_tensor_core_coarse_scores_have_fp32_accuracy(sb, orc, metric, d, nlist, nq):
+    rng = np.random.default_rng(d + nlist)
+    cent = rng.standard_normal((nlist, d)).astype(np.float32)
+    q = rng.standard_normal((nq, d)).astype(np.float32)
+    g = sb.IVFFlatIndex(d, nlist=nlist, metric=metric)
+    g.set_centroids(cent)
+    exact = orc.coarse_similarity(q, cent, metric, dtype=np.float64)
+    scale = np.abs(q.astype(np.float64)) @ np.abs(cent.astype(np.float64)).T * (2 if metric == "L2" else 1)
+    if metric == "L2":
+        scale = scale + (cent.astype(np.float64) ** 2).sum(1)[None, :]
+    errs = {}
+    for impl in (0, 1):  # 0 = tcgen05 3xTF32, 1 = fp32 SIMT
+        g.set_param("coarse_impl", impl)
+        lists, sc = g.probe(q, min(nlist, 64), with_scores=True)
+        ref = np.take_along_axis(exact, lists.astype(np.int64), axis=1)
+        errs[impl] = float(np.max(np.abs(sc - ref) / np.take_along_axis(scale, lists.astype(np.int64), axis=1)))
+        # ranking is the exact ranking up to rounding-level ties
+        want = orc.top_desc(exact, min(nlist, 64))
+        for r in range(nq):
+            if not np.array_equal(lists[r], want[r]):
+                a, b = np.sort(exact[r][lists[r]]), np.sort(exact[r][want[r]])
+                assert np.allclose(a, b, rtol=1e-5, atol=1e-5 * scale[r].max()), (impl, r)
+    # error relative to sum |a||b|: fp32 FMA chains give ~1.5e-7; 3xTF32 on the tensor pipe (truncating
+    # accumulation over K/8 x 3 MMAs) measures ~2e-6 at K=3072; plain TF32 would be ~5e-4
+    assert errs[1] < 1e-6 and errs[0] < 5e-6, errs
+
+
+@pytest.mark.parametrize("metric", ["IP", "L2"])
+def test_tensor_core_fused_argmax_matches_simt(sb, orc, metric):
+    # n >= 4096 takes the fused contraction+argmax kernel; nlist spans several slabs and a ragged tail
+    n, d, nlist = 9000, 2048, 6500
+    rng = np.random.default_rng(3)
+    x = unit_rows(rng, n, d)
+    cent = unit_rows(rng, nlist, d) * rng.uniform(0.5, 1.5, (nlist, 1)).astype(np.float32)
+    g = sb.IVFFlatIndex(d, nlist=nlist, metric=metric)
+    g.set_centroids(cent)
+    a_tc = g.assign(x)
+    g.set_param("coarse_impl", 1)
+    a_simt = g.assign(x)
+    exact = orc.coarse_similarity(x, cent, metric, dtype=np.float64)
+    a_ref = np.argmax(exact, axis=1)
+    for a in (a_tc, a_simt):
+        diff = np.flatnonzero(a != a_ref)
+        assert diff.size < 10
+        for r in diff:  # only rounding-level ties may differ
+            assert abs(exact[r, a[r]] - exact[r, a_ref[r]]) <= 1e-5 * abs(exact[r, a_ref[r]]) + 1e-6
