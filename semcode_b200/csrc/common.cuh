@@ -99,6 +99,23 @@ struct FilterDev {
     uint32_t n_repo_bits;
 };
 
+#ifdef __CUDACC__
+// fused scalar predicate of the list scans: tombstone | language bitmap | repo bitmap
+__device__ __forceinline__ bool filter_pass(const FilterDev &f, uint32_t tag) {
+    if (tag & kTagRemoved) return false;
+    if (f.flags & 1u) {
+        const uint32_t lang = tag & 0xffu;
+        if (!((f.lang_bits[lang >> 5] >> (lang & 31u)) & 1u)) return false;
+    }
+    if (f.flags & 2u) {
+        const uint32_t repo = (tag >> 8) & kTagRepoMax;
+        if (repo >= f.n_repo_bits) return false;
+        if (!((__ldg(f.repo_bits + (repo >> 5)) >> (repo & 31u)) & 1u)) return false;
+    }
+    return true;
+}
+#endif
+
 struct ScanArgs {
     const float *q;  // [nq, ds]
     int ds;
@@ -122,6 +139,18 @@ cudaError_t launch_plan_pairs(const int32_t *probe, int64_t npairs, const int32_
 cudaError_t launch_exclusive_scan_i64(const int64_t *in, int64_t n, int64_t *out, cudaStream_t st);
 cudaError_t launch_exclusive_scan_i32(const int32_t *in, int64_t n, int32_t *out, cudaStream_t st);
 cudaError_t launch_scan_pages(const ScanArgs &a, int variant, int num_sms, int *launches, cudaStream_t st);
+
+// list-major scan (scan_lists.cu): the probed lists are read ONCE per batch and scored against every query
+// that probes them.  Scratch (all device, caller-sized): cnt/cursor/n32/n8 [nlist], lq_off/off32/off8 [nlist+1],
+// lq [npairs], counters [2].  Writes the same candidate layout as launch_scan_pages.
+struct ListPlan {
+    int32_t nlist;
+    int32_t *cnt, *cursor, *n32, *n8;  // [nlist]
+    int32_t *lq_off, *off32, *off8;    // [nlist+1]
+    int32_t *lq;                       // [npairs] pair ids grouped by list
+    int32_t *counters;                 // [2] work counters of the two tile variants
+};
+cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int num_sms, int *launches, cudaStream_t st);
 // final top-k over the candidates of each query + id translation
 cudaError_t launch_select_candidates(const ScanArgs &a, int64_t nq, int k, float *out_dist, int64_t *out_ids,
                                      cudaStream_t st);

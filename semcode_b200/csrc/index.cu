@@ -168,9 +168,10 @@ struct sc_index {
     // scratch (stream ordered; ev_done chains calls made on different streams)
     DevBuf s_q, s_scores, s_probe, s_pairpages, s_pageoff, s_cand, s_outd, s_outi, s_repobits;
     DevBuf s_x, s_xpad, s_ids, s_repo, s_lang, s_assign, s_best, s_pos, s_lenold, s_need, s_npg, s_needoff, s_bad;
-    DevBuf s_sums, s_counts, s_obj, s_rows, s_rm, s_cnt, s_ahi, s_alo;
+    DevBuf s_sums, s_counts, s_obj, s_rows, s_rm, s_cnt, s_ahi, s_alo, s_lplan;
     int64_t scratch_budget = (int64_t)2 << 30;
     int scan_variant = 0;
+    int scan_mode = 0;  // 0 = auto, 1 = query-major (scan.cu), 2 = list-major (scan_lists.cu)
     cudaEvent_t ev_done = nullptr;
 
     // profiling of the last search
@@ -537,9 +538,10 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
     const int64_t per_query = ((lists || all_lists) ? 0 : (int64_t)ix->nlist * 4) + (int64_t)np * 20 + pb * kPageRows * 4 +
                               (int64_t)ix->ds * 4 + (int64_t)k * 12;
     int64_t nqc = std::max<int64_t>(1, ix->scratch_budget / per_query);
-    nqc = std::min(nqc, nq);
-    if (!lists && nqc >= 128) nqc = (nqc / 128) * 128;  // whole GEMM tiles
-    nqc = std::min(nqc, nq);
+    if (nqc >= nq)
+        nqc = nq;  // one pass
+    else if (!lists && nqc >= 128)
+        nqc = (nqc / 128) * 128;  // whole GEMM tiles
 
     const int64_t npairs_max = nqc * np;
     if (!lists && !all_lists) CU(ix->s_scores.reserve((size_t)nqc * ix->nlist * 4));
@@ -594,7 +596,29 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
         a.slab_shift = ix->slab_shift;
         a.cand = ix->s_cand.as<float>();
         a.filt = fdev;
-        CU(launch_scan_pages(a, ix->scan_variant, ix->num_sms, &ix->prof_scan_launches, st));
+        // large batches re-probe the same lists: read each list once and score it against all its queries
+        const bool list_major = ix->ds >= 128 && npairs <= (int64_t)INT32_MAX &&
+                                (ix->scan_mode == 2 || (ix->scan_mode == 0 && npairs >= 2 * (int64_t)ix->nlist));
+        if (list_major) {
+            const size_t nl = (size_t)ix->nlist;
+            const size_t words = 4 * nl + 3 * (nl + 1) + (size_t)npairs + 2 + 16;
+            CU(ix->s_lplan.reserve(words * 4));
+            int32_t *w = ix->s_lplan.as<int32_t>();
+            ListPlan lp;
+            lp.nlist = ix->nlist;
+            lp.cnt = w;
+            lp.cursor = w + nl;
+            lp.n32 = w + 2 * nl;
+            lp.n8 = w + 3 * nl;
+            lp.lq_off = w + 4 * nl;
+            lp.off32 = lp.lq_off + nl + 1;
+            lp.off8 = lp.off32 + nl + 1;
+            lp.counters = lp.off8 + nl + 1;
+            lp.lq = lp.counters + 2;
+            CU(launch_scan_lists(a, lp, ix->num_sms, &ix->prof_scan_launches, st));
+        } else {
+            CU(launch_scan_pages(a, ix->scan_variant, ix->num_sms, &ix->prof_scan_launches, st));
+        }
         SC(prof_mark(ix, st));
         float *od = outd_dev ? out_dist + s * k : ix->s_outd.as<float>();
         int64_t *oi = outi_dev ? out_ids + s * k : ix->s_outi.as<int64_t>();
@@ -706,7 +730,7 @@ int sc_index_destroy(sc_index_t *ix) {
     for (DevBuf *b : {&ix->s_q, &ix->s_scores, &ix->s_probe, &ix->s_pairpages, &ix->s_pageoff, &ix->s_cand, &ix->s_outd,
                       &ix->s_outi, &ix->s_repobits, &ix->s_x, &ix->s_xpad, &ix->s_ids, &ix->s_repo, &ix->s_lang,
                       &ix->s_assign, &ix->s_best, &ix->s_pos, &ix->s_lenold, &ix->s_need, &ix->s_npg, &ix->s_needoff,
-                      &ix->s_bad, &ix->s_sums, &ix->s_counts, &ix->s_obj, &ix->s_rows, &ix->s_rm, &ix->s_cnt, &ix->s_ahi, &ix->s_alo})
+                      &ix->s_bad, &ix->s_sums, &ix->s_counts, &ix->s_obj, &ix->s_rows, &ix->s_rm, &ix->s_cnt, &ix->s_ahi, &ix->s_alo, &ix->s_lplan})
         b->release();
     for (void *p : {(void *)ix->centroids, (void *)ix->cnorm, (void *)ix->cent_hi, (void *)ix->cent_lo, (void *)ix->d_tab, (void *)ix->list_len, (void *)ix->pt_off,
                     (void *)ix->pt_off_alt, (void *)ix->pt, (void *)ix->pt_alt, (void *)ix->prof_rows})
@@ -1105,7 +1129,7 @@ int sc_index_stats(sc_index_t *ix, sc_stats_t *out) {
                             &ix->s_outd, &ix->s_outi, &ix->s_repobits, &ix->s_x, &ix->s_xpad, &ix->s_ids, &ix->s_repo,
                             &ix->s_lang, &ix->s_assign, &ix->s_best, &ix->s_pos, &ix->s_lenold, &ix->s_need, &ix->s_npg,
                             &ix->s_needoff, &ix->s_bad, &ix->s_sums, &ix->s_counts, &ix->s_obj, &ix->s_rows, &ix->s_rm,
-                            &ix->s_cnt, &ix->s_ahi, &ix->s_alo})
+                            &ix->s_cnt, &ix->s_ahi, &ix->s_alo, &ix->s_lplan})
         sb += (int64_t)b->cap;
     out->bytes_scratch = sb;
     int32_t mx = 0, mn = ix->nlist > 0 ? INT32_MAX : 0;
@@ -1218,6 +1242,11 @@ int sc_index_set_param(sc_index_t *ix, const char *name, int64_t value) {
     if (strcmp(name, "scan_variant") == 0) {
         if (value < 0 || value > 4) return fail(SC_ERR_INVALID, "scan_variant must be in [0,4]");
         ix->scan_variant = (int)value;
+        return SC_OK;
+    }
+    if (strcmp(name, "scan_mode") == 0) {
+        if (value < 0 || value > 2) return fail(SC_ERR_INVALID, "scan_mode: 0 = auto, 1 = query-major, 2 = list-major");
+        ix->scan_mode = (int)value;
         return SC_OK;
     }
     if (strcmp(name, "coarse_impl") == 0) {

@@ -37,20 +37,6 @@ __global__ void plan_pairs_kernel(const int32_t *__restrict__ probe, int64_t npa
     pair_pages[i] = pages;
 }
 
-__device__ __forceinline__ bool filter_pass(const FilterDev &f, uint32_t tag) {
-    if (tag & kTagRemoved) return false;
-    if (f.flags & 1u) {
-        const uint32_t lang = tag & 0xffu;
-        if (!((f.lang_bits[lang >> 5] >> (lang & 31u)) & 1u)) return false;
-    }
-    if (f.flags & 2u) {
-        const uint32_t repo = (tag >> 8) & kTagRepoMax;
-        if (repo >= f.n_repo_bits) return false;
-        if (!((__ldg(f.repo_bits + (repo >> 5)) >> (repo & 31u)) & 1u)) return false;
-    }
-    return true;
-}
-
 template <bool L2>
 __device__ __forceinline__ float accum4(float acc, const float4 &x, const float4 &q) {
     if (L2) {

@@ -419,6 +419,53 @@ class IVFFlatIndex:
                 np.cumsum(new_sizes, out=off[1:])
         return off, vecs, ids, tags
 
+    # -- persistence ----------------------------------------------------------------------------------
+    def save(self, path: str) -> None:
+        """Write the index as memory-mappable .npy files under directory `path`
+        (centroids, CSR lists with live rows only, ids, tags) plus meta.json."""
+        import json
+        import os
+
+        os.makedirs(path, exist_ok=True)
+        off, vecs, ids, tags = self.export_csr(live_only=True)
+        trained = self.is_trained
+        np.save(os.path.join(path, "centroids.npy"), self.get_centroids() if trained else np.zeros((0, self.dim), np.float32))
+        np.save(os.path.join(path, "list_off.npy"), off)
+        np.save(os.path.join(path, "vecs.npy"), vecs)
+        np.save(os.path.join(path, "ids.npy"), ids)
+        np.save(os.path.join(path, "tags.npy"), tags)
+        meta = {"format": 1, "dim": self.dim, "nlist": self.nlist, "metric": self.metric, "ntotal": int(off[-1]),
+                "trained": bool(trained)}
+        tmp = os.path.join(path, "meta.json.tmp")
+        with open(tmp, "w") as f:
+            json.dump(meta, f)
+        os.replace(tmp, os.path.join(path, "meta.json"))  # meta.json last: its presence marks a complete snapshot
+
+    @classmethod
+    def load(cls, path: str, device: int = 0, chunk_rows: int = 1 << 18) -> "IVFFlatIndex":
+        import json
+        import os
+
+        with open(os.path.join(path, "meta.json")) as f:
+            meta = json.load(f)
+        if meta.get("format") != 1:
+            raise ValueError(f"unknown snapshot format {meta.get('format')!r}")
+        idx = cls(meta["dim"], nlist=meta["nlist"], metric=meta["metric"], device=device)
+        if not meta["trained"]:
+            return idx
+        idx.set_centroids(np.load(os.path.join(path, "centroids.npy")))
+        off = np.load(os.path.join(path, "list_off.npy"))
+        vecs = np.load(os.path.join(path, "vecs.npy"), mmap_mode="r")
+        ids = np.load(os.path.join(path, "ids.npy"), mmap_mode="r")
+        tags = np.load(os.path.join(path, "tags.npy"), mmap_mode="r")
+        lists = np.repeat(np.arange(meta["nlist"], dtype=np.int32), np.diff(off))
+        for s in range(0, int(off[-1]), chunk_rows):
+            e = min(int(off[-1]), s + chunk_rows)
+            t = np.asarray(tags[s:e])
+            idx.add(np.ascontiguousarray(vecs[s:e]), np.ascontiguousarray(ids[s:e]),
+                    (t >> np.uint32(8)) & np.uint32((1 << 23) - 1), (t & np.uint32(0xFF)).astype(np.uint8), lists=lists[s:e])
+        return idx
+
     # -- profiling / tuning -------------------------------------------------------------------------
     def set_profiling(self, enabled: bool) -> None:
         _capi.check(self._L.sc_index_set_profiling(self._h, 1 if enabled else 0))

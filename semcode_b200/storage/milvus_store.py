@@ -177,6 +177,7 @@ class GpuCollection:
         self.device = int(device)
         self.seal_rows = int(seal_rows) if seal_rows else KMEANS_MIN_POINTS_PER_CENTROID * self.nlist
         self.train_niter = int(train_niter)
+        self.persist_dir: Optional[str] = None
         self._lock = threading.RLock()
         # host scalar columns, indexed by row number (== the int64 id stored next to the vector)
         self._pk: List[Optional[str]] = []
@@ -199,7 +200,61 @@ class GpuCollection:
         return None
 
     def flush(self) -> None:
-        return None
+        """Collection.flush(): with a persist directory configured, write the snapshot."""
+        if self.persist_dir:
+            self.save(self.persist_dir)
+
+    # -- persistence (SURVEY.md section 8f rank 1: connect() on an existing collection just loads,
+    #    milvus_store.py:51-54; Milvus keeps its data in a volume, docker-compose.yml:13-14) -----------
+    def save(self, path: str) -> None:
+        with self._lock:
+            os.makedirs(path, exist_ok=True)
+            self._growing.save(os.path.join(path, "growing"))
+            if self._ivf is not None:
+                self._ivf.save(os.path.join(path, "ivf"))
+            with open(os.path.join(path, "columns.jsonl.tmp"), "w") as f:
+                for r, pk in enumerate(self._pk):
+                    if pk is None:
+                        f.write("null\n")
+                    else:
+                        f.write(json.dumps([pk, self._repo[r], self._path[r], self._language[r], self._text[r],
+                                            self._metadata[r]]) + "\n")
+            os.replace(os.path.join(path, "columns.jsonl.tmp"), os.path.join(path, "columns.jsonl"))
+            meta = {"format": 1, "name": self.name, "dim": self.dim, "nlist": self.nlist, "metric": self.metric,
+                    "seal_rows": self.seal_rows, "train_niter": self.train_niter, "has_ivf": self._ivf is not None,
+                    "growing_rows": self._growing_rows, "repo_vocab": self._repo_vocab, "lang_vocab": self._lang_vocab}
+            with open(os.path.join(path, "collection.json.tmp"), "w") as f:
+                json.dump(meta, f)
+            os.replace(os.path.join(path, "collection.json.tmp"), os.path.join(path, "collection.json"))
+
+    @classmethod
+    def load(cls, path: str, device: int = 0) -> "GpuCollection":
+        with open(os.path.join(path, "collection.json")) as f:
+            meta = json.load(f)
+        col = cls(meta["name"], meta["dim"], nlist=meta["nlist"], metric=meta["metric"], device=device,
+                  seal_rows=meta["seal_rows"], train_niter=meta["train_niter"])
+        col._growing.close()
+        col._growing = IVFFlatIndex.load(os.path.join(path, "growing"), device=device)
+        col._growing_rows = int(meta["growing_rows"])
+        if meta["has_ivf"]:
+            col._ivf = IVFFlatIndex.load(os.path.join(path, "ivf"), device=device)
+        col._repo_vocab = {k: int(v) for k, v in meta["repo_vocab"].items()}
+        col._lang_vocab = {k: int(v) for k, v in meta["lang_vocab"].items()}
+        with open(os.path.join(path, "columns.jsonl")) as f:
+            for r, line in enumerate(f):
+                row = json.loads(line)
+                if row is None:
+                    row = [None, "", "", "", "", None]
+                pk, repo, pth, lang, text, md = row
+                col._pk.append(pk)
+                col._repo.append(repo)
+                col._path.append(pth)
+                col._language.append(lang)
+                col._text.append(text)
+                col._metadata.append(md)
+                if pk is not None:
+                    col._row_of[pk] = r
+        return col
 
     @property
     def num_entities(self) -> int:
@@ -475,6 +530,16 @@ class MilvusVectorStore:
                     )
                 existing.load()
                 return existing
+            persist = _setting("ivf_persist_dir", "")
+            snap = os.path.join(persist, self.collection_name) if persist else ""
+            if snap and os.path.exists(os.path.join(snap, "collection.json")):
+                collection = GpuCollection.load(snap, device=_setting("ivf_device", 0))
+                if collection.dim != self.dim:
+                    collection.close()
+                    raise ValueError(f"snapshot {snap!r} has dim {collection.dim}, requested {self.dim}")
+                collection.persist_dir = snap
+                _REGISTRY[self.collection_name] = collection
+                return collection
             log.info("creating_milvus_collection", collection=self.collection_name, dim=self.dim)
             collection = GpuCollection(
                 self.collection_name,
@@ -485,6 +550,7 @@ class MilvusVectorStore:
                 seal_rows=_setting("ivf_seal_rows", 0) or None,
                 train_niter=_setting("ivf_train_niter", 25),
             )
+            collection.persist_dir = snap or None
             collection.load()
             _REGISTRY[self.collection_name] = collection
             return collection
@@ -557,3 +623,7 @@ class MilvusVectorStore:
 
     def build_index(self, niter: Optional[int] = None, centroids=None):
         return self._require().build_index(niter=niter, centroids=centroids)
+
+    def flush(self) -> None:
+        """Persist the collection when `ivf_persist_dir` (SEMCODE_IVF_PERSIST_DIR) is configured."""
+        self._require().flush()

@@ -460,3 +460,66 @@ def test_tensor_core_fused_argmax_matches_simt(sb, orc, metric):
         assert diff.size < 10
         for r in diff:  # only rounding-level ties may differ
             assert abs(exact[r, a[r]] - exact[r, a_ref[r]]) <= 1e-5 * abs(exact[r, a_ref[r]]) + 1e-6
+
+
+# ---- list-major scan (scan_lists.cu) == query-major scan (scan.cu) == oracle ---------------------------
+@pytest.mark.parametrize("metric", ["IP", "L2"])
+@pytest.mark.parametrize("d,nlist,nq,nprobe", [(768, 16, 100, 9), (200, 7, 41, 7), (128, 40, 300, 5), (3072, 8, 70, 3)])
+def test_list_major_scan_matches_query_major_and_oracle(sb, orc, metric, d, nlist, nq, nprobe):
+    # few lists + many queries -> every list is probed by 1..nq queries: exercises the 32- and 8-query
+    # tiles, ragged chunks (counts like 33, 40, 9), ragged row tiles and a partial last k-stage (d=200)
+    n = 5000
+    x, q, cent, ids = make_case(orc, n, d, nlist, nq, metric, seed=d + nq)
+    rng = np.random.default_rng(1)
+    repo = rng.integers(0, 5, n).astype(np.uint32)
+    g, oidx, _ = build_pair(sb, orc, x, ids, cent, metric, repo=repo)
+    g.remove_ids(ids[::17])
+    probes = orc.coarse_probe(q, cent, metric, nprobe)
+    probes[::7, -1] = -1  # skipped probe slots
+    mask = orc.row_mask(oidx, removed_ids=ids[::17])
+    out = {}
+    for mode in (1, 2):
+        g.set_param("scan_mode", mode)
+        out[mode] = g.search(q, 10, lists=probes)
+        out[mode, "f"] = g.search(q, 10, lists=probes, repos=[1, 3])
+    rd, ri = orc.search(oidx, q, 10, nprobe, mask=mask, probes=probes_valid(orc, probes))
+    for key in (1, 2):
+        assert_topk_parity(out[key][0], out[key][1], rd, ri, f"mode {key} {metric} d={d}")
+    fmask = mask | orc.row_mask(oidx, repos=[1, 3])
+    fd, fi = orc.search(oidx, q, 10, nprobe, mask=fmask, probes=probes_valid(orc, probes))
+    for key in ((1, "f"), (2, "f")):
+        assert_topk_parity(out[key][0], out[key][1], fd, fi, f"filtered mode {key} {metric} d={d}")
+    np.testing.assert_array_equal(out[1][1], out[2][1])
+
+
+def probes_valid(orc, probes):
+    """The NumPy oracle indexes list_off with every probe: map the skipped (-1) slots to an empty
+    trailing list by handing it a ragged Python structure instead."""
+
+    class _Rows:
+        def __init__(self, p):
+            self.p = p
+
+        def __getitem__(self, qi):
+            r = self.p[qi]
+            return r[r >= 0]
+
+    return _Rows(probes)
+
+
+def test_list_major_auto_mode_full_search(sb, orc):
+    # nq * nprobe >= 2 * nlist switches the scan to list-major automatically
+    x, q, cent, ids = make_case(orc, 30000, 256, 64, 600, "IP", seed=77)
+    g, oidx, _ = build_pair(sb, orc, x, ids, cent, "IP")
+    d0, i0 = g.search(q, 10, nprobe=12)  # 7200 pairs >= 128: auto -> list-major
+    g.set_param("scan_mode", 1)
+    d1, i1 = g.search(q, 10, nprobe=12)
+    np.testing.assert_array_equal(i0, i1)
+    assert_topk_parity(d0, i0, d1, i1, "auto vs query-major")
+    g.set_profiling(True)
+    g.set_param("scan_mode", 0)
+    g.search(q, 10, nprobe=12)
+    assert g.last_search_times().scan_launches == 8  # plan kernels + the two tile variants
+    g.set_param("scan_mode", 1)
+    g.search(q, 10, nprobe=12)
+    assert g.last_search_times().scan_launches == 1

@@ -1,0 +1,79 @@
+"""Multi-GPU: ShardedIVFFlat over NCCL (one process per GPU) equals the single-GPU index.
+Needs >= 2 visible GPUs (run with `gpurun --gpus 2`); skipped on a 1-GPU box."""
+
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, ret):
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import semcode_b200 as sb
+        from helpers import assert_topk_parity, unit_rows
+        from semcode_b200.sharded import ShardedIVFFlat
+
+        rng = np.random.default_rng(0)
+        n, d, nlist, nq = 40000, 256, 128, 300
+        x, q = unit_rows(rng, n, d), unit_rows(rng, nq, d)
+        ids = np.arange(n, dtype=np.int64) * 5 + 2
+        for metric in ("IP", "L2"):
+            sh = ShardedIVFFlat(d, nlist, metric, device=rank)
+            obj = sh.train(torch.from_numpy(x[rank::world]).cuda(), niter=4, seed=3)
+            # single-GPU Lloyd from the same initial centroids over ALL rows gives the same centroids
+            from semcode_b200.index import kmeans_init_rows
+
+            init = x[0::world][kmeans_init_rows(len(x[0::world]), nlist, 3)]
+            one = sb.IVFFlatIndex(d, nlist=nlist, metric=metric, device=rank)
+            obj1 = one.train(x, niter=4, init_centroids=init, max_points_per_centroid=0)
+            np.testing.assert_allclose(obj, obj1, rtol=1e-6)
+            np.testing.assert_allclose(sh.local.get_centroids(), one.get_centroids(), rtol=1e-4, atol=1e-6)
+            # identical centroids on both sides for the search comparison
+            one2 = sb.IVFFlatIndex(d, nlist=nlist, metric=metric, device=rank)
+            one2.set_centroids(sh.local.get_centroids())
+            one2.add(x, ids)
+            for a, b in ((0, 7), (7, 20001), (20001, n)):
+                sh.add(x[a:b], ids[a:b])
+            assert sh.ntotal == n
+            rd, ri = one2.search(q, 10, nprobe=8)
+            gd, gi = sh.search(q, 10, nprobe=8)
+            assert_topk_parity(gd.cpu().numpy(), gi.cpu().numpy(), rd, ri, f"sharded {metric}")
+            gd, gi = sh.search(torch.from_numpy(q).cuda(), 10, nprobe=8, langs=[0])
+            assert_topk_parity(gd.cpu().numpy(), gi.cpu().numpy(), rd, ri, f"sharded filtered {metric}")
+        ret[rank] = "ok"
+    except Exception:
+        import traceback
+
+        ret[rank] = traceback.format_exc()
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_nccl_equals_single_gpu(native_lib):
+    import torch
+    import torch.multiprocessing as mp
+
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert all(v == "ok" for v in dict(ret).values()) and len(ret) == world, dict(ret)

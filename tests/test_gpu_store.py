@@ -177,3 +177,39 @@ def test_golden_fixtures_through_the_c_abi(native_lib):
         assert agree > 0.995
     d2, i2 = g.search(q, 10, nprobe=16)
     assert_topk_parity(d2[same], i2[same], d[same], i[same], "full path vs preassigned")
+
+
+def test_snapshot_round_trip(store_mod, monkeypatch, tmp_path):
+    """connect() on an existing collection loads it (milvus_store.py:51-54) -- here from a snapshot dir."""
+    rng = np.random.default_rng(5)
+    n, d = 1500, 40
+    x = unit_rows(rng, n, d)
+    monkeypatch.setattr(store_mod.milvus_store.settings, "ivf_nlist", 8, raising=False)
+    monkeypatch.setattr(store_mod.milvus_store.settings, "ivf_train_niter", 3, raising=False)
+    monkeypatch.setattr(store_mod.milvus_store.settings, "ivf_persist_dir", str(tmp_path), raising=False)
+    store = store_mod.MilvusVectorStore("t_share", dim=d)
+    store.connect()
+    ids = [f"k{i}" for i in range(n)]
+    store.upsert_arrays(ids[:1000], x[:1000], repos=["a"] * 1000, languages=["python"] * 1000,
+                        texts=[f"t{i}" for i in range(1000)], metadata=[{"i": i} for i in range(1000)])
+    assert store._collection.index is not None  # sealed at 39 * 8 rows
+    store.upsert_arrays(ids[1000:], x[1000:], repos=["b"] * 500, languages=["cpp"] * 500)
+    store.upsert_arrays(["k3"], x[3:4] * -1.0, repos=["a"], languages=["python"])  # a replaced row
+    q = unit_rows(rng, 12, d)
+    before = store.search_batch(q, top_k=7, nprobe=8)
+    fb = store.search(q[0].tolist(), top_k=5, nprobe=8, repos=["b"])
+    store.flush()
+    store_mod.drop_collection("t_share")
+    again = store_mod.MilvusVectorStore("t_share", dim=d)
+    again.connect()
+    col = again._collection
+    assert col.num_entities == n and col.index is not None and col.index.ntotal == n
+    after = again.search_batch(q, top_k=7, nprobe=8)
+    assert [[h.id for h in hits] for hits in after] == [[h.id for h in hits] for hits in before]
+    np.testing.assert_allclose([[h.distance for h in hits] for hits in after], [[h.distance for h in hits] for hits in before], rtol=1e-6)
+    assert after[0][0].entity.get("metadata") == before[0][0].entity.get("metadata")
+    fa = again.search(q[0].tolist(), top_k=5, nprobe=8, repos=["b"])
+    assert [h.id for h in fa[0]] == [h.id for h in fb[0]] and all(h.entity.get("repo") == "b" for h in fa[0])
+    # upserts keep working on the reloaded collection (primary-key map restored)
+    again.upsert_arrays(["k5"], x[5:6], repos=["a"], languages=["python"])
+    assert col.num_entities == n
