@@ -67,6 +67,8 @@ def parse_args():
     p.add_argument("--dataset", default="iid", choices=["iid", "clustered"],
                    help="synthetic set of SURVEY.md 8d: A (iid Gaussian) or B (Zipf-clustered)")
     p.add_argument("--coarse-impl", type=int, default=0, help="0 = tcgen05 3xTF32, 1 = fp32 SIMT")
+    p.add_argument("--scan-mode", type=int, default=0, help="0 = auto, 1 = query-major, 2 = list-major")
+    p.add_argument("--lists-cfg", type=int, default=0, help="tile configuration of the list-major kernel")
     return p.parse_args()
 
 
@@ -121,7 +123,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -322,6 +324,10 @@ def run_ours(args):
         g.set_param("scan_variant", args.scan_variant)
     if args.coarse_impl:
         g.set_param("coarse_impl", args.coarse_impl)
+    if args.scan_mode:
+        g.set_param("scan_mode", args.scan_mode)
+    if args.lists_cfg:
+        g.set_param("lists_cfg", args.lists_cfg)
     cent = torch.empty((nlist, d), dtype=torch.float32, device=dev)
     if rank == 0:
         tr = gen_rows(torch, 0, min(args.train_rows, n), d, 1234, dev, args.dataset)
@@ -432,18 +438,37 @@ def run_ours(args):
     ms_total = float(ms_total.item())
     launches_per_step = t.total_launches + (1 if world > 1 else 0)
     # per-phase distribution over a few profiled steps (same inputs; outside the headline timing)
+    unique_rows = []
     for i in range(min(args.steps, 8)):
         step_device(i)
         torch.cuda.synchronize()
         t = g.last_search_times()
         scan_ms.append(t.scan_ms)
         scanned_rows.append(t.scanned_rows)
+        unique_rows.append(t.unique_rows)
         phase["coarse"] += t.coarse_ms
         phase["select"] += t.probe_select_ms
         phase["plan"] += t.plan_ms
         phase["scan"] += t.scan_ms
         phase["topk"] += t.topk_ms
     nprof = len(scan_ms)
+    list_major = statistics.mean(unique_rows) > 0
+    # the query-major kernel on the same workload (the regime the HBM-fraction claim of SURVEY.md 8d is made in:
+    # it streams every probed list once per (query, list) pair, so logical bytes == DRAM bytes)
+    qm = None
+    if list_major and not args.scan_mode:
+        g.set_param("scan_mode", 1)
+        qms, qrows, qtot = [], [], []
+        for i in range(min(args.steps, 4) + 1):
+            step_device(i)
+            torch.cuda.synchronize()
+            t = g.last_search_times()
+            if i:
+                qms.append(t.scan_ms)
+                qrows.append(t.scanned_rows)
+                qtot.append(t.total_ms)
+        g.set_param("scan_mode", 0)
+        qm = (statistics.mean(qms), statistics.mean(qrows), statistics.mean(qtot))
     g.set_profiling(False)
 
     ms_e2e, _, _ = timed(step_e2e, args.steps)
@@ -482,11 +507,15 @@ def run_ours(args):
                     traffic = ent["dram_bytes_per_launch"]
     except Exception:
         traffic = None
-    bytes_per_step = statistics.mean(scanned_rows) * 4 * d  # this rank's slice
+    logical_bytes = statistics.mean(scanned_rows) * 4 * d  # this rank's slice: one pass per (query, list) pair
     scan_s = statistics.mean(scan_ms) / 1e3
+    if list_major:  # compulsory bytes: every DISTINCT probed list once
+        bytes_per_step = statistics.mean(unique_rows) * 4 * d
+        kernel_name = "scan_lists_kernel (list-major: plan + 32-query and 8-query tiles)"
+    else:
+        bytes_per_step = logical_bytes
+        kernel_name = "scan_pages_kernel (query-major)"
     achieved = bytes_per_step / scan_s / 1e9
-    qps = nq * args.steps / (ms_total / 1e3)
-    e2e_qps = nq * args.steps / (ms_e2e / 1e3)
     line = {
         "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -496,11 +525,17 @@ def run_ours(args):
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {
-            "bound": "hbm", "kernel": "scan_pages_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": achieved / peaks["hbm_gbs"], "frac_of_8TBps_nominal": achieved / 8000.0, "peak_source": peak_src,
-            "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_step, "kernel_ms": scan_s * 1e3,
-            "kernel_share_of_step": (phase["scan"] / nprof) / (ms_total / args.steps),
+            "traffic": traffic if not list_major else None, "algorithmic_bytes_per_launch": bytes_per_step,
+            "logical_bytes_per_launch": logical_bytes, "logical_GBps": logical_bytes / scan_s / 1e9,
+            "kernel_ms": scan_s * 1e3, "kernel_share_of_step": (phase["scan"] / nprof) / (ms_total / args.steps),
         },
+        "roofline_query_major": None if qm is None else {
+            "bound": "hbm", "kernel": "scan_pages_kernel (query-major, forced with scan_mode=1 on the same workload)",
+            "achieved": qm[1] * 4 * d / (qm[0] / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": qm[1] * 4 * d / (qm[0] / 1e3) / 1e9 / peaks["hbm_gbs"], "traffic": traffic,
+            "algorithmic_bytes_per_launch": qm[1] * 4 * d, "kernel_ms": qm[0], "qps_query_major": nq / qm[2] * 1e3},
         "phases_ms": {kname: v / nprof for kname, v in phase.items()},
         "clocks": clocks,
         "build_s": {"train": t_train, "total": t_build},

@@ -73,7 +73,8 @@ typedef struct sc_stats {
 typedef struct sc_search_times {
     float coarse_ms, probe_select_ms, plan_ms, scan_ms, topk_ms, total_ms;
     int64_t scanned_rows;  /* rows whose distance was evaluated (sum over queries) */
-    int64_t scanned_pages; /* 32-row pages visited (sum over queries) */
+    int64_t unique_rows;   /* list-major scan only: rows of the DISTINCT lists probed by the batch, i.e. the
+                              compulsory rows; 0 when the query-major scan ran */
     int32_t scan_launches; /* launches of the list-scan kernel */
     int32_t total_launches;
 } sc_search_times_t;

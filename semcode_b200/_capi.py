@@ -65,7 +65,7 @@ class ScSearchTimes(C.Structure):
     _fields_ = [
         ("coarse_ms", C.c_float), ("probe_select_ms", C.c_float), ("plan_ms", C.c_float), ("scan_ms", C.c_float),
         ("topk_ms", C.c_float), ("total_ms", C.c_float),
-        ("scanned_rows", C.c_int64), ("scanned_pages", C.c_int64),
+        ("scanned_rows", C.c_int64), ("unique_rows", C.c_int64),
         ("scan_launches", C.c_int32), ("total_launches", C.c_int32),
     ]
 

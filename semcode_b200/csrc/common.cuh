@@ -149,8 +149,9 @@ struct ListPlan {
     int32_t *lq_off, *off32, *off8;    // [nlist+1]
     int32_t *lq;                       // [npairs] pair ids grouped by list
     int32_t *counters;                 // [2] work counters of the two tile variants
+    unsigned long long *unique_rows;   // optional: += rows of every list probed at least once
 };
-cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int num_sms, int *launches, cudaStream_t st);
+cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int num_sms, int *launches, cudaStream_t st);
 // final top-k over the candidates of each query + id translation
 cudaError_t launch_select_candidates(const ScanArgs &a, int64_t nq, int k, float *out_dist, int64_t *out_ids,
                                      cudaStream_t st);

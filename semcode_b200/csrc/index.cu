@@ -169,8 +169,9 @@ struct sc_index {
     DevBuf s_q, s_scores, s_probe, s_pairpages, s_pageoff, s_cand, s_outd, s_outi, s_repobits;
     DevBuf s_x, s_xpad, s_ids, s_repo, s_lang, s_assign, s_best, s_pos, s_lenold, s_need, s_npg, s_needoff, s_bad;
     DevBuf s_sums, s_counts, s_obj, s_rows, s_rm, s_cnt, s_ahi, s_alo, s_lplan;
-    int64_t scratch_budget = (int64_t)2 << 30;
+    int64_t scratch_budget = (int64_t)8 << 30;  // search scratch ceiling (candidates dominate); sc_index_set_param("scratch_bytes")
     int scan_variant = 0;
+    int lists_cfg = 0;  // tile configuration of the list-major kernel (experiments)
     int scan_mode = 0;  // 0 = auto, 1 = query-major (scan.cu), 2 = list-major (scan_lists.cu)
     cudaEvent_t ev_done = nullptr;
 
@@ -528,8 +529,8 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
     SC(build_filter(ix, filt, st, &fdev));
     if (ix->profiling) {
         clear_prof(ix);
-        if (!ix->prof_rows) CU(cudaMalloc(&ix->prof_rows, 8));
-        CU(cudaMemsetAsync(ix->prof_rows, 0, 8, st));
+        if (!ix->prof_rows) CU(cudaMalloc(&ix->prof_rows, 16));
+        CU(cudaMemsetAsync(ix->prof_rows, 0, 16, st));
     }
 
     // worst-case pages one query can touch -> candidate scratch per query
@@ -538,10 +539,14 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
     const int64_t per_query = ((lists || all_lists) ? 0 : (int64_t)ix->nlist * 4) + (int64_t)np * 20 + pb * kPageRows * 4 +
                               (int64_t)ix->ds * 4 + (int64_t)k * 12;
     int64_t nqc = std::max<int64_t>(1, ix->scratch_budget / per_query);
-    if (nqc >= nq)
+    if (nqc >= nq) {
         nqc = nq;  // one pass
-    else if (!lists && nqc >= 128)
-        nqc = (nqc / 128) * 128;  // whole GEMM tiles
+    } else {
+        // equal passes: the list-major scan amortises a list over the queries of ONE pass
+        const int64_t passes = (nq + nqc - 1) / nqc;
+        nqc = (nq + passes - 1) / passes;
+        if (!lists && nqc >= 128) nqc = std::min<int64_t>(((nqc + 127) / 128) * 128, nq);  // whole GEMM tiles
+    }
 
     const int64_t npairs_max = nqc * np;
     if (!lists && !all_lists) CU(ix->s_scores.reserve((size_t)nqc * ix->nlist * 4));
@@ -598,7 +603,7 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
         a.filt = fdev;
         // large batches re-probe the same lists: read each list once and score it against all its queries
         const bool list_major = ix->ds >= 128 && npairs <= (int64_t)INT32_MAX &&
-                                (ix->scan_mode == 2 || (ix->scan_mode == 0 && npairs >= 2 * (int64_t)ix->nlist));
+                                (ix->scan_mode == 2 || (ix->scan_mode == 0 && 2 * npairs >= 3 * (int64_t)ix->nlist));
         if (list_major) {
             const size_t nl = (size_t)ix->nlist;
             const size_t words = 4 * nl + 3 * (nl + 1) + (size_t)npairs + 2 + 16;
@@ -615,7 +620,8 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
             lp.off8 = lp.off32 + nl + 1;
             lp.counters = lp.off8 + nl + 1;
             lp.lq = lp.counters + 2;
-            CU(launch_scan_lists(a, lp, ix->num_sms, &ix->prof_scan_launches, st));
+            lp.unique_rows = ix->profiling ? ix->prof_rows + 1 : nullptr;
+            CU(launch_scan_lists(a, lp, ix->lists_cfg, ix->num_sms, &ix->prof_scan_launches, st));
         } else {
             CU(launch_scan_pages(a, ix->scan_variant, ix->num_sms, &ix->prof_scan_launches, st));
         }
@@ -1222,10 +1228,10 @@ int sc_index_last_search_times(sc_index_t *ix, sc_search_times_t *out) {
     float tot = 0.f;
     CU(cudaEventElapsedTime(&tot, ix->prof_ev.front(), ix->prof_ev.back()));
     out->total_ms = tot;
-    unsigned long long rows = 0;
-    if (ix->prof_rows) CU(cudaMemcpy(&rows, ix->prof_rows, 8, cudaMemcpyDeviceToHost));
-    out->scanned_rows = (int64_t)rows;
-    out->scanned_pages = 0;
+    unsigned long long rows[2] = {0, 0};
+    if (ix->prof_rows) CU(cudaMemcpy(rows, ix->prof_rows, 16, cudaMemcpyDeviceToHost));
+    out->scanned_rows = (int64_t)rows[0];
+    out->unique_rows = (int64_t)rows[1];
     out->scan_launches = ix->prof_scan_launches;
     out->total_launches = ix->prof_total_launches;
     return SC_OK;
@@ -1242,6 +1248,11 @@ int sc_index_set_param(sc_index_t *ix, const char *name, int64_t value) {
     if (strcmp(name, "scan_variant") == 0) {
         if (value < 0 || value > 4) return fail(SC_ERR_INVALID, "scan_variant must be in [0,4]");
         ix->scan_variant = (int)value;
+        return SC_OK;
+    }
+    if (strcmp(name, "lists_cfg") == 0) {
+        if (value < 0 || value > 2) return fail(SC_ERR_INVALID, "lists_cfg must be in [0,2]");
+        ix->lists_cfg = (int)value;
         return SC_OK;
     }
     if (strcmp(name, "scan_mode") == 0) {

@@ -9,9 +9,10 @@
 // FAISS IVFFlatScanner::scan_codes loop (reference src/semcode/storage/milvus_store.py:141-147).
 //
 // Work item = (list, chunk of <= QT queries); CTAs pull items from an atomic counter.  Per item the
-// CTA walks the list in tiles of 128 rows x 64 floats, double-buffered with cp.async (16-byte
-// copies, zero-fill for ragged edges), and keeps a 4 x (QT/8) register tile per thread:
-//   QT = 32  lists probed by many queries   FP32-pipe bound (16 FMA per 2 LDS.128)
+// CTA walks the list in tiles of 128 rows x 64 floats through a cp.async ring (16-byte copies,
+// zero-fill for ragged edges) and keeps a register tile of RPT rows x 8 queries per thread, as packed
+// fp32 pairs (FFMA2):
+//   QT = 32  lists probed by many queries   FP32-pipe bound (measured ceiling ~37 TFLOP/s on B200)
 //   QT = 8   lists probed by <= 8 queries   HBM bound
 // The result lands in the same per-pair candidate layout the query-major kernel writes, so the
 // top-k selection (select.cu) is unchanged.
@@ -22,9 +23,6 @@ namespace sc {
 
 namespace {
 
-constexpr int RB = 128;      // rows per tile
-constexpr int BKX = 64;      // floats per k-stage
-constexpr int LDS_ = BKX + 4;  // padded row stride in floats (272 B: consecutive rows shift 4 banks)
 constexpr int NT = 256;
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool valid) {
@@ -33,7 +31,6 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool va
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // ---- planning: invert (query, list) pairs into per-list query groups ----------------------------------
 __global__ void count_list_pairs_kernel(const int32_t *__restrict__ probe, int64_t npairs, const int32_t *__restrict__ list_len,
@@ -45,10 +42,12 @@ __global__ void count_list_pairs_kernel(const int32_t *__restrict__ probe, int64
 }
 
 __global__ void plan_items_kernel(const int32_t *__restrict__ cnt, int32_t nlist, int32_t *__restrict__ n32,
-                                  int32_t *__restrict__ n8) {
+                                  int32_t *__restrict__ n8, const int32_t *__restrict__ list_len,
+                                  unsigned long long *__restrict__ unique_rows) {
     const int32_t l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nlist) return;
     const int32_t c = cnt[l];
+    if (unique_rows != nullptr && c > 0) atomicAdd(unique_rows, (unsigned long long)list_len[l]);
     int32_t a = c / 32, b = 0;
     const int32_t rem = c - a * 32;
     if (rem > 8)
@@ -68,12 +67,35 @@ __global__ void fill_list_pairs_kernel(const int32_t *__restrict__ probe, int64_
     if (l >= 0 && l < nlist && list_len[l] > 0) lq[lq_off[l] + atomicAdd(cursor + l, 1)] = (int32_t)i;
 }
 
-template <int QT>
+// ---- the tile kernel ------------------------------------------------------------------------------------
+// 256 threads = 8 warps.  Lanes run over ROWS (row = lane + 32*i), so an x fragment load is a conflict-free
+// 512-byte LDS.128 and a q fragment load is a single-wavefront broadcast; each thread owns RPT rows x 8
+// queries.  The k range of a stage is split over KS warp groups (split-K inside the CTA) so that all
+// 8 warps have work on one 128-row tile; the KS partial tiles are summed through shared memory once
+// per row tile.
+//   QT = 32: KS = 2, RPT = 4 (warp = 128 rows x 8 queries), 5.3 FFMA per shared-memory wavefront
+//   QT =  8: KS = 4, RPT = 2 (warp =  64 rows x 8 queries), HBM-bound regime
+template <int QT, int BKX, int NS, int RB, int RPT_>
+struct TileCfg {
+    static constexpr int QG = QT / 8;                 // query groups of 8
+    static constexpr int RPT = RPT_;                  // rows per thread
+    static constexpr int RG = RB / (32 * RPT);        // row groups
+    static constexpr int WPK = QG * RG;               // warps per k-split
+    static constexpr int KS = 8 / WPK;                // k-splits
+    static constexpr int LD = BKX + 4;                // padded row stride (floats): rows shift 4 banks
+    static constexpr int K4S = (BKX / 4) / KS;        // k4-steps per warp per stage
+    static constexpr int RING = 4;                    // row-table ring (tiles)
+};
+
+template <int QT, int BKX, int NS, int RB, int RPT>
 struct TileSmem {
-    float xs[2][RB][LDS_];
-    float qs[2][QT][LDS_];
-    const float *rowptr[2][RB];
-    uint8_t live[2][RB];
+    using C = TileCfg<QT, BKX, NS, RB, RPT>;
+    static_assert(C::KS >= 1 && C::K4S >= 1 && C::KS * C::WPK == 8 && (256 % (BKX / 4)) == 0, "bad tile configuration");
+    float xs[NS][RB][C::LD];
+    float qs[NS][QT][C::LD];
+    float red[C::KS > 1 ? C::KS - 1 : 1][QT][RB];
+    const float *rowptr[C::RING][RB];
+    uint8_t live[C::RING][RB];
     const float *qptr[QT];
     int64_t cbase[QT];
     int32_t item;
@@ -92,18 +114,44 @@ __device__ __forceinline__ int32_t owner_of(const int32_t *__restrict__ off, int
     return lo;
 }
 
-template <int QT, bool L2>
+// packed fp32 pairs (sm_100 FFMA2): two exact fp32 FMAs per issued instruction
+__device__ __forceinline__ void fma2(unsigned long long &acc, unsigned long long a, unsigned long long b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
+    unsigned long long r, m1;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(m1) : "f"(-1.0f));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(b), "l"(m1), "l"(a));  // a - b, exactly rounded
+    return r;
+}
+__device__ __forceinline__ float sum2(unsigned long long v) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return lo + hi;
+}
+
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int QT, int BKX, int NS, int RB, int RPT, bool L2>
 __global__ void __launch_bounds__(NT, 2) scan_lists_kernel(const ScanArgs a, const ListPlan p, int which) {
+    using C = TileCfg<QT, BKX, NS, RB, RPT>;
+    using SM = TileSmem<QT, BKX, NS, RB, RPT>;
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    TileSmem<QT> &sm = *reinterpret_cast<TileSmem<QT> *>(smem_raw);
-    constexpr int NQ = QT / 8;  // queries per thread
-    const int tid = threadIdx.x;
-    const int tx = tid & 7, ty = tid >> 3;  // query group / row group
+    SM &sm = *reinterpret_cast<SM *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ks = warp / C::WPK;                   // k-split of this warp
+    const int qg = (warp % C::WPK) % C::QG;         // query group (8 queries)
+    const int rg = (warp % C::WPK) / C::QG;         // row group
+    const int row0 = rg * 32 * C::RPT + lane;       // rows row0 + 32*i
     const int32_t *item_off = QT == 32 ? p.off32 : p.off8;
     const int32_t total = item_off[p.nlist];
     const int ds = a.ds;
     const int KB = (ds + BKX - 1) / BKX;
     const int slab_mask = (1 << a.slab_shift) - 1;
+    constexpr int CPR = BKX / 4;  // 16-byte chunks per row segment
 
     for (;;) {
         __syncthreads();  // previous item fully consumed (smem tables reused)
@@ -143,118 +191,158 @@ __global__ void __launch_bounds__(NT, 2) scan_lists_kernel(const ScanArgs a, con
                     ptr = a.slabs->vec[slab] + slot * ds;
                     ok = filter_pass(a.filt, __ldg(a.slabs->tags[slab] + slot));
                 }
-                sm.rowptr[tile & 1][tid] = ptr;
-                sm.live[tile & 1][tid] = ok ? 1 : 0;
+                sm.rowptr[tile % C::RING][tid] = ptr;
+                sm.live[tile % C::RING][tid] = ok ? 1 : 0;
             }
         };
-        auto issue = [&](int s) {  // cp.async the operands of flattened stage s into buffer s & 1
+        auto issue = [&](int s) {  // cp.async the operands of flattened stage s into ring slot s % NS
             const int tile = s / KB, kb = s - tile * KB;
-            const int buf = s & 1;
+            const int buf = s % NS;
             const int k0 = kb * BKX;
-            const int c = tid & 15;  // 16-byte chunk within the 256-byte row segment
+            const int c = tid % CPR;  // 16-byte chunk within the row segment
             const bool kin = k0 + c * 4 < ds;
+            constexpr int RPI = NT / CPR;  // rows covered per pass
 #pragma unroll
-            for (int i = 0; i < RB / 16; ++i) {
-                const int r = (tid >> 4) + 16 * i;
-                const bool valid = kin && (tile * RB + r < len);
-                cp_async16(&sm.xs[buf][r][c * 4], sm.rowptr[tile & 1][r] + k0 + c * 4, valid);
+            for (int i = 0; i < (RB + RPI - 1) / RPI; ++i) {
+                const int r = tid / CPR + RPI * i;
+                if (RB % RPI == 0 || r < RB) {
+                    const bool valid = kin && (tile * RB + r < len);
+                    cp_async16(&sm.xs[buf][r][c * 4], sm.rowptr[tile % C::RING][r] + k0 + c * 4, valid);
+                }
             }
 #pragma unroll
-            for (int i = 0; i < (QT * 16 + NT - 1) / NT; ++i) {
+            for (int i = 0; i < (QT * CPR + NT - 1) / NT; ++i) {
                 const int idx = tid + i * NT;
-                if (idx < QT * 16) {
-                    const int j = idx >> 4;
+                if (idx < QT * CPR) {
+                    const int j = idx / CPR;
                     cp_async16(&sm.qs[buf][j][c * 4], sm.qptr[j] + k0 + c * 4, kin && j < nqi);
                 }
             }
-            cp_async_commit();
         };
 
-        prep_rows(0);
+        // prologue: row tables for every tile the first NS stages touch, then NS-1 stages in flight
+        int prepped = -1;
+        {
+            const int need = min(ntiles - 1, (NS - 1) / KB + 1);
+            for (int t = 0; t <= need; ++t) prep_rows(t);
+            prepped = need;
+        }
         __syncthreads();
-        issue(0);
+#pragma unroll
+        for (int s = 0; s < NS - 1; ++s) {
+            if (s < S) issue(s);
+            cp_async_commit();
+        }
 
-        float acc[4][NQ];
-        for (int s = 0; s < S; ++s) {
-            const int tile = s / KB, kb = s - tile * KB;
-            const int buf = s & 1;
-            cp_async_wait_all();
-            __syncthreads();  // stage s visible; everyone is done with buffer (s+1)&1 and the older row table
-            if (s + 1 < S) issue(s + 1);
-            if (kb == 0) {
-                if (tile + 1 < ntiles) prep_rows(tile + 1);  // first needed KB-1 >= 1 iterations from now
+        // packed accumulators: acc2[i][j] = (sum over even k, sum over odd k) -> one FFMA2 per two products
+        unsigned long long acc2[C::RPT][8];
+        auto k4_step = [&](int buf, int k4) {
+            ulonglong2 xv[C::RPT];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < C::RPT; ++i)
+                xv[i] = *reinterpret_cast<const ulonglong2 *>(&sm.xs[buf][row0 + 32 * i][k4 * 4]);
 #pragma unroll
-                    for (int j = 0; j < NQ; ++j) acc[i][j] = 0.f;
-            }
-#pragma unroll 4
-            for (int k4 = 0; k4 < BKX / 4; ++k4) {
-                float4 xv[4], qv[NQ];
+            for (int j = 0; j < 8; ++j) {
+                const ulonglong2 qv = *reinterpret_cast<const ulonglong2 *>(&sm.qs[buf][qg * 8 + j][k4 * 4]);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4 *>(&sm.xs[buf][ty + 32 * i][k4 * 4]);
-#pragma unroll
-                for (int j = 0; j < NQ; ++j) qv[j] = *reinterpret_cast<const float4 *>(&sm.qs[buf][tx + 8 * j][k4 * 4]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < NQ; ++j) {
-                        if (L2) {
-                            const float d0 = xv[i].x - qv[j].x, d1 = xv[i].y - qv[j].y, d2 = xv[i].z - qv[j].z,
-                                        d3 = xv[i].w - qv[j].w;
-                            acc[i][j] = fmaf(d0, d0, acc[i][j]);
-                            acc[i][j] = fmaf(d1, d1, acc[i][j]);
-                            acc[i][j] = fmaf(d2, d2, acc[i][j]);
-                            acc[i][j] = fmaf(d3, d3, acc[i][j]);
-                        } else {
-                            acc[i][j] = fmaf(xv[i].x, qv[j].x, acc[i][j]);
-                            acc[i][j] = fmaf(xv[i].y, qv[j].y, acc[i][j]);
-                            acc[i][j] = fmaf(xv[i].z, qv[j].z, acc[i][j]);
-                            acc[i][j] = fmaf(xv[i].w, qv[j].w, acc[i][j]);
-                        }
-                    }
-            }
-            if (kb == KB - 1) {  // tile finished: one candidate per (row slot, query)
-#pragma unroll
-                for (int j = 0; j < NQ; ++j) {
-                    const int64_t cb = sm.cbase[tx + 8 * j];
-                    if (cb < 0) continue;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int32_t r = tile * RB + ty + 32 * i;
-                        if (r < slots) {
-                            const bool ok = r < len && sm.live[tile & 1][ty + 32 * i];
-                            a.cand[cb + r] = ok ? (L2 ? -acc[i][j] : acc[i][j]) : -INFINITY;
-                        }
+                for (int i = 0; i < C::RPT; ++i) {
+                    if (L2) {
+                        const unsigned long long d0 = sub2(xv[i].x, qv.x), d1 = sub2(xv[i].y, qv.y);
+                        fma2(acc2[i][j], d0, d0);
+                        fma2(acc2[i][j], d1, d1);
+                    } else {
+                        fma2(acc2[i][j], xv[i].x, qv.x);
+                        fma2(acc2[i][j], xv[i].y, qv.y);
                     }
                 }
             }
+        };
+        for (int s = 0; s < S; ++s) {
+            const int tile = s / KB, kb = s - tile * KB;
+            const int buf = s % NS;
+            cp_async_wait<NS - 2>();
+            __syncthreads();  // stage s visible to all; ring slot (s-1) % NS and older row tables are free
+            if (s + NS - 1 < S) issue(s + NS - 1);
+            cp_async_commit();
+            {  // row table of the tile whose first stage is issued in the NEXT iteration
+                const int tn = min(ntiles - 1, (s + NS) / KB);
+                if (tn > prepped) {
+                    prep_rows(tn);
+                    prepped = tn;
+                }
+            }
+            if (kb == 0) {
+#pragma unroll
+                for (int i = 0; i < C::RPT; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc2[i][j] = 0ull;
+            }
+            const int kv = (min(ds - kb * BKX, BKX)) >> 2;  // valid k4-steps of this stage
+            if (kv == BKX / 4) {
+#pragma unroll
+                for (int t = 0; t < C::K4S; ++t) k4_step(buf, ks * C::K4S + t);
+            } else {  // ragged last stage (dim not a multiple of the stage width)
+#pragma unroll 1
+                for (int t = 0; t < C::K4S; ++t)
+                    if (ks * C::K4S + t < kv) k4_step(buf, ks * C::K4S + t);
+            }
+            if (kb == KB - 1) {  // tile finished: fold even/odd and the k-splits, one candidate per (row slot, query)
+                if (ks > 0) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+#pragma unroll
+                        for (int i = 0; i < C::RPT; ++i) sm.red[ks - 1][qg * 8 + j][row0 + 32 * i] = sum2(acc2[i][j]);
+                }
+                __syncthreads();
+                if (ks == 0) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int64_t cb = sm.cbase[qg * 8 + j];
+                        if (cb < 0) continue;
+#pragma unroll
+                        for (int i = 0; i < C::RPT; ++i) {
+                            const int rr = row0 + 32 * i;
+                            const int32_t r = tile * RB + rr;
+                            if (r < slots) {
+                                float v = sum2(acc2[i][j]);
+#pragma unroll
+                                for (int h = 0; h < C::KS - 1; ++h) v += sm.red[h][qg * 8 + j][rr];
+                                const bool ok = r < len && sm.live[tile % C::RING][rr];
+                                a.cand[cb + r] = ok ? (L2 ? -v : v) : -INFINITY;
+                            }
+                        }
+                    }
+                }
+                // sm.red is next written at the end of the following tile, >= KB >= 2 barriers from here
+            }
         }
+        cp_async_wait<0>();
     }
 }
 
-template <int QT>
+template <int QT, int BKX, int NS, int RB, int RPT>
 cudaError_t launch_lists_variant(const ScanArgs &a, const ListPlan &p, int num_sms, cudaStream_t st) {
-    const size_t smem = sizeof(TileSmem<QT>);
+    const size_t smem = sizeof(TileSmem<QT, BKX, NS, RB, RPT>);
     const int which = QT == 32 ? 0 : 1;
+    const int per_sm = smem * 2 + 2048 <= 227 * 1024 ? 2 : 1;
     cudaError_t e;
     if (a.metric == 1) {
-        auto kern = scan_lists_kernel<QT, true>;
+        auto kern = scan_lists_kernel<QT, BKX, NS, RB, RPT, true>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kern<<<num_sms * 2, NT, smem, st>>>(a, p, which);
+        kern<<<num_sms * per_sm, NT, smem, st>>>(a, p, which);
     } else {
-        auto kern = scan_lists_kernel<QT, false>;
+        auto kern = scan_lists_kernel<QT, BKX, NS, RB, RPT, false>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kern<<<num_sms * 2, NT, smem, st>>>(a, p, which);
+        kern<<<num_sms * per_sm, NT, smem, st>>>(a, p, which);
     }
     return cudaGetLastError();
 }
 
 }  // namespace
 
-cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int num_sms, int *launches, cudaStream_t st) {
+cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int num_sms, int *launches, cudaStream_t st) {
     if (a.npairs <= 0) return cudaSuccess;
     if (a.npairs > (int64_t)INT32_MAX) return cudaErrorInvalidValue;
     cudaError_t e;
@@ -263,14 +351,27 @@ cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int num_sms,
     if ((e = cudaMemsetAsync(p.cursor, 0, (size_t)p.nlist * 4, st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(p.counters, 0, 8, st)) != cudaSuccess) return e;
     count_list_pairs_kernel<<<pb, 256, 0, st>>>(a.probe, a.npairs, a.list_len, p.nlist, p.cnt);
-    plan_items_kernel<<<lb, 256, 0, st>>>(p.cnt, p.nlist, p.n32, p.n8);
+    plan_items_kernel<<<lb, 256, 0, st>>>(p.cnt, p.nlist, p.n32, p.n8, a.list_len, p.unique_rows);
     if ((e = launch_exclusive_scan_i32(p.cnt, p.nlist, p.lq_off, st)) != cudaSuccess) return e;
     if ((e = launch_exclusive_scan_i32(p.n32, p.nlist, p.off32, st)) != cudaSuccess) return e;
     if ((e = launch_exclusive_scan_i32(p.n8, p.nlist, p.off8, st)) != cudaSuccess) return e;
     fill_list_pairs_kernel<<<pb, 256, 0, st>>>(a.probe, a.npairs, a.list_len, p.nlist, p.lq_off, p.cursor, p.lq);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    if ((e = launch_lists_variant<32>(a, p, num_sms, st)) != cudaSuccess) return e;
-    if ((e = launch_lists_variant<8>(a, p, num_sms, st)) != cudaSuccess) return e;
+    // tile configurations <QT, floats per k-stage, pipeline stages>; cfg picks the experiment (0 = default)
+    switch (cfg) {
+        case 1:
+            if ((e = launch_lists_variant<32, 64, 2, 128, 4>(a, p, num_sms, st)) != cudaSuccess) return e;
+            if ((e = launch_lists_variant<8, 128, 4, 32, 1>(a, p, num_sms, st)) != cudaSuccess) return e;
+            break;
+        case 2:
+            if ((e = launch_lists_variant<32, 64, 2, 128, 4>(a, p, num_sms, st)) != cudaSuccess) return e;
+            if ((e = launch_lists_variant<8, 256, 2, 32, 1>(a, p, num_sms, st)) != cudaSuccess) return e;
+            break;
+        default:
+            if ((e = launch_lists_variant<32, 64, 2, 128, 4>(a, p, num_sms, st)) != cudaSuccess) return e;
+            if ((e = launch_lists_variant<8, 64, 2, 128, 2>(a, p, num_sms, st)) != cudaSuccess) return e;
+            break;
+    }
     if (launches) *launches += 8;
     return cudaSuccess;
 }

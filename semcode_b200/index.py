@@ -89,6 +89,7 @@ class SearchTimes:
     topk_ms: float
     total_ms: float
     scanned_rows: int
+    unique_rows: int
     scan_launches: int
     total_launches: int
 
@@ -474,7 +475,7 @@ class IVFFlatIndex:
         t = _capi.ScSearchTimes()
         _capi.check(self._L.sc_index_last_search_times(self._h, C.byref(t)))
         return SearchTimes(t.coarse_ms, t.probe_select_ms, t.plan_ms, t.scan_ms, t.topk_ms, t.total_ms,
-                           int(t.scanned_rows), int(t.scan_launches), int(t.total_launches))
+                           int(t.scanned_rows), int(t.unique_rows), int(t.scan_launches), int(t.total_launches))
 
     def set_param(self, name: str, value: int) -> None:
         _capi.check(self._L.sc_index_set_param(self._h, name.encode(), int(value)))
