@@ -135,8 +135,9 @@ struct ScanArgs {
 
 cudaError_t launch_plan_pairs(const int32_t *probe, int64_t npairs, const int32_t *list_len, int32_t nlist,
                               int64_t *pair_pages, unsigned long long *rows_total, cudaStream_t st);
-// exclusive prefix sum of int64 in[n] -> out[n+1] (out[n] = total); single launch
-cudaError_t launch_exclusive_scan_i64(const int64_t *in, int64_t n, int64_t *out, cudaStream_t st);
+// exclusive prefix sum of in[n] -> out[n+1] (out[n] = total).  The int64 variant takes an optional scratch of
+// 2 * (n / 4096 + 2) elements and then runs as a two-level scan for large n
+cudaError_t launch_exclusive_scan_i64(const int64_t *in, int64_t n, int64_t *out, int64_t *scratch, cudaStream_t st);
 cudaError_t launch_exclusive_scan_i32(const int32_t *in, int64_t n, int32_t *out, cudaStream_t st);
 cudaError_t launch_scan_pages(const ScanArgs &a, int variant, int num_sms, int *launches, cudaStream_t st);
 

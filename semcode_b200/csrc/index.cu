@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <mutex>
+#include <queue>
 #include <string>
 #include <vector>
 
@@ -168,7 +169,7 @@ struct sc_index {
     // scratch (stream ordered; ev_done chains calls made on different streams)
     DevBuf s_q, s_scores, s_probe, s_pairpages, s_pageoff, s_cand, s_outd, s_outi, s_repobits;
     DevBuf s_x, s_xpad, s_ids, s_repo, s_lang, s_assign, s_best, s_pos, s_lenold, s_need, s_npg, s_needoff, s_bad;
-    DevBuf s_sums, s_counts, s_obj, s_rows, s_rm, s_cnt, s_ahi, s_alo, s_lplan;
+    DevBuf s_sums, s_counts, s_obj, s_rows, s_rm, s_cnt, s_ahi, s_alo, s_lplan, s_scan;
     int64_t scratch_budget = (int64_t)8 << 30;  // search scratch ceiling (candidates dominate); sc_index_set_param("scratch_bytes")
     int scan_variant = 0;
     int lists_cfg = 0;  // tile configuration of the list-major kernel (experiments)
@@ -553,6 +554,7 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
     if (!lists) CU(ix->s_probe.reserve((size_t)npairs_max * 4));
     CU(ix->s_pairpages.reserve((size_t)npairs_max * 8));
     CU(ix->s_pageoff.reserve((size_t)(npairs_max + 1) * 8));
+    CU(ix->s_scan.reserve((size_t)(2 * (npairs_max / 4096 + 2)) * 8));
     CU(ix->s_cand.reserve((size_t)nqc * pb * kPageRows * 4));
     if (!outd_dev) CU(ix->s_outd.reserve((size_t)nqc * k * 4));
     if (!outi_dev) CU(ix->s_outi.reserve((size_t)nqc * k * 8));
@@ -583,7 +585,8 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
         SC(prof_mark(ix, st));
         CU(launch_plan_pairs(probe, npairs, ix->list_len, ix->nlist, ix->s_pairpages.as<int64_t>(),
                              ix->profiling ? ix->prof_rows : nullptr, st));
-        CU(launch_exclusive_scan_i64(ix->s_pairpages.as<int64_t>(), npairs, ix->s_pageoff.as<int64_t>(), st));
+        CU(launch_exclusive_scan_i64(ix->s_pairpages.as<int64_t>(), npairs, ix->s_pageoff.as<int64_t>(),
+                                     ix->s_scan.as<int64_t>(), st));
         SC(prof_mark(ix, st));
         ScanArgs a;
         memset(&a, 0, sizeof(a));
@@ -736,7 +739,7 @@ int sc_index_destroy(sc_index_t *ix) {
     for (DevBuf *b : {&ix->s_q, &ix->s_scores, &ix->s_probe, &ix->s_pairpages, &ix->s_pageoff, &ix->s_cand, &ix->s_outd,
                       &ix->s_outi, &ix->s_repobits, &ix->s_x, &ix->s_xpad, &ix->s_ids, &ix->s_repo, &ix->s_lang,
                       &ix->s_assign, &ix->s_best, &ix->s_pos, &ix->s_lenold, &ix->s_need, &ix->s_npg, &ix->s_needoff,
-                      &ix->s_bad, &ix->s_sums, &ix->s_counts, &ix->s_obj, &ix->s_rows, &ix->s_rm, &ix->s_cnt, &ix->s_ahi, &ix->s_alo, &ix->s_lplan})
+                      &ix->s_bad, &ix->s_sums, &ix->s_counts, &ix->s_obj, &ix->s_rows, &ix->s_rm, &ix->s_cnt, &ix->s_ahi, &ix->s_alo, &ix->s_lplan, &ix->s_scan})
         b->release();
     for (void *p : {(void *)ix->centroids, (void *)ix->cnorm, (void *)ix->cent_hi, (void *)ix->cent_lo, (void *)ix->d_tab, (void *)ix->list_len, (void *)ix->pt_off,
                     (void *)ix->pt_off_alt, (void *)ix->pt, (void *)ix->pt_alt, (void *)ix->prof_rows})
@@ -882,17 +885,26 @@ int sc_index_kmeans_update(sc_index_t *ix, const double *sums, const int32_t *co
     std::vector<int32_t> hc(ix->nlist);
     CU(cudaMemcpyAsync(hc.data(), counts, (size_t)ix->nlist * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    // donor = currently largest cluster (ties -> lowest index), as oracle/ivf_numpy.py::split_empty_clusters;
+    // a heap keeps this O((empties + nlist) log nlist) instead of one argmax scan per empty cluster
     int nsplit = 0;
     std::vector<int64_t> c64(hc.begin(), hc.end());
+    typedef std::pair<int64_t, int> Ent;  // (count, -index): max-heap on count, then on lower index
+    std::priority_queue<Ent> heap;
+    for (int j = 0; j < ix->nlist; ++j)
+        if (c64[j] >= 2) heap.push(Ent(c64[j], -j));
     for (int ci = 0; ci < ix->nlist; ++ci) {
         if (c64[ci] != 0) continue;
-        int cj = 0;
-        for (int j = 1; j < ix->nlist; ++j)
-            if (c64[j] > c64[cj]) cj = j;
+        while (!heap.empty() && heap.top().first != c64[-heap.top().second]) heap.pop();  // stale entries
+        if (heap.empty()) break;
+        const int cj = -heap.top().second;
         if (c64[cj] < 2) break;
+        heap.pop();
         CU(launch_split_centroid(ix->centroids, ix->ds, ci, cj, st));
         c64[ci] = c64[cj] / 2;
         c64[cj] -= c64[ci];
+        if (c64[ci] >= 2) heap.push(Ent(c64[ci], -ci));
+        if (c64[cj] >= 2) heap.push(Ent(c64[cj], -cj));
         ++nsplit;
     }
     SC(update_cnorm(ix, st));
@@ -1135,7 +1147,7 @@ int sc_index_stats(sc_index_t *ix, sc_stats_t *out) {
                             &ix->s_outd, &ix->s_outi, &ix->s_repobits, &ix->s_x, &ix->s_xpad, &ix->s_ids, &ix->s_repo,
                             &ix->s_lang, &ix->s_assign, &ix->s_best, &ix->s_pos, &ix->s_lenold, &ix->s_need, &ix->s_npg,
                             &ix->s_needoff, &ix->s_bad, &ix->s_sums, &ix->s_counts, &ix->s_obj, &ix->s_rows, &ix->s_rm,
-                            &ix->s_cnt, &ix->s_ahi, &ix->s_alo, &ix->s_lplan})
+                            &ix->s_cnt, &ix->s_ahi, &ix->s_alo, &ix->s_lplan, &ix->s_scan})
         sb += (int64_t)b->cap;
     out->bytes_scratch = sb;
     int32_t mx = 0, mn = ix->nlist > 0 ? INT32_MAX : 0;

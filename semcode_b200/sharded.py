@@ -115,15 +115,33 @@ class ShardedIVFFlat:
         return int(t.item())
 
     # -- search ---------------------------------------------------------------------------------------
-    def search(self, q, k: int, nprobe: int = 16, repos=None, langs=None):
+    def probe(self, q, nprobe: int):
+        """Coarse pass split over the ranks: rank r ranks the centroids for its 1/G of the queries, one
+        all-gather of [nq, nprobe] int32 gives every rank the full probe table (centroids are replicated,
+        so this equals the unsplit coarse pass)."""
+        nq = q.shape[0]
+        nprobe = min(int(nprobe), self.nlist)
+        per = (nq + self.world - 1) // self.world
+        lo, hi = min(nq, self.rank * per), min(nq, (self.rank + 1) * per)
+        mine = torch.full((per, nprobe), -1, dtype=torch.int32, device=q.device)
+        if hi > lo:
+            mine[: hi - lo] = torch.as_tensor(self.local.probe(q[lo:hi].contiguous(), nprobe), device=q.device)
+        full = torch.empty((self.world * per, nprobe), dtype=torch.int32, device=q.device)
+        dist.all_gather_into_tensor(full, mine, group=self.group)
+        return full[:nq]
+
+    def search(self, q, k: int, nprobe: int = 16, repos=None, langs=None, shard_coarse: bool = True):
         """Every rank passes the same queries and receives the same merged (dist, ids) tensors."""
         dev = self.local.tensor_device()
         if not torch.is_tensor(q):
             q = torch.from_numpy(np.ascontiguousarray(q, dtype=np.float32))
         q = q.to(dev, torch.float32)
-        d, i = self.local.search(q, k, nprobe=nprobe, repos=repos, langs=langs)
         if self.world == 1:
-            return d, i
+            return self.local.search(q, k, nprobe=nprobe, repos=repos, langs=langs)
+        if shard_coarse and hasattr(self.local, "probe") and q.shape[0] >= 2 * self.world:
+            d, i = self.local.search(q, k, repos=repos, langs=langs, lists=self.probe(q, nprobe))
+        else:
+            d, i = self.local.search(q, k, nprobe=nprobe, repos=repos, langs=langs)
         nq = d.shape[0]
         # concatenated layout [world*nq, k] (accepted by every backend), viewed as [world, nq, k]
         gd = torch.empty((self.world * nq, k), dtype=d.dtype, device=d.device)

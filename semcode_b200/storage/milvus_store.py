@@ -228,7 +228,7 @@ class GpuCollection:
             os.replace(os.path.join(path, "collection.json.tmp"), os.path.join(path, "collection.json"))
 
     @classmethod
-    def load(cls, path: str, device: int = 0) -> "GpuCollection":
+    def from_snapshot(cls, path: str, device: int = 0) -> "GpuCollection":
         with open(os.path.join(path, "collection.json")) as f:
             meta = json.load(f)
         col = cls(meta["name"], meta["dim"], nlist=meta["nlist"], metric=meta["metric"], device=device,
@@ -533,7 +533,7 @@ class MilvusVectorStore:
             persist = _setting("ivf_persist_dir", "")
             snap = os.path.join(persist, self.collection_name) if persist else ""
             if snap and os.path.exists(os.path.join(snap, "collection.json")):
-                collection = GpuCollection.load(snap, device=_setting("ivf_device", 0))
+                collection = GpuCollection.from_snapshot(snap, device=_setting("ivf_device", 0))
                 if collection.dim != self.dim:
                     collection.close()
                     raise ValueError(f"snapshot {snap!r} has dim {collection.dim}, requested {self.dim}")
