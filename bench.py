@@ -312,8 +312,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         # NCCL_DEBUG=VERSION/INFO prints to stdout; stdout must carry exactly one JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("SEMCODE_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        if not os.environ.get("SEMCODE_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner would otherwise land on stdout
         dist.init_process_group("nccl", device_id=dev)
     n, d, nlist, k, nprobe, nq = args.n, args.dim, args.nlist, args.k, args.nprobe, args.nq
     t_build0 = time.time()

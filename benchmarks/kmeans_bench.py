@@ -42,8 +42,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        if not os.environ.get("SEMCODE_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner would otherwise land on stdout
         dist.init_process_group("nccl", device_id=dev)
     n, d, nlist = a.rows_per_gpu, a.dim, a.nlist
     x = bench.gen_rows(torch, rank * n, (rank + 1) * n, d, 1234, dev, a.dataset)

@@ -342,6 +342,8 @@ cudaError_t launch_lists_variant(const ScanArgs &a, const ListPlan &p, int num_s
 
 }  // namespace
 
+cudaError_t launch_scan_lists8_bulk(const ScanArgs &a, const ListPlan &p, int num_sms, cudaStream_t st);
+
 cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int num_sms, int *launches, cudaStream_t st) {
     if (a.npairs <= 0) return cudaSuccess;
     if (a.npairs > (int64_t)INT32_MAX) return cudaErrorInvalidValue;
@@ -358,20 +360,19 @@ cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int
     fill_list_pairs_kernel<<<pb, 256, 0, st>>>(a.probe, a.npairs, a.list_len, p.nlist, p.lq_off, p.cursor, p.lq);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     // tile configurations <QT, floats per k-stage, pipeline stages>; cfg picks the experiment (0 = default)
-    switch (cfg) {
-        case 1:
-            if ((e = launch_lists_variant<32, 64, 2, 128, 4>(a, p, num_sms, st)) != cudaSuccess) return e;
-            if ((e = launch_lists_variant<8, 128, 4, 32, 1>(a, p, num_sms, st)) != cudaSuccess) return e;
-            break;
-        case 2:
-            if ((e = launch_lists_variant<32, 64, 2, 128, 4>(a, p, num_sms, st)) != cudaSuccess) return e;
-            if ((e = launch_lists_variant<8, 256, 2, 32, 1>(a, p, num_sms, st)) != cudaSuccess) return e;
-            break;
-        default:
-            if ((e = launch_lists_variant<32, 64, 2, 128, 4>(a, p, num_sms, st)) != cudaSuccess) return e;
-            if ((e = launch_lists_variant<8, 64, 2, 128, 2>(a, p, num_sms, st)) != cudaSuccess) return e;
-            break;
+    // 32-query and 8-query tiles: cp.async ring kernels.  cfg selects experiments: 2 = 32-float stages for the
+    // 32-query tile, 3 = bulk-copy/mbarrier kernel (scan_lists_bulk.cu) for the 8-query tile when the dimension allows.
+    if (cfg == 2) {
+        if ((e = launch_lists_variant<32, 32, 3, 128, 4>(a, p, num_sms, st)) != cudaSuccess) return e;
+    } else {
+        if ((e = launch_lists_variant<32, 64, 2, 128, 4>(a, p, num_sms, st)) != cudaSuccess) return e;
     }
+    e = cfg == 3 ? launch_scan_lists8_bulk(a, p, num_sms, st) : cudaErrorNotSupported;
+    if (e == cudaErrorNotSupported) {
+        cudaGetLastError();
+        e = launch_lists_variant<8, 64, 2, 128, 2>(a, p, num_sms, st);
+    }
+    if (e != cudaSuccess) return e;
     if (launches) *launches += 8;
     return cudaSuccess;
 }

@@ -523,3 +523,21 @@ def test_list_major_auto_mode_full_search(sb, orc):
     g.set_param("scan_mode", 1)
     g.search(q, 10, nprobe=12)
     assert g.last_search_times().scan_launches == 1
+
+
+@pytest.mark.parametrize("metric", ["IP", "L2"])
+def test_bulk_copy_list_major_tile_matches(sb, orc, metric):
+    """lists_cfg = 3: the cp.async.bulk / mbarrier variant of the 8-query tile (dim % 128 == 0, <= 1024)."""
+    for d in (128, 768, 1024):
+        x, q, cent, ids = make_case(orc, 4000, d, 24, 90, metric, seed=d)
+        g, oidx, _ = build_pair(sb, orc, x, ids, cent, metric)
+        g.remove_ids(ids[::13])
+        probes = orc.coarse_probe(q, cent, metric, 2)  # ~7.5 queries per list: 8-query items dominate
+        g.set_param("scan_mode", 1)
+        d1, i1 = g.search(q, 10, lists=probes)
+        g.set_param("scan_mode", 2)
+        g.set_param("lists_cfg", 3)
+        d3, i3 = g.search(q, 10, lists=probes)
+        assert_topk_parity(d3, i3, d1, i1, f"bulk {metric} d={d}")
+        rd, ri = orc.search(oidx, q, 10, 2, mask=orc.row_mask(oidx, removed_ids=ids[::13]), probes=probes)
+        assert_topk_parity(d3, i3, rd, ri, f"bulk vs oracle {metric} d={d}")
