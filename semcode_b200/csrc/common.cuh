@@ -78,7 +78,11 @@ cudaError_t launch_gemm_tc_scores(const float *ahi, const float *alo, int64_t M,
 // values already stored in best_val / best_idx in (for centroid slabs); ties -> lowest index
 cudaError_t launch_gemm_tc_argmax(const float *ahi, const float *alo, int64_t M, const float *bhi, const float *blo, int N,
                                   int K, float alpha, const float *bias, float *best_val, int32_t *best_idx, int n_base,
-                                  int merge, int num_sms, cudaStream_t st);
+                                  int merge, int num_sms, unsigned long long *packed, cudaStream_t st);
+// packed != nullptr: 256x256 tiles; every launch atomicMax-merges (key << 32 | ~index) into packed[M] (zeroed by the
+// caller before the first slab) and launch_unpack_argmax writes best_val / best_idx afterwards.  packed == nullptr:
+// 128x256 tiles, results straight into best_val / best_idx (merge flag as above).
+cudaError_t launch_unpack_argmax(const unsigned long long *packed, int64_t M, float *best_val, int32_t *best_idx, cudaStream_t st);
 
 // out[r] = sum_k x[r,k]^2
 cudaError_t launch_row_norms(const float *x, int64_t rows, int ds, float *out, cudaStream_t st);

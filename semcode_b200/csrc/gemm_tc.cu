@@ -47,6 +47,7 @@ struct TcArgs {
     int32_t *best_idx;  // ARGMAX: [M]
     int n_base;         // ARGMAX: added to the column index (slab offset)
     int merge;          // ARGMAX: 1 = compare with the values already in best_val/best_idx
+    unsigned long long *packed;  // ARGMAX over 256x256 tiles: [M] (key << 32 | ~index), merged with atomicMax
     int m_tiles, n_tiles;
 };
 
@@ -323,6 +324,199 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
     }
 }
 
+// ---- 256 x 256 tile variant of the fused argmax (bulk assignment / k-means) -------------------------------
+// The 128 x 256 kernel above is L2->SMEM bound: hi+lo of A (128 rows) and B (256 rows) = 96 KB per 1536
+// MMA cycles = 62 B/cycle/SM, above what L2 delivers, so the tensor pipe idles ~40 % of the time.  Here one
+// CTA owns TWO 128-row halves that share every B tile: 64 KB per 1536 MMA cycles (-33 % traffic per MAC).
+// To fit three stages the k-block shrinks to 16 floats (64-byte rows, 64-byte swizzle); the two 128x256
+// accumulators fill all 512 TMEM columns, so the epilogue is not overlapped with the next tile's MMAs
+// (~3 % of a tile at K = 768).
+namespace big {
+constexpr int BM2 = 256, BN2 = 256, BK2 = 16, STAGES2 = 3;
+constexpr int A2_BYTES = BM2 * BK2 * 4;                    // 16 KB (both halves)
+constexpr int B2_BYTES = BN2 * BK2 * 4;                    // 16 KB
+constexpr int STAGE2_BYTES = 2 * (A2_BYTES + B2_BYTES);    // 64 KB
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
+}  // namespace big
+
+// K-major operand tile, 64-byte swizzle: rows of 64 B, 8-row atoms 512 B apart
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(512u >> 4) << 32;  // stride byte offset
+    d |= (uint64_t)1 << 46;            // descriptor version (sm_100)
+    d |= (uint64_t)4 << 61;            // SWIZZLE_64B
+    return d;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc256_argmax_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
+                         const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo, const TcArgs a) {
+    using namespace big;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES2 * STAGE2_BYTES);
+    // bars: [0,S) full  [S,2S) empty  [2S] accumulators full  [2S+1] accumulators empty
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES2 + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES2 + s); };
+    const uint32_t tfull_bar = bar0 + 8u * (2 * STAGES2), tempty_bar = bar0 + 8u * (2 * STAGES2 + 1);
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES2; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tfull_bar, 1);
+        mbar_init(tempty_bar, 4);  // one arrival per epilogue warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int kblocks = (a.K + BK2 - 1) / BK2;
+    // flat (row tile, centroid tile) order with the centroid tile fastest: the CTAs that run at the same time
+    // share a handful of A row tiles (and the whole B slab), so both operands are served from L2 -- a CTA that
+    // sweeps all centroid tiles of its own row tile re-streams 1.5 MB of A per tile from DRAM (measured:
+    // 51.8 GB of DRAM reads per 400k x 8192 launch).  The per-row best is therefore merged across CTAs with
+    // one 64-bit atomicMax per row per tile on a packed (order-preserving key, ~index) word.
+    auto tile = [&](int i, int &mt, int &nt) {
+        const int64_t t = (int64_t)blockIdx.x + (int64_t)i * gridDim.x;
+        if (t >= (int64_t)a.m_tiles * a.n_tiles) return false;
+        mt = (int)(t / a.n_tiles);
+        nt = (int)(t % a.n_tiles);
+        return true;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---- TMA producer ----
+            int stage = 0;
+            uint32_t phase = 0;
+            int mt, nt;
+            for (int i = 0; tile(i, mt, nt); ++i) {
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sa = smem_u32(smem + stage * STAGE2_BYTES);
+                    mbar_expect_tx(full_bar(stage), STAGE2_BYTES);
+                    tma_load_2d(sa, &map_ahi, full_bar(stage), kb * BK2, mt * BM2);
+                    tma_load_2d(sa + A2_BYTES, &map_alo, full_bar(stage), kb * BK2, mt * BM2);
+                    tma_load_2d(sa + 2 * A2_BYTES, &map_bhi, full_bar(stage), kb * BK2, nt * BN2);
+                    tma_load_2d(sa + 2 * A2_BYTES + B2_BYTES, &map_blo, full_bar(stage), kb * BK2, nt * BN2);
+                    if (++stage == STAGES2) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ---- MMA issuer ----
+            constexpr uint32_t idesc = umma_idesc_tf32(128, BN2);
+            int stage = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            int mt, nt;
+            for (int i = 0; tile(i, mt, nt); ++i) {
+                mbar_wait(tempty_bar, acc_phase ^ 1u);  // epilogue has drained both accumulators
+                tc_fence_after();
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * STAGE2_BYTES);
+                    const uint64_t d_bhi = umma_desc_sw64(sa + 2 * A2_BYTES), d_blo = umma_desc_sw64(sa + 2 * A2_BYTES + B2_BYTES);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {  // the two 128-row halves share the B tile
+                        const uint64_t d_ahi = umma_desc_sw64(sa + h * (A2_BYTES / 2)), d_alo = umma_desc_sw64(sa + A2_BYTES + h * (A2_BYTES / 2));
+                        const uint32_t tmem_d = tmem_base + (uint32_t)(h * BN2);
+#pragma unroll
+                        for (int ks = 0; ks < BK2 / 8; ++ks) {
+                            const uint64_t off = (uint64_t)((ks * 8 * 4) >> 4);
+                            umma_tf32(tmem_d, d_ahi + off, d_bhi + off, idesc, (kb | ks) != 0 ? 1u : 0u);
+                            umma_tf32(tmem_d, d_ahi + off, d_blo + off, idesc, 1u);
+                            umma_tf32(tmem_d, d_alo + off, d_bhi + off, idesc, 1u);
+                        }
+                    }
+                    umma_commit(empty_bar(stage));
+                    if (++stage == STAGES2) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                umma_commit(tfull_bar);
+                acc_phase ^= 1u;
+            }
+        }
+    } else {
+        // ---- epilogue warps 2..5: TMEM lane quarter (warp % 4); one row per thread in EACH half ----
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        uint32_t acc_phase = 0;
+        int mt, nt;
+        for (int i = 0; tile(i, mt, nt); ++i) {
+            mbar_wait(tfull_bar, acc_phase);
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int64_t m = (int64_t)mt * BM2 + h * 128 + row;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(h * BN2);
+                float best = -INFINITY;
+                int best_i = 0x7fffffff;
+#pragma unroll 1
+                for (int c = 0; c < BN2; c += 32) {
+                    float v[32];
+                    tmem_ld32(taddr + (uint32_t)c, v);
+                    const int n0 = nt * BN2 + c;
+                    if (n0 >= a.N) continue;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = n0 + j;
+                        if (n < a.N) {
+                            float sc = a.alpha * v[j];
+                            if (a.bias) sc -= __ldg(a.bias + n);
+                            if (sc > best) {  // strict: ties keep the lowest index (columns ascend)
+                                best = sc;
+                                best_i = a.n_base + n;
+                            }
+                        }
+                    }
+                }
+                if (m < a.M && best_i != 0x7fffffff) {
+                    const unsigned long long w = ((unsigned long long)f2key(best) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)best_i);
+                    atomicMax(a.packed + m, w);  // larger key wins; equal keys -> lower index wins
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar);
+            acc_phase ^= 1u;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+__global__ void unpack_argmax_kernel(const unsigned long long *__restrict__ packed, int64_t M, float *__restrict__ best_val,
+                                     int32_t *__restrict__ best_idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const unsigned long long w = packed[i];
+    best_idx[i] = w == 0ull ? 0 : (int32_t)(0xffffffffu - (uint32_t)w);
+    if (best_val) best_val[i] = w == 0ull ? -INFINITY : key2f((uint32_t)(w >> 32));
+}
+
 __global__ void split_tf32_kernel(const float4 *__restrict__ x, int64_t n4, float4 *__restrict__ hi, float4 *__restrict__ lo) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         const float4 v = __ldg(x + i);
@@ -362,16 +556,16 @@ EncodeTiledFn encode_fn() {
 }
 
 // row-major fp32 [rows, K] (row stride K floats) as a 2-D tiled map with boxes of [box_rows x 32 floats], 128B swizzle
-bool make_map(CUtensorMap *map, const float *base, int64_t rows, int K, int box_rows) {
+bool make_map(CUtensorMap *map, const float *base, int64_t rows, int K, int box_rows, int box_k = BK) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)K * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    const cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+              CU_TENSOR_MAP_INTERLEAVE_NONE, box_k * 4 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <bool ARGMAX>
@@ -419,7 +613,7 @@ cudaError_t launch_gemm_tc_scores(const float *ahi, const float *alo, int64_t M,
 
 cudaError_t launch_gemm_tc_argmax(const float *ahi, const float *alo, int64_t M, const float *bhi, const float *blo, int N,
                                   int K, float alpha, const float *bias, float *best_val, int32_t *best_idx, int n_base,
-                                  int merge, int num_sms, cudaStream_t st) {
+                                  int merge, int num_sms, unsigned long long *packed, cudaStream_t st) {
     TcArgs a;
     memset(&a, 0, sizeof(a));
     a.alpha = alpha;
@@ -428,7 +622,31 @@ cudaError_t launch_gemm_tc_argmax(const float *ahi, const float *alo, int64_t M,
     a.best_idx = best_idx;
     a.n_base = n_base;
     a.merge = merge;
-    return launch_tc<true>(ahi, alo, M, bhi, blo, N, K, a, num_sms, st);
+    a.packed = packed;
+    if (packed == nullptr || M <= 0 || N <= 0) return launch_tc<true>(ahi, alo, M, bhi, blo, N, K, a, num_sms, st);
+    // 256 x 256 tiles, 64-byte swizzle
+    using namespace big;
+    CUtensorMap mah, mal, mbh, mbl;
+    if (!make_map(&mah, ahi, M, K, BM2, BK2) || !make_map(&mal, alo, M, K, BM2, BK2) || !make_map(&mbh, bhi, N, K, BN2, BK2) ||
+        !make_map(&mbl, blo, N, K, BN2, BK2))
+        return cudaErrorInvalidValue;
+    a.M = M;
+    a.N = N;
+    a.K = K;
+    a.m_tiles = (int)((M + BM2 - 1) / BM2);
+    a.n_tiles = (N + BN2 - 1) / BN2;
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc256_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+    if (e != cudaSuccess) return e;
+    const int64_t work = (int64_t)a.m_tiles * a.n_tiles;
+    const int grid = (int)(work < num_sms ? work : num_sms);
+    gemm_tc256_argmax_kernel<<<grid, NTHREADS, SMEM2_BYTES, st>>>(mah, mal, mbh, mbl, a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unpack_argmax(const unsigned long long *packed, int64_t M, float *best_val, int32_t *best_idx, cudaStream_t st) {
+    if (M <= 0) return cudaSuccess;
+    unpack_argmax_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(packed, M, best_val, best_idx);
+    return cudaGetLastError();
 }
 
 }  // namespace sc

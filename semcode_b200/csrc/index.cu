@@ -148,6 +148,7 @@ struct sc_index {
     float *cent_hi = nullptr;    // [nlist, ds] tf32(c)           } 3xTF32 operands of the tcgen05
     float *cent_lo = nullptr;    // [nlist, ds] tf32(c - cent_hi) } coarse contraction (gemm_tc.cu)
     int coarse_impl = 0;         // 0 = tcgen05 3xTF32, 1 = fp32 SIMT (exact-fp32 reference kernel)
+    int tc_variant = 0;          // fused argmax tile: 0 = 256x256 (64 B swizzle), 1 = 128x256 (128 B swizzle)
 
     // paged lists
     int slab_shift = 0;
@@ -169,7 +170,7 @@ struct sc_index {
     // scratch (stream ordered; ev_done chains calls made on different streams)
     DevBuf s_q, s_scores, s_probe, s_pairpages, s_pageoff, s_cand, s_outd, s_outi, s_repobits;
     DevBuf s_x, s_xpad, s_ids, s_repo, s_lang, s_assign, s_best, s_pos, s_lenold, s_need, s_npg, s_needoff, s_bad;
-    DevBuf s_sums, s_counts, s_obj, s_rows, s_rm, s_cnt, s_ahi, s_alo, s_lplan, s_scan;
+    DevBuf s_sums, s_counts, s_obj, s_rows, s_rm, s_cnt, s_ahi, s_alo, s_lplan, s_scan, s_packed;
     int64_t scratch_budget = (int64_t)8 << 30;  // search scratch ceiling (candidates dominate); sc_index_set_param("scratch_bytes")
     int scan_variant = 0;
     int lists_cfg = 0;  // tile configuration of the list-major kernel (experiments)
@@ -353,12 +354,19 @@ int coarse_assign(sc_index *ix, const float *xd, int64_t n, int32_t *assign, flo
         }
         int64_t slab = (((int64_t)48 << 20) / ((int64_t)ix->ds * 8)) / 256 * 256;
         slab = std::max<int64_t>(256, std::min<int64_t>(slab, ix->nlist));
+        unsigned long long *packed = nullptr;
+        if (ix->tc_variant == 0) {  // 256x256 tiles: per-row best merged across CTAs and slabs with atomicMax
+            CU(ix->s_packed.reserve((size_t)n * 8));
+            packed = ix->s_packed.as<unsigned long long>();
+            CU(cudaMemsetAsync(packed, 0, (size_t)n * 8, st));
+        }
         for (int64_t c0 = 0; c0 < ix->nlist; c0 += slab) {
             const int nc = (int)std::min<int64_t>(slab, ix->nlist - c0);
             CU(launch_gemm_tc_argmax(ix->s_ahi.as<float>(), ix->s_alo.as<float>(), n, ix->cent_hi + c0 * ix->ds,
                                      ix->cent_lo + c0 * ix->ds, nc, ix->ds, l2 ? 2.f : 1.f, l2 ? ix->cnorm + c0 : nullptr, bv,
-                                     assign, (int)c0, c0 > 0 ? 1 : 0, ix->num_sms, st));
+                                     assign, (int)c0, c0 > 0 ? 1 : 0, ix->num_sms, packed, st));
         }
+        if (packed) CU(launch_unpack_argmax(packed, n, bv, assign, st));
         return SC_OK;
     }
     const int64_t ch = coarse_chunk_rows(ix, n);
@@ -605,8 +613,12 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
         a.cand = ix->s_cand.as<float>();
         a.filt = fdev;
         // large batches re-probe the same lists: read each list once and score it against all its queries
+        // (auto: only when lists are probed ~1.5x on average AND are long enough for 128-row tiles -- with
+        //  < 128 rows per list, e.g. an 8-way row shard of C2, the query-major kernel measures faster)
+        const bool long_lists = ix->ntotal + ix->nremoved >= (int64_t)128 * ix->nlist;
         const bool list_major = ix->ds >= 128 && npairs <= (int64_t)INT32_MAX &&
-                                (ix->scan_mode == 2 || (ix->scan_mode == 0 && 2 * npairs >= 3 * (int64_t)ix->nlist));
+                                (ix->scan_mode == 2 ||
+                                 (ix->scan_mode == 0 && long_lists && 2 * npairs >= 3 * (int64_t)ix->nlist));
         if (list_major) {
             const size_t nl = (size_t)ix->nlist;
             const size_t words = 4 * nl + 3 * (nl + 1) + (size_t)npairs + 2 + 16;
@@ -739,7 +751,7 @@ int sc_index_destroy(sc_index_t *ix) {
     for (DevBuf *b : {&ix->s_q, &ix->s_scores, &ix->s_probe, &ix->s_pairpages, &ix->s_pageoff, &ix->s_cand, &ix->s_outd,
                       &ix->s_outi, &ix->s_repobits, &ix->s_x, &ix->s_xpad, &ix->s_ids, &ix->s_repo, &ix->s_lang,
                       &ix->s_assign, &ix->s_best, &ix->s_pos, &ix->s_lenold, &ix->s_need, &ix->s_npg, &ix->s_needoff,
-                      &ix->s_bad, &ix->s_sums, &ix->s_counts, &ix->s_obj, &ix->s_rows, &ix->s_rm, &ix->s_cnt, &ix->s_ahi, &ix->s_alo, &ix->s_lplan, &ix->s_scan})
+                      &ix->s_bad, &ix->s_sums, &ix->s_counts, &ix->s_obj, &ix->s_rows, &ix->s_rm, &ix->s_cnt, &ix->s_ahi, &ix->s_alo, &ix->s_lplan, &ix->s_scan, &ix->s_packed})
         b->release();
     for (void *p : {(void *)ix->centroids, (void *)ix->cnorm, (void *)ix->cent_hi, (void *)ix->cent_lo, (void *)ix->d_tab, (void *)ix->list_len, (void *)ix->pt_off,
                     (void *)ix->pt_off_alt, (void *)ix->pt, (void *)ix->pt_alt, (void *)ix->prof_rows})
@@ -1147,7 +1159,7 @@ int sc_index_stats(sc_index_t *ix, sc_stats_t *out) {
                             &ix->s_outd, &ix->s_outi, &ix->s_repobits, &ix->s_x, &ix->s_xpad, &ix->s_ids, &ix->s_repo,
                             &ix->s_lang, &ix->s_assign, &ix->s_best, &ix->s_pos, &ix->s_lenold, &ix->s_need, &ix->s_npg,
                             &ix->s_needoff, &ix->s_bad, &ix->s_sums, &ix->s_counts, &ix->s_obj, &ix->s_rows, &ix->s_rm,
-                            &ix->s_cnt, &ix->s_ahi, &ix->s_alo, &ix->s_lplan, &ix->s_scan})
+                            &ix->s_cnt, &ix->s_ahi, &ix->s_alo, &ix->s_lplan, &ix->s_scan, &ix->s_packed})
         sb += (int64_t)b->cap;
     out->bytes_scratch = sb;
     int32_t mx = 0, mn = ix->nlist > 0 ? INT32_MAX : 0;
@@ -1270,6 +1282,11 @@ int sc_index_set_param(sc_index_t *ix, const char *name, int64_t value) {
     if (strcmp(name, "scan_mode") == 0) {
         if (value < 0 || value > 2) return fail(SC_ERR_INVALID, "scan_mode: 0 = auto, 1 = query-major, 2 = list-major");
         ix->scan_mode = (int)value;
+        return SC_OK;
+    }
+    if (strcmp(name, "tc_variant") == 0) {
+        if (value != 0 && value != 1) return fail(SC_ERR_INVALID, "tc_variant: 0 = 256x256 tiles, 1 = 128x256 tiles");
+        ix->tc_variant = (int)value;
         return SC_OK;
     }
     if (strcmp(name, "coarse_impl") == 0) {

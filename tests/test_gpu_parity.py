@@ -450,12 +450,14 @@ def test_tensor_core_fused_argmax_matches_simt(sb, orc, metric):
     cent = unit_rows(rng, nlist, d) * rng.uniform(0.5, 1.5, (nlist, 1)).astype(np.float32)
     g = sb.IVFFlatIndex(d, nlist=nlist, metric=metric)
     g.set_centroids(cent)
-    a_tc = g.assign(x)
+    a_tc = g.assign(x)  # 256 x 256 tiles (64-byte swizzle)
+    g.set_param("tc_variant", 1)
+    a_tc1 = g.assign(x)  # 128 x 256 tiles (128-byte swizzle)
     g.set_param("coarse_impl", 1)
     a_simt = g.assign(x)
     exact = orc.coarse_similarity(x, cent, metric, dtype=np.float64)
     a_ref = np.argmax(exact, axis=1)
-    for a in (a_tc, a_simt):
+    for a in (a_tc, a_tc1, a_simt):
         diff = np.flatnonzero(a != a_ref)
         assert diff.size < 10
         for r in diff:  # only rounding-level ties may differ
@@ -511,7 +513,7 @@ def test_list_major_auto_mode_full_search(sb, orc):
     # nq * nprobe >= 2 * nlist switches the scan to list-major automatically
     x, q, cent, ids = make_case(orc, 30000, 256, 64, 600, "IP", seed=77)
     g, oidx, _ = build_pair(sb, orc, x, ids, cent, "IP")
-    d0, i0 = g.search(q, 10, nprobe=12)  # 7200 pairs >= 128: auto -> list-major
+    d0, i0 = g.search(q, 10, nprobe=12)  # 7200 pairs >= 1.5 * 64 lists of ~470 rows: auto -> list-major
     g.set_param("scan_mode", 1)
     d1, i1 = g.search(q, 10, nprobe=12)
     np.testing.assert_array_equal(i0, i1)
