@@ -17,7 +17,7 @@ q = bench.gen_rows(torch, 0, 4096, d, 4321, dev)
 g.set_profiling(True)
 ref = {}
 for nq, nprobe in ((4096, 128), (4096, 32), (4096, 8), (1024, 32), (4096, 16)):
-    for mode, cfg in ((1, 0), (2, 0), (2, 1)):
+    for mode, cfg in ((1, 0), (2, 0)):
         if mode == 1 and nq * nprobe > 200000: 
             reps = 1
         else:

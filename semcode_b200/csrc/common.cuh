@@ -146,14 +146,15 @@ cudaError_t launch_exclusive_scan_i32(const int32_t *in, int64_t n, int32_t *out
 cudaError_t launch_scan_pages(const ScanArgs &a, int variant, int num_sms, int *launches, cudaStream_t st);
 
 // list-major scan (scan_lists.cu): the probed lists are read ONCE per batch and scored against every query
-// that probes them.  Scratch (all device, caller-sized): cnt/cursor/n32/n8 [nlist], lq_off/off32/off8 [nlist+1],
-// lq [npairs], counters [2].  Writes the same candidate layout as launch_scan_pages.
+// that probes them.  Scratch (all device, caller-sized): cnt/cursor/n32/n8/n4 [nlist], lq_off/off32/off8/off4
+// [nlist+1], lq [npairs], counters [4].  Writes the same candidate layout as launch_scan_pages.
 struct ListPlan {
     int32_t nlist;
-    int32_t *cnt, *cursor, *n32, *n8;  // [nlist]
-    int32_t *lq_off, *off32, *off8;    // [nlist+1]
+    int32_t *cnt, *cursor, *n32, *n8, *n4;    // [nlist]
+    int32_t *lq_off, *off32, *off8, *off4;    // [nlist+1]
     int32_t *lq;                       // [npairs] pair ids grouped by list
-    int32_t *counters;                 // [2] work counters of the two tile variants
+    int32_t *counters;                 // [4] work counters of the tile variants (32 / 8 / 4 queries)
+    int32_t *mq_pages, *mq_pgoff;      // [nlist], [nlist+1]: pages of the lists the multi-query page scan handles
     unsigned long long *unique_rows;   // optional: += rows of every list probed at least once
 };
 cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int num_sms, int *launches, cudaStream_t st);

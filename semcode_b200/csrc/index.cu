@@ -613,15 +613,15 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
         a.cand = ix->s_cand.as<float>();
         a.filt = fdev;
         // large batches re-probe the same lists: read each list once and score it against all its queries
-        // (auto: only when lists are probed ~1.5x on average AND are long enough for 128-row tiles -- with
-        //  < 128 rows per list, e.g. an 8-way row shard of C2, the query-major kernel measures faster)
-        const bool long_lists = ix->ntotal + ix->nremoved >= (int64_t)128 * ix->nlist;
+        // (auto: when a list is probed ~0.75x or more on average -- 53 % or fewer of the pair passes hit a
+        //  distinct list -- and lists hold at least a page; measured break-even on C2 is near 0.5x)
+        const bool long_lists = ix->ntotal + ix->nremoved >= (int64_t)kPageRows * ix->nlist;
         const bool list_major = ix->ds >= 128 && npairs <= (int64_t)INT32_MAX &&
                                 (ix->scan_mode == 2 ||
-                                 (ix->scan_mode == 0 && long_lists && 2 * npairs >= 3 * (int64_t)ix->nlist));
+                                 (ix->scan_mode == 0 && long_lists && 4 * npairs >= 3 * (int64_t)ix->nlist));
         if (list_major) {
             const size_t nl = (size_t)ix->nlist;
-            const size_t words = 4 * nl + 3 * (nl + 1) + (size_t)npairs + 2 + 16;
+            const size_t words = 6 * nl + 5 * (nl + 1) + (size_t)npairs + 4 + 16;
             CU(ix->s_lplan.reserve(words * 4));
             int32_t *w = ix->s_lplan.as<int32_t>();
             ListPlan lp;
@@ -630,11 +630,15 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
             lp.cursor = w + nl;
             lp.n32 = w + 2 * nl;
             lp.n8 = w + 3 * nl;
-            lp.lq_off = w + 4 * nl;
+            lp.n4 = w + 4 * nl;
+            lp.lq_off = w + 5 * nl;
             lp.off32 = lp.lq_off + nl + 1;
             lp.off8 = lp.off32 + nl + 1;
-            lp.counters = lp.off8 + nl + 1;
-            lp.lq = lp.counters + 2;
+            lp.off4 = lp.off8 + nl + 1;
+            lp.mq_pages = lp.off4 + nl + 1;
+            lp.mq_pgoff = lp.mq_pages + nl;
+            lp.counters = lp.mq_pgoff + nl + 1;
+            lp.lq = lp.counters + 4;
             lp.unique_rows = ix->profiling ? ix->prof_rows + 1 : nullptr;
             CU(launch_scan_lists(a, lp, ix->lists_cfg, ix->num_sms, &ix->prof_scan_launches, st));
         } else {

@@ -42,20 +42,23 @@ __global__ void count_list_pairs_kernel(const int32_t *__restrict__ probe, int64
 }
 
 __global__ void plan_items_kernel(const int32_t *__restrict__ cnt, int32_t nlist, int32_t *__restrict__ n32,
-                                  int32_t *__restrict__ n8, const int32_t *__restrict__ list_len,
+                                  int32_t *__restrict__ n8, int32_t *__restrict__ n4, const int32_t *__restrict__ list_len,
                                   unsigned long long *__restrict__ unique_rows) {
     const int32_t l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nlist) return;
     const int32_t c = cnt[l];
     if (unique_rows != nullptr && c > 0) atomicAdd(unique_rows, (unsigned long long)list_len[l]);
-    int32_t a = c / 32, b = 0;
+    int32_t a = c / 32, b = 0, d = 0;
     const int32_t rem = c - a * 32;
     if (rem > 8)
         ++a;  // a ragged 32-chunk costs less than re-reading the list for several 8-chunks
-    else if (rem > 0)
+    else if (rem > 4)
         b = 1;
+    else if (rem > 0)
+        d = 1;
     n32[l] = a;
     n8[l] = b;
+    n4[l] = d;
 }
 
 __global__ void fill_list_pairs_kernel(const int32_t *__restrict__ probe, int64_t npairs, const int32_t *__restrict__ list_len,
@@ -77,7 +80,8 @@ __global__ void fill_list_pairs_kernel(const int32_t *__restrict__ probe, int64_
 //   QT =  8: KS = 4, RPT = 2 (warp =  64 rows x 8 queries), HBM-bound regime
 template <int QT, int BKX, int NS, int RB, int RPT_>
 struct TileCfg {
-    static constexpr int QG = QT / 8;                 // query groups of 8
+    static constexpr int QPT = QT < 8 ? QT : 8;       // queries per thread
+    static constexpr int QG = QT / QPT;               // query groups
     static constexpr int RPT = RPT_;                  // rows per thread
     static constexpr int RG = RB / (32 * RPT);        // row groups
     static constexpr int WPK = QG * RG;               // warps per k-split
@@ -146,7 +150,7 @@ __global__ void __launch_bounds__(NT, 2) scan_lists_kernel(const ScanArgs a, con
     const int qg = (warp % C::WPK) % C::QG;         // query group (8 queries)
     const int rg = (warp % C::WPK) / C::QG;         // row group
     const int row0 = rg * 32 * C::RPT + lane;       // rows row0 + 32*i
-    const int32_t *item_off = QT == 32 ? p.off32 : p.off8;
+    const int32_t *item_off = QT == 32 ? p.off32 : (QT == 8 ? p.off8 : p.off4);
     const int32_t total = item_off[p.nlist];
     const int ds = a.ds;
     const int KB = (ds + BKX - 1) / BKX;
@@ -235,15 +239,15 @@ __global__ void __launch_bounds__(NT, 2) scan_lists_kernel(const ScanArgs a, con
         }
 
         // packed accumulators: acc2[i][j] = (sum over even k, sum over odd k) -> one FFMA2 per two products
-        unsigned long long acc2[C::RPT][8];
+        unsigned long long acc2[C::RPT][C::QPT];
         auto k4_step = [&](int buf, int k4) {
             ulonglong2 xv[C::RPT];
 #pragma unroll
             for (int i = 0; i < C::RPT; ++i)
                 xv[i] = *reinterpret_cast<const ulonglong2 *>(&sm.xs[buf][row0 + 32 * i][k4 * 4]);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const ulonglong2 qv = *reinterpret_cast<const ulonglong2 *>(&sm.qs[buf][qg * 8 + j][k4 * 4]);
+            for (int j = 0; j < C::QPT; ++j) {
+                const ulonglong2 qv = *reinterpret_cast<const ulonglong2 *>(&sm.qs[buf][qg * C::QPT + j][k4 * 4]);
 #pragma unroll
                 for (int i = 0; i < C::RPT; ++i) {
                     if (L2) {
@@ -275,7 +279,7 @@ __global__ void __launch_bounds__(NT, 2) scan_lists_kernel(const ScanArgs a, con
 #pragma unroll
                 for (int i = 0; i < C::RPT; ++i)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc2[i][j] = 0ull;
+                    for (int j = 0; j < C::QPT; ++j) acc2[i][j] = 0ull;
             }
             const int kv = (min(ds - kb * BKX, BKX)) >> 2;  // valid k4-steps of this stage
             if (kv == BKX / 4) {
@@ -289,15 +293,15 @@ __global__ void __launch_bounds__(NT, 2) scan_lists_kernel(const ScanArgs a, con
             if (kb == KB - 1) {  // tile finished: fold even/odd and the k-splits, one candidate per (row slot, query)
                 if (ks > 0) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
+                    for (int j = 0; j < C::QPT; ++j)
 #pragma unroll
-                        for (int i = 0; i < C::RPT; ++i) sm.red[ks - 1][qg * 8 + j][row0 + 32 * i] = sum2(acc2[i][j]);
+                        for (int i = 0; i < C::RPT; ++i) sm.red[ks - 1][qg * C::QPT + j][row0 + 32 * i] = sum2(acc2[i][j]);
                 }
                 __syncthreads();
                 if (ks == 0) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int64_t cb = sm.cbase[qg * 8 + j];
+                    for (int j = 0; j < C::QPT; ++j) {
+                        const int64_t cb = sm.cbase[qg * C::QPT + j];
                         if (cb < 0) continue;
 #pragma unroll
                         for (int i = 0; i < C::RPT; ++i) {
@@ -306,7 +310,7 @@ __global__ void __launch_bounds__(NT, 2) scan_lists_kernel(const ScanArgs a, con
                             if (r < slots) {
                                 float v = sum2(acc2[i][j]);
 #pragma unroll
-                                for (int h = 0; h < C::KS - 1; ++h) v += sm.red[h][qg * 8 + j][rr];
+                                for (int h = 0; h < C::KS - 1; ++h) v += sm.red[h][qg * C::QPT + j][rr];
                                 const bool ok = r < len && sm.live[tile % C::RING][rr];
                                 a.cand[cb + r] = ok ? (L2 ? -v : v) : -INFINITY;
                             }
@@ -323,7 +327,7 @@ __global__ void __launch_bounds__(NT, 2) scan_lists_kernel(const ScanArgs a, con
 template <int QT, int BKX, int NS, int RB, int RPT>
 cudaError_t launch_lists_variant(const ScanArgs &a, const ListPlan &p, int num_sms, cudaStream_t st) {
     const size_t smem = sizeof(TileSmem<QT, BKX, NS, RB, RPT>);
-    const int which = QT == 32 ? 0 : 1;
+    const int which = QT == 32 ? 0 : (QT == 8 ? 1 : 2);
     const int per_sm = smem * 2 + 2048 <= 227 * 1024 ? 2 : 1;
     cudaError_t e;
     if (a.metric == 1) {
@@ -343,6 +347,7 @@ cudaError_t launch_lists_variant(const ScanArgs &a, const ListPlan &p, int num_s
 }  // namespace
 
 cudaError_t launch_scan_lists8_bulk(const ScanArgs &a, const ListPlan &p, int num_sms, cudaStream_t st);
+cudaError_t launch_scan_mq(const ScanArgs &a, const ListPlan &p, int32_t *pages, int32_t *pgoff, int num_sms, cudaStream_t st);
 
 cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int num_sms, int *launches, cudaStream_t st) {
     if (a.npairs <= 0) return cudaSuccess;
@@ -351,12 +356,13 @@ cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int
     const unsigned pb = (unsigned)((a.npairs + 255) / 256), lb = (unsigned)((p.nlist + 255) / 256);
     if ((e = cudaMemsetAsync(p.cnt, 0, (size_t)p.nlist * 4, st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(p.cursor, 0, (size_t)p.nlist * 4, st)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(p.counters, 0, 8, st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(p.counters, 0, 16, st)) != cudaSuccess) return e;
     count_list_pairs_kernel<<<pb, 256, 0, st>>>(a.probe, a.npairs, a.list_len, p.nlist, p.cnt);
-    plan_items_kernel<<<lb, 256, 0, st>>>(p.cnt, p.nlist, p.n32, p.n8, a.list_len, p.unique_rows);
+    plan_items_kernel<<<lb, 256, 0, st>>>(p.cnt, p.nlist, p.n32, p.n8, p.n4, a.list_len, p.unique_rows);
     if ((e = launch_exclusive_scan_i32(p.cnt, p.nlist, p.lq_off, st)) != cudaSuccess) return e;
     if ((e = launch_exclusive_scan_i32(p.n32, p.nlist, p.off32, st)) != cudaSuccess) return e;
     if ((e = launch_exclusive_scan_i32(p.n8, p.nlist, p.off8, st)) != cudaSuccess) return e;
+    if ((e = launch_exclusive_scan_i32(p.n4, p.nlist, p.off4, st)) != cudaSuccess) return e;
     fill_list_pairs_kernel<<<pb, 256, 0, st>>>(a.probe, a.npairs, a.list_len, p.nlist, p.lq_off, p.cursor, p.lq);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     // tile configurations <QT, floats per k-stage, pipeline stages>; cfg picks the experiment (0 = default)
@@ -373,7 +379,13 @@ cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int
         e = launch_lists_variant<8, 64, 2, 128, 2>(a, p, num_sms, st);
     }
     if (e != cudaSuccess) return e;
-    if (launches) *launches += 8;
+    // lists probed by <= 4 queries: multi-query page scan (scan_mq.cu); cfg 1 keeps the 4-query cp.async tile
+    if (cfg == 1 || a.ds > 1024) {  // (the per-warp query slice of the page scan is 16 * dim bytes of shared memory)
+        if ((e = launch_lists_variant<4, 64, 2, 128, 2>(a, p, num_sms, st)) != cudaSuccess) return e;
+    } else {
+        if ((e = launch_scan_mq(a, p, p.mq_pages, p.mq_pgoff, num_sms, st)) != cudaSuccess) return e;
+    }
+    if (launches) *launches += 10;
     return cudaSuccess;
 }
 

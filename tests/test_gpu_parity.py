@@ -521,7 +521,7 @@ def test_list_major_auto_mode_full_search(sb, orc):
     g.set_profiling(True)
     g.set_param("scan_mode", 0)
     g.search(q, 10, nprobe=12)
-    assert g.last_search_times().scan_launches == 8  # plan kernels + the two tile variants
+    assert g.last_search_times().scan_launches == 10  # plan kernels + the three tile variants
     g.set_param("scan_mode", 1)
     g.search(q, 10, nprobe=12)
     assert g.last_search_times().scan_launches == 1
