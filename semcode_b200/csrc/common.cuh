@@ -155,6 +155,9 @@ struct ListPlan {
     int32_t *lq;                       // [npairs] pair ids grouped by list
     int32_t *counters;                 // [4] work counters of the tile variants (32 / 8 / 4 queries)
     int32_t *mq_pages, *mq_pgoff;      // [nlist], [nlist+1]: pages of the lists the multi-query page scan handles
+    // optional fork/join: the (few, long) tile items run on side streams while the page scan fills the GPU
+    cudaStream_t side[2];
+    cudaEvent_t ev_fork, ev_join[2];
     unsigned long long *unique_rows;   // optional: += rows of every list probed at least once
 };
 cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int num_sms, int *launches, cudaStream_t st);

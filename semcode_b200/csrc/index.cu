@@ -176,6 +176,9 @@ struct sc_index {
     int lists_cfg = 0;  // tile configuration of the list-major kernel (experiments)
     int scan_mode = 0;  // 0 = auto, 1 = query-major (scan.cu), 2 = list-major (scan_lists.cu)
     cudaEvent_t ev_done = nullptr;
+    cudaStream_t side[2] = {nullptr, nullptr};  // fork/join streams of the list-major scan
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    int lists_fork = 0;  // measured slower on C2 (tile CTAs pin shared memory the page scan needs): off by default
 
     // profiling of the last search
     bool profiling = false;
@@ -640,6 +643,11 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
             lp.counters = lp.mq_pgoff + nl + 1;
             lp.lq = lp.counters + 4;
             lp.unique_rows = ix->profiling ? ix->prof_rows + 1 : nullptr;
+            for (int i = 0; i < 2; ++i) {
+                lp.side[i] = ix->lists_fork ? ix->side[i] : nullptr;
+                lp.ev_join[i] = ix->ev_join[i];
+            }
+            lp.ev_fork = ix->ev_fork;
             CU(launch_scan_lists(a, lp, ix->lists_cfg, ix->num_sms, &ix->prof_scan_launches, st));
         } else {
             CU(launch_scan_pages(a, ix->scan_variant, ix->num_sms, &ix->prof_scan_launches, st));
@@ -731,6 +739,11 @@ int sc_index_create(int32_t dim, int32_t metric, int32_t nlist, int32_t device, 
     if (e == cudaSuccess) e = cudaMalloc(&ix->pt_off_alt, (size_t)(nlist + 1) * 4);
     if (e == cudaSuccess) e = cudaMalloc(&ix->pt, 1024 * 4);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->ev_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->ev_fork, cudaEventDisableTiming);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaStreamCreateWithFlags(&ix->side[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->ev_join[i], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaMemset(ix->list_len, 0, (size_t)nlist * 4);
     if (e == cudaSuccess) e = cudaMemset(ix->pt_off, 0, (size_t)(nlist + 1) * 4);
     if (e == cudaSuccess) e = cudaMemset(ix->d_tab, 0, sizeof(SlabTable));
@@ -761,6 +774,11 @@ int sc_index_destroy(sc_index_t *ix) {
                     (void *)ix->pt_off_alt, (void *)ix->pt, (void *)ix->pt_alt, (void *)ix->prof_rows})
         if (p) cudaFree(p);
     if (ix->ev_done) cudaEventDestroy(ix->ev_done);
+    if (ix->ev_fork) cudaEventDestroy(ix->ev_fork);
+    for (int i = 0; i < 2; ++i) {
+        if (ix->ev_join[i]) cudaEventDestroy(ix->ev_join[i]);
+        if (ix->side[i]) cudaStreamDestroy(ix->side[i]);
+    }
     delete ix->h_tab;
     cudaGetLastError();
     delete ix;
@@ -1276,6 +1294,10 @@ int sc_index_set_param(sc_index_t *ix, const char *name, int64_t value) {
     if (strcmp(name, "scan_variant") == 0) {
         if (value < 0 || value > 4) return fail(SC_ERR_INVALID, "scan_variant must be in [0,4]");
         ix->scan_variant = (int)value;
+        return SC_OK;
+    }
+    if (strcmp(name, "lists_fork") == 0) {
+        ix->lists_fork = value != 0;
         return SC_OK;
     }
     if (strcmp(name, "lists_cfg") == 0) {

@@ -366,24 +366,42 @@ cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int
     fill_list_pairs_kernel<<<pb, 256, 0, st>>>(a.probe, a.npairs, a.list_len, p.nlist, p.lq_off, p.cursor, p.lq);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     // tile configurations <QT, floats per k-stage, pipeline stages>; cfg picks the experiment (0 = default)
-    // 32-query and 8-query tiles: cp.async ring kernels.  cfg selects experiments: 2 = 32-float stages for the
-    // 32-query tile, 3 = bulk-copy/mbarrier kernel (scan_lists_bulk.cu) for the 8-query tile when the dimension allows.
-    if (cfg == 2) {
-        if ((e = launch_lists_variant<32, 32, 3, 128, 4>(a, p, num_sms, st)) != cudaSuccess) return e;
-    } else {
-        if ((e = launch_lists_variant<32, 64, 2, 128, 4>(a, p, num_sms, st)) != cudaSuccess) return e;
+    // Three independent consumers of the plan.  The tile kernels (lists probed by > 4 queries) usually hold few,
+    // long items; the page scan (<= 4 queries) holds most of the bytes.  With side streams the tile kernels are
+    // launched first and the page scan fills the SMs they leave free, instead of three kernels back to back.
+    // cfg selects experiments: 1 = 4-query cp.async tile instead of the page scan, 2 = 32-float stages for the
+    // 32-query tile, 3 = bulk-copy/mbarrier kernel (scan_lists_bulk.cu) for the 8-query tile.
+    const bool fork = p.side[0] != nullptr && p.side[1] != nullptr;
+    cudaStream_t s32 = fork ? p.side[0] : st, s8 = fork ? p.side[1] : st;
+    if (fork) {
+        if ((e = cudaEventRecord(p.ev_fork, st)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(s32, p.ev_fork, 0)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(s8, p.ev_fork, 0)) != cudaSuccess) return e;
     }
-    e = cfg == 3 ? launch_scan_lists8_bulk(a, p, num_sms, st) : cudaErrorNotSupported;
+    if (cfg == 2) {
+        if ((e = launch_lists_variant<32, 32, 3, 128, 4>(a, p, num_sms, s32)) != cudaSuccess) return e;
+    } else {
+        if ((e = launch_lists_variant<32, 64, 2, 128, 4>(a, p, num_sms, s32)) != cudaSuccess) return e;
+    }
+    e = cfg == 3 ? launch_scan_lists8_bulk(a, p, num_sms, s8) : cudaErrorNotSupported;
     if (e == cudaErrorNotSupported) {
         cudaGetLastError();
-        e = launch_lists_variant<8, 64, 2, 128, 2>(a, p, num_sms, st);
+        e = launch_lists_variant<8, 64, 2, 128, 2>(a, p, num_sms, s8);
     }
     if (e != cudaSuccess) return e;
-    // lists probed by <= 4 queries: multi-query page scan (scan_mq.cu); cfg 1 keeps the 4-query cp.async tile
+    if (fork) {
+        if ((e = cudaEventRecord(p.ev_join[0], s32)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(p.ev_join[1], s8)) != cudaSuccess) return e;
+    }
+    // lists probed by <= 4 queries: multi-query page scan (scan_mq.cu)
     if (cfg == 1 || a.ds > 1024) {  // (the per-warp query slice of the page scan is 16 * dim bytes of shared memory)
         if ((e = launch_lists_variant<4, 64, 2, 128, 2>(a, p, num_sms, st)) != cudaSuccess) return e;
     } else {
         if ((e = launch_scan_mq(a, p, p.mq_pages, p.mq_pgoff, num_sms, st)) != cudaSuccess) return e;
+    }
+    if (fork) {
+        if ((e = cudaStreamWaitEvent(st, p.ev_join[0], 0)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(st, p.ev_join[1], 0)) != cudaSuccess) return e;
     }
     if (launches) *launches += 10;
     return cudaSuccess;
