@@ -522,7 +522,7 @@ def run_ours(args):
     scan_s = statistics.mean(scan_ms) / 1e3
     if list_major:  # compulsory bytes: every DISTINCT probed list once
         bytes_per_step = statistics.mean(unique_rows) * 4 * d
-        kernel_name = "scan_lists_kernel (list-major: plan + 32-query and 8-query tiles)"
+        kernel_name = "list-major scan: scan_mq_kernel (lists probed by <= 4 queries) + scan_lists_kernel tiles (8 / 32 queries) + plan"
     else:
         bytes_per_step = logical_bytes
         kernel_name = "scan_pages_kernel (query-major)"
