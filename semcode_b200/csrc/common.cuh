@@ -84,6 +84,9 @@ cudaError_t launch_gemm_tc_argmax(const float *ahi, const float *alo, int64_t M,
 // 128x256 tiles, results straight into best_val / best_idx (merge flag as above).
 cudaError_t launch_unpack_argmax(const unsigned long long *packed, int64_t M, float *best_val, int32_t *best_idx, cudaStream_t st);
 
+// C[nq,N] = alpha * q.B^T - bias[n] for nq <= 16 (one warp per row of B); cudaErrorNotSupported when it does not fit
+cudaError_t launch_coarse_small(const float *q, int64_t nq, const float *cent, int nlist, int ds, float alpha, const float *bias,
+                                float *scores, int num_sms, cudaStream_t st);
 // out[r] = sum_k x[r,k]^2
 cudaError_t launch_row_norms(const float *x, int64_t rows, int ds, float *out, cudaStream_t st);
 // per row: index of the largest score (ties -> lowest index) and the score

@@ -5,6 +5,8 @@
 // the centroids, reached from reference src/semcode/storage/milvus_store.py:141-147) and for
 // k-means/list assignment (quantizer->assign, milvus_store.py:128-130).  Roofline: FP32 FMA pipe
 // (148 SMs x 128 lanes x 2 flop x clock); operands stream from L2.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace sc {
@@ -117,6 +119,48 @@ gemm_nt_kernel(const float *__restrict__ A, int64_t M, const float *__restrict__
     }
 }
 
+// ---- coarse scores for tiny batches (nq <= 16): one warp per centroid, queries staged in shared memory --------
+// At batch 1 the 128-row MMA tile is >99 % padding and the TMA/MMA pipeline costs ~45 us of latency; streaming the
+// centroid table once (nlist * 4 * dim bytes, 50 MB at C2: ~8 us from HBM, less from L2) is the roofline here.
+// Exact fp32 (FFMA), same epilogue as the contraction kernels: S = alpha * q.c - bias[c].
+template <int NQ>
+__global__ void __launch_bounds__(256) coarse_small_kernel(const float *__restrict__ q, int nq, const float *__restrict__ cent,
+                                                           int nlist, int ds, float alpha, const float *__restrict__ bias,
+                                                           float *__restrict__ scores) {
+    extern __shared__ __align__(16) float4 qs4[];  // [nq][ds4]
+    const int ds4 = ds >> 2;
+    for (int i = threadIdx.x; i < nq * ds4; i += blockDim.x) qs4[i] = __ldg(reinterpret_cast<const float4 *>(q) + i);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = blockIdx.x * 8 + warp; c < nlist; c += gridDim.x * 8) {
+        const float4 *row = reinterpret_cast<const float4 *>(cent + (int64_t)c * ds);
+        float acc[NQ];
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) acc[j] = 0.f;
+        for (int k = lane; k < ds4; k += 32) {
+            const float4 x = ld_stream_f4(row + k);
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) {
+                if (j < nq) {
+                    const float4 v = qs4[j * ds4 + k];
+                    acc[j] = fmaf(x.x, v.x, acc[j]);
+                    acc[j] = fmaf(x.y, v.y, acc[j]);
+                    acc[j] = fmaf(x.z, v.z, acc[j]);
+                    acc[j] = fmaf(x.w, v.w, acc[j]);
+                }
+            }
+        }
+        const float b = bias ? __ldg(bias + c) : 0.f;
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) {
+            if (j < nq) {
+                const float sum = warp_sum(acc[j]);
+                if (lane == 0) scores[(int64_t)j * nlist + c] = alpha * sum - b;
+            }
+        }
+    }
+}
+
 __global__ void row_norms_kernel(const float *__restrict__ x, int64_t rows, int ds, float *__restrict__ out) {
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -180,6 +224,25 @@ cudaError_t launch_gemm_nt(const float *A, int64_t M, const float *B, int N, int
     if (M <= 0 || N <= 0) return cudaSuccess;
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
     gemm_nt_kernel<<<grid, 256, 0, st>>>(A, M, B, N, K, bnorm, C);
+    return cudaGetLastError();
+}
+
+// returns cudaErrorNotSupported when the batch does not fit (caller uses the contraction kernels)
+cudaError_t launch_coarse_small(const float *q, int64_t nq, const float *cent, int nlist, int ds, float alpha, const float *bias,
+                                float *scores, int num_sms, cudaStream_t st) {
+    if (nq < 1 || nq > 16) return cudaErrorNotSupported;
+    const size_t smem = (size_t)nq * ds * 4;
+    if (smem > 96 * 1024) return cudaErrorNotSupported;
+    const int grid = std::min((nlist + 7) / 8, num_sms * 16);
+    cudaError_t e;
+#define SC_LAUNCH_SMALL(NQ)                                                                                            \
+    {                                                                                                                  \
+        auto kern = coarse_small_kernel<NQ>;                                                                           \
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e; \
+        kern<<<grid, 256, smem, st>>>(q, (int)nq, cent, nlist, ds, alpha, bias, scores);                               \
+    }
+    if (nq == 1) SC_LAUNCH_SMALL(1) else if (nq <= 4) SC_LAUNCH_SMALL(4) else SC_LAUNCH_SMALL(16)
+#undef SC_LAUNCH_SMALL
     return cudaGetLastError();
 }
 

@@ -148,6 +148,7 @@ struct sc_index {
     float *cent_hi = nullptr;    // [nlist, ds] tf32(c)           } 3xTF32 operands of the tcgen05
     float *cent_lo = nullptr;    // [nlist, ds] tf32(c - cent_hi) } coarse contraction (gemm_tc.cu)
     int coarse_impl = 0;         // 0 = tcgen05 3xTF32, 1 = fp32 SIMT (exact-fp32 reference kernel)
+    int small_coarse = 1;        // batches of <= 16 rows use coarse_small_kernel
     int tc_variant = 0;          // fused argmax tile: 0 = 256x256 (64 B swizzle), 1 = 128x256 (128 B swizzle)
 
     // paged lists
@@ -320,6 +321,13 @@ bool use_tc(const sc_index *ix) { return ix->coarse_impl == 0 && ix->ds >= 32; }
 // scores[m, nlist] = similarity to maximise (IP: x.c ; L2: 2 x.c - |c|^2) of device rows xd[m, ds]
 int coarse_scores(sc_index *ix, const float *xd, int64_t m, float *scores, cudaStream_t st) {
     const bool l2 = ix->metric == SC_METRIC_L2;
+    if (m <= 16 && ix->small_coarse) {  // tiny batches: stream the centroid table once, exact fp32
+        const cudaError_t e = launch_coarse_small(xd, m, ix->centroids, ix->nlist, ix->ds, l2 ? 2.f : 1.f,
+                                                  l2 ? ix->cnorm : nullptr, scores, ix->num_sms, st);
+        if (e == cudaSuccess) return SC_OK;
+        if (e != cudaErrorNotSupported) CU(e);
+        cudaGetLastError();
+    }
     if (!use_tc(ix)) {
         CU(launch_gemm_nt(xd, m, ix->centroids, ix->nlist, ix->ds, l2 ? ix->cnorm : nullptr, scores, st));
         return SC_OK;
@@ -1308,6 +1316,10 @@ int sc_index_set_param(sc_index_t *ix, const char *name, int64_t value) {
     if (strcmp(name, "scan_mode") == 0) {
         if (value < 0 || value > 2) return fail(SC_ERR_INVALID, "scan_mode: 0 = auto, 1 = query-major, 2 = list-major");
         ix->scan_mode = (int)value;
+        return SC_OK;
+    }
+    if (strcmp(name, "small_coarse") == 0) {
+        ix->small_coarse = value != 0;
         return SC_OK;
     }
     if (strcmp(name, "tc_variant") == 0) {

@@ -67,10 +67,15 @@ __global__ void __launch_bounds__(256, MINB) scan_pages_kernel(const ScanArgs a)
     const int64_t W = a.page_off[a.npairs];
     const int64_t nwarps = (int64_t)gridDim.x * wpb;
     const int64_t gw = (int64_t)blockIdx.x * wpb + warp;
-    const int64_t per = (W + nwarps - 1) / nwarps;
-    const int64_t w0 = gw * per;
-    const int64_t w1 = (w0 + per < W) ? (w0 + per) : W;
-    if (w0 >= w1) return;
+    // small batches: fewer pages than warps -> split every page into 2 or 4 row ranges so that all SMs stream
+    const int sub_shift = (W * 4 <= nwarps) ? 2 : ((W * 2 <= nwarps) ? 1 : 0);
+    const int part_rows = kPageRows >> sub_shift;
+    const int64_t units = W << sub_shift;
+    const int64_t per = (units + nwarps - 1) / nwarps;
+    const int64_t u0 = gw * per;
+    const int64_t u1 = (u0 + per < units) ? (u0 + per) : units;
+    if (u0 >= u1) return;
+    const int64_t w0 = u0 >> sub_shift;
 
     // pair that owns page w0: last i with page_off[i] <= w0 (pairs with no pages are skipped)
     int64_t lo = 0, hi = a.npairs;
@@ -89,7 +94,10 @@ __global__ void __launch_bounds__(256, MINB) scan_pages_kernel(const ScanArgs a)
     bool fresh = true;
     const int slab_mask = (1 << a.slab_shift) - 1;
 
-    for (int64_t w = w0; w < w1; ++w) {
+    for (int64_t u = u0; u < u1; ++u) {
+        const int64_t w = u >> sub_shift;
+        const uint32_t part = (uint32_t)(u & ((1 << sub_shift) - 1));
+        const uint32_t part_mask = (part_rows == 32 ? 0xffffffffu : ((1u << part_rows) - 1u)) << (part * part_rows);
         while (w >= pair_end) {
             ++pair;
             pair_start = pair_end;
@@ -117,9 +125,9 @@ __global__ void __launch_bounds__(256, MINB) scan_pages_kernel(const ScanArgs a)
         const int rows = min(kPageRows, len - j * kPageRows);
         const uint32_t tag = __ldg(a.slabs->tags[slab] + slot0 + lane);
         const bool live = lane < rows && filter_pass(a.filt, tag);
-        uint32_t m = __ballot_sync(0xffffffffu, live);
+        uint32_t m = __ballot_sync(0xffffffffu, live) & part_mask;
         float *cpage = a.cand + w * kPageRows;
-        if (!live) cpage[lane] = -INFINITY;
+        if (!live && ((part_mask >> lane) & 1u)) cpage[lane] = -INFINITY;
         const float4 *vbase = reinterpret_cast<const float4 *>(a.slabs->vec[slab]) + slot0 * ds4;
 
         while (m) {

@@ -420,6 +420,7 @@ def test_tensor_core_coarse_scores_have_fp32_accuracy(sb, orc, metric, d, nlist,
     q = rng.standard_normal((nq, d)).astype(np.float32)
     g = sb.IVFFlatIndex(d, nlist=nlist, metric=metric)
     g.set_centroids(cent)
+    g.set_param("small_coarse", 0)  # keep tiny batches on the contraction kernels under test here
     exact = orc.coarse_similarity(q, cent, metric, dtype=np.float64)
     scale = np.abs(q.astype(np.float64)) @ np.abs(cent.astype(np.float64)).T * (2 if metric == "L2" else 1)
     if metric == "L2":
@@ -543,3 +544,69 @@ def test_bulk_copy_list_major_tile_matches(sb, orc, metric):
         assert_topk_parity(d3, i3, d1, i1, f"bulk {metric} d={d}")
         rd, ri = orc.search(oidx, q, 10, 2, mask=orc.row_mask(oidx, removed_ids=ids[::13]), probes=probes)
         assert_topk_parity(d3, i3, rd, ri, f"bulk vs oracle {metric} d={d}")
+
+
+# ---- randomized shapes: every scan route against the oracle ---------------------------------------------
+def test_randomized_shapes_all_scan_routes(sb, orc):
+    rng = np.random.default_rng(20261018)
+    for trial in range(14):
+        d = int(rng.choice([4, 20, 64, 100, 128, 200, 256, 384, 768, 1024, 1536]))
+        n = int(rng.integers(200, 6000))
+        nlist = int(rng.integers(1, 48))
+        nq = int(rng.integers(1, 260))
+        nprobe = int(rng.integers(1, nlist + 1))
+        k = int(rng.choice([1, 5, 10, 64, 300]))
+        metric = "IP" if trial % 2 == 0 else "L2"
+        x = rng.standard_normal((n, d)).astype(np.float32)
+        q = rng.standard_normal((nq, d)).astype(np.float32)
+        # skewed list sizes: a few centroids attract most rows
+        cent = x[rng.integers(0, n, nlist)] * rng.uniform(0.2, 2.0, (nlist, 1)).astype(np.float32)
+        ids = rng.permutation(10 * n)[:n].astype(np.int64)
+        repo = rng.integers(0, 6, n).astype(np.uint32)
+        lang = rng.integers(0, 3, n).astype(np.uint8)
+        g, oidx, _ = build_pair(sb, orc, x, ids, cent, metric, repo, lang)
+        gone = ids[rng.random(n) < 0.05]
+        if gone.size:
+            g.remove_ids(gone)
+        use_filter = trial % 3 == 0
+        mask = orc.row_mask(oidx, repos=[1, 2, 4] if use_filter else None, langs=[0, 2] if use_filter else None,
+                            removed_ids=gone if gone.size else None)
+        probes = orc.coarse_probe(q, cent, metric, nprobe)
+        rd, ri = orc.search(oidx, q, k, nprobe, mask=mask, probes=probes)
+        kw = dict(repos=[1, 2, 4], langs=[0, 2]) if use_filter else {}
+        for mode in (1, 2):
+            g.set_param("scan_mode", mode)
+            gd, gi = g.search(q, k, lists=probes, **kw)
+            assert_topk_parity(gd, gi, rd, ri, f"trial {trial} mode {mode} {metric} d={d} n={n} nlist={nlist} nq={nq} "
+                                               f"nprobe={nprobe} k={k} filter={use_filter}")
+            assert_sorted(gd, gi, metric == "IP")
+        g.close()
+
+
+# ---- small batches: streamed coarse pass + sub-page split of the query-major scan -------------------------
+@pytest.mark.parametrize("metric", ["IP", "L2"])
+@pytest.mark.parametrize("d,nq", [(768, 1), (768, 3), (100, 16), (3072, 2), (30, 5)])
+def test_small_batch_path(sb, orc, metric, d, nq):
+    x, q, cent, ids = make_case(orc, 7000, d, 50, nq, metric, seed=d * 31 + nq)
+    g, oidx, _ = build_pair(sb, orc, x, ids, cent, metric)
+    exact = orc.coarse_similarity(q, cent, metric, dtype=np.float64)
+    lists, sc = g.probe(q, 11, with_scores=True)
+    want = orc.top_desc(exact, 11)
+    for r in range(nq):
+        if not np.array_equal(lists[r], want[r]):
+            assert np.allclose(np.sort(exact[r][lists[r]]), np.sort(exact[r][want[r]]), rtol=1e-5, atol=1e-6)
+        assert close(sc[r], exact[r][lists[r]].astype(np.float32)).all()
+    g.set_param("small_coarse", 0)
+    lists_tc = g.probe(q, 11)
+    assert np.mean([sorted(a) == sorted(b) for a, b in zip(lists, lists_tc)]) >= 0.5  # same ranking up to near-ties
+    g.set_param("small_coarse", 1)
+    for nprobe in (1, 4, 50):  # 3 .. 150 pages for one query: 4-, 2- and 1-way page splits
+        probes = orc.coarse_probe(q, cent, metric, nprobe)
+        rd, ri = orc.search(oidx, q, 10, nprobe, probes=probes)
+        g.set_param("scan_mode", 1)
+        gd, gi = g.search(q, 10, lists=probes)
+        assert_topk_parity(gd, gi, rd, ri, f"small batch {metric} d={d} nq={nq} nprobe={nprobe}")
+        gd2, gi2 = g.search(q, 10, lists=probes, repos=[0])
+        assert_topk_parity(gd2, gi2, rd, ri, "all rows carry repo tag 0")
+        gd3, gi3 = g.search(q, 10, lists=probes, repos=[7])
+        assert (gi3 == -1).all()
