@@ -25,7 +25,7 @@ from .index import KMEANS_NITER, KMEANS_SEED, metric_code
 
 class ShardedIVFFlat:
     def __init__(self, dim: int, nlist: int, metric="IP", device: Optional[int] = None, group=None,
-                 engine=None, merge: Optional[Callable] = None):
+                 engine=None, merge: Optional[Callable] = None, shard_by: str = "rows"):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialised (one process per GPU)")
         self.group = group
@@ -41,6 +41,13 @@ class ShardedIVFFlat:
             merge = merge or (lambda pd, pi, k: merge_topk(pd, pi, k, self.metric, device))
         if merge is None:
             raise ValueError("a custom engine needs a merge function")
+        if shard_by not in ("rows", "lists"):
+            raise ValueError("shard_by must be 'rows' or 'lists'")
+        # "rows":  every list's rows are dealt round-robin to the ranks (each rank holds 1/G of every list)
+        # "lists": list l lives entirely on rank l % G (whole lists per rank: longer per-rank lists, which the
+        #          list-major scan prefers; each query's probes are split over the ranks instead of its rows)
+        # Either way the union of the shards is exactly the single index, so merged results are identical.
+        self.shard_by = shard_by
         self.local = engine
         self._merge = merge
         self._next_row = 0  # global round-robin cursor, identical on every rank
@@ -90,6 +97,22 @@ class ShardedIVFFlat:
         """Every rank passes the SAME global batch; rank r keeps the rows whose global arrival
         number is congruent to r (round-robin deal), so each list is spread evenly."""
         n = x.shape[0]
+        if self.shard_by == "lists":
+            lists = self.local.assign(x)  # every rank ranks the whole batch; it keeps the rows of ITS lists
+            lists_np = lists.cpu().numpy() if torch.is_tensor(lists) else np.asarray(lists)
+            keep = np.flatnonzero(lists_np % self.world == self.rank)
+            if keep.size == 0:
+                return
+
+            def pick(a):
+                if a is None:
+                    return None
+                if torch.is_tensor(a):
+                    return a[torch.from_numpy(keep).to(a.device)].contiguous()
+                return np.ascontiguousarray(np.asarray(a)[keep])
+
+            self.local.add(pick(x), pick(ids), pick(repo_tags), pick(lang_tags), lists=lists_np[keep].astype(np.int32))
+            return
         first = (self.rank - self._next_row) % self.world
         sl = slice(first, n, self.world)
         self._next_row = (self._next_row + n) % self.world
@@ -138,7 +161,12 @@ class ShardedIVFFlat:
         q = q.to(dev, torch.float32)
         if self.world == 1:
             return self.local.search(q, k, nprobe=nprobe, repos=repos, langs=langs)
-        if shard_coarse and hasattr(self.local, "probe") and q.shape[0] >= 2 * self.world:
+        if self.shard_by == "lists":
+            probes = self.probe(q, nprobe) if q.shape[0] >= 2 * self.world else torch.as_tensor(
+                self.local.probe(q, min(int(nprobe), self.nlist)), device=dev)
+            mine = torch.where(probes % self.world == self.rank, probes, torch.full_like(probes, -1))  # -1 = skipped
+            d, i = self.local.search(q, k, repos=repos, langs=langs, lists=mine.contiguous())
+        elif shard_coarse and hasattr(self.local, "probe") and q.shape[0] >= 2 * self.world:
             d, i = self.local.search(q, k, repos=repos, langs=langs, lists=self.probe(q, nprobe))
         else:
             d, i = self.local.search(q, k, nprobe=nprobe, repos=repos, langs=langs)

@@ -31,8 +31,8 @@ def _worker(rank, world, port, ret):
         n, d, nlist, nq = 40000, 256, 128, 300
         x, q = unit_rows(rng, n, d), unit_rows(rng, nq, d)
         ids = np.arange(n, dtype=np.int64) * 5 + 2
-        for metric in ("IP", "L2"):
-            sh = ShardedIVFFlat(d, nlist, metric, device=rank)
+        for metric, shard_by in (("IP", "rows"), ("L2", "rows"), ("IP", "lists"), ("L2", "lists")):
+            sh = ShardedIVFFlat(d, nlist, metric, device=rank, shard_by=shard_by)
             obj = sh.train(torch.from_numpy(x[rank::world]).cuda(), niter=4, seed=3)
             # single-GPU Lloyd from the same initial centroids over ALL rows gives the same centroids
             from semcode_b200.index import kmeans_init_rows
@@ -51,9 +51,9 @@ def _worker(rank, world, port, ret):
             assert sh.ntotal == n
             rd, ri = one2.search(q, 10, nprobe=8)
             gd, gi = sh.search(q, 10, nprobe=8)
-            assert_topk_parity(gd.cpu().numpy(), gi.cpu().numpy(), rd, ri, f"sharded {metric}")
+            assert_topk_parity(gd.cpu().numpy(), gi.cpu().numpy(), rd, ri, f"sharded {metric} {shard_by}")
             gd, gi = sh.search(torch.from_numpy(q).cuda(), 10, nprobe=8, langs=[0])
-            assert_topk_parity(gd.cpu().numpy(), gi.cpu().numpy(), rd, ri, f"sharded filtered {metric}")
+            assert_topk_parity(gd.cpu().numpy(), gi.cpu().numpy(), rd, ri, f"sharded filtered {metric} {shard_by}")
         ret[rank] = "ok"
     except Exception:
         import traceback
