@@ -71,6 +71,9 @@ def parse_args():
     p.add_argument("--coarse-impl", type=int, default=0, help="0 = tcgen05 3xTF32, 1 = fp32 SIMT")
     p.add_argument("--scan-mode", type=int, default=0, help="0 = auto, 1 = query-major, 2 = list-major")
     p.add_argument("--lists-cfg", type=int, default=0, help="tile configuration of the list-major kernel")
+    p.add_argument("--shard-sim", type=int, default=1,
+                   help="single-GPU run over ONE rank's shard of a G-way row-sharded index (rows i with i %% G == 0 of the "
+                        "same stream, same centroids): what each rank of --gpus G scans, without the exchange")
     p.add_argument("--shard-by", default="rows", choices=["rows", "lists"],
                    help="N > 1: deal every list's rows round-robin (rows) or whole lists (list l on rank l %% N)")
     return p.parse_args()
@@ -294,6 +297,7 @@ def workload_config(args, nq_override=None):
                     f"(BASELINE.json configs[1])",
         "n": args.n, "dim": args.dim, "nlist": args.nlist, "nprobe": args.nprobe, "nq": nq_override or args.nq,
         "k": args.k, "metric": args.metric, "dataset": args.dataset, "shard_by": args.shard_by if args.gpus > 1 else None,
+        "shard_sim": args.shard_sim if args.shard_sim > 1 else None,
         "l2_policy": "inputs larger than L2: every step streams nq*nprobe lists (>> 126 MB) and rotates query batches",
     }
 
@@ -356,6 +360,8 @@ def run_ours(args):
             keep = torch.nonzero(lists % world == rank).squeeze(1)
             g.add(x[keep].contiguous(), ids[keep].contiguous(), lists=lists[keep].contiguous())
             del lists, keep
+        elif args.shard_sim > 1:
+            g.add(x[0::args.shard_sim].contiguous(), ids[0::args.shard_sim].contiguous())
         else:
             g.add(x, ids)
         del x, ids

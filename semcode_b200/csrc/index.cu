@@ -1309,7 +1309,7 @@ int sc_index_set_param(sc_index_t *ix, const char *name, int64_t value) {
         return SC_OK;
     }
     if (strcmp(name, "lists_cfg") == 0) {
-        if (value < 0 || value > 3) return fail(SC_ERR_INVALID, "lists_cfg must be in [0,3]");
+        if (value < 0 || value > 2) return fail(SC_ERR_INVALID, "lists_cfg must be in [0,2]");
         ix->lists_cfg = (int)value;
         return SC_OK;
     }

@@ -41,7 +41,11 @@ __global__ void count_list_pairs_kernel(const int32_t *__restrict__ probe, int64
     if (l >= 0 && l < nlist && list_len[l] > 0) atomicAdd(cnt + l, 1);
 }
 
-__global__ void plan_items_kernel(const int32_t *__restrict__ cnt, int32_t nlist, int32_t *__restrict__ n32,
+// A list probed by c queries becomes c / 32 tile items of 32 queries plus a remainder:
+//   rem > rem8_max  one more (ragged) 32-query tile item: FP32-bound, ~2.8 list reads of time
+//   rem 5..rem8_max ceil(rem / 8) passes of the 8-query page scan (n8 = passes)
+//   rem 1..4        one pass of the 4-query page scan
+__global__ void plan_items_kernel(const int32_t *__restrict__ cnt, int32_t nlist, int32_t rem8_max, int32_t *__restrict__ n32,
                                   int32_t *__restrict__ n8, int32_t *__restrict__ n4, const int32_t *__restrict__ list_len,
                                   unsigned long long *__restrict__ unique_rows) {
     const int32_t l = blockIdx.x * blockDim.x + threadIdx.x;
@@ -50,10 +54,10 @@ __global__ void plan_items_kernel(const int32_t *__restrict__ cnt, int32_t nlist
     if (unique_rows != nullptr && c > 0) atomicAdd(unique_rows, (unsigned long long)list_len[l]);
     int32_t a = c / 32, b = 0, d = 0;
     const int32_t rem = c - a * 32;
-    if (rem > 8)
-        ++a;  // a ragged 32-chunk costs less than re-reading the list for several 8-chunks
+    if (rem > rem8_max)
+        ++a;
     else if (rem > 4)
-        b = 1;
+        b = (rem + 7) / 8;
     else if (rem > 0)
         d = 1;
     n32[l] = a;
@@ -150,7 +154,7 @@ __global__ void __launch_bounds__(NT, 2) scan_lists_kernel(const ScanArgs a, con
     const int qg = (warp % C::WPK) % C::QG;         // query group (8 queries)
     const int rg = (warp % C::WPK) / C::QG;         // row group
     const int row0 = rg * 32 * C::RPT + lane;       // rows row0 + 32*i
-    const int32_t *item_off = QT == 32 ? p.off32 : (QT == 8 ? p.off8 : p.off4);
+    const int32_t *item_off = QT == 32 ? p.off32 : p.off8;
     const int32_t total = item_off[p.nlist];
     const int ds = a.ds;
     const int KB = (ds + BKX - 1) / BKX;
@@ -327,7 +331,7 @@ __global__ void __launch_bounds__(NT, 2) scan_lists_kernel(const ScanArgs a, con
 template <int QT, int BKX, int NS, int RB, int RPT>
 cudaError_t launch_lists_variant(const ScanArgs &a, const ListPlan &p, int num_sms, cudaStream_t st) {
     const size_t smem = sizeof(TileSmem<QT, BKX, NS, RB, RPT>);
-    const int which = QT == 32 ? 0 : (QT == 8 ? 1 : 2);
+    const int which = QT == 32 ? 0 : 1;
     const int per_sm = smem * 2 + 2048 <= 227 * 1024 ? 2 : 1;
     cudaError_t e;
     if (a.metric == 1) {
@@ -346,9 +350,11 @@ cudaError_t launch_lists_variant(const ScanArgs &a, const ListPlan &p, int num_s
 
 }  // namespace
 
-cudaError_t launch_scan_lists8_bulk(const ScanArgs &a, const ListPlan &p, int num_sms, cudaStream_t st);
-cudaError_t launch_scan_mq(const ScanArgs &a, const ListPlan &p, int32_t *pages, int32_t *pgoff, int num_sms, cudaStream_t st);
+cudaError_t launch_scan_mq(const ScanArgs &a, const ListPlan &p, int bucket, int32_t *pages, int32_t *pgoff, int num_sms,
+                           cudaStream_t st);
 
+// cfg selects experiments: 0 = default; 1 = cp.async tile kernel (QT = 8) for remainders of 5..8 queries instead of
+// the 8-query page scan; 2 = 32-float stages for the 32-query tile
 cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int num_sms, int *launches, cudaStream_t st) {
     if (a.npairs <= 0) return cudaSuccess;
     if (a.npairs > (int64_t)INT32_MAX) return cudaErrorInvalidValue;
@@ -358,52 +364,36 @@ cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int
     if ((e = cudaMemsetAsync(p.cursor, 0, (size_t)p.nlist * 4, st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(p.counters, 0, 16, st)) != cudaSuccess) return e;
     count_list_pairs_kernel<<<pb, 256, 0, st>>>(a.probe, a.npairs, a.list_len, p.nlist, p.cnt);
-    plan_items_kernel<<<lb, 256, 0, st>>>(p.cnt, p.nlist, p.n32, p.n8, p.n4, a.list_len, p.unique_rows);
+    plan_items_kernel<<<lb, 256, 0, st>>>(p.cnt, p.nlist, cfg == 1 ? 8 : 16, p.n32, p.n8, p.n4, a.list_len, p.unique_rows);
     if ((e = launch_exclusive_scan_i32(p.cnt, p.nlist, p.lq_off, st)) != cudaSuccess) return e;
     if ((e = launch_exclusive_scan_i32(p.n32, p.nlist, p.off32, st)) != cudaSuccess) return e;
-    if ((e = launch_exclusive_scan_i32(p.n8, p.nlist, p.off8, st)) != cudaSuccess) return e;
-    if ((e = launch_exclusive_scan_i32(p.n4, p.nlist, p.off4, st)) != cudaSuccess) return e;
+    if (cfg == 1 && (e = launch_exclusive_scan_i32(p.n8, p.nlist, p.off8, st)) != cudaSuccess) return e;
     fill_list_pairs_kernel<<<pb, 256, 0, st>>>(a.probe, a.npairs, a.list_len, p.nlist, p.lq_off, p.cursor, p.lq);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    // tile configurations <QT, floats per k-stage, pipeline stages>; cfg picks the experiment (0 = default)
-    // Three independent consumers of the plan.  The tile kernels (lists probed by > 4 queries) usually hold few,
-    // long items; the page scan (<= 4 queries) holds most of the bytes.  With side streams the tile kernels are
-    // launched first and the page scan fills the SMs they leave free, instead of three kernels back to back.
-    // cfg selects experiments: 1 = 4-query cp.async tile instead of the page scan, 2 = 32-float stages for the
-    // 32-query tile, 3 = bulk-copy/mbarrier kernel (scan_lists_bulk.cu) for the 8-query tile.
-    const bool fork = p.side[0] != nullptr && p.side[1] != nullptr;
-    cudaStream_t s32 = fork ? p.side[0] : st, s8 = fork ? p.side[1] : st;
+    // Three consumers of the plan.  The 32-query tile kernel holds the FP32-bound items (lists probed by many
+    // queries); the two page scans hold the HBM-bound remainders, every warp an equal share of the pages, so they
+    // have no tail however few lists a bucket holds.  With side streams the tile kernel is launched first and the
+    // page scans fill the SMs it leaves free.
+    const bool fork = p.side[0] != nullptr;
+    cudaStream_t s32 = fork ? p.side[0] : st;
     if (fork) {
         if ((e = cudaEventRecord(p.ev_fork, st)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(s32, p.ev_fork, 0)) != cudaSuccess) return e;
-        if ((e = cudaStreamWaitEvent(s8, p.ev_fork, 0)) != cudaSuccess) return e;
     }
     if (cfg == 2) {
         if ((e = launch_lists_variant<32, 32, 3, 128, 4>(a, p, num_sms, s32)) != cudaSuccess) return e;
     } else {
         if ((e = launch_lists_variant<32, 64, 2, 128, 4>(a, p, num_sms, s32)) != cudaSuccess) return e;
     }
-    e = cfg == 3 ? launch_scan_lists8_bulk(a, p, num_sms, s8) : cudaErrorNotSupported;
-    if (e == cudaErrorNotSupported) {
-        cudaGetLastError();
-        e = launch_lists_variant<8, 64, 2, 128, 2>(a, p, num_sms, s8);
-    }
-    if (e != cudaSuccess) return e;
-    if (fork) {
-        if ((e = cudaEventRecord(p.ev_join[0], s32)) != cudaSuccess) return e;
-        if ((e = cudaEventRecord(p.ev_join[1], s8)) != cudaSuccess) return e;
-    }
-    // lists probed by <= 4 queries: multi-query page scan (scan_mq.cu)
-    if (cfg == 1 || a.ds > 1024) {  // (the per-warp query slice of the page scan is 16 * dim bytes of shared memory)
-        if ((e = launch_lists_variant<4, 64, 2, 128, 2>(a, p, num_sms, st)) != cudaSuccess) return e;
+    if (fork && (e = cudaEventRecord(p.ev_join[0], s32)) != cudaSuccess) return e;
+    if (cfg == 1) {
+        if ((e = launch_lists_variant<8, 64, 2, 128, 2>(a, p, num_sms, st)) != cudaSuccess) return e;
     } else {
-        if ((e = launch_scan_mq(a, p, p.mq_pages, p.mq_pgoff, num_sms, st)) != cudaSuccess) return e;
+        if ((e = launch_scan_mq(a, p, 1, p.mq_pages, p.mq_pgoff, num_sms, st)) != cudaSuccess) return e;
     }
-    if (fork) {
-        if ((e = cudaStreamWaitEvent(st, p.ev_join[0], 0)) != cudaSuccess) return e;
-        if ((e = cudaStreamWaitEvent(st, p.ev_join[1], 0)) != cudaSuccess) return e;
-    }
-    if (launches) *launches += 10;
+    if ((e = launch_scan_mq(a, p, 0, p.mq_pages, p.mq_pgoff, num_sms, st)) != cudaSuccess) return e;
+    if (fork && (e = cudaStreamWaitEvent(st, p.ev_join[0], 0)) != cudaSuccess) return e;
+    if (launches) *launches += 12;
     return cudaSuccess;
 }
 

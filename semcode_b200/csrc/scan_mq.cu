@@ -1,27 +1,34 @@
 // K5c: multi-query page scan -- the HBM-bound end of the list-major path.
 //
-// A list that is probed by only 1..4 queries of the batch is streamed ONCE, exactly the way the
-// query-major kernel (scan.cu) streams it -- persistent warps with equal page ranges, 128-bit
-// ld.global.nc.L1::no_allocate loads, R rows x U float4 per lane in flight, fused tag predicate --
-// and every row is scored against all of the list's queries (staged in the warp's shared-memory
-// slice) before the registers are recycled.  Compared with the shared-memory tiles of scan_lists.cu
-// this keeps ~100 KB of loads in flight per SM with no CTA barrier, which is what the 4.3 TB/s ceiling
-// of the cp.async tiles was missing.  Results go to the same per-pair candidate layout.
+// A list whose remainder group holds 1..MQ queries of the batch is streamed ONCE per group, exactly the way
+// the query-major kernel (scan.cu) streams it -- persistent warps with equal page ranges, 128-bit
+// ld.global.nc.L1::no_allocate loads, R rows x U float4 per lane in flight, fused tag predicate -- and every
+// row is scored against all MQ queries of the group before the registers are recycled.
+//
+//   bucket 0: MQ = 4, R = 2, U <= 6   lists with 1..4 (remaining) queries, one pass
+//   bucket 1: MQ = 8, R = 4, U <= 3   lists with 5..16 (remaining) queries, one or two passes of 8
+//
+// The vector dimension is cut into SLICES of 32*U float4 (<= 768 floats for MQ = 4, <= 384 for MQ = 8), so the
+// per-warp query stage is MQ * 32*U * 16 B <= 12 KB whatever the dimension is (16 warps per SM at dim 3072 as
+// at dim 768).  Per (page, slice) the warp stages the MQ query slices from L2, streams the slice of every live
+// row of the page, reduces the R*MQ partial sums with one transposing butterfly (31 shuffles for 32 sums
+// instead of 160) and adds them into a per-warp [MQ][32] shared-memory page accumulator; the finished page is
+// written to the candidate array with coalesced 128-byte stores.  A single-slice dimension (768 with MQ = 4)
+// stages its queries once per list.
 // Replaces the same FAISS IVFFlatScanner::scan_codes loop (reference src/semcode/storage/milvus_store.py:141-147).
-// Algorithmic bytes: rows of each list x 4 x dim, once (compulsory).
+// Algorithmic bytes: rows of each list x 4 x dim, once per pass (compulsory for one pass).
 #include "common.cuh"
 
 namespace sc {
 
 namespace {
 
-constexpr int MQ = 4;  // queries per pass
-
-__global__ void mq_pages_kernel(const int32_t *__restrict__ n4, const int32_t *__restrict__ list_len, int32_t nlist,
+// units[l] = pages(l) * passes(l)   (passes = n4[l] for bucket 0, n8[l] for bucket 1)
+__global__ void mq_pages_kernel(const int32_t *__restrict__ passes, const int32_t *__restrict__ list_len, int32_t nlist,
                                 int32_t *__restrict__ pages) {
     const int32_t l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nlist) return;
-    pages[l] = n4[l] ? (list_len[l] + kPageRows - 1) / kPageRows : 0;
+    pages[l] = passes[l] * ((list_len[l] + kPageRows - 1) / kPageRows);
 }
 
 template <bool L2>
@@ -41,15 +48,54 @@ __device__ __forceinline__ float mq_accum4(float acc, const float4 &x, const flo
     return acc;
 }
 
-// pgoff [nlist+1]: exclusive prefix of the pages of the lists handled here (0 for the others)
-template <int R, int U, bool L2, bool EXACT>
-__global__ void __launch_bounds__(256, 2) scan_mq_kernel(const ScanArgs a, const ListPlan p, const int32_t *__restrict__ pgoff) {
+// Sum each of v[0..N) over the 32 lanes; returns, in lane L, the total of v[L / (32 / N)]  (N = 8 or 32).
+// Halving exchange: at offset o the upper lanes keep the upper half of the live values and send the lower half.
+template <int N>
+__device__ __forceinline__ float reduce_transpose(float (&v)[N], int lane) {
+    int o = 16;
+#pragma unroll
+    for (int n = N; n > 1; n >>= 1, o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const float send = up ? v[i] : v[i + n / 2];
+            const float keep = up ? v[i + n / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    float r = v[0];
+#pragma unroll
+    for (int oo = (32 / N) >> 1; oo > 0; oo >>= 1) r += __shfl_xor_sync(0xffffffffu, r, oo);
+    return r;
+}
+
+constexpr int kTotLd = 33;  // page accumulator [MQ][33]: row-major over rows, one pad word per query
+
+// per-warp shared memory: query slices [MQ][32*U] float4 | candidate bases [MQ] int64 | query pointers [MQ] |
+// page accumulator [MQ][33] float
+template <int MQ, int U>
+__host__ __device__ constexpr size_t mq_warp_floats() {
+    return ((size_t)MQ * 32 * U * 4 + (size_t)MQ * 4 + (size_t)MQ * kTotLd + 3) / 4 * 4;
+}
+
+// pgoff [nlist+1]: exclusive prefix of the units (pages x passes) of the lists handled here (0 for the others)
+template <int MQ, int R, int U, bool L2, bool EXACT>
+__global__ void __launch_bounds__(256, 2)
+    scan_mq_kernel(const ScanArgs a, const ListPlan p, const int32_t *__restrict__ pgoff) {
     extern __shared__ __align__(16) float4 qsmem[];
+    constexpr int N = R * MQ;
+    constexpr int SL4 = 32 * U;  // float4 per slice
+    static_assert(N == 8 || N == 32, "reduce_transpose covers 8 or 32 partial sums");
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int wpb = blockDim.x >> 5;
     const int ds4 = a.ds >> 2;
-    float4 *qs = qsmem + (size_t)warp * MQ * ds4;  // [MQ][ds4]
+    const int nslices = (ds4 + SL4 - 1) / SL4;
+    constexpr size_t WF = mq_warp_floats<MQ, U>();  // floats per warp, 16-byte multiple
+    float4 *qs = qsmem + (size_t)warp * (WF / 4);                                 // [MQ][SL4]
+    int64_t *cbs = reinterpret_cast<int64_t *>(qs + MQ * SL4);                    // [MQ] candidate base or -1
+    const float4 **qgs = reinterpret_cast<const float4 **>(cbs + MQ);             // [MQ] query row or nullptr
+    float *tot = reinterpret_cast<float *>(qgs + MQ);                             // [MQ][kTotLd]
 
     const int32_t W = pgoff[p.nlist];
     const int64_t nwarps = (int64_t)gridDim.x * wpb;
@@ -60,7 +106,7 @@ __global__ void __launch_bounds__(256, 2) scan_mq_kernel(const ScanArgs a, const
     const int32_t w0 = (int32_t)w0l;
     const int32_t w1 = (w0 + per < W) ? (w0 + per) : W;
 
-    // list that owns page w0: last l with pgoff[l] <= w0 (lists without pages are skipped)
+    // list that owns unit w0: last l with pgoff[l] <= w0 (lists without units are skipped)
     int32_t lo = 0, hi = p.nlist;
     while (hi - lo > 1) {
         const int32_t mid = (lo + hi) >> 1;
@@ -71,70 +117,88 @@ __global__ void __launch_bounds__(256, 2) scan_mq_kernel(const ScanArgs a, const
     }
     int32_t l = lo;
     int32_t l_start = pgoff[l], l_end = pgoff[l + 1];
-    int32_t len = 0, ptbase = 0, nqi = 0;
-    int64_t cb[MQ];
-#pragma unroll
-    for (int j = 0; j < MQ; ++j) cb[j] = -1;
-    bool fresh = true;
+    int32_t len = 0, ptbase = 0, npg = 1, cur_pass = -1;
+    bool new_list = true;
     const int slab_mask = (1 << a.slab_shift) - 1;
+    // which (row, query) total this lane receives from reduce_transpose
+    const int my_idx = lane / (32 / N);
+    const int my_r = my_idx / MQ, my_j = my_idx % MQ;
+    const bool my_owner = (lane % (32 / N)) == 0;
 
     for (int32_t w = w0; w < w1; ++w) {
         while (w >= l_end) {
             ++l;
             l_start = l_end;
             l_end = pgoff[l + 1];
-            fresh = true;
+            new_list = true;
         }
-        if (fresh) {
-            fresh = false;
+        if (new_list) {
+            new_list = false;
             len = a.list_len[l];
             ptbase = a.pt_off[l];
-            const int32_t qbase = p.lq_off[l] + 32 * p.n32[l];
-            nqi = min(MQ, p.lq_off[l + 1] - qbase);
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < MQ; ++j) {
-                cb[j] = -1;
-                if (j < nqi) {
-                    const int32_t pair = p.lq[qbase + j];
-                    cb[j] = a.page_off[pair] * kPageRows;
-                    const float4 *qg = reinterpret_cast<const float4 *>(a.q + (int64_t)(pair / a.nprobe) * a.ds);
-                    for (int c = lane; c < ds4; c += 32) qs[j * ds4 + c] = __ldg(qg + c);
-                } else {
-                    for (int c = lane; c < ds4; c += 32) qs[j * ds4 + c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            npg = (len + kPageRows - 1) / kPageRows;
+            cur_pass = -1;
+        }
+        const int32_t ul = w - l_start;
+        const int32_t pass = ul / npg;
+        const int32_t jpage = ul - pass * npg;
+        bool restage = nslices > 1;
+        if (pass != cur_pass) {
+            cur_pass = pass;
+            restage = true;
+            const int32_t qbase = p.lq_off[l] + 32 * p.n32[l] + MQ * pass;
+            const int nqi = min(MQ, p.lq_off[l + 1] - qbase);
+            __syncwarp();  // the previous pass's readers are done with cbs / qgs
+            if (lane < MQ) {
+                int64_t cb = -1;
+                const float4 *qg = nullptr;
+                if (lane < nqi) {
+                    const int32_t pair = p.lq[qbase + lane];
+                    cb = a.page_off[pair] * kPageRows;
+                    qg = reinterpret_cast<const float4 *>(a.q + (int64_t)(pair / a.nprobe) * a.ds);
                 }
+                cbs[lane] = cb;
+                qgs[lane] = qg;
             }
             __syncwarp();
         }
-        const int32_t jpage = w - l_start;
         const int32_t page = __ldg(a.pt + ptbase + jpage);
         const int slab = page >> a.slab_shift;
         const int64_t slot0 = (int64_t)(page & slab_mask) * kPageRows;
         const int rows = min(kPageRows, len - jpage * kPageRows);
         const uint32_t tag = __ldg(a.slabs->tags[slab] + slot0 + lane);
         const bool live = lane < rows && filter_pass(a.filt, tag);
-        uint32_t m = __ballot_sync(0xffffffffu, live);
+        const uint32_t live_mask = __ballot_sync(0xffffffffu, live);
         const int64_t poff = (int64_t)jpage * kPageRows;
-        if (!live) {
-#pragma unroll
-            for (int j = 0; j < MQ; ++j)
-                if (cb[j] >= 0) a.cand[cb[j] + poff + lane] = -INFINITY;
-        }
         const float4 *vbase = reinterpret_cast<const float4 *>(a.slabs->vec[slab]) + slot0 * ds4;
+#pragma unroll
+        for (int j = 0; j < MQ; ++j) tot[j * kTotLd + lane] = 0.f;
 
-        while (m) {
-            int row[R];
+        for (int s = 0; s < nslices; ++s) {
+            const int c0 = s * SL4;
+            if (restage) {
+                __syncwarp();  // the previous slice's readers are done with qs
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                row[r] = m ? (__ffs(m) - 1) : -1;
-                m &= m - 1;
+                for (int j = 0; j < MQ; ++j) {
+                    const float4 *qg = qgs[j];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int c = c0 + lane + 32 * u;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (qg != nullptr && (EXACT || c < ds4)) v = __ldg(qg + c);
+                        qs[j * SL4 + lane + 32 * u] = v;
+                    }
+                }
             }
-            float acc[R][MQ];
+            __syncwarp();  // qs and the zeroed / partial tot visible to the whole warp
+            uint32_t m = live_mask;
+            while (m) {
+                int row[R];
 #pragma unroll
-            for (int r = 0; r < R; ++r)
-#pragma unroll
-                for (int j = 0; j < MQ; ++j) acc[r][j] = 0.f;
-            for (int c0 = 0; c0 < ds4; c0 += 32 * U) {
+                for (int r = 0; r < R; ++r) {
+                    row[r] = m ? (__ffs(m) - 1) : -1;
+                    m &= m - 1;
+                }
                 float4 x[R][U];
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
@@ -147,58 +211,77 @@ __global__ void __launch_bounds__(256, 2) scan_mq_kernel(const ScanArgs a, const
                             x[r][u] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
+                float acc[N];
+#pragma unroll
+                for (int i = 0; i < N; ++i) acc[i] = 0.f;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const bool kin = EXACT || c0 + lane + 32 * u < ds4;
 #pragma unroll
                     for (int j = 0; j < MQ; ++j) {
-                        float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (kin) qv = qs[j * ds4 + c0 + lane + 32 * u];
-                        if (L2 && !kin) continue;  // padded lanes: x == q == 0 anyway
+                        const float4 qv = qs[j * SL4 + lane + 32 * u];
 #pragma unroll
-                        for (int r = 0; r < R; ++r) acc[r][j] = mq_accum4<L2>(acc[r][j], x[r][u], qv);
+                        for (int r = 0; r < R; ++r) acc[r * MQ + j] = mq_accum4<L2>(acc[r * MQ + j], x[r][u], qv);
                     }
                 }
+                const float t = reduce_transpose<N>(acc, lane);
+                int myrow = row[0];
+#pragma unroll
+                for (int r = 1; r < R; ++r)
+                    if (my_r == r) myrow = row[r];
+                if (my_owner && myrow >= 0) tot[my_j * kTotLd + myrow] += t;  // one owner per (row, query): no race
             }
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-#pragma unroll
-                for (int j = 0; j < MQ; ++j) {
-                    const float s = warp_sum(acc[r][j]);
-                    if (lane == 0 && row[r] >= 0 && cb[j] >= 0) a.cand[cb[j] + poff + row[r]] = L2 ? -s : s;
-                }
+            restage = nslices > 1;
         }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < MQ; ++j) {
+            const int64_t cb = cbs[j];
+            if (cb >= 0) {
+                const float v = tot[j * kTotLd + lane];
+                a.cand[cb + poff + lane] = live ? (L2 ? -v : v) : -INFINITY;
+            }
+        }
+        __syncwarp();  // tot is re-zeroed for the next page
     }
 }
 
-template <int R, int U, bool L2, bool EXACT>
+template <int MQ, int R, int U, bool L2, bool EXACT>
 cudaError_t launch_mq_variant(const ScanArgs &a, const ListPlan &p, const int32_t *pgoff, int num_sms, cudaStream_t st) {
-    auto kern = scan_mq_kernel<R, U, L2, EXACT>;
-    const size_t per_warp = (size_t)MQ * a.ds * sizeof(float);
-    int wpb = 8;
-    while (wpb > 1 && per_warp * wpb > (size_t)100 * 1024) wpb >>= 1;
-    const size_t smem = per_warp * wpb;
-    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    auto kern = scan_mq_kernel<MQ, R, U, L2, EXACT>;
+    constexpr size_t per_warp = mq_warp_floats<MQ, U>() * sizeof(float);
+    constexpr int wpb = 8;
+    constexpr size_t smem = per_warp * wpb;
+    static_assert(2 * (smem + 1024) <= 227 * 1024, "two CTAs per SM must fit");
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<num_sms * 2, wpb * 32, smem, st>>>(a, p, pgoff);
     return cudaGetLastError();
 }
 
+template <int MQ, int R, int U, bool EXACT>
+cudaError_t launch_mq_metric(const ScanArgs &a, const ListPlan &p, const int32_t *pgoff, int num_sms, cudaStream_t st) {
+    return a.metric == 1 ? launch_mq_variant<MQ, R, U, true, EXACT>(a, p, pgoff, num_sms, st)
+                         : launch_mq_variant<MQ, R, U, false, EXACT>(a, p, pgoff, num_sms, st);
+}
+
 }  // namespace
 
-// scratch: pages [nlist], pgoff [nlist+1] (int32)
-cudaError_t launch_scan_mq(const ScanArgs &a, const ListPlan &p, int32_t *pages, int32_t *pgoff, int num_sms, cudaStream_t st) {
-    mq_pages_kernel<<<(p.nlist + 255) / 256, 256, 0, st>>>(p.n4, a.list_len, p.nlist, pages);
+// bucket 0: lists with p.n4[l] passes of <= 4 queries; bucket 1: p.n8[l] passes of <= 8 queries.
+// scratch: pages [nlist], pgoff [nlist+1] (int32), reused by consecutive launches on the same stream
+cudaError_t launch_scan_mq(const ScanArgs &a, const ListPlan &p, int bucket, int32_t *pages, int32_t *pgoff, int num_sms,
+                           cudaStream_t st) {
+    mq_pages_kernel<<<(p.nlist + 255) / 256, 256, 0, st>>>(bucket == 0 ? p.n4 : p.n8, a.list_len, p.nlist, pages);
     cudaError_t e = launch_exclusive_scan_i32(pages, p.nlist, pgoff, st);
     if (e != cudaSuccess) return e;
     const int ds4 = a.ds >> 2;
-    const bool l2 = a.metric == 1;
-    if (ds4 % 192 == 0)
-        return l2 ? launch_mq_variant<2, 6, true, true>(a, p, pgoff, num_sms, st) : launch_mq_variant<2, 6, false, true>(a, p, pgoff, num_sms, st);
-    if (ds4 % 128 == 0)
-        return l2 ? launch_mq_variant<2, 4, true, true>(a, p, pgoff, num_sms, st) : launch_mq_variant<2, 4, false, true>(a, p, pgoff, num_sms, st);
-    return l2 ? launch_mq_variant<2, 4, true, false>(a, p, pgoff, num_sms, st) : launch_mq_variant<2, 4, false, false>(a, p, pgoff, num_sms, st);
+    if (bucket == 0) {
+        if (ds4 % 192 == 0) return launch_mq_metric<4, 2, 6, true>(a, p, pgoff, num_sms, st);
+        if (ds4 % 128 == 0) return launch_mq_metric<4, 2, 4, true>(a, p, pgoff, num_sms, st);
+        return launch_mq_metric<4, 2, 4, false>(a, p, pgoff, num_sms, st);
+    }
+    if (ds4 % 96 == 0) return launch_mq_metric<8, 4, 3, true>(a, p, pgoff, num_sms, st);
+    if (ds4 % 64 == 0) return launch_mq_metric<8, 4, 2, true>(a, p, pgoff, num_sms, st);
+    return launch_mq_metric<8, 4, 3, false>(a, p, pgoff, num_sms, st);
 }
 
 }  // namespace sc

@@ -522,28 +522,33 @@ def test_list_major_auto_mode_full_search(sb, orc):
     g.set_profiling(True)
     g.set_param("scan_mode", 0)
     g.search(q, 10, nprobe=12)
-    assert g.last_search_times().scan_launches == 10  # plan kernels + the three tile variants
+    assert g.last_search_times().scan_launches == 12  # plan kernels + the 32-query tile + the two page scans
     g.set_param("scan_mode", 1)
     g.search(q, 10, nprobe=12)
     assert g.last_search_times().scan_launches == 1
 
 
 @pytest.mark.parametrize("metric", ["IP", "L2"])
-def test_bulk_copy_list_major_tile_matches(sb, orc, metric):
-    """lists_cfg = 3: the cp.async.bulk / mbarrier variant of the 8-query tile (dim % 128 == 0, <= 1024)."""
-    for d in (128, 768, 1024):
-        x, q, cent, ids = make_case(orc, 4000, d, 24, 90, metric, seed=d)
+@pytest.mark.parametrize("per_list", [3, 7, 13])
+def test_multi_query_page_scan_buckets_and_slices(sb, orc, metric, per_list):
+    """The two multi-query page scans (scan_mq.cu): remainders of 1..4 queries (bucket 0), 5..16 queries in one or
+    two passes of 8 (bucket 1), over single-slice, multi-slice and ragged-slice dimensions; also the cp.async tile
+    kept as lists_cfg = 1."""
+    for d in (128, 200, 768, 1024, 2048, 3072):
+        n = 3000 if d <= 1024 else 1500
+        x, q, cent, ids = make_case(orc, n, d, 24, 12 * per_list, metric, seed=d + per_list)
         g, oidx, _ = build_pair(sb, orc, x, ids, cent, metric)
         g.remove_ids(ids[::13])
-        probes = orc.coarse_probe(q, cent, metric, 2)  # ~7.5 queries per list: 8-query items dominate
+        probes = orc.coarse_probe(q, cent, metric, 2)  # ~per_list queries per list
         g.set_param("scan_mode", 1)
         d1, i1 = g.search(q, 10, lists=probes)
-        g.set_param("scan_mode", 2)
-        g.set_param("lists_cfg", 3)
-        d3, i3 = g.search(q, 10, lists=probes)
-        assert_topk_parity(d3, i3, d1, i1, f"bulk {metric} d={d}")
         rd, ri = orc.search(oidx, q, 10, 2, mask=orc.row_mask(oidx, removed_ids=ids[::13]), probes=probes)
-        assert_topk_parity(d3, i3, rd, ri, f"bulk vs oracle {metric} d={d}")
+        for cfg in (0, 1):
+            g.set_param("scan_mode", 2)
+            g.set_param("lists_cfg", cfg)
+            d3, i3 = g.search(q, 10, lists=probes)
+            assert_topk_parity(d3, i3, d1, i1, f"mq cfg={cfg} {metric} d={d}")
+            assert_topk_parity(d3, i3, rd, ri, f"mq cfg={cfg} vs oracle {metric} d={d}")
 
 
 # ---- randomized shapes: every scan route against the oracle ---------------------------------------------
