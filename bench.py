@@ -74,6 +74,9 @@ def parse_args():
     p.add_argument("--shard-sim", type=int, default=1,
                    help="single-GPU run over ONE rank's shard of a G-way row-sharded index (rows i with i %% G == 0 of the "
                         "same stream, same centroids): what each rank of --gpus G scans, without the exchange")
+    p.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
+                   help="N > 1: p2p = probe rows and partial top-k stored straight into the peers' buffers by the kernels "
+                        "that produce them (NVLink peer memory), merge kernel waits on flags; nccl = all-gathers + merge")
     p.add_argument("--shard-by", default="rows", choices=["rows", "lists"],
                    help="N > 1: deal every list's rows round-robin (rows) or whole lists (list l on rank l %% N)")
     return p.parse_args()
@@ -385,7 +388,26 @@ def run_ours(args):
     probe_mine = torch.full((per, min(nprobe, nlist)), -1, dtype=torch.int32, device=dev)
     probe_all = torch.empty((world * per, min(nprobe, nlist)), dtype=torch.int32, device=dev)
 
+    ex, ex_err = None, None
+    if world > 1 and args.exchange != "nccl" and args.shard_by == "rows":
+        ok = torch.zeros(1, dtype=torch.int32, device=dev)
+        try:
+            from semcode_b200.index import PeerExchange
+
+            ex = PeerExchange(local, None, 64 << 20)
+            ok += 1
+        except Exception as e:
+            ex_err = f"{type(e).__name__}: {e}"
+        dist.all_reduce(ok)
+        if int(ok.item()) != world:
+            ex = None
+            if args.exchange == "p2p":
+                raise SystemExit(f"--exchange p2p: peer-memory exchange unavailable ({ex_err})")
+
     def search_sharded(qs):
+        if ex is not None:  # ONE C-ABI call: split coarse pass + probe scatter + scan + top-k scatter + waiting merge
+            g.search(qs, k, nprobe=nprobe, out=(out_d, out_i), exchange=ex)
+            return out_d, out_i
         # the coarse pass is split over the ranks too (centroids are replicated): rank r ranks the centroids
         # for its 1/G of the batch, one small all-gather distributes the probe table
         if my_hi > my_lo:
@@ -467,7 +489,8 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
     ms_total = float(ms_total.item())
-    launches_per_step = t.total_launches + (4 if world > 1 else 0)  # + coarse split (gemm, select, split) and merge
+    # NCCL route: + coarse split (gemm, select, split) and merge launched from here; the fused route counts its own
+    launches_per_step = t.total_launches + (4 if world > 1 and ex is None else 0)
     # per-phase distribution over a few profiled steps (same inputs; outside the headline timing)
     unique_rows = []
     for i in range(min(args.steps, 8)):
@@ -573,6 +596,11 @@ def run_ours(args):
         "clocks": clocks,
         "build_s": {"train": t_train, "total": t_build},
     }
+    if world > 1:
+        line["config"]["exchange"] = "p2p-fused (peer-memory stores + flags, no collective call)" if ex is not None else \
+            f"nccl all-gather + merge ({ex_err or 'requested'})"
+        if ex is not None:
+            line["exchange_timed_out"] = ex.status()[0]
 
     # ---- optional nprobe x nq sweep --------------------------------------------------------------------
     if args.sweep and world == 1:

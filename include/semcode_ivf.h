@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SC_ABI_VERSION 1
+#define SC_ABI_VERSION 2
 
 typedef enum sc_status {
     SC_OK = 0,
@@ -147,6 +147,30 @@ int sc_index_search_preassigned(sc_index_t *idx, const float *q, int64_t nq, int
  *    part_dist/part_ids [parts,nq,kin] (device) -> out [nq,k] best first; ids < 0 are ignored. -- */
 int sc_merge_topk(const float *part_dist, const int64_t *part_ids, int32_t parts, int64_t nq, int32_t kin,
                   int32_t k, int32_t metric, float *out_dist, int64_t *out_ids, int32_t device, void *stream);
+
+/* -- fused cross-GPU exchange (one process per GPU; NVLink / NVSwitch peer memory).  Replaces the Milvus
+ *    proxy's scatter of a search to the query nodes and its gather + reduce of their partial results
+ *    [EXT] behind the same Collection.search call (milvus_store.py:141-147).
+ *    peer_buffers[p] (HOST array of `world` DEVICE pointers, valid on `device`): rank p's exchange buffer as
+ *    mapped into this process -- e.g. torch.distributed._symmetric_memory buffer_ptrs, cudaIpcOpenMemHandle
+ *    or cuMemMap of a fabric handle; peer_buffers[rank] is this rank's own buffer.  All buffers have
+ *    buffer_bytes bytes, are zero-filled before the first use, and stay alive until sc_exchange_destroy.
+ *    Every rank must make the same sequence of sc_index_search_sharded calls (same nq, k, nprobe). --------- */
+typedef struct sc_exchange sc_exchange_t; /* opaque */
+int sc_exchange_create(int32_t rank, int32_t world, const void *const *peer_buffers, int64_t buffer_bytes,
+                       int32_t device, sc_exchange_t **out);
+int sc_exchange_destroy(sc_exchange_t *ex);
+/* timed_out (host, nullable): 1 when a wait for a peer gave up (results of that step are invalid);
+ * epoch (host, nullable): number of exchange steps issued.  Synchronises the device. */
+int sc_exchange_status(sc_exchange_t *ex, int32_t *timed_out, int64_t *epoch);
+/* One search step of a row-sharded index: `idx` holds this rank's rows, every rank passes the same queries.
+ * lists == NULL: the coarse pass is split over the ranks (rank r ranks the centroids for its 1/world of the
+ * batch and STORES the probe rows into every peer's table); the top-k epilogue STORES this rank's partial
+ * result into every peer's gather slot and publishes a flag; the merge kernel waits for the flags of all peers
+ * and writes the merged [nq,k] result to out_dist / out_ids (identical on every rank).  No collective call. */
+int sc_index_search_sharded(sc_index_t *idx, sc_exchange_t *ex, const float *q, int64_t nq, int32_t k, int32_t nprobe,
+                            const int32_t *lists, const sc_filter_t *filter, float *out_dist, int64_t *out_ids,
+                            void *stream);
 
 /* -- introspection / export (persistence, CPU baseline, tests) -------------------------------- */
 int sc_index_stats(sc_index_t *idx, sc_stats_t *out);

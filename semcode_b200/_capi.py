@@ -33,6 +33,7 @@ SYMBOLS = [
     "sc_index_add_preassigned", "sc_index_remove_ids", "sc_index_search", "sc_index_search_preassigned",
     "sc_merge_topk", "sc_index_stats", "sc_index_list_sizes", "sc_index_export_list", "sc_index_set_profiling",
     "sc_index_last_search_times", "sc_index_set_param",
+    "sc_exchange_create", "sc_exchange_destroy", "sc_exchange_status", "sc_index_search_sharded",
 ]
 
 
@@ -113,6 +114,10 @@ def lib():
         "sc_index_set_profiling": [vp, i32],
         "sc_index_last_search_times": [vp, C.POINTER(ScSearchTimes)],
         "sc_index_set_param": [vp, C.c_char_p, i64],
+        "sc_exchange_create": [i32, i32, C.POINTER(vp), i64, i32, C.POINTER(vp)],
+        "sc_exchange_destroy": [vp],
+        "sc_exchange_status": [vp, C.POINTER(i32), C.POINTER(i64)],
+        "sc_index_search_sharded": [vp, vp, vp, i64, i32, i32, vp, C.POINTER(ScFilter), vp, vp, vp],
     }
     for name, args in sig.items():
         fn = getattr(L, name)

@@ -140,6 +140,34 @@ struct ScanArgs {
     FilterDev filt;
 };
 
+// ---- cross-GPU exchange over peer-mapped memory (NVLink / NVSwitch), one process per GPU -------------------
+// The top-k epilogue of rank r stores its partial result straight into every peer's gather slot r and the
+// last CTA publishes the step's epoch to every peer's flag word r; the consumer kernel on each peer spins on
+// its own (local) flag words.  No collective library call, no extra copy: the exchange rides on the stores
+// of the kernel that produced the data.
+constexpr int kMaxPeers = 8;
+struct PeerSignal {
+    int world;                               // 0 = no exchange (plain local output)
+    unsigned int *done;                      // local CTA counter, zero between launches
+    unsigned long long *flag[kMaxPeers];     // peer p's flag word for THIS rank
+    unsigned long long epoch;
+};
+struct PeerWait {
+    int world;                               // 0 = nothing to wait for
+    const unsigned long long *flags;         // local flag words [world], written by the peers
+    unsigned long long epoch;
+    unsigned int *status;                    // local; set to 1 when a peer did not arrive within timeout_ns
+    unsigned long long timeout_ns;
+};
+struct PeerTopk {
+    float *d[kMaxPeers];                     // peer p's [nq, k] slot of THIS rank
+    int64_t *i[kMaxPeers];
+};
+struct PeerRows {
+    int32_t *p[kMaxPeers];                   // peer p's probe table [nq, nprobe]
+    int64_t row0;                            // first row of THIS rank's slice
+};
+
 cudaError_t launch_plan_pairs(const int32_t *probe, int64_t npairs, const int32_t *list_len, int32_t nlist,
                               int64_t *pair_pages, unsigned long long *rows_total, cudaStream_t st);
 // exclusive prefix sum of in[n] -> out[n+1] (out[n] = total).  The int64 variant takes an optional scratch of
@@ -169,6 +197,15 @@ cudaError_t launch_select_candidates(const ScanArgs &a, int64_t nq, int k, float
                                      cudaStream_t st);
 cudaError_t launch_merge_topk(const float *part_dist, const int64_t *part_ids, int parts, int64_t nq, int kin, int k,
                               int metric, float *out_dist, int64_t *out_ids, cudaStream_t st);
+// exchange variants (select.cu): the same selections, writing into every peer / waiting for every peer
+cudaError_t launch_select_rows_peers(const float *scores, int64_t M, int N, int k, const PeerRows &rows,
+                                     const PeerSignal &sig, cudaStream_t st);
+cudaError_t launch_select_candidates_peers(const ScanArgs &a, int64_t nq, int k, const PeerTopk &out, const PeerSignal &sig,
+                                           cudaStream_t st);
+cudaError_t launch_merge_topk_wait(const float *part_dist, const int64_t *part_ids, int parts, int64_t nq, int kin, int k,
+                                   int metric, float *out_dist, int64_t *out_ids, const PeerWait &wait, cudaStream_t st);
+cudaError_t launch_peer_signal(const PeerSignal &sig, cudaStream_t st);  // a rank with an empty slice still publishes
+cudaError_t launch_peer_wait(const PeerWait &wait, cudaStream_t st);     // orders the stream after the peers' stores
 
 // list maintenance
 cudaError_t launch_count_positions(const int32_t *assign, int64_t n, int32_t nlist, int32_t *list_len, int32_t *pos,

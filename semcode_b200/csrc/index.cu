@@ -191,7 +191,64 @@ struct sc_index {
     std::mutex mu;
 };
 
+// ------------------------------------------------------------------------------------------------
+// cross-GPU exchange (one per rank): peer-mapped symmetric buffers, no collective library on the data path
+// ------------------------------------------------------------------------------------------------
+// Layout of every rank's buffer (identical on all ranks):
+//   [0, 512)      probe flags  [world] u64: flag p = last epoch whose probe rows rank p has stored here
+//   [512, 1024)   top-k flags  [world] u64: flag p = last epoch whose partial top-k rank p has stored here
+//   [4096, ...)   two halves (epoch parity), each: probe table [nq, nprobe] i32 | part_dist [world, nq, k] f32 |
+//                 part_ids [world, nq, k] i64
+// Double buffering by epoch parity is enough: a rank can only run one step ahead of its slowest peer, because
+// finishing step s needs every peer's step-s partials, which a peer stores after it finished reading step s-1.
+struct sc_exchange {
+    int rank = 0, world = 1, device = 0;
+    char *peer[kMaxPeers] = {nullptr};
+    size_t bytes = 0;
+    unsigned long long epoch = 0;
+    unsigned int *done = nullptr;    // [2] CTA counters (probe select, top-k select)
+    unsigned int *status = nullptr;  // [1] 1 = a wait timed out
+    unsigned long long timeout_ns = 10ull * 1000 * 1000 * 1000;
+};
+constexpr size_t kExHeader = 4096;
+
 namespace {
+
+struct ExLayout {
+    size_t probes, part_d, part_i, end;  // byte offsets from the start of the buffer
+};
+inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+// offsets of the three regions for this epoch's half; `end` > bytes means "does not fit"
+ExLayout exchange_layout(const sc_exchange *ex, int64_t nq, int np, int k) {
+    const size_t half = ((ex->bytes - kExHeader) / 2) & ~(size_t)255;
+    ExLayout L;
+    L.probes = kExHeader + (size_t)(ex->epoch & 1ull) * half;
+    L.part_d = L.probes + align256((size_t)nq * np * 4);
+    L.part_i = L.part_d + align256((size_t)ex->world * nq * k * 4);
+    L.end = L.part_i + align256((size_t)ex->world * nq * k * 8);
+    if (L.end - L.probes > half) L.end = ex->bytes + 1;
+    return L;
+}
+PeerSignal make_signal(const sc_exchange *ex, int kind) {
+    PeerSignal s;
+    memset(&s, 0, sizeof(s));
+    s.world = ex->world;
+    s.done = ex->done + kind;
+    s.epoch = ex->epoch;
+    for (int p = 0; p < ex->world; ++p)
+        s.flag[p] = reinterpret_cast<unsigned long long *>(ex->peer[p] + 512 * kind) + ex->rank;
+    return s;
+}
+PeerWait make_wait(const sc_exchange *ex, int kind) {
+    PeerWait w;
+    memset(&w, 0, sizeof(w));
+    w.world = ex->world;
+    w.flags = reinterpret_cast<const unsigned long long *>(ex->peer[ex->rank] + 512 * kind);
+    w.epoch = ex->epoch;
+    w.status = ex->status;
+    w.timeout_ns = ex->timeout_ns;
+    return w;
+}
 
 size_t page_bytes(const sc_index *ix) { return (size_t)kPageRows * ix->ds * sizeof(float); }
 
@@ -530,13 +587,17 @@ int prof_mark(sc_index *ix, cudaStream_t st) {
     return SC_OK;
 }
 
+// ex != nullptr: this index is one shard of a row-sharded index.  The coarse pass (when `lists` is NULL) is split
+// over the ranks and the probe rows are stored into every peer's table; the top-k epilogue stores this rank's
+// partial result into every peer's gather slot and the merge kernel waits for the peers' flags (select.cu).
 int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, const int32_t *lists,
-                const sc_filter_t *filt, float *out_dist, int64_t *out_ids, cudaStream_t st) {
+                const sc_filter_t *filt, float *out_dist, int64_t *out_ids, cudaStream_t st, sc_exchange *ex = nullptr) {
     if (nq < 0) return fail(SC_ERR_INVALID, "nq < 0");
     if (k < 1 || k > kMaxK) return fail(SC_ERR_INVALID, "k must be in [1, %d]", kMaxK);
     if (nprobe < 1) return fail(SC_ERR_INVALID, "nprobe must be >= 1");
     SC(require_trained(ix));
-    if (nq == 0) return SC_OK;
+    if (nq == 0 && !ex) return SC_OK;
+    if (nq == 0) return fail(SC_ERR_INVALID, "an exchange step needs nq >= 1 on every rank");
     if (!q || !out_dist || !out_ids) return fail(SC_ERR_INVALID, "q / out_dist / out_ids must not be NULL");
     const int np = lists ? nprobe : std::min(nprobe, ix->nlist);
     const bool all_lists = !lists && np == ix->nlist;
@@ -559,6 +620,19 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
     const int64_t per_query = ((lists || all_lists) ? 0 : (int64_t)ix->nlist * 4) + (int64_t)np * 20 + pb * kPageRows * 4 +
                               (int64_t)ix->ds * 4 + (int64_t)k * 12;
     int64_t nqc = std::max<int64_t>(1, ix->scratch_budget / per_query);
+    ExLayout exl{};
+    if (ex) {
+        if (ex->device != ix->device) return fail(SC_ERR_INVALID, "exchange and index live on different devices");
+        // an exchange step is ONE pass on every rank (the ranks' list lengths differ, so a per-rank chunking
+        // rule would desynchronise them): the scratch budget is not applied here, the caller bounds nq
+        nqc = nq;
+        exl = exchange_layout(ex, nq, np, k);
+        if (exl.end > ex->bytes)  // depends on (nq, nprobe, k, world) only: every rank fails alike, before the epoch moves
+            return fail(SC_ERR_INVALID, "exchange buffer of %zu bytes is too small for nq=%lld nprobe=%d k=%d world=%d",
+                        ex->bytes, (long long)nq, np, k, ex->world);
+        ex->epoch += 1;  // every rank makes the same calls, so the epochs agree
+        exl = exchange_layout(ex, nq, np, k);
+    }
     if (nqc >= nq) {
         nqc = nq;  // one pass
     } else {
@@ -594,6 +668,20 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
             CU(cudaGetLastError());
             probe = ix->s_probe.as<int32_t>();
             ix->prof_total_launches += 1;
+        } else if (ex) {
+            // this rank ranks the centroids for its 1/world of the batch and stores the rows into every peer's table
+            const int64_t per = (m + ex->world - 1) / ex->world;
+            const int64_t lo = std::min<int64_t>(m, (int64_t)ex->rank * per), hi = std::min<int64_t>(m, lo + per);
+            if (hi > lo) SC(coarse_scores(ix, qd + lo * ix->ds, hi - lo, ix->s_scores.as<float>(), st));
+            SC(prof_mark(ix, st));
+            PeerRows rows;
+            memset(&rows, 0, sizeof(rows));
+            for (int p = 0; p < ex->world; ++p) rows.p[p] = reinterpret_cast<int32_t *>(ex->peer[p] + exl.probes);
+            rows.row0 = lo;
+            CU(launch_select_rows_peers(ix->s_scores.as<float>(), hi - lo, ix->nlist, np, rows, make_signal(ex, 0), st));
+            CU(launch_peer_wait(make_wait(ex, 0), st));
+            probe = reinterpret_cast<const int32_t *>(ex->peer[ex->rank] + exl.probes);
+            ix->prof_total_launches += (use_tc(ix) ? 3 : 2) + 1;
         } else {
             SC(coarse_scores(ix, qd, m, ix->s_scores.as<float>(), st));
             SC(prof_mark(ix, st));
@@ -663,7 +751,23 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
         SC(prof_mark(ix, st));
         float *od = outd_dev ? out_dist + s * k : ix->s_outd.as<float>();
         int64_t *oi = outi_dev ? out_ids + s * k : ix->s_outi.as<int64_t>();
-        CU(launch_select_candidates(a, m, k, od, oi, st));
+        if (ex) {
+            PeerTopk pk;
+            memset(&pk, 0, sizeof(pk));
+            const size_t slot = (size_t)ex->rank * m * k;
+            for (int p = 0; p < ex->world; ++p) {
+                pk.d[p] = reinterpret_cast<float *>(ex->peer[p] + exl.part_d) + slot;
+                pk.i[p] = reinterpret_cast<int64_t *>(ex->peer[p] + exl.part_i) + slot;
+            }
+            CU(launch_select_candidates_peers(a, m, k, pk, make_signal(ex, 1), st));
+            char *mine = ex->peer[ex->rank];
+            CU(launch_merge_topk_wait(reinterpret_cast<const float *>(mine + exl.part_d),
+                                      reinterpret_cast<const int64_t *>(mine + exl.part_i), ex->world, m, k, k, ix->metric,
+                                      od, oi, make_wait(ex, 1), st));
+            ix->prof_total_launches += 1;
+        } else {
+            CU(launch_select_candidates(a, m, k, od, oi, st));
+        }
         SC(prof_mark(ix, st));
         ix->prof_total_launches += 4;
         if (!outd_dev) CU(cudaMemcpyAsync(out_dist + s * k, od, (size_t)m * k * 4, cudaMemcpyDeviceToHost, st));
@@ -1152,6 +1256,66 @@ int sc_index_search_preassigned(sc_index_t *ix, const float *q, int64_t nq, int3
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
     return search_impl(ix, q, nq, k, nprobe, lists, filter, out_dist, out_ids, (cudaStream_t)stream);
+}
+
+int sc_exchange_create(int32_t rank, int32_t world, const void *const *peer_buffers, int64_t buffer_bytes, int32_t device,
+                       sc_exchange_t **out) {
+    if (!out) return fail(SC_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
+        return fail(SC_ERR_INVALID, "rank %d / world %d: world must be in [1, %d]", rank, world, kMaxPeers);
+    if (!peer_buffers) return fail(SC_ERR_INVALID, "peer_buffers is NULL");
+    if (buffer_bytes < (int64_t)(kExHeader + (64 << 10))) return fail(SC_ERR_INVALID, "exchange buffers must hold at least 68 KiB");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(SC_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    for (int p = 0; p < world; ++p) {
+        if (!peer_buffers[p] || ((uintptr_t)peer_buffers[p] & 255)) return fail(SC_ERR_INVALID, "peer buffer %d is NULL or not 256-byte aligned", p);
+    }
+    sc_exchange *ex = new sc_exchange();
+    ex->rank = rank;
+    ex->world = world;
+    ex->device = device;
+    ex->bytes = (size_t)buffer_bytes;
+    for (int p = 0; p < world; ++p) ex->peer[p] = (char *)peer_buffers[p];
+    unsigned int *w = nullptr;
+    cudaError_t e = cudaMalloc(&w, 16);
+    if (e == cudaSuccess) e = cudaMemset(w, 0, 16);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        delete ex;
+        return fail(SC_ERR_CUDA, "exchange counters: %s", cudaGetErrorString(e));
+    }
+    ex->done = w;
+    ex->status = w + 2;
+    *out = ex;
+    return SC_OK;
+}
+
+int sc_exchange_destroy(sc_exchange_t *ex) {
+    if (!ex) return SC_OK;
+    DeviceGuard g(ex->device);
+    if (ex->done) cudaFree(ex->done);
+    delete ex;
+    return SC_OK;
+}
+
+int sc_exchange_status(sc_exchange_t *ex, int32_t *timed_out, int64_t *epoch) {
+    if (!ex) return fail(SC_ERR_INVALID, "exchange is NULL");
+    DeviceGuard g(ex->device);
+    unsigned int st = 0;
+    CU(cudaMemcpy(&st, ex->status, 4, cudaMemcpyDeviceToHost));  // synchronises the device's prior work
+    if (timed_out) *timed_out = (int32_t)st;
+    if (epoch) *epoch = (int64_t)ex->epoch;
+    return SC_OK;
+}
+
+int sc_index_search_sharded(sc_index_t *ix, sc_exchange_t *ex, const float *q, int64_t nq, int32_t k, int32_t nprobe,
+                            const int32_t *lists, const sc_filter_t *filter, float *out_dist, int64_t *out_ids, void *stream) {
+    if (!ix) return fail(SC_ERR_INVALID, "idx is NULL");
+    if (!ex) return fail(SC_ERR_INVALID, "exchange is NULL");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    return search_impl(ix, q, nq, k, nprobe, lists, filter, out_dist, out_ids, (cudaStream_t)stream, ex);
 }
 
 int sc_merge_topk(const float *part_dist, const int64_t *part_ids, int32_t parts, int64_t nq, int32_t kin, int32_t k,

@@ -72,10 +72,12 @@ __device__ __forceinline__ float reduce_transpose(float (&v)[N], int lane) {
 constexpr int kTotLd = 33;  // page accumulator [MQ][33]: row-major over rows, one pad word per query
 
 // per-warp shared memory: query slices [MQ][32*U] float4 | candidate bases [MQ] int64 | query pointers [MQ] |
-// page accumulator [MQ][33] float
+// (MQ = 8 only) page accumulator [MQ][33] float.  With MQ = 4 the page accumulator lives in registers (lane = row):
+// two CTAs of 8 warps then need 2 x 97.5 KB, which leaves the 196 KB carve-out and 60 KB of L1 for the streaming
+// loads in flight (measured: the same kernel with 2 x 101 KB -> 228 KB carve-out, 28 KB of L1, streams 11 % slower)
 template <int MQ, int U>
 __host__ __device__ constexpr size_t mq_warp_floats() {
-    return ((size_t)MQ * 32 * U * 4 + (size_t)MQ * 4 + (size_t)MQ * kTotLd + 3) / 4 * 4;
+    return ((size_t)MQ * 32 * U * 4 + (size_t)MQ * 4 + (MQ > 4 ? (size_t)MQ * kTotLd : 0) + 3) / 4 * 4;
 }
 
 // pgoff [nlist+1]: exclusive prefix of the units (pages x passes) of the lists handled here (0 for the others)
@@ -86,6 +88,7 @@ __global__ void __launch_bounds__(256, 2)
     constexpr int N = R * MQ;
     constexpr int SL4 = 32 * U;  // float4 per slice
     static_assert(N == 8 || N == 32, "reduce_transpose covers 8 or 32 partial sums");
+    constexpr bool SMEM_TOT = MQ > 4;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int wpb = blockDim.x >> 5;
@@ -171,8 +174,12 @@ __global__ void __launch_bounds__(256, 2)
         const uint32_t live_mask = __ballot_sync(0xffffffffu, live);
         const int64_t poff = (int64_t)jpage * kPageRows;
         const float4 *vbase = reinterpret_cast<const float4 *>(a.slabs->vec[slab]) + slot0 * ds4;
+        float treg[MQ];  // MQ = 4: this lane's row of the page, one total per query
 #pragma unroll
-        for (int j = 0; j < MQ; ++j) tot[j * kTotLd + lane] = 0.f;
+        for (int j = 0; j < MQ; ++j) {
+            treg[j] = 0.f;
+            if (SMEM_TOT) tot[j * kTotLd + lane] = 0.f;
+        }
 
         for (int s = 0; s < nslices; ++s) {
             const int c0 = s * SL4;
@@ -223,12 +230,22 @@ __global__ void __launch_bounds__(256, 2)
                         for (int r = 0; r < R; ++r) acc[r * MQ + j] = mq_accum4<L2>(acc[r * MQ + j], x[r][u], qv);
                     }
                 }
-                const float t = reduce_transpose<N>(acc, lane);
-                int myrow = row[0];
+                if (SMEM_TOT) {
+                    const float t = reduce_transpose<N>(acc, lane);
+                    int myrow = row[0];
 #pragma unroll
-                for (int r = 1; r < R; ++r)
-                    if (my_r == r) myrow = row[r];
-                if (my_owner && myrow >= 0) tot[my_j * kTotLd + myrow] += t;  // one owner per (row, query): no race
+                    for (int r = 1; r < R; ++r)
+                        if (my_r == r) myrow = row[r];
+                    if (my_owner && myrow >= 0) tot[my_j * kTotLd + myrow] += t;  // one owner per (row, query): no race
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+#pragma unroll
+                        for (int j = 0; j < MQ; ++j) {
+                            const float t = warp_sum(acc[r * MQ + j]);
+                            if (lane == row[r]) treg[j] += t;
+                        }
+                }
             }
             restage = nslices > 1;
         }
@@ -237,7 +254,7 @@ __global__ void __launch_bounds__(256, 2)
         for (int j = 0; j < MQ; ++j) {
             const int64_t cb = cbs[j];
             if (cb >= 0) {
-                const float v = tot[j * kTotLd + lane];
+                const float v = SMEM_TOT ? tot[j * kTotLd + lane] : treg[j];
                 a.cand[cb + poff + lane] = live ? (L2 ? -v : v) : -INFINITY;
             }
         }

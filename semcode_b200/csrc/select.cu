@@ -30,6 +30,57 @@ __device__ __forceinline__ unsigned long long pack_pair(uint32_t key, uint32_t i
     return ((unsigned long long)key << 32) | (unsigned long long)(0xffffffffu - idx);
 }
 
+// ---- exchange over peer-mapped memory ----------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Every thread of every CTA has issued its (remote) stores.  The last CTA to arrive publishes the epoch to
+// every peer: fence.sys by each writer -> CTA barrier -> device-scope counter -> fence.sys -> release stores.
+__device__ __forceinline__ void peer_signal(const PeerSignal &s) {
+    if (s.world <= 0) return;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(s.done, 1u);
+        if (prev == gridDim.x - 1) {
+            atomicExch(s.done, 0u);  // ready for the next launch on this stream
+            __threadfence_system();
+            for (int p = 0; p < s.world; ++p) st_release_sys_u64(s.flag[p], s.epoch);
+        }
+    }
+}
+
+// Spin (thread p on peer p's flag word) until every peer has published `epoch`; bounded by timeout_ns so that a
+// missing peer becomes an error status instead of a hung GPU.
+__device__ __forceinline__ void peer_wait(const PeerWait &w) {
+    if (w.world <= 0) return;
+    if ((int)threadIdx.x < w.world) {
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys_u64(w.flags + threadIdx.x) < w.epoch) {
+            if (global_timer_ns() - t0 > w.timeout_ns) {
+                atomicExch(w.status, 1u);
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void peer_signal_kernel(PeerSignal s) { peer_signal(s); }
+__global__ void peer_wait_kernel(PeerWait w) { peer_wait(w); }
+
 // ---- candidate sources ----------------------------------------------------------------------
 struct RowsSrc {
     const float *s;
@@ -37,6 +88,8 @@ struct RowsSrc {
     int k;
     int32_t *out_idx;
     float *out_val;
+    int world;       // > 0: write the row into every peer's probe table instead of out_idx
+    PeerRows peers;
     struct View {
         const float *p;
         uint32_t n;
@@ -44,6 +97,11 @@ struct RowsSrc {
     };
     __device__ __forceinline__ View view(int64_t q) const { return View{s + q * (int64_t)N, (uint32_t)N}; }
     __device__ __forceinline__ void emit(int64_t q, int j, bool valid, float score, uint32_t idx) const {
+        if (world > 0) {
+            const int64_t o = (peers.row0 + q) * k + j;
+            for (int p = 0; p < world; ++p) peers.p[p][o] = valid ? (int32_t)idx : -1;
+            return;
+        }
         out_idx[q * k + j] = valid ? (int32_t)idx : -1;
         if (out_val) out_val[q * k + j] = valid ? score : -INFINITY;
     }
@@ -54,6 +112,19 @@ struct CandSrc {
     int k;
     float *out_dist;
     int64_t *out_ids;
+    int world;       // > 0: store the result into every peer's gather slot of this rank instead of out_*
+    PeerTopk peers;
+    __device__ __forceinline__ void put(int64_t o, float d, int64_t id) const {
+        if (world > 0) {
+            for (int p = 0; p < world; ++p) {
+                peers.d[p][o] = d;
+                peers.i[p][o] = id;
+            }
+            return;
+        }
+        out_dist[o] = d;
+        out_ids[o] = id;
+    }
     struct View {
         const float *p;
         uint32_t n;
@@ -66,8 +137,7 @@ struct CandSrc {
     __device__ __forceinline__ void emit(int64_t q, int j, bool valid, float score, uint32_t idx) const {
         const bool ip = a.metric == 0;
         if (!valid) {
-            out_dist[q * k + j] = ip ? -FLT_MAX : FLT_MAX;
-            out_ids[q * k + j] = -1;
+            put(q * k + j, ip ? -FLT_MAX : FLT_MAX, -1);
             return;
         }
         const int64_t w = a.page_off[q * a.nprobe] + (idx >> 5);
@@ -85,8 +155,7 @@ struct CandSrc {
         const int32_t page = a.pt[a.pt_off[l] + (int32_t)(w - a.page_off[lo])];
         const int slab = page >> a.slab_shift;
         const int64_t slot = (int64_t)(page & ((1 << a.slab_shift) - 1)) * kPageRows + r;
-        out_ids[q * k + j] = a.slabs->ids[slab][slot];
-        out_dist[q * k + j] = ip ? score : -score;
+        put(q * k + j, ip ? score : -score, a.slabs->ids[slab][slot]);
     }
 };
 
@@ -110,8 +179,8 @@ struct MergeSrc {
         uint32_t n;
         __device__ __forceinline__ float load(uint32_t i) const {
             const int64_t o = m->off(q, i);
-            if (m->pi[o] < 0) return -INFINITY;
-            const float d = m->pd[o];
+            if (__ldcg(m->pi + o) < 0) return -INFINITY;  // L2 loads: the partials may come from peers' stores
+            const float d = __ldcg(m->pd + o);
             return m->metric == 0 ? d : -d;
         }
     };
@@ -123,8 +192,8 @@ struct MergeSrc {
             return;
         }
         const int64_t o = off(q, idx);
-        out_dist[q * k + j] = pd[o];
-        out_ids[q * k + j] = pi[o];
+        out_dist[q * k + j] = __ldcg(pd + o);
+        out_ids[q * k + j] = __ldcg(pi + o);
     }
 };
 
@@ -140,8 +209,7 @@ __device__ __forceinline__ T warp_incl_scan(T v, int lane) {
 }
 
 template <class Src>
-__global__ void __launch_bounds__(SEL_T) select_topk_kernel(Src src, int k) {
-    __shared__ SelShared sh;
+__device__ __forceinline__ void select_topk_body(const Src &src, int k, SelShared &sh) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t q = blockIdx.x;
     const typename Src::View view = src.view(q);
@@ -275,6 +343,15 @@ __global__ void __launch_bounds__(SEL_T) select_topk_kernel(Src src, int k) {
     }
 }
 
+// wait: peers whose stores this kernel consumes (merge); sig: peers that consume this kernel's stores
+template <class Src>
+__global__ void __launch_bounds__(SEL_T) select_topk_kernel(Src src, int k, PeerWait wait, PeerSignal sig) {
+    __shared__ SelShared sh;
+    peer_wait(wait);
+    select_topk_body(src, k, sh);
+    peer_signal(sig);
+}
+
 // ---- exclusive prefix sums (single CTA; inputs are at most nq*nprobe or nlist long) -----------
 template <typename T>
 __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const T *__restrict__ in, int64_t n, T *__restrict__ out) {
@@ -356,16 +433,42 @@ __global__ void __launch_bounds__(1024) scan_block_kernel(const T *__restrict__ 
 cudaError_t launch_select_rows(const float *scores, int64_t M, int N, int k, int32_t *out_idx, float *out_val,
                                cudaStream_t st) {
     if (M <= 0) return cudaSuccess;
-    RowsSrc src{scores, N, k, out_idx, out_val};
-    select_topk_kernel<RowsSrc><<<(unsigned)M, SEL_T, 0, st>>>(src, k);
+    RowsSrc src{scores, N, k, out_idx, out_val, 0, PeerRows{}};
+    select_topk_kernel<RowsSrc><<<(unsigned)M, SEL_T, 0, st>>>(src, k, PeerWait{}, PeerSignal{});
+    return cudaGetLastError();
+}
+
+cudaError_t launch_select_rows_peers(const float *scores, int64_t M, int N, int k, const PeerRows &rows,
+                                     const PeerSignal &sig, cudaStream_t st) {
+    if (M <= 0) return launch_peer_signal(sig, st);
+    RowsSrc src{scores, N, k, nullptr, nullptr, sig.world, rows};
+    select_topk_kernel<RowsSrc><<<(unsigned)M, SEL_T, 0, st>>>(src, k, PeerWait{}, sig);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_peer_signal(const PeerSignal &sig, cudaStream_t st) {
+    peer_signal_kernel<<<1, 32, 0, st>>>(sig);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_peer_wait(const PeerWait &wait, cudaStream_t st) {
+    peer_wait_kernel<<<1, 32, 0, st>>>(wait);
     return cudaGetLastError();
 }
 
 cudaError_t launch_select_candidates(const ScanArgs &a, int64_t nq, int k, float *out_dist, int64_t *out_ids,
                                      cudaStream_t st) {
     if (nq <= 0) return cudaSuccess;
-    CandSrc src{a, k, out_dist, out_ids};
-    select_topk_kernel<CandSrc><<<(unsigned)nq, SEL_T, 0, st>>>(src, k);
+    CandSrc src{a, k, out_dist, out_ids, 0, PeerTopk{}};
+    select_topk_kernel<CandSrc><<<(unsigned)nq, SEL_T, 0, st>>>(src, k, PeerWait{}, PeerSignal{});
+    return cudaGetLastError();
+}
+
+cudaError_t launch_select_candidates_peers(const ScanArgs &a, int64_t nq, int k, const PeerTopk &out, const PeerSignal &sig,
+                                           cudaStream_t st) {
+    if (nq <= 0) return launch_peer_signal(sig, st);
+    CandSrc src{a, k, nullptr, nullptr, sig.world, out};
+    select_topk_kernel<CandSrc><<<(unsigned)nq, SEL_T, 0, st>>>(src, k, PeerWait{}, sig);
     return cudaGetLastError();
 }
 
@@ -373,7 +476,15 @@ cudaError_t launch_merge_topk(const float *part_dist, const int64_t *part_ids, i
                               int metric, float *out_dist, int64_t *out_ids, cudaStream_t st) {
     if (nq <= 0) return cudaSuccess;
     MergeSrc src{part_dist, part_ids, parts, nq, kin, k, metric, out_dist, out_ids};
-    select_topk_kernel<MergeSrc><<<(unsigned)nq, SEL_T, 0, st>>>(src, k);
+    select_topk_kernel<MergeSrc><<<(unsigned)nq, SEL_T, 0, st>>>(src, k, PeerWait{}, PeerSignal{});
+    return cudaGetLastError();
+}
+
+cudaError_t launch_merge_topk_wait(const float *part_dist, const int64_t *part_ids, int parts, int64_t nq, int kin, int k,
+                                   int metric, float *out_dist, int64_t *out_ids, const PeerWait &wait, cudaStream_t st) {
+    if (nq <= 0) return cudaSuccess;
+    MergeSrc src{part_dist, part_ids, parts, nq, kin, k, metric, out_dist, out_ids};
+    select_topk_kernel<MergeSrc><<<(unsigned)nq, SEL_T, 0, st>>>(src, k, wait, PeerSignal{});
     return cudaGetLastError();
 }
 

@@ -315,11 +315,14 @@ class IVFFlatIndex:
         langs: Optional[Iterable[int]] = None,
         lists: Optional[Array] = None,
         out: Optional[Tuple[Array, Array]] = None,
+        exchange: Optional["PeerExchange"] = None,
     ) -> Tuple[Array, Array]:
         """Top-k per query: (dist [nq,k] fp32, ids [nq,k] int64), best first, id -1 = no result.
 
         CUDA-tensor queries give CUDA-tensor results without synchronising the stream; numpy / CPU
-        queries give numpy results (synchronous)."""
+        queries give numpy results (synchronous).  With `exchange` this index is one shard of a row-sharded
+        index and the call is one fused step (sc_index_search_sharded): every rank passes the same queries
+        and receives the same merged result."""
         q = _as_rows(q, self.dim, "q")
         nq = q.shape[0]
         k = int(k)
@@ -334,7 +337,22 @@ class IVFFlatIndex:
             ids = np.empty((nq, k), dtype=np.int64)
         f, keep = self._filter(repos, langs)
         fp = C.byref(f) if f is not None else None
-        if lists is None:
+        if lists is not None:
+            if _is_tensor(lists):
+                lists = lists.to(torch.int32).contiguous()
+            else:
+                lists = np.ascontiguousarray(np.asarray(lists, dtype=np.int32))
+            if lists.shape[0] != nq:
+                raise ValueError("lists: one row of probes per query expected")
+        if exchange is not None:
+            _capi.check(
+                self._L.sc_index_search_sharded(
+                    self._h, exchange.handle, _capi.ptr(q, "f32"), nq, k,
+                    int(nprobe) if lists is None else int(lists.shape[1]), _capi.ptr(lists, "i32") if lists is not None else None,
+                    fp, _capi.ptr(dist, "f32"), _capi.ptr(ids, "i64"), self._stream(),
+                )
+            )
+        elif lists is None:
             _capi.check(
                 self._L.sc_index_search(
                     self._h, _capi.ptr(q, "f32"), nq, k, int(nprobe), fp, _capi.ptr(dist, "f32"),
@@ -342,12 +360,6 @@ class IVFFlatIndex:
                 )
             )
         else:
-            if _is_tensor(lists):
-                lists = lists.to(torch.int32).contiguous()
-            else:
-                lists = np.ascontiguousarray(np.asarray(lists, dtype=np.int32))
-            if lists.shape[0] != nq:
-                raise ValueError("lists: one row of probes per query expected")
             _capi.check(
                 self._L.sc_index_search_preassigned(
                     self._h, _capi.ptr(q, "f32"), nq, k, int(lists.shape[1]), _capi.ptr(lists, "i32"), fp,
@@ -479,6 +491,57 @@ class IVFFlatIndex:
 
     def set_param(self, name: str, value: int) -> None:
         _capi.check(self._L.sc_index_set_param(self._h, name.encode(), int(value)))
+
+
+class PeerExchange:
+    """Peer-mapped exchange buffers of one rank (sc_exchange_t): the fused scatter/gather of a sharded search.
+
+    torch is the plumbing: `torch.distributed._symmetric_memory` allocates one buffer per rank and maps every
+    peer's buffer into this process over NVLink; the kernels of libsemcode_ivf store into / spin on those
+    mappings directly (no NCCL call on the data path).  Raises when symmetric memory cannot be set up; the
+    caller (ShardedIVFFlat) then keeps the NCCL all-gather + merge route."""
+
+    def __init__(self, device: int, group=None, nbytes: int = 64 << 20):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        self.device = int(device)
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        if self.world > 8:
+            raise ValueError("PeerExchange covers the GPUs of one box (world <= 8)")
+        dev = torch.device("cuda", self.device)
+        g = group if group is not None else dist.group.WORLD
+        self._buf = symm.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        self._hdl = symm.rendezvous(self._buf, g)
+        self._buf.zero_()
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)  # every rank's flags are zero before anybody stores into them
+        ptrs = [int(p) for p in self._hdl.buffer_ptrs]
+        if len(ptrs) != self.world or any(p == 0 for p in ptrs):
+            raise RuntimeError("symmetric memory rendezvous returned no peer pointers")
+        arr = (C.c_void_p * self.world)(*ptrs)
+        h = C.c_void_p()
+        _capi.check(_capi.lib().sc_exchange_create(self.rank, self.world, arr, int(nbytes), self.device, C.byref(h)))
+        self.handle = h
+        self.nbytes = int(nbytes)
+
+    def status(self) -> Tuple[bool, int]:
+        """(timed_out, steps issued); synchronises the device."""
+        t, e = C.c_int32(0), C.c_int64(0)
+        _capi.check(_capi.lib().sc_exchange_status(self.handle, C.byref(t), C.byref(e)))
+        return bool(t.value), int(e.value)
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            _capi.lib().sc_exchange_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def merge_topk(part_dist, part_ids, k: int, metric, device: Optional[int] = None):

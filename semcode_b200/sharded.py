@@ -25,7 +25,8 @@ from .index import KMEANS_NITER, KMEANS_SEED, metric_code
 
 class ShardedIVFFlat:
     def __init__(self, dim: int, nlist: int, metric="IP", device: Optional[int] = None, group=None,
-                 engine=None, merge: Optional[Callable] = None, shard_by: str = "rows"):
+                 engine=None, merge: Optional[Callable] = None, shard_by: str = "rows", exchange: str = "auto",
+                 exchange_bytes: int = 64 << 20):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialised (one process per GPU)")
         self.group = group
@@ -51,6 +52,26 @@ class ShardedIVFFlat:
         self.local = engine
         self._merge = merge
         self._next_row = 0  # global round-robin cursor, identical on every rank
+        # "p2p": scatter of the probe rows and gather + merge of the partial top-k fused into the engine's kernels
+        # over peer-mapped memory (PeerExchange); "nccl": all-gather + merge kernel; "auto": p2p when it can be set up
+        if exchange not in ("auto", "p2p", "nccl"):
+            raise ValueError("exchange must be 'auto', 'p2p' or 'nccl'")
+        self.exchange = None
+        self.exchange_error: Optional[str] = None
+        if exchange != "nccl" and self.world > 1 and hasattr(engine, "_h"):
+            ok = torch.zeros(1, dtype=torch.int32, device=engine.tensor_device())
+            try:
+                from .index import PeerExchange
+
+                self.exchange = PeerExchange(engine.device, group, exchange_bytes)
+                ok += 1
+            except Exception as e:  # symmetric memory unavailable on this box / build
+                self.exchange_error = f"{type(e).__name__}: {e}"
+            dist.all_reduce(ok, group=group)  # all ranks or none
+            if int(ok.item()) != self.world:
+                self.exchange = None
+                if exchange == "p2p":
+                    raise RuntimeError(f"peer-memory exchange unavailable: {self.exchange_error}")
 
     # -- coarse quantizer -------------------------------------------------------------------------
     def set_centroids(self, centroids=None, src: int = 0) -> None:
@@ -161,6 +182,18 @@ class ShardedIVFFlat:
         q = q.to(dev, torch.float32)
         if self.world == 1:
             return self.local.search(q, k, nprobe=nprobe, repos=repos, langs=langs)
+        if self.exchange is not None and self.shard_by == "rows" and q.shape[0] >= 1:
+            # fused steps of at most 8192 queries: split coarse pass, probe rows and partial top-k stored into the
+            # peers' buffers by the kernels that produce them, merge kernel waiting on the peers' flags
+            np_ = min(int(nprobe), self.nlist)
+            step = 8192
+            while step > 1 and 2 * (step * np_ * 4 + self.world * step * k * 12 + 1024) + 4096 > self.exchange.nbytes:
+                step //= 2  # same arithmetic on every rank
+            outs = [self.local.search(q[s:s + step], k, nprobe=nprobe, repos=repos, langs=langs, exchange=self.exchange)
+                    for s in range(0, q.shape[0], step)]
+            if len(outs) == 1:
+                return outs[0]
+            return torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
         if self.shard_by == "lists":
             probes = self.probe(q, nprobe) if q.shape[0] >= 2 * self.world else torch.as_tensor(
                 self.local.probe(q, min(int(nprobe), self.nlist)), device=dev)

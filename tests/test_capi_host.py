@@ -21,8 +21,8 @@ def test_header_symbols_are_exported(native_lib):
     assert declared == set(_capi.SYMBOLS), declared ^ set(_capi.SYMBOLS)
     for name in declared:
         assert hasattr(native_lib, name), f"{name} is declared in the header but not exported"
-    assert native_lib.sc_abi_version() == 1
-    assert re.search(r"#define SC_ABI_VERSION 1\b", hdr)
+    assert native_lib.sc_abi_version() == 2
+    assert re.search(r"#define SC_ABI_VERSION 2\b", hdr)
 
 
 def test_struct_layouts_match_header():

@@ -551,6 +551,44 @@ def test_multi_query_page_scan_buckets_and_slices(sb, orc, metric, per_list):
             assert_topk_parity(d3, i3, rd, ri, f"mq cfg={cfg} vs oracle {metric} d={d}")
 
 
+def test_sharded_step_with_a_one_rank_exchange(sb, orc):
+    """sc_index_search_sharded with world = 1 (the exchange buffer is this GPU's own memory): the peer stores,
+    the flag publication and the waiting merge run on one GPU and must reproduce the plain search."""
+    import ctypes as C
+
+    import torch
+
+    from semcode_b200 import _capi
+
+    x, q, cent, ids = make_case(orc, 5000, 128, 16, 70, "IP", seed=5)
+    g, oidx, _ = build_pair(sb, orc, x, ids, cent, "IP")
+    nbytes = 8 << 20
+    buf = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    arr = (C.c_void_p * 1)(buf.data_ptr())
+    h = C.c_void_p()
+    L = _capi.lib()
+    _capi.check(L.sc_exchange_create(0, 1, arr, nbytes, 0, C.byref(h)))
+
+    class Ex:
+        handle = h
+
+    try:
+        for rep, (m, k, nprobe) in enumerate(((70, 10, 4), (1, 5, 16), (33, 50, 7), (70, 10, 4))):
+            d0, i0 = g.search(q[:m], k, nprobe=nprobe)
+            d1, i1 = g.search(torch.from_numpy(q[:m]).cuda(), k, nprobe=nprobe, exchange=Ex)
+            assert_topk_parity(d1.cpu().numpy(), i1.cpu().numpy(), d0, i0, f"one-rank exchange step {rep}")
+            probes = orc.coarse_probe(q[:m], cent, "IP", nprobe)
+            d2, i2 = g.search(torch.from_numpy(q[:m]).cuda(), k, lists=probes, exchange=Ex)
+            assert_topk_parity(d2.cpu().numpy(), i2.cpu().numpy(), d0, i0, f"one-rank exchange, given lists, step {rep}")
+        t, e = C.c_int32(0), C.c_int64(0)
+        _capi.check(L.sc_exchange_status(h, C.byref(t), C.byref(e)))
+        assert t.value == 0 and e.value == 8
+        with pytest.raises(_capi.NativeError, match="too small"):
+            g.search(torch.from_numpy(np.repeat(q, 40, axis=0)).cuda(), 2048, nprobe=16, exchange=Ex)
+    finally:
+        L.sc_exchange_destroy(h)
+
+
 # ---- randomized shapes: every scan route against the oracle ---------------------------------------------
 def test_randomized_shapes_all_scan_routes(sb, orc):
     rng = np.random.default_rng(20261018)

@@ -31,8 +31,11 @@ def _worker(rank, world, port, ret):
         n, d, nlist, nq = 40000, 256, 128, 300
         x, q = unit_rows(rng, n, d), unit_rows(rng, nq, d)
         ids = np.arange(n, dtype=np.int64) * 5 + 2
-        for metric, shard_by in (("IP", "rows"), ("L2", "rows"), ("IP", "lists"), ("L2", "lists")):
-            sh = ShardedIVFFlat(d, nlist, metric, device=rank, shard_by=shard_by)
+        kinds = []
+        for metric, shard_by, exchange in (("IP", "rows", "auto"), ("L2", "rows", "auto"), ("IP", "rows", "nccl"),
+                                           ("IP", "lists", "nccl"), ("L2", "lists", "nccl")):
+            sh = ShardedIVFFlat(d, nlist, metric, device=rank, shard_by=shard_by, exchange=exchange)
+            kinds.append("p2p" if sh.exchange is not None else f"nccl ({sh.exchange_error})")
             obj = sh.train(torch.from_numpy(x[rank::world]).cuda(), niter=4, seed=3)
             # single-GPU Lloyd from the same initial centroids over ALL rows gives the same centroids
             from semcode_b200.index import kmeans_init_rows
@@ -54,7 +57,16 @@ def _worker(rank, world, port, ret):
             assert_topk_parity(gd.cpu().numpy(), gi.cpu().numpy(), rd, ri, f"sharded {metric} {shard_by}")
             gd, gi = sh.search(torch.from_numpy(q).cuda(), 10, nprobe=8, langs=[0])
             assert_topk_parity(gd.cpu().numpy(), gi.cpu().numpy(), rd, ri, f"sharded filtered {metric} {shard_by}")
-        ret[rank] = "ok"
+            # back-to-back steps of changing shape (epoch parity double buffering), incl. fewer queries than ranks
+            for rep, m in enumerate((1, 300, 37, 2, 300, 128)):
+                kk = 10 if rep % 2 == 0 else 33
+                rd, ri = one2.search(q[:m], kk, nprobe=5 + rep)
+                gd, gi = sh.search(torch.from_numpy(q[:m]).cuda(), kk, nprobe=5 + rep)
+                assert_topk_parity(gd.cpu().numpy(), gi.cpu().numpy(), rd, ri, f"sharded step {rep} {metric} {shard_by}")
+            if sh.exchange is not None:
+                timed_out, steps = sh.exchange.status()
+                assert not timed_out and steps == 8
+        ret[rank] = "ok " + "; ".join(kinds)
     except Exception:
         import traceback
 
@@ -76,4 +88,5 @@ def test_sharded_nccl_equals_single_gpu(native_lib):
         port = s.getsockname()[1]
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
-    assert all(v == "ok" for v in dict(ret).values()) and len(ret) == world, dict(ret)
+    assert all(str(v).startswith("ok") for v in dict(ret).values()) and len(ret) == world, dict(ret)
+    print(dict(ret))  # which exchange ran (p2p = fused peer-memory exchange, nccl = all-gather + merge)
