@@ -176,17 +176,19 @@ cudaError_t launch_exclusive_scan_i64(const int64_t *in, int64_t n, int64_t *out
 cudaError_t launch_exclusive_scan_i32(const int32_t *in, int64_t n, int32_t *out, cudaStream_t st);
 cudaError_t launch_scan_pages(const ScanArgs &a, int variant, int num_sms, int *launches, cudaStream_t st);
 
-// list-major scan (scan_lists.cu): the probed lists are read ONCE per batch and scored against every query
-// that probes them.  Scratch (all device, caller-sized): cnt/cursor/n32/n8/n4 [nlist], lq_off/off32/off8/off4
-// [nlist+1], lq [npairs], counters [4].  Writes the same candidate layout as launch_scan_pages.
+// list-major scan (scan_lists.cu, scan_mq.cu): the probed lists are read ONCE per batch and scored against every
+// query that probes them.  Scratch (all device, caller-sized): cnt | cursor | counters adjacent (one memset),
+// n32 [nlist], lq_off / off32 / pg8off / pg4off [nlist+1], lq [npairs].  Writes the same candidate layout as
+// launch_scan_pages.
 struct ListPlan {
     int32_t nlist;
-    int32_t *cnt, *cursor, *n32, *n8, *n4;    // [nlist]
-    int32_t *lq_off, *off32, *off8, *off4;    // [nlist+1]
+    int32_t *cnt, *cursor;             // [nlist] queries per list, fill cursor
+    int32_t *counters;                 // [4] work counter of the tile kernel (directly after cursor)
+    int32_t *n32;                      // [nlist] 32-query tile items per list
+    int32_t *lq_off, *off32;           // [nlist+1] exclusive prefixes of cnt / n32
+    int32_t *pg8off, *pg4off;          // [nlist+1] exclusive prefixes of the page x pass units of the two page scans
     int32_t *lq;                       // [npairs] pair ids grouped by list
-    int32_t *counters;                 // [4] work counters of the tile variants (32 / 8 / 4 queries)
-    int32_t *mq_pages, *mq_pgoff;      // [nlist], [nlist+1]: pages of the lists the multi-query page scan handles
-    // optional fork/join: the (few, long) tile items run on side streams while the page scan fills the GPU
+    // optional fork/join: the (few, long) tile items run on a side stream while the page scans fill the GPU
     cudaStream_t side[2];
     cudaEvent_t ev_fork, ev_join[2];
     unsigned long long *unique_rows;   // optional: += rows of every list probed at least once

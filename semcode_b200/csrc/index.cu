@@ -720,24 +720,20 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
                                  (ix->scan_mode == 0 && long_lists && 4 * npairs >= 3 * (int64_t)ix->nlist));
         if (list_major) {
             const size_t nl = (size_t)ix->nlist;
-            const size_t words = 6 * nl + 5 * (nl + 1) + (size_t)npairs + 4 + 16;
+            const size_t words = 3 * nl + 4 + 4 * (nl + 1) + (size_t)npairs + 16;
             CU(ix->s_lplan.reserve(words * 4));
             int32_t *w = ix->s_lplan.as<int32_t>();
             ListPlan lp;
             lp.nlist = ix->nlist;
             lp.cnt = w;
             lp.cursor = w + nl;
-            lp.n32 = w + 2 * nl;
-            lp.n8 = w + 3 * nl;
-            lp.n4 = w + 4 * nl;
-            lp.lq_off = w + 5 * nl;
+            lp.counters = w + 2 * nl;
+            lp.n32 = lp.counters + 4;
+            lp.lq_off = lp.n32 + nl;
             lp.off32 = lp.lq_off + nl + 1;
-            lp.off8 = lp.off32 + nl + 1;
-            lp.off4 = lp.off8 + nl + 1;
-            lp.mq_pages = lp.off4 + nl + 1;
-            lp.mq_pgoff = lp.mq_pages + nl;
-            lp.counters = lp.mq_pgoff + nl + 1;
-            lp.lq = lp.counters + 4;
+            lp.pg8off = lp.off32 + nl + 1;
+            lp.pg4off = lp.pg8off + nl + 1;
+            lp.lq = lp.pg4off + nl + 1;
             lp.unique_rows = ix->profiling ? ix->prof_rows + 1 : nullptr;
             for (int i = 0; i < 2; ++i) {
                 lp.side[i] = ix->lists_fork ? ix->side[i] : nullptr;

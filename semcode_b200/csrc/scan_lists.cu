@@ -41,28 +41,102 @@ __global__ void count_list_pairs_kernel(const int32_t *__restrict__ probe, int64
     if (l >= 0 && l < nlist && list_len[l] > 0) atomicAdd(cnt + l, 1);
 }
 
-// A list probed by c queries becomes c / 32 tile items of 32 queries plus a remainder:
-//   rem > rem8_max  one more (ragged) 32-query tile item: FP32-bound, ~2.8 list reads of time
-//   rem 5..rem8_max ceil(rem / 8) passes of the 8-query page scan (n8 = passes)
-//   rem 1..4        one pass of the 4-query page scan
-__global__ void plan_items_kernel(const int32_t *__restrict__ cnt, int32_t nlist, int32_t rem8_max, int32_t *__restrict__ n32,
-                                  int32_t *__restrict__ n8, int32_t *__restrict__ n4, const int32_t *__restrict__ list_len,
-                                  unsigned long long *__restrict__ unique_rows) {
-    const int32_t l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= nlist) return;
-    const int32_t c = cnt[l];
-    if (unique_rows != nullptr && c > 0) atomicAdd(unique_rows, (unsigned long long)list_len[l]);
-    int32_t a = c / 32, b = 0, d = 0;
-    const int32_t rem = c - a * 32;
-    if (rem > rem8_max)
-        ++a;
-    else if (rem > 4)
-        b = (rem + 7) / 8;
-    else if (rem > 0)
-        d = 1;
-    n32[l] = a;
-    n8[l] = b;
-    n4[l] = d;
+// One CTA plans every list.  A list probed by c queries becomes c / 32 tile items of 32 queries plus a remainder:
+//   rem > 16     one more (ragged) 32-query tile item: FP32-bound, ~2.8 list reads of time
+//   rem 5..16    ceil(rem / 8) passes of the 8-query page scan
+//   rem 1..4     one pass of the 4-query page scan
+// and four exclusive prefix sums are produced in the same sweep: lq_off (queries per list), off32 (tile items),
+// pg8off / pg4off (page x pass units of the two page scans).  (Seven launches in the first version.)
+__global__ void __launch_bounds__(1024) plan_lists_kernel(const int32_t *__restrict__ cnt, const int32_t *__restrict__ list_len,
+                                                          int32_t nlist, int32_t *__restrict__ n32, int32_t *__restrict__ lq_off,
+                                                          int32_t *__restrict__ off32, int32_t *__restrict__ pg8off,
+                                                          int32_t *__restrict__ pg4off,
+                                                          unsigned long long *__restrict__ unique_rows) {
+    __shared__ int32_t warp_tot[4][32];
+    __shared__ int32_t blk_tot[4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int IPT = 4;
+    int32_t carry[4] = {0, 0, 0, 0};
+    unsigned long long rows = 0;
+    for (int32_t base = 0; base < nlist; base += 1024 * IPT) {
+        const int32_t i0 = base + tid * IPT;
+        int32_t v[4][IPT];
+        int32_t local[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+            const int32_t l = i0 + j;
+            int32_t c = 0, a = 0, u8 = 0, u4 = 0;
+            if (l < nlist) {
+                c = cnt[l];
+                const int32_t len = list_len[l];
+                const int32_t pages = (len + kPageRows - 1) / kPageRows;
+                if (c > 0) rows += (unsigned long long)len;
+                a = c / 32;
+                const int32_t rem = c - a * 32;
+                if (rem > 16)
+                    ++a;
+                else if (rem > 4)
+                    u8 = ((rem + 7) / 8) * pages;
+                else if (rem > 0)
+                    u4 = pages;
+                n32[l] = a;
+            }
+            v[0][j] = c;
+            v[1][j] = a;
+            v[2][j] = u8;
+            v[3][j] = u4;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) local[t] += v[t][j];
+        }
+        int32_t incl[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            int32_t x = local[t];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            incl[t] = x;
+            if (lane == 31) warp_tot[t][warp] = x;
+        }
+        __syncthreads();
+        if (warp < 4) {  // warp t scans the 32 warp totals of quantity t
+            const int32_t t0 = warp_tot[warp][lane];
+            int32_t x = t0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            warp_tot[warp][lane] = x - t0;
+            if (lane == 31) blk_tot[warp] = x;
+        }
+        __syncthreads();
+        int32_t *const outs[4] = {lq_off, off32, pg8off, pg4off};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            int32_t run = carry[t] + warp_tot[t][warp] + incl[t] - local[t];
+#pragma unroll
+            for (int j = 0; j < IPT; ++j) {
+                if (i0 + j < nlist) outs[t][i0 + j] = run;
+                run += v[t][j];
+            }
+            carry[t] += blk_tot[t];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        lq_off[nlist] = carry[0];
+        off32[nlist] = carry[1];
+        pg8off[nlist] = carry[2];
+        pg4off[nlist] = carry[3];
+    }
+    if (unique_rows != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rows += __shfl_xor_sync(0xffffffffu, rows, o);
+        if (lane == 0 && rows) atomicAdd(unique_rows, rows);
+    }
 }
 
 __global__ void fill_list_pairs_kernel(const int32_t *__restrict__ probe, int64_t npairs, const int32_t *__restrict__ list_len,
@@ -154,7 +228,7 @@ __global__ void __launch_bounds__(NT, 2) scan_lists_kernel(const ScanArgs a, con
     const int qg = (warp % C::WPK) % C::QG;         // query group (8 queries)
     const int rg = (warp % C::WPK) / C::QG;         // row group
     const int row0 = rg * 32 * C::RPT + lane;       // rows row0 + 32*i
-    const int32_t *item_off = QT == 32 ? p.off32 : p.off8;
+    const int32_t *item_off = p.off32;
     const int32_t total = item_off[p.nlist];
     const int ds = a.ds;
     const int KB = (ds + BKX - 1) / BKX;
@@ -169,7 +243,7 @@ __global__ void __launch_bounds__(NT, 2) scan_lists_kernel(const ScanArgs a, con
         if (item >= total) break;
         const int32_t l = owner_of(item_off, p.nlist, item);
         const int32_t chunk = item - item_off[l];
-        const int32_t qbase = p.lq_off[l] + (QT == 32 ? 32 * chunk : 32 * p.n32[l]);
+        const int32_t qbase = p.lq_off[l] + 32 * chunk;
         const int32_t nqi = min(QT, p.lq_off[l + 1] - qbase);
         const int32_t len = a.list_len[l];
         const int32_t ptbase = a.pt_off[l];
@@ -331,7 +405,7 @@ __global__ void __launch_bounds__(NT, 2) scan_lists_kernel(const ScanArgs a, con
 template <int QT, int BKX, int NS, int RB, int RPT>
 cudaError_t launch_lists_variant(const ScanArgs &a, const ListPlan &p, int num_sms, cudaStream_t st) {
     const size_t smem = sizeof(TileSmem<QT, BKX, NS, RB, RPT>);
-    const int which = QT == 32 ? 0 : 1;
+    const int which = 0;
     const int per_sm = smem * 2 + 2048 <= 227 * 1024 ? 2 : 1;
     cudaError_t e;
     if (a.metric == 1) {
@@ -350,29 +424,23 @@ cudaError_t launch_lists_variant(const ScanArgs &a, const ListPlan &p, int num_s
 
 }  // namespace
 
-cudaError_t launch_scan_mq(const ScanArgs &a, const ListPlan &p, int bucket, int32_t *pages, int32_t *pgoff, int num_sms,
-                           cudaStream_t st);
+cudaError_t launch_scan_mq(const ScanArgs &a, const ListPlan &p, int bucket, const int32_t *pgoff, int num_sms, cudaStream_t st);
 
-// cfg selects experiments: 0 = default; 1 = cp.async tile kernel (QT = 8) for remainders of 5..8 queries instead of
-// the 8-query page scan; 2 = 32-float stages for the 32-query tile
+// cfg selects experiments: 0 = default; 2 = 32-float stages for the 32-query tile
 cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int num_sms, int *launches, cudaStream_t st) {
     if (a.npairs <= 0) return cudaSuccess;
     if (a.npairs > (int64_t)INT32_MAX) return cudaErrorInvalidValue;
     cudaError_t e;
-    const unsigned pb = (unsigned)((a.npairs + 255) / 256), lb = (unsigned)((p.nlist + 255) / 256);
-    if ((e = cudaMemsetAsync(p.cnt, 0, (size_t)p.nlist * 4, st)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(p.cursor, 0, (size_t)p.nlist * 4, st)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(p.counters, 0, 16, st)) != cudaSuccess) return e;
+    const unsigned pb = (unsigned)((a.npairs + 255) / 256);
+    // cnt | cursor | counters are adjacent: one memset
+    if ((e = cudaMemsetAsync(p.cnt, 0, (size_t)(2 * p.nlist + 4) * 4, st)) != cudaSuccess) return e;
     count_list_pairs_kernel<<<pb, 256, 0, st>>>(a.probe, a.npairs, a.list_len, p.nlist, p.cnt);
-    plan_items_kernel<<<lb, 256, 0, st>>>(p.cnt, p.nlist, cfg == 1 ? 8 : 16, p.n32, p.n8, p.n4, a.list_len, p.unique_rows);
-    if ((e = launch_exclusive_scan_i32(p.cnt, p.nlist, p.lq_off, st)) != cudaSuccess) return e;
-    if ((e = launch_exclusive_scan_i32(p.n32, p.nlist, p.off32, st)) != cudaSuccess) return e;
-    if (cfg == 1 && (e = launch_exclusive_scan_i32(p.n8, p.nlist, p.off8, st)) != cudaSuccess) return e;
+    plan_lists_kernel<<<1, 1024, 0, st>>>(p.cnt, a.list_len, p.nlist, p.n32, p.lq_off, p.off32, p.pg8off, p.pg4off, p.unique_rows);
     fill_list_pairs_kernel<<<pb, 256, 0, st>>>(a.probe, a.npairs, a.list_len, p.nlist, p.lq_off, p.cursor, p.lq);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     // Three consumers of the plan.  The 32-query tile kernel holds the FP32-bound items (lists probed by many
     // queries); the two page scans hold the HBM-bound remainders, every warp an equal share of the pages, so they
-    // have no tail however few lists a bucket holds.  With side streams the tile kernel is launched first and the
+    // have no tail however few lists a bucket holds.  With a side stream the tile kernel is launched first and the
     // page scans fill the SMs it leaves free.
     const bool fork = p.side[0] != nullptr;
     cudaStream_t s32 = fork ? p.side[0] : st;
@@ -386,14 +454,10 @@ cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int
         if ((e = launch_lists_variant<32, 64, 2, 128, 4>(a, p, num_sms, s32)) != cudaSuccess) return e;
     }
     if (fork && (e = cudaEventRecord(p.ev_join[0], s32)) != cudaSuccess) return e;
-    if (cfg == 1) {
-        if ((e = launch_lists_variant<8, 64, 2, 128, 2>(a, p, num_sms, st)) != cudaSuccess) return e;
-    } else {
-        if ((e = launch_scan_mq(a, p, 1, p.mq_pages, p.mq_pgoff, num_sms, st)) != cudaSuccess) return e;
-    }
-    if ((e = launch_scan_mq(a, p, 0, p.mq_pages, p.mq_pgoff, num_sms, st)) != cudaSuccess) return e;
+    if ((e = launch_scan_mq(a, p, 1, p.pg8off, num_sms, st)) != cudaSuccess) return e;
+    if ((e = launch_scan_mq(a, p, 0, p.pg4off, num_sms, st)) != cudaSuccess) return e;
     if (fork && (e = cudaStreamWaitEvent(st, p.ev_join[0], 0)) != cudaSuccess) return e;
-    if (launches) *launches += 12;
+    if (launches) *launches += 6;
     return cudaSuccess;
 }
 

@@ -23,14 +23,6 @@ namespace sc {
 
 namespace {
 
-// units[l] = pages(l) * passes(l)   (passes = n4[l] for bucket 0, n8[l] for bucket 1)
-__global__ void mq_pages_kernel(const int32_t *__restrict__ passes, const int32_t *__restrict__ list_len, int32_t nlist,
-                                int32_t *__restrict__ pages) {
-    const int32_t l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= nlist) return;
-    pages[l] = passes[l] * ((list_len[l] + kPageRows - 1) / kPageRows);
-}
-
 template <bool L2>
 __device__ __forceinline__ float mq_accum4(float acc, const float4 &x, const float4 &q) {
     if (L2) {
@@ -283,13 +275,9 @@ cudaError_t launch_mq_metric(const ScanArgs &a, const ListPlan &p, const int32_t
 
 }  // namespace
 
-// bucket 0: lists with p.n4[l] passes of <= 4 queries; bucket 1: p.n8[l] passes of <= 8 queries.
-// scratch: pages [nlist], pgoff [nlist+1] (int32), reused by consecutive launches on the same stream
-cudaError_t launch_scan_mq(const ScanArgs &a, const ListPlan &p, int bucket, int32_t *pages, int32_t *pgoff, int num_sms,
-                           cudaStream_t st) {
-    mq_pages_kernel<<<(p.nlist + 255) / 256, 256, 0, st>>>(bucket == 0 ? p.n4 : p.n8, a.list_len, p.nlist, pages);
-    cudaError_t e = launch_exclusive_scan_i32(pages, p.nlist, pgoff, st);
-    if (e != cudaSuccess) return e;
+// bucket 0: remainders of 1..4 queries (one pass); bucket 1: remainders of 5..16 queries (passes of 8).
+// pgoff [nlist+1]: exclusive prefix of the bucket's page x pass units (plan_lists_kernel)
+cudaError_t launch_scan_mq(const ScanArgs &a, const ListPlan &p, int bucket, const int32_t *pgoff, int num_sms, cudaStream_t st) {
     const int ds4 = a.ds >> 2;
     if (bucket == 0) {
         if (ds4 % 192 == 0) return launch_mq_metric<4, 2, 6, true>(a, p, pgoff, num_sms, st);

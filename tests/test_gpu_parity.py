@@ -522,7 +522,7 @@ def test_list_major_auto_mode_full_search(sb, orc):
     g.set_profiling(True)
     g.set_param("scan_mode", 0)
     g.search(q, 10, nprobe=12)
-    assert g.last_search_times().scan_launches == 12  # plan kernels + the 32-query tile + the two page scans
+    assert g.last_search_times().scan_launches == 6  # count, plan, fill + the 32-query tile + the two page scans
     g.set_param("scan_mode", 1)
     g.search(q, 10, nprobe=12)
     assert g.last_search_times().scan_launches == 1
@@ -532,8 +532,8 @@ def test_list_major_auto_mode_full_search(sb, orc):
 @pytest.mark.parametrize("per_list", [3, 7, 13])
 def test_multi_query_page_scan_buckets_and_slices(sb, orc, metric, per_list):
     """The two multi-query page scans (scan_mq.cu): remainders of 1..4 queries (bucket 0), 5..16 queries in one or
-    two passes of 8 (bucket 1), over single-slice, multi-slice and ragged-slice dimensions; also the cp.async tile
-    kept as lists_cfg = 1."""
+    two passes of 8 (bucket 1), over single-slice, multi-slice and ragged-slice dimensions (lists_cfg = 2 only changes
+    the stage width of the 32-query tile)."""
     for d in (128, 200, 768, 1024, 2048, 3072):
         n = 3000 if d <= 1024 else 1500
         x, q, cent, ids = make_case(orc, n, d, 24, 12 * per_list, metric, seed=d + per_list)
@@ -543,7 +543,7 @@ def test_multi_query_page_scan_buckets_and_slices(sb, orc, metric, per_list):
         g.set_param("scan_mode", 1)
         d1, i1 = g.search(q, 10, lists=probes)
         rd, ri = orc.search(oidx, q, 10, 2, mask=orc.row_mask(oidx, removed_ids=ids[::13]), probes=probes)
-        for cfg in (0, 1):
+        for cfg in (0, 2):
             g.set_param("scan_mode", 2)
             g.set_param("lists_cfg", cfg)
             d3, i3 = g.search(q, 10, lists=probes)
