@@ -551,21 +551,25 @@ def run_ours(args):
         return
 
     peaks, peak_src = measured_peaks()
-    traffic = None
-    try:  # DRAM bytes of the scan kernel from the committed ncu --set full capture of this workload
+    traffic, traffic_lm = None, None
+    try:  # DRAM bytes of the scan kernels from the committed ncu --set full captures of this workload (1 GPU)
         with open(os.path.join(ROOT, "profiles", "scan_traffic.json")) as f:
             for ent in json.load(f)["captures"]:
                 mm = ent["match"]
-                if all(mm[key] == val for key, val in (("n", n), ("dim", d), ("nlist", nlist), ("nprobe", nprobe),
-                                                       ("nq", nq), ("dataset", args.dataset))):
-                    traffic = ent["dram_bytes_per_launch"]
+                if world == 1 and args.shard_sim == 1 and all(mm[key] == val for key, val in (
+                        ("n", n), ("dim", d), ("nlist", nlist), ("nprobe", nprobe), ("nq", nq), ("dataset", args.dataset))):
+                    if ent.get("scan", "query-major") == "list-major":
+                        traffic_lm = ent["dram_bytes_per_launch"]
+                    else:
+                        traffic = ent["dram_bytes_per_launch"]
     except Exception:
-        traffic = None
+        traffic, traffic_lm = None, None
     logical_bytes = statistics.mean(scanned_rows) * 4 * d  # this rank's slice: one pass per (query, list) pair
     scan_s = statistics.mean(scan_ms) / 1e3
     if list_major:  # compulsory bytes: every DISTINCT probed list once
         bytes_per_step = statistics.mean(unique_rows) * 4 * d
-        kernel_name = "list-major scan: scan_mq_kernel (lists probed by <= 4 queries) + scan_lists_kernel tiles (8 / 32 queries) + plan"
+        kernel_name = ("list-major scan: scan_mq_kernel<4> (remainders of 1..4 queries per list) + scan_mq_kernel<8> (5..16) + "
+                       "scan_lists_kernel (32-query tiles) + plan")
     else:
         bytes_per_step = logical_bytes
         kernel_name = "scan_pages_kernel (query-major)"
@@ -583,7 +587,7 @@ def run_ours(args):
         "roofline": {
             "bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": achieved / peaks["hbm_gbs"], "frac_of_8TBps_nominal": achieved / 8000.0, "peak_source": peak_src,
-            "traffic": traffic if not list_major else None, "algorithmic_bytes_per_launch": bytes_per_step,
+            "traffic": traffic if not list_major else traffic_lm, "algorithmic_bytes_per_launch": bytes_per_step,
             "logical_bytes_per_launch": logical_bytes, "logical_GBps": logical_bytes / scan_s / 1e9,
             "kernel_ms": scan_s * 1e3, "kernel_share_of_step": (phase["scan"] / nprof) / (ms_total / args.steps),
         },
