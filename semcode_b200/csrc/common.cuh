@@ -184,7 +184,9 @@ struct ListPlan {
     int32_t nlist;
     int32_t *cnt, *cursor;             // [nlist] queries per list, fill cursor
     int32_t *counters;                 // [4] work counter of the tile kernel (directly after cursor)
-    int32_t *n32;                      // [nlist] 32-query tile items per list
+    int32_t chunk;                     // queries per tile item: 32 (FFMA tiles) or 64 (tcgen05 tiles)
+    float *qsplit;                     // tcgen05 tiles: 2 x [nq, ds] tf32 terms (hi, lo) of the queries (scratch)
+    int32_t *n32;                      // [nlist] tile items (of `chunk` queries) per list
     int32_t *lq_off, *off32;           // [nlist+1] exclusive prefixes of cnt / n32
     int32_t *pg8off, *pg4off;          // [nlist+1] exclusive prefixes of the page x pass units of the two page scans
     int32_t *lq;                       // [npairs] pair ids grouped by list
@@ -194,6 +196,8 @@ struct ListPlan {
     unsigned long long *unique_rows;   // optional: += rows of every list probed at least once
 };
 cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int num_sms, int *launches, cudaStream_t st);
+// tile items on the tensor cores (scan_lists_tc.cu): inner product, ds % 32 == 0, p.chunk == 64
+cudaError_t launch_scan_lists_tc(const ScanArgs &a, const ListPlan &p, int num_sms, cudaStream_t st);
 // final top-k over the candidates of each query + id translation
 cudaError_t launch_select_candidates(const ScanArgs &a, int64_t nq, int k, float *out_dist, int64_t *out_ids,
                                      cudaStream_t st);

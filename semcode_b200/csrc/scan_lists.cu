@@ -41,14 +41,15 @@ __global__ void count_list_pairs_kernel(const int32_t *__restrict__ probe, int64
     if (l >= 0 && l < nlist && list_len[l] > 0) atomicAdd(cnt + l, 1);
 }
 
-// One CTA plans every list.  A list probed by c queries becomes c / 32 tile items of 32 queries plus a remainder:
-//   rem > 16     one more (ragged) 32-query tile item: FP32-bound, ~2.8 list reads of time
-//   rem 5..16    ceil(rem / 8) passes of the 8-query page scan
+// One CTA plans every list.  A list probed by c queries becomes c / chunk tile items of `chunk` queries (32 for the
+// FFMA tiles, 64 for the tcgen05 tiles) plus a remainder:
+//   rem > T      one more (ragged) tile item; T = 16 for the FFMA tiles, 8 for the tcgen05 tiles
+//   rem 5..T     ceil(rem / 8) passes of the 8-query page scan
 //   rem 1..4     one pass of the 4-query page scan
 // and four exclusive prefix sums are produced in the same sweep: lq_off (queries per list), off32 (tile items),
 // pg8off / pg4off (page x pass units of the two page scans).  (Seven launches in the first version.)
 __global__ void __launch_bounds__(1024) plan_lists_kernel(const int32_t *__restrict__ cnt, const int32_t *__restrict__ list_len,
-                                                          int32_t nlist, int32_t *__restrict__ n32, int32_t *__restrict__ lq_off,
+                                                          int32_t nlist, int32_t chunk, int32_t min_items, int32_t *__restrict__ n32, int32_t *__restrict__ lq_off,
                                                           int32_t *__restrict__ off32, int32_t *__restrict__ pg8off,
                                                           int32_t *__restrict__ pg4off,
                                                           unsigned long long *__restrict__ unique_rows) {
@@ -56,6 +57,19 @@ __global__ void __launch_bounds__(1024) plan_lists_kernel(const int32_t *__restr
     __shared__ int32_t blk_tot[4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int IPT = 4;
+    // a ragged tile item costs ~2.8 list reads of time on the FFMA tiles (two passes of 8 are cheaper up to 16
+    // queries) but about 1.6 on the tcgen05 tiles (cheaper than two passes from 9 queries on) -- provided there are
+    // enough items to fill the GPU: an item is walked by ONE CTA (~100 us), so a handful of them is a pure tail
+    __shared__ int32_t n_over8;
+    if (tid == 0) n_over8 = 0;
+    __syncthreads();
+    if (chunk == 64) {
+        int32_t mine = 0;
+        for (int32_t l = tid; l < nlist; l += 1024) mine += cnt[l] > 8 ? 1 : 0;
+        if (mine) atomicAdd(&n_over8, mine);
+    }
+    __syncthreads();
+    const int32_t rem_tile = (chunk == 64 && n_over8 >= min_items) ? 8 : 16;
     int32_t carry[4] = {0, 0, 0, 0};
     unsigned long long rows = 0;
     for (int32_t base = 0; base < nlist; base += 1024 * IPT) {
@@ -71,9 +85,9 @@ __global__ void __launch_bounds__(1024) plan_lists_kernel(const int32_t *__restr
                 const int32_t len = list_len[l];
                 const int32_t pages = (len + kPageRows - 1) / kPageRows;
                 if (c > 0) rows += (unsigned long long)len;
-                a = c / 32;
-                const int32_t rem = c - a * 32;
-                if (rem > 16)
+                a = c / chunk;
+                const int32_t rem = c - a * chunk;
+                if (rem > rem_tile)
                     ++a;
                 else if (rem > 4)
                     u8 = ((rem + 7) / 8) * pages;
@@ -426,7 +440,7 @@ cudaError_t launch_lists_variant(const ScanArgs &a, const ListPlan &p, int num_s
 
 cudaError_t launch_scan_mq(const ScanArgs &a, const ListPlan &p, int bucket, const int32_t *pgoff, int num_sms, cudaStream_t st);
 
-// cfg selects experiments: 0 = default; 2 = 32-float stages for the 32-query tile
+// p.chunk == 64 (set by the caller): tcgen05 tiles; else FFMA tiles, cfg 2 = their 32-float-stage variant
 cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int num_sms, int *launches, cudaStream_t st) {
     if (a.npairs <= 0) return cudaSuccess;
     if (a.npairs > (int64_t)INT32_MAX) return cudaErrorInvalidValue;
@@ -435,7 +449,8 @@ cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int
     // cnt | cursor | counters are adjacent: one memset
     if ((e = cudaMemsetAsync(p.cnt, 0, (size_t)(2 * p.nlist + 4) * 4, st)) != cudaSuccess) return e;
     count_list_pairs_kernel<<<pb, 256, 0, st>>>(a.probe, a.npairs, a.list_len, p.nlist, p.cnt);
-    plan_lists_kernel<<<1, 1024, 0, st>>>(p.cnt, a.list_len, p.nlist, p.n32, p.lq_off, p.off32, p.pg8off, p.pg4off, p.unique_rows);
+    plan_lists_kernel<<<1, 1024, 0, st>>>(p.cnt, a.list_len, p.nlist, p.chunk, 2 * num_sms, p.n32, p.lq_off, p.off32, p.pg8off, p.pg4off,
+                                          p.unique_rows);
     fill_list_pairs_kernel<<<pb, 256, 0, st>>>(a.probe, a.npairs, a.list_len, p.nlist, p.lq_off, p.cursor, p.lq);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     // Three consumers of the plan.  The 32-query tile kernel holds the FP32-bound items (lists probed by many
@@ -448,7 +463,9 @@ cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int
         if ((e = cudaEventRecord(p.ev_fork, st)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(s32, p.ev_fork, 0)) != cudaSuccess) return e;
     }
-    if (cfg == 2) {
+    if (p.chunk == 64) {  // tcgen05 tiles (index.cu picked chunk = 64 only when the kernel applies)
+        if ((e = launch_scan_lists_tc(a, p, num_sms, s32)) != cudaSuccess) return e;
+    } else if (cfg == 2) {
         if ((e = launch_lists_variant<32, 32, 3, 128, 4>(a, p, num_sms, s32)) != cudaSuccess) return e;
     } else {
         if ((e = launch_lists_variant<32, 64, 2, 128, 4>(a, p, num_sms, s32)) != cudaSuccess) return e;
@@ -457,7 +474,7 @@ cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int
     if ((e = launch_scan_mq(a, p, 1, p.pg8off, num_sms, st)) != cudaSuccess) return e;
     if ((e = launch_scan_mq(a, p, 0, p.pg4off, num_sms, st)) != cudaSuccess) return e;
     if (fork && (e = cudaStreamWaitEvent(st, p.ev_join[0], 0)) != cudaSuccess) return e;
-    if (launches) *launches += 6;
+    if (launches) *launches += p.chunk == 64 ? 7 : 6;
     return cudaSuccess;
 }
 

@@ -1,0 +1,526 @@
+// K5d: list-major scan on the tensor cores, for lists probed by MANY queries of the batch (inner product).
+//
+// With nq * nprobe >> nlist a probed list meets tens of queries (32 on average at nq 4096, nprobe 128, nlist
+// 16384): scoring it is a [rows x dim] x [dim x queries] contraction, and the exact-fp32 FFMA tiles of
+// scan_lists.cu top out at the FP32 pipe (~37 TFLOP/s measured) -- 21 ms per batch where HBM needs 4.7 ms.
+// Here the same work item (list, chunk of <= 64 queries) runs on tcgen05:
+//
+//   D[128 rows, 64 queries] (fp32, TMEM) += A[128 x 32] . B[64 x 32]^T      kind::tf32, per 32-float k-block
+//
+// fp32 accuracy comes from splitting every operand into two tf32 terms ON THE FLY (the lists stay plain fp32 in
+// HBM, nothing is stored twice): hi = tf32(x), lo = tf32(x - hi); product = hi.hi + hi.lo + lo.hi (3 MMAs; a third
+// term changed no digit of the result -- the accuracy limit is the accumulation, see NACC below).
+// The query rows are split once per batch into two global arrays (a few MB); list rows are split by the loader
+// warps between their cp.async landing and the MMA.
+//
+// CTA = 10 warps, one CTA per SM, items dealt round-robin (no counter: every role derives the same sequence):
+//   warps 0-7  A loader/splitter: cp.async 16-byte copies of the raw A k-block (rows through the page table)
+//              straight into a 128-byte-swizzled K-major tile of the raw ring, 5 stages in flight; when a stage
+//              has landed each thread splits the 4 float4 it copied (hi in place, lo into the lo ring),
+//              fence.proxy.async, one mbarrier arrival per warp
+//   warp 8     B loader: cp.async of the pre-split query k-blocks (hi | lo) into the B ring, 3 stages in flight
+//   warps 9-11 MMA issuers (one lane each), one per product term -- hi.hi, hi.lo, lo.hi -- 4 tcgen05.mma 128x64x8 per
+//              stage each into their own accumulators.  (One issuer for all 12 was the bottleneck: a 128x64x8
+//              MMA occupies the tensor pipe for 32 cycles but costs ~100 cycles of uniform-register traffic to
+//              issue.)  tcgen05.commit by each issuer frees the stage / publishes the tile (two tiles x four
+//              64-column accumulators = all 512 TMEM columns; see NACC below)
+//   warps 12-15 epilogue: tcgen05.ld of the finished 128x64 tile (sum of its accumulators), fused tag predicate,
+//              one coalesced 128-byte store per (query, 32 rows) into the per-pair candidate layout shared with
+//              the other scans
+// Replaces the same FAISS IVFFlatScanner::scan_codes loop (reference src/semcode/storage/milvus_store.py:141-147).
+// Bound: HBM (each list once per 64 queries) once the tensor pipe has >= 6x headroom over FFMA.
+#include "common.cuh"
+
+namespace sc {
+
+namespace {
+
+constexpr int TM = 128, TN = 64, TK = 32;
+constexpr int A_TILE = TM * TK * 4;  // 16 KB
+constexpr int B_TILE = TN * TK * 4;  // 8 KB
+// The tensor core adds every 128x64x8 product block into the fp32 accumulator with truncation, so ONE accumulation
+// chain of 3 x dim/8 additions carries a biased error of ~1e-6 on unit vectors (measured: 1.3e-6 at dim 768, 2.1e-6 at
+// dim 3072, the same with 2 or 3 tf32 terms) -- above the 1e-5 relative bar for scores of ~0.1.  Each tile therefore
+// keeps NACC = 4 accumulators: #0 and #1 take the small cross terms (hi.lo, lo.hi: 2^-11 of the result), #2 and #3
+// take the hi.hi blocks of the even and odd k-steps; the epilogue adds the four in fp32 (round to nearest).  Shorter
+// chains over smaller partial sums cut the truncation error ~10x, to the level of an FFMA chain (measured 1.8e-7
+// at dim 768, 2.6e-7 at dim 3072).
+constexpr int NACC = 4;
+constexpr int TMEM_COLS_TC = 512;  // two tiles x NACC 64-column accumulators
+
+// Shared memory: three rings, so that the bytes in flight from HBM are not tied to the operand staging.
+//   R  NR x 16 KB  raw A k-blocks (cp.async target); split in place into the hi operand; freed by the stage's MMAs
+//   L   2 x 16 KB  lo operand of A
+//   B  NB x 16 KB  hi | lo k-blocks of the (pre-split) queries, loaded by their own warp
+// NR - 2 = 5 raw stages (80 KB per SM, 11.8 MB per GPU) are in flight while one is split and one is multiplied.
+constexpr int NR = 7, NL = 2, NB = 4;
+constexpr int SMEM_TC = NR * A_TILE + NL * A_TILE + NB * 2 * B_TILE + 1024 /*align*/ + 1024 /*barriers, tables*/;
+constexpr int NAW = 8;        // A loader/splitter warps
+constexpr int NMW = 3;        // MMA issuer warps (one lane each), one per product term
+constexpr int NT_TC2 = (NAW + 1 + NMW + 4) * 32;  // + 1 B loader warp, 4 epilogue warps
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row atoms 1024 B apart (same as gemm_tc.cu)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t smem_dst, const void *gmem, bool valid) {
+    const int sz = valid ? 16 : 0;  // src-size 0 => 16 bytes of zeros
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t b;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(x));
+    return __uint_as_float(b);
+}
+
+// byte offset of 16-byte chunk c (0..7) of row r inside a 128-byte-swizzled K-major tile
+__device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
+
+// out[s][i] = s-th tf32 term of x[i]
+constexpr int NSPLIT = 2;
+__global__ void split_rows_kernel(const float4 *__restrict__ x, int64_t n4, float4 *__restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(x + i);
+        const float in[4] = {v.x, v.y, v.z, v.w};
+        float t[NSPLIT][4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float rem = in[e];
+#pragma unroll
+            for (int s = 0; s < NSPLIT; ++s) {
+                t[s][e] = to_tf32(rem);
+                rem -= t[s][e];
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < NSPLIT; ++s) out[(int64_t)s * n4 + i] = make_float4(t[s][0], t[s][1], t[s][2], t[s][3]);
+    }
+}
+
+struct TcItem {
+    int32_t l, len, ptbase, qbase, nqi, ntiles;
+};
+
+__device__ __forceinline__ int32_t owner_of_tc(const int32_t *__restrict__ off, int32_t n, int32_t v) {
+    int32_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const int32_t mid = (lo + hi) >> 1;
+        if (off[mid] <= v)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ bool load_item(const ScanArgs &a, const ListPlan &p, int32_t item, int32_t total, TcItem &I) {
+    if (item >= total) return false;
+    I.l = owner_of_tc(p.off32, p.nlist, item);
+    const int32_t chunk = item - p.off32[I.l];
+    I.qbase = p.lq_off[I.l] + TN * chunk;
+    I.nqi = min(TN, p.lq_off[I.l + 1] - I.qbase);
+    I.len = a.list_len[I.l];
+    I.ptbase = a.pt_off[I.l];
+    I.ntiles = (I.len + TM - 1) / TM;
+    return true;
+}
+
+// walks the CTA's (item, tile, k-block) sequence one stage at a time
+struct StageCursor {
+    TcItem I;
+    int32_t n = 0;
+    int tile = 0, kb = 0;
+    bool valid = false, fresh_item = true, fresh_tile = true;
+    __device__ __forceinline__ void start(const ScanArgs &a, const ListPlan &p, int32_t total) {
+        valid = load_item(a, p, (int32_t)blockIdx.x, total, I);
+    }
+    __device__ __forceinline__ void advance(const ScanArgs &a, const ListPlan &p, int32_t total, int KB) {
+        if (++kb == KB) {
+            kb = 0;
+            fresh_tile = true;
+            if (++tile == I.ntiles) {
+                tile = 0;
+                ++n;
+                fresh_item = true;
+                valid = load_item(a, p, (int32_t)(blockIdx.x + (int64_t)n * gridDim.x), total, I);
+            }
+        }
+    }
+};
+
+__global__ void __launch_bounds__(NT_TC2, 1) scan_lists_tc_kernel(const ScanArgs a, const ListPlan p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *ringR = smem;                                // NR x A_TILE: raw -> hi
+    uint8_t *ringL = ringR + NR * A_TILE;                 // NL x A_TILE: lo
+    uint8_t *ringB = ringL + NL * A_TILE;                 // NB x (hi | lo) B_TILE
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ringB + NB * 2 * B_TILE);
+    // bars: [0,NR) stage done (one commit per issuer; frees R slot s%NR, L slot s%NL, B slot s%NB)   [NR,NR+NL) A ready (NAW warps)
+    //       [NR+NL,NR+NL+NB) B ready (1 warp)   then 2 tile full (commit), 2 tile empty (4 epilogue warps)
+    constexpr int NBARS = NR + NL + NB + 4;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + NBARS);
+    int64_t *cbE = reinterpret_cast<int64_t *>(bars + NBARS + 2);  // [TN] candidate bases of the epilogue's current item
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar0 = smem_u32(bars);
+    auto done_bar = [&](int s) { return bar0 + 8u * s; };
+    auto aready_bar = [&](int s) { return bar0 + 8u * (NR + s); };
+    auto bready_bar = [&](int s) { return bar0 + 8u * (NR + NL + s); };
+    auto tfull_bar = [&](int acc) { return bar0 + 8u * (NR + NL + NB + acc); };
+    auto tempty_bar = [&](int acc) { return bar0 + 8u * (NR + NL + NB + 2 + acc); };
+    // the MMAs of stage x (>= 0) have completed: everything they read may be overwritten
+    auto wait_stage_done = [&](int x) {
+        if (x >= 0) mbar_wait(done_bar(x % NR), ((uint32_t)(x / NR)) & 1u);
+    };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NR; ++s) mbar_init(done_bar(s), NMW);
+        for (int s = 0; s < NL; ++s) mbar_init(aready_bar(s), NAW);
+        for (int s = 0; s < NB; ++s) mbar_init(bready_bar(s), 1);
+        for (int acc = 0; acc < 2; ++acc) {
+            mbar_init(tfull_bar(acc), NMW);
+            mbar_init(tempty_bar(acc), 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_async_smem();
+    }
+    if (warp == NAW + 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS_TC)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int32_t total = p.off32[p.nlist];
+    const int KB = a.ds / TK;  // launcher guarantees ds % 32 == 0
+    const int slab_mask = (1 << a.slab_shift) - 1;
+
+    if (warp < NAW) {
+        // ---------------- A loader / splitter ----------------
+        constexpr int CPT = TM * 8 / (NAW * 32);  // 16-byte cells per thread per stage (4)
+        constexpr int RSTEP = NAW * 4;            // rows between a thread's cells (32)
+        const int t = threadIdx.x;  // 0..NAW*32-1
+        const int c = t & 7;        // 16-byte chunk of the 128-byte k-block
+        const int r0 = t >> 3;      // rows r0 + RSTEP*i
+        uint32_t cell[CPT];
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) cell[i] = swz(r0 + RSTEP * i, c);
+        StageCursor cur;
+        cur.start(a, p, total);
+        const float *rowp[CPT];
+        int issued = 0, done = 0;
+        constexpr int AHEAD = NR - 2;  // raw stages in flight
+
+        auto issue = [&]() {
+            if (cur.fresh_tile) {
+                cur.fresh_tile = false;
+                // (a bulk L2 prefetch of the next tile's pages was tried here: it doubled the DRAM reads -- 65 GB
+                //  instead of 33 GB per batch, L2 hit rate 12 % -- because the lines were evicted before use)
+#pragma unroll
+                for (int i = 0; i < CPT; ++i) {
+                    const int32_t r = cur.tile * TM + r0 + RSTEP * i;
+                    rowp[i] = nullptr;
+                    if (r < cur.I.len) {
+                        const int32_t page = __ldg(a.pt + cur.I.ptbase + (r >> 5));
+                        rowp[i] = a.slabs->vec[page >> a.slab_shift] + ((int64_t)(page & slab_mask) * kPageRows + (r & 31)) * a.ds;
+                    }
+                }
+            }
+            wait_stage_done(issued - NR);
+            const uint32_t sbase = smem_u32(ringR + (issued % NR) * A_TILE);
+            const int k0 = cur.kb * TK + c * 4;
+#pragma unroll
+            for (int i = 0; i < CPT; ++i)
+                cp_async16_zfill(sbase + cell[i], rowp[i] ? (const void *)(rowp[i] + k0) : (const void *)a.q, rowp[i] != nullptr);
+            ++issued;
+            cur.advance(a, p, total, KB);
+        };
+
+#pragma unroll 1
+        for (int s = 0; s < AHEAD; ++s) {
+            if (cur.valid) issue();
+            cp_async_commit_group();
+        }
+#pragma unroll 1
+        while (done < issued) {
+            cp_async_wait_group<AHEAD - 1>();  // this thread's copies of stage `done` have landed
+            wait_stage_done(done - NL);         // the lo slot is free
+            const uint32_t sr = smem_u32(ringR + (done % NR) * A_TILE);
+            const uint32_t sl = smem_u32(ringL + (done % NL) * A_TILE);
+            // three phases (all loads, all arithmetic, all stores) so that the cells do not serialise on aliasing
+            float4 v[CPT], h[CPT], l[CPT];
+#pragma unroll
+            for (int i = 0; i < CPT; ++i)
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "r"(sr + cell[i]));
+#pragma unroll
+            for (int i = 0; i < CPT; ++i) {
+                h[i].x = to_tf32(v[i].x);
+                h[i].y = to_tf32(v[i].y);
+                h[i].z = to_tf32(v[i].z);
+                h[i].w = to_tf32(v[i].w);
+                l[i].x = to_tf32(v[i].x - h[i].x);
+                l[i].y = to_tf32(v[i].y - h[i].y);
+                l[i].z = to_tf32(v[i].z - h[i].z);
+                l[i].w = to_tf32(v[i].w - h[i].w);
+            }
+#pragma unroll
+            for (int i = 0; i < CPT; ++i) {
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sr + cell[i]), "f"(h[i].x), "f"(h[i].y), "f"(h[i].z), "f"(h[i].w) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sl + cell[i]), "f"(l[i].x), "f"(l[i].y), "f"(l[i].z), "f"(l[i].w) : "memory");
+            }
+            fence_async_smem();  // generic-proxy writes (cp.async + the stores above) -> visible to the MMA's async proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(aready_bar(done % NL));
+            ++done;
+            if (cur.valid) issue();
+            cp_async_commit_group();
+        }
+        cp_async_wait_group<0>();
+    } else if (warp == NAW) {
+        // ---------------- B loader: 64 query rows x 8 chunks x (hi | lo) per stage = 32 copies per lane ----------------
+        const int c = lane & 7, r0 = lane >> 3;  // rows r0 + 4*i, i < 16
+        const int64_t qstride = (a.npairs / a.nprobe) * (int64_t)a.ds;  // floats per split array
+        StageCursor cur;
+        cur.start(a, p, total);
+        int64_t qoff[16];
+        int issued = 0, done = 0;
+        constexpr int BAHEAD = NB - 1;
+        auto issue = [&]() {
+            if (cur.fresh_item) {
+                cur.fresh_item = false;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int j = r0 + 4 * i;
+                    qoff[i] = -1;
+                    if (j < cur.I.nqi) qoff[i] = (int64_t)(p.lq[cur.I.qbase + j] / a.nprobe) * a.ds;
+                }
+            }
+            wait_stage_done(issued - NB);
+            const uint32_t sbase = smem_u32(ringB + (issued % NB) * 2 * B_TILE);
+            const int k0 = cur.kb * TK + c * 4;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const uint32_t o = swz(r0 + 4 * i, c);
+                const bool ok = qoff[i] >= 0;
+                cp_async16_zfill(sbase + o, ok ? (const void *)(p.qsplit + qoff[i] + k0) : (const void *)a.q, ok);
+                cp_async16_zfill(sbase + B_TILE + o, ok ? (const void *)(p.qsplit + qstride + qoff[i] + k0) : (const void *)a.q, ok);
+            }
+            ++issued;
+            cur.advance(a, p, total, KB);
+        };
+#pragma unroll 1
+        for (int s = 0; s < BAHEAD; ++s) {
+            if (cur.valid) issue();
+            cp_async_commit_group();
+        }
+#pragma unroll 1
+        while (done < issued) {
+            cp_async_wait_group<BAHEAD - 1>();
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bready_bar(done % NB));
+            ++done;
+            if (cur.valid) issue();
+            cp_async_commit_group();
+        }
+        cp_async_wait_group<0>();
+    } else if (warp <= NAW + NMW) {
+        // ---------------- MMA issuers: term 0 = hi.hi -> accumulators 2 / 3 (even / odd k-steps), term 1 = hi.lo -> 0,
+        //                  term 2 = lo.hi -> 1 ----------------
+        if (lane == 0) {
+            const int term = warp - (NAW + 1);
+            constexpr uint32_t idesc = umma_idesc_tf32(TM, TN);
+            int sc = 0, acc = 0, sR = 0, sL = 0, sB = 0;
+            uint32_t acc_phase = 0, phL = 0, phB = 0;
+            TcItem I;
+            for (int32_t n = 0; load_item(a, p, (int32_t)(blockIdx.x + (int64_t)n * gridDim.x), total, I); ++n) {
+                for (int tile = 0; tile < I.ntiles; ++tile) {
+                    mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                    tc_fence_after();
+                    const uint32_t tmem_t = tmem_base + (uint32_t)(acc * NACC * TN);
+                    for (int kb = 0; kb < KB; ++kb, ++sc) {
+                        mbar_wait(aready_bar(sL), phL);
+                        mbar_wait(bready_bar(sB), phB);
+                        tc_fence_after();
+                        const uint32_t aop = term == 2 ? smem_u32(ringL + sL * A_TILE) : smem_u32(ringR + sR * A_TILE);
+                        const uint32_t bop = smem_u32(ringB + sB * 2 * B_TILE) + (term == 1 ? B_TILE : 0);
+                        const uint64_t da = umma_desc_sw128(aop), db = umma_desc_sw128(bop);
+                        if (term == 0) {
+#pragma unroll
+                            for (int ks = 0; ks < TK / 8; ++ks) {
+                                const uint64_t off = (uint64_t)((ks * 8 * 4) >> 4);
+                                umma_tf32(tmem_t + (uint32_t)((2 + (ks & 1)) * TN), da + off, db + off, idesc, (kb != 0 || ks >= 2) ? 1u : 0u);
+                            }
+                        } else {
+                            const uint32_t tmem_d = tmem_t + (uint32_t)((term - 1) * TN);
+#pragma unroll
+                            for (int ks = 0; ks < TK / 8; ++ks) {
+                                const uint64_t off = (uint64_t)((ks * 8 * 4) >> 4);
+                                umma_tf32(tmem_d, da + off, db + off, idesc, (kb | ks) != 0 ? 1u : 0u);
+                            }
+                        }
+                        umma_commit(done_bar(sR));
+                        if (++sR == NR) sR = 0;
+                        if (++sL == NL) {
+                            sL = 0;
+                            phL ^= 1u;
+                        }
+                        if (++sB == NB) {
+                            sB = 0;
+                            phB ^= 1u;
+                        }
+                    }
+                    umma_commit(tfull_bar(acc));
+                    if (++acc == 2) {
+                        acc = 0;
+                        acc_phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else {
+        // ---------------- epilogue (the last four warps) ----------------
+        const int quarter = warp & 3;
+        const int et = threadIdx.x - (NAW + 1 + NMW) * 32;  // 0..127
+        const int row = quarter * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        TcItem I;
+        for (int32_t n = 0; load_item(a, p, (int32_t)(blockIdx.x + (int64_t)n * gridDim.x), total, I); ++n) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // everybody is done with the previous item's bases
+            if (et < TN) cbE[et] = et < I.nqi ? a.page_off[p.lq[I.qbase + et]] * kPageRows : -1;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int32_t slots = ((I.len + kPageRows - 1) / kPageRows) * kPageRows;
+            for (int tile = 0; tile < I.ntiles; ++tile) {
+                const int32_t r = tile * TM + row;
+                bool live = false;
+                if (r < I.len) {
+                    const int32_t page = __ldg(a.pt + I.ptbase + (r >> 5));
+                    live = filter_pass(a.filt, __ldg(a.slabs->tags[page >> a.slab_shift] + (int64_t)(page & slab_mask) * kPageRows + (r & 31)));
+                }
+                mbar_wait(tfull_bar(acc), acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * NACC * TN);
+#pragma unroll 1
+                for (int h = 0; h < TN / 32; ++h) {
+                    float v[32], w[32];
+                    float x[32];
+                    tmem_ld32(taddr + (uint32_t)(0 * TN + h * 32), v);  // the two cross terms
+                    tmem_ld32(taddr + (uint32_t)(1 * TN + h * 32), w);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = v[j] + w[j];
+                    tmem_ld32(taddr + (uint32_t)(2 * TN + h * 32), v);  // hi.hi, even and odd k-steps
+                    tmem_ld32(taddr + (uint32_t)(3 * TN + h * 32), w);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = (v[j] + w[j]) + x[j];
+                    if (r < slots) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int jj = h * 32 + j;
+                            if (jj < I.nqi) a.cand[cbE[jj] + r] = live ? v[j] : -INFINITY;
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(acc));
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1u;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == NAW + 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS_TC) : "memory");
+    }
+}
+
+}  // namespace
+
+// items: (list, chunk of 64 queries) from p.off32 (plan_lists_kernel with chunk = 64); p.qsplit holds 2 x [nq, ds]
+cudaError_t launch_scan_lists_tc(const ScanArgs &a, const ListPlan &p, int num_sms, cudaStream_t st) {
+    if (a.metric != 0 || (a.ds % TK) != 0 || p.chunk != TN || p.qsplit == nullptr) return cudaErrorNotSupported;
+    const int64_t n4 = (a.npairs / a.nprobe) * (int64_t)a.ds / 4;
+    const int64_t want = (n4 + 255) / 256;
+    split_rows_kernel<<<(unsigned)(want < num_sms * 8 ? want : num_sms * 8), 256, 0, st>>>(
+        reinterpret_cast<const float4 *>(a.q), n4, reinterpret_cast<float4 *>(p.qsplit));
+    cudaError_t e = cudaFuncSetAttribute(scan_lists_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TC);
+    if (e != cudaSuccess) return e;
+    scan_lists_tc_kernel<<<num_sms, NT_TC2, SMEM_TC, st>>>(a, p);
+    return cudaGetLastError();
+}
+
+}  // namespace sc

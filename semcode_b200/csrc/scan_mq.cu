@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256, 2)
         if (pass != cur_pass) {
             cur_pass = pass;
             restage = true;
-            const int32_t qbase = p.lq_off[l] + 32 * p.n32[l] + MQ * pass;
+            const int32_t qbase = p.lq_off[l] + p.chunk * p.n32[l] + MQ * pass;
             const int nqi = min(MQ, p.lq_off[l + 1] - qbase);
             __syncwarp();  // the previous pass's readers are done with cbs / qgs
             if (lane < MQ) {
