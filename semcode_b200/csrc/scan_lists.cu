@@ -46,7 +46,8 @@ __global__ void count_list_pairs_kernel(const int32_t *__restrict__ probe, int64
 //   rem > T      one more (ragged) tile item; T = 16 for the FFMA tiles, 8 for the tcgen05 tiles
 //   rem 5..T     ceil(rem / 8) passes of the 8-query page scan
 //   rem 1..4     one pass of the 4-query page scan
-// and four exclusive prefix sums are produced in the same sweep: lq_off (queries per list), off32 (tile items),
+// and four exclusive prefix sums are produced in the same sweep: lq_off (queries per list), off32 (tile items; for
+// the tcgen05 tiles: items x 128-row tiles, the unit its CTAs share out in equal ranges),
 // pg8off / pg4off (page x pass units of the two page scans).  (Seven launches in the first version.)
 __global__ void __launch_bounds__(1024) plan_lists_kernel(const int32_t *__restrict__ cnt, const int32_t *__restrict__ list_len,
                                                           int32_t nlist, int32_t chunk, int32_t min_items, int32_t *__restrict__ n32, int32_t *__restrict__ lq_off,
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(1024) plan_lists_kernel(const int32_t *__restr
     __shared__ int32_t warp_tot[4][32];
     __shared__ int32_t blk_tot[4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int IPT = 4;
+    constexpr int IPT = 8;  // 16384 lists in two sweeps of the CTA
     // a ragged tile item costs ~2.8 list reads of time on the FFMA tiles (two passes of 8 are cheaper up to 16
     // queries) but about 1.6 on the tcgen05 tiles (cheaper than two passes from 9 queries on) -- provided there are
     // enough items to fill the GPU: an item is walked by ONE CTA (~100 us), so a handful of them is a pure tail
@@ -79,11 +80,12 @@ __global__ void __launch_bounds__(1024) plan_lists_kernel(const int32_t *__restr
 #pragma unroll
         for (int j = 0; j < IPT; ++j) {
             const int32_t l = i0 + j;
-            int32_t c = 0, a = 0, u8 = 0, u4 = 0;
+            int32_t c = 0, a = 0, u8 = 0, u4 = 0, tiles = 1;
             if (l < nlist) {
                 c = cnt[l];
                 const int32_t len = list_len[l];
                 const int32_t pages = (len + kPageRows - 1) / kPageRows;
+                if (chunk == 64) tiles = (len + 127) / 128;
                 if (c > 0) rows += (unsigned long long)len;
                 a = c / chunk;
                 const int32_t rem = c - a * chunk;
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(1024) plan_lists_kernel(const int32_t *__restr
                 n32[l] = a;
             }
             v[0][j] = c;
-            v[1][j] = a;
+            v[1][j] = a * tiles;  // FFMA tiles: items; tcgen05 tiles: (item, 128-row tile) units
             v[2][j] = u8;
             v[3][j] = u4;
 #pragma unroll

@@ -164,10 +164,6 @@ __global__ void split_rows_kernel(const float4 *__restrict__ x, int64_t n4, floa
     }
 }
 
-struct TcItem {
-    int32_t l, len, ptbase, qbase, nqi, ntiles;
-};
-
 __device__ __forceinline__ int32_t owner_of_tc(const int32_t *__restrict__ off, int32_t n, int32_t v) {
     int32_t lo = 0, hi = n;
     while (hi - lo > 1) {
@@ -180,37 +176,47 @@ __device__ __forceinline__ int32_t owner_of_tc(const int32_t *__restrict__ off, 
     return lo;
 }
 
-__device__ __forceinline__ bool load_item(const ScanArgs &a, const ListPlan &p, int32_t item, int32_t total, TcItem &I) {
-    if (item >= total) return false;
-    I.l = owner_of_tc(p.off32, p.nlist, item);
-    const int32_t chunk = item - p.off32[I.l];
-    I.qbase = p.lq_off[I.l] + TN * chunk;
-    I.nqi = min(TN, p.lq_off[I.l + 1] - I.qbase);
-    I.len = a.list_len[I.l];
-    I.ptbase = a.pt_off[I.l];
-    I.ntiles = (I.len + TM - 1) / TM;
-    return true;
-}
-
-// walks the CTA's (item, tile, k-block) sequence one stage at a time
-struct StageCursor {
-    TcItem I;
-    int32_t n = 0;
-    int tile = 0, kb = 0;
-    bool valid = false, fresh_item = true, fresh_tile = true;
-    __device__ __forceinline__ void start(const ScanArgs &a, const ListPlan &p, int32_t total) {
-        valid = load_item(a, p, (int32_t)blockIdx.x, total, I);
+// Work unit = (list, chunk of 64 queries, 128-row tile); p.off32 is the exclusive prefix of chunks(l) * tiles(l)
+// (plan_lists_kernel with chunk = 64).  Every CTA owns an equal, contiguous range of units -- a list of any length
+// or multiplicity is spread over as many CTAs as it has tiles, so skewed lists neither queue behind one CTA nor
+// leave a tail -- and every warp role walks the same range with its own cursor.
+struct UnitCursor {
+    int32_t u = 0, u1 = 0;
+    int32_t l = 0, len = 0, ptbase = 0, ntiles = 1, nchunks = 0, chunk = 0, tile = 0, qbase = 0, nqi = 0;
+    bool valid = false, new_chunk = false;
+    __device__ __forceinline__ void set_chunk(const ListPlan &p) {
+        qbase = p.lq_off[l] + TN * chunk;
+        nqi = min(TN, p.lq_off[l + 1] - qbase);
+        new_chunk = true;
     }
-    __device__ __forceinline__ void advance(const ScanArgs &a, const ListPlan &p, int32_t total, int KB) {
-        if (++kb == KB) {
-            kb = 0;
-            fresh_tile = true;
-            if (++tile == I.ntiles) {
-                tile = 0;
-                ++n;
-                fresh_item = true;
-                valid = load_item(a, p, (int32_t)(blockIdx.x + (int64_t)n * gridDim.x), total, I);
-            }
+    __device__ __forceinline__ void locate(const ScanArgs &a, const ListPlan &p) {
+        l = owner_of_tc(p.off32, p.nlist, u);
+        len = a.list_len[l];
+        ptbase = a.pt_off[l];
+        ntiles = (len + TM - 1) / TM;
+        nchunks = p.n32[l];
+        const int32_t local = u - p.off32[l];
+        chunk = local / ntiles;
+        tile = local - chunk * ntiles;
+        set_chunk(p);
+    }
+    __device__ __forceinline__ void start(const ScanArgs &a, const ListPlan &p, int32_t u0_, int32_t u1_) {
+        u = u0_;
+        u1 = u1_;
+        valid = u < u1;
+        if (valid) locate(a, p);
+    }
+    __device__ __forceinline__ void next_unit(const ScanArgs &a, const ListPlan &p) {
+        if (++u >= u1) {
+            valid = false;
+            return;
+        }
+        if (++tile == ntiles) {
+            tile = 0;
+            if (++chunk == nchunks)
+                locate(a, p);
+            else
+                set_chunk(p);
         }
     }
 };
@@ -260,6 +266,9 @@ __global__ void __launch_bounds__(NT_TC2, 1) scan_lists_tc_kernel(const ScanArgs
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int32_t total = p.off32[p.nlist];
+    const int32_t per_cta = (int32_t)(((int64_t)total + gridDim.x - 1) / gridDim.x);
+    const int32_t u0 = (int32_t)min((int64_t)total, (int64_t)blockIdx.x * per_cta);
+    const int32_t u1 = (int32_t)min((int64_t)total, (int64_t)u0 + per_cta);
     const int KB = a.ds / TK;  // launcher guarantees ds % 32 == 0
     const int slab_mask = (1 << a.slab_shift) - 1;
 
@@ -273,35 +282,38 @@ __global__ void __launch_bounds__(NT_TC2, 1) scan_lists_tc_kernel(const ScanArgs
         uint32_t cell[CPT];
 #pragma unroll
         for (int i = 0; i < CPT; ++i) cell[i] = swz(r0 + RSTEP * i, c);
-        StageCursor cur;
-        cur.start(a, p, total);
+        UnitCursor cur;
+        cur.start(a, p, u0, u1);
+        int kb = 0;
         const float *rowp[CPT];
         int issued = 0, done = 0;
         constexpr int AHEAD = NR - 2;  // raw stages in flight
 
         auto issue = [&]() {
-            if (cur.fresh_tile) {
-                cur.fresh_tile = false;
+            if (kb == 0) {
                 // (a bulk L2 prefetch of the next tile's pages was tried here: it doubled the DRAM reads -- 65 GB
                 //  instead of 33 GB per batch, L2 hit rate 12 % -- because the lines were evicted before use)
 #pragma unroll
                 for (int i = 0; i < CPT; ++i) {
                     const int32_t r = cur.tile * TM + r0 + RSTEP * i;
                     rowp[i] = nullptr;
-                    if (r < cur.I.len) {
-                        const int32_t page = __ldg(a.pt + cur.I.ptbase + (r >> 5));
+                    if (r < cur.len) {
+                        const int32_t page = __ldg(a.pt + cur.ptbase + (r >> 5));
                         rowp[i] = a.slabs->vec[page >> a.slab_shift] + ((int64_t)(page & slab_mask) * kPageRows + (r & 31)) * a.ds;
                     }
                 }
             }
             wait_stage_done(issued - NR);
             const uint32_t sbase = smem_u32(ringR + (issued % NR) * A_TILE);
-            const int k0 = cur.kb * TK + c * 4;
+            const int k0 = kb * TK + c * 4;
 #pragma unroll
             for (int i = 0; i < CPT; ++i)
                 cp_async16_zfill(sbase + cell[i], rowp[i] ? (const void *)(rowp[i] + k0) : (const void *)a.q, rowp[i] != nullptr);
             ++issued;
-            cur.advance(a, p, total, KB);
+            if (++kb == KB) {
+                kb = 0;
+                cur.next_unit(a, p);
+            }
         };
 
 #pragma unroll 1
@@ -348,24 +360,25 @@ __global__ void __launch_bounds__(NT_TC2, 1) scan_lists_tc_kernel(const ScanArgs
         // ---------------- B loader: 64 query rows x 8 chunks x (hi | lo) per stage = 32 copies per lane ----------------
         const int c = lane & 7, r0 = lane >> 3;  // rows r0 + 4*i, i < 16
         const int64_t qstride = (a.npairs / a.nprobe) * (int64_t)a.ds;  // floats per split array
-        StageCursor cur;
-        cur.start(a, p, total);
+        UnitCursor cur;
+        cur.start(a, p, u0, u1);
+        int kb = 0;
         int64_t qoff[16];
         int issued = 0, done = 0;
         constexpr int BAHEAD = NB - 1;
         auto issue = [&]() {
-            if (cur.fresh_item) {
-                cur.fresh_item = false;
+            if (cur.new_chunk) {
+                cur.new_chunk = false;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int j = r0 + 4 * i;
                     qoff[i] = -1;
-                    if (j < cur.I.nqi) qoff[i] = (int64_t)(p.lq[cur.I.qbase + j] / a.nprobe) * a.ds;
+                    if (j < cur.nqi) qoff[i] = (int64_t)(p.lq[cur.qbase + j] / a.nprobe) * a.ds;
                 }
             }
             wait_stage_done(issued - NB);
             const uint32_t sbase = smem_u32(ringB + (issued % NB) * 2 * B_TILE);
-            const int k0 = cur.kb * TK + c * 4;
+            const int k0 = kb * TK + c * 4;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const uint32_t o = swz(r0 + 4 * i, c);
@@ -374,7 +387,10 @@ __global__ void __launch_bounds__(NT_TC2, 1) scan_lists_tc_kernel(const ScanArgs
                 cp_async16_zfill(sbase + B_TILE + o, ok ? (const void *)(p.qsplit + qstride + qoff[i] + k0) : (const void *)a.q, ok);
             }
             ++issued;
-            cur.advance(a, p, total, KB);
+            if (++kb == KB) {
+                kb = 0;
+                cur.next_unit(a, p);
+            }
         };
 #pragma unroll 1
         for (int s = 0; s < BAHEAD; ++s) {
@@ -400,9 +416,8 @@ __global__ void __launch_bounds__(NT_TC2, 1) scan_lists_tc_kernel(const ScanArgs
             constexpr uint32_t idesc = umma_idesc_tf32(TM, TN);
             int sc = 0, acc = 0, sR = 0, sL = 0, sB = 0;
             uint32_t acc_phase = 0, phL = 0, phB = 0;
-            TcItem I;
-            for (int32_t n = 0; load_item(a, p, (int32_t)(blockIdx.x + (int64_t)n * gridDim.x), total, I); ++n) {
-                for (int tile = 0; tile < I.ntiles; ++tile) {
+            {
+                for (int32_t unit = u0; unit < u1; ++unit) {  // the issuers need no list fields: one tile per unit
                     mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                     tc_fence_after();
                     const uint32_t tmem_t = tmem_base + (uint32_t)(acc * NACC * TN);
@@ -453,13 +468,17 @@ __global__ void __launch_bounds__(NT_TC2, 1) scan_lists_tc_kernel(const ScanArgs
         const int row = quarter * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
-        TcItem I;
-        for (int32_t n = 0; load_item(a, p, (int32_t)(blockIdx.x + (int64_t)n * gridDim.x), total, I); ++n) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // everybody is done with the previous item's bases
-            if (et < TN) cbE[et] = et < I.nqi ? a.page_off[p.lq[I.qbase + et]] * kPageRows : -1;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+        UnitCursor I;
+        for (I.start(a, p, u0, u1); I.valid; I.next_unit(a, p)) {
+            if (I.new_chunk) {  // same decision in all four warps
+                I.new_chunk = false;
+                asm volatile("bar.sync 1, 128;" ::: "memory");  // everybody is done with the previous chunk's bases
+                if (et < TN) cbE[et] = et < I.nqi ? a.page_off[p.lq[I.qbase + et]] * kPageRows : -1;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
             const int32_t slots = ((I.len + kPageRows - 1) / kPageRows) * kPageRows;
-            for (int tile = 0; tile < I.ntiles; ++tile) {
+            {
+                const int tile = I.tile;
                 const int32_t r = tile * TM + row;
                 bool live = false;
                 if (r < I.len) {
