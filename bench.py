@@ -286,7 +286,7 @@ def run_reference(args):
         "config": workload_config(args, nq_override=nq),
         "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{nq} queries/step x nprobe {args.nprobe} over lists of {per_list} rows "
-                                   f"(10M/{nlist}); oracle/ivf_oracle.c, OpenMP over queries"},
+                                   f"({n}/{nlist}); oracle/ivf_oracle.c, OpenMP over queries"},
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
