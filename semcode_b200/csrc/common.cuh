@@ -183,7 +183,7 @@ cudaError_t launch_scan_pages(const ScanArgs &a, int variant, int num_sms, int *
 struct ListPlan {
     int32_t nlist;
     int32_t *cnt, *cursor;             // [nlist] queries per list, fill cursor
-    int32_t *counters;                 // [4] work counter of the tile kernel (directly after cursor)
+    int32_t *counters;                 // [4] (directly after cursor) 0: work counter of the FFMA tile kernel, 1: lists probed by > 8 queries
     int32_t chunk;                     // queries per tile item: 32 (FFMA tiles) or 64 (tcgen05 tiles)
     float *qsplit;                     // tcgen05 tiles: 2 x [nq, ds] tf32 terms (hi, lo) of the queries (scratch)
     int32_t *n32;                      // [nlist] tile items (of `chunk` queries) per list

@@ -33,12 +33,15 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool va
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 
 // ---- planning: invert (query, list) pairs into per-list query groups ----------------------------------
+// cnt[l] = queries probing list l; *over8 = lists probed by more than 8 queries (the plan's tile-item threshold)
 __global__ void count_list_pairs_kernel(const int32_t *__restrict__ probe, int64_t npairs, const int32_t *__restrict__ list_len,
-                                        int32_t nlist, int32_t *__restrict__ cnt) {
+                                        int32_t nlist, int32_t *__restrict__ cnt, int32_t *__restrict__ over8) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npairs) return;
     const int32_t l = probe[i];
-    if (l >= 0 && l < nlist && list_len[l] > 0) atomicAdd(cnt + l, 1);
+    if (l >= 0 && l < nlist && list_len[l] > 0) {
+        if (atomicAdd(cnt + l, 1) == 8) atomicAdd(over8, 1);
+    }
 }
 
 // One CTA plans every list.  A list probed by c queries becomes c / chunk tile items of `chunk` queries (32 for the
@@ -50,7 +53,8 @@ __global__ void count_list_pairs_kernel(const int32_t *__restrict__ probe, int64
 // the tcgen05 tiles: items x 128-row tiles, the unit its CTAs share out in equal ranges),
 // pg8off / pg4off (page x pass units of the two page scans).  (Seven launches in the first version.)
 __global__ void __launch_bounds__(1024) plan_lists_kernel(const int32_t *__restrict__ cnt, const int32_t *__restrict__ list_len,
-                                                          int32_t nlist, int32_t chunk, int32_t min_items, int32_t *__restrict__ n32, int32_t *__restrict__ lq_off,
+                                                          int32_t nlist, int32_t chunk, int32_t min_items,
+                                                          const int32_t *__restrict__ over8, int32_t *__restrict__ n32, int32_t *__restrict__ lq_off,
                                                           int32_t *__restrict__ off32, int32_t *__restrict__ pg8off,
                                                           int32_t *__restrict__ pg4off,
                                                           unsigned long long *__restrict__ unique_rows) {
@@ -61,16 +65,7 @@ __global__ void __launch_bounds__(1024) plan_lists_kernel(const int32_t *__restr
     // a ragged tile item costs ~2.8 list reads of time on the FFMA tiles (two passes of 8 are cheaper up to 16
     // queries) but about 1.6 on the tcgen05 tiles (cheaper than two passes from 9 queries on) -- provided there are
     // enough items to fill the GPU: an item is walked by ONE CTA (~100 us), so a handful of them is a pure tail
-    __shared__ int32_t n_over8;
-    if (tid == 0) n_over8 = 0;
-    __syncthreads();
-    if (chunk == 64) {
-        int32_t mine = 0;
-        for (int32_t l = tid; l < nlist; l += 1024) mine += cnt[l] > 8 ? 1 : 0;
-        if (mine) atomicAdd(&n_over8, mine);
-    }
-    __syncthreads();
-    const int32_t rem_tile = (chunk == 64 && n_over8 >= min_items) ? 8 : 16;
+    const int32_t rem_tile = (chunk == 64 && *over8 >= min_items) ? 8 : 16;
     int32_t carry[4] = {0, 0, 0, 0};
     unsigned long long rows = 0;
     for (int32_t base = 0; base < nlist; base += 1024 * IPT) {
@@ -450,8 +445,8 @@ cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int
     const unsigned pb = (unsigned)((a.npairs + 255) / 256);
     // cnt | cursor | counters are adjacent: one memset
     if ((e = cudaMemsetAsync(p.cnt, 0, (size_t)(2 * p.nlist + 4) * 4, st)) != cudaSuccess) return e;
-    count_list_pairs_kernel<<<pb, 256, 0, st>>>(a.probe, a.npairs, a.list_len, p.nlist, p.cnt);
-    plan_lists_kernel<<<1, 1024, 0, st>>>(p.cnt, a.list_len, p.nlist, p.chunk, 2 * num_sms, p.n32, p.lq_off, p.off32, p.pg8off, p.pg4off,
+    count_list_pairs_kernel<<<pb, 256, 0, st>>>(a.probe, a.npairs, a.list_len, p.nlist, p.cnt, p.counters + 1);
+    plan_lists_kernel<<<1, 1024, 0, st>>>(p.cnt, a.list_len, p.nlist, p.chunk, 2 * num_sms, p.counters + 1, p.n32, p.lq_off, p.off32, p.pg8off, p.pg4off,
                                           p.unique_rows);
     fill_list_pairs_kernel<<<pb, 256, 0, st>>>(a.probe, a.npairs, a.list_len, p.nlist, p.lq_off, p.cursor, p.lq);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
