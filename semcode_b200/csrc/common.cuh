@@ -168,22 +168,29 @@ struct PeerRows {
     int64_t row0;                            // first row of THIS rank's slice
 };
 
+// pair plan (scan.cu): page_off [npairs + 1] = exclusive prefix of the pages of every (query, list) pair, one launch
+// (single-pass scan, decoupled look-back).  look: plan_pairs_look_words(npairs) 64-bit words of scratch, zero when
+// first used; epoch: differs from the recent launches on the same scratch (22 bits are used: the caller counts up and
+// zeroes the scratch when the count wraps).  rows_total (optional): += rows of every pair's list
+size_t plan_pairs_look_words(int64_t npairs);
 cudaError_t launch_plan_pairs(const int32_t *probe, int64_t npairs, const int32_t *list_len, int32_t nlist,
-                              int64_t *pair_pages, unsigned long long *rows_total, cudaStream_t st);
-// exclusive prefix sum of in[n] -> out[n+1] (out[n] = total).  The int64 variant takes an optional scratch of
-// 2 * (n / 4096 + 2) elements and then runs as a two-level scan for large n
-cudaError_t launch_exclusive_scan_i64(const int64_t *in, int64_t n, int64_t *out, int64_t *scratch, cudaStream_t st);
+                              int64_t *page_off, unsigned long long *look, uint32_t epoch,
+                              unsigned long long *rows_total, cudaStream_t st);
+// exclusive prefix sum of in[n] -> out[n+1] (out[n] = total), one CTA (inputs are nlist long)
 cudaError_t launch_exclusive_scan_i32(const int32_t *in, int64_t n, int32_t *out, cudaStream_t st);
 cudaError_t launch_scan_pages(const ScanArgs &a, int variant, int num_sms, int *launches, cudaStream_t st);
 
 // list-major scan (scan_lists.cu, scan_mq.cu): the probed lists are read ONCE per batch and scored against every
-// query that probes them.  Scratch (all device, caller-sized): cnt | cursor | counters adjacent (one memset),
+// query that probes them.  Scratch (all device, caller-sized): cnt | cursor | counters | agg adjacent (one memset;
+// 2 * nlist + 4 is even, so agg is 8-byte aligned when cnt is),
 // n32 [nlist], lq_off / off32 / pg8off / pg4off [nlist+1], lq [npairs].  Writes the same candidate layout as
 // launch_scan_pages.
 struct ListPlan {
     int32_t nlist;
     int32_t *cnt, *cursor;             // [nlist] queries per list, fill cursor
-    int32_t *counters;                 // [4] (directly after cursor) 0: work counter of the FFMA tile kernel, 1: lists probed by > 8 queries
+    int32_t *counters;                 // [4] (directly after cursor) 0: work counter of the FFMA tile kernel, 1: lists probed by > 8 queries,
+                                       //     2: ticket counter of the plan kernel
+    unsigned long long *agg;           // [list_plan_ctas(nlist)][4] (directly after counters) per-CTA totals of the plan's four prefix sums
     int32_t chunk;                     // queries per tile item: 32 (FFMA tiles) or 64 (tcgen05 tiles)
     float *qsplit;                     // tcgen05 tiles: 2 x [nq, ds] tf32 terms (hi, lo) of the queries (scratch)
     int32_t *n32;                      // [nlist] tile items (of `chunk` queries) per list
@@ -195,6 +202,7 @@ struct ListPlan {
     cudaEvent_t ev_fork, ev_join[2];
     unsigned long long *unique_rows;   // optional: += rows of every list probed at least once
 };
+int list_plan_ctas(int32_t nlist);
 cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int num_sms, int *launches, cudaStream_t st);
 // tile items on the tensor cores (scan_lists_tc.cu): inner product, ds % 32 == 0, p.chunk == 64
 cudaError_t launch_scan_lists_tc(const ScanArgs &a, const ListPlan &p, int num_sms, cudaStream_t st);

@@ -169,7 +169,7 @@ struct sc_index {
     int64_t ntotal = 0, nremoved = 0;
 
     // scratch (stream ordered; ev_done chains calls made on different streams)
-    DevBuf s_q, s_scores, s_probe, s_pairpages, s_pageoff, s_cand, s_outd, s_outi, s_repobits;
+    DevBuf s_q, s_scores, s_probe, s_pageoff, s_cand, s_outd, s_outi, s_repobits;
     DevBuf s_x, s_xpad, s_ids, s_repo, s_lang, s_assign, s_best, s_pos, s_lenold, s_need, s_npg, s_needoff, s_bad;
     DevBuf s_sums, s_counts, s_obj, s_rows, s_rm, s_cnt, s_ahi, s_alo, s_lplan, s_scan, s_packed, s_qsplit;
     int64_t scratch_budget = (int64_t)8 << 30;  // search scratch ceiling (candidates dominate); sc_index_set_param("scratch_bytes")
@@ -179,6 +179,7 @@ struct sc_index {
     cudaEvent_t ev_done = nullptr;
     cudaStream_t side[2] = {nullptr, nullptr};  // fork/join streams of the list-major scan
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    uint32_t plan_epoch = 0;  // launch counter of the pair plan's look-back words (s_scan)
     int lists_fork = 0;  // measured slower on C2 (tile CTAs pin shared memory the page scan needs): off by default
 
     // profiling of the last search
@@ -608,6 +609,8 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
     SC(begin_call(ix, st));
     FilterDev fdev;
     SC(build_filter(ix, filt, st, &fdev));
+    ix->prof_scan_launches = 0;  // launch counts describe the last call, profiled or not
+    ix->prof_total_launches = 0;
     if (ix->profiling) {
         clear_prof(ix);
         if (!ix->prof_rows) CU(cudaMalloc(&ix->prof_rows, 16));
@@ -645,9 +648,15 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
     const int64_t npairs_max = nqc * np;
     if (!lists && !all_lists) CU(ix->s_scores.reserve((size_t)nqc * ix->nlist * 4));
     if (!lists) CU(ix->s_probe.reserve((size_t)npairs_max * 4));
-    CU(ix->s_pairpages.reserve((size_t)npairs_max * 8));
     CU(ix->s_pageoff.reserve((size_t)(npairs_max + 1) * 8));
-    CU(ix->s_scan.reserve((size_t)(2 * (npairs_max / 4096 + 2)) * 8));
+    {   // look-back words of the pair plan: zero when (re)allocated and when the 22-bit epoch wraps
+        const void *before = ix->s_scan.p;
+        CU(ix->s_scan.reserve(plan_pairs_look_words(npairs_max) * 8));
+        if (ix->s_scan.p != before) {
+            CU(cudaMemsetAsync(ix->s_scan.p, 0, ix->s_scan.cap, st));
+            ix->plan_epoch = 0;
+        }
+    }
     CU(ix->s_cand.reserve((size_t)nqc * pb * kPageRows * 4));
     if (!outd_dev) CU(ix->s_outd.reserve((size_t)nqc * k * 4));
     if (!outi_dev) CU(ix->s_outi.reserve((size_t)nqc * k * 8));
@@ -690,10 +699,12 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
             ix->prof_total_launches += use_tc(ix) ? 3 : 2;
         }
         SC(prof_mark(ix, st));
-        CU(launch_plan_pairs(probe, npairs, ix->list_len, ix->nlist, ix->s_pairpages.as<int64_t>(),
-                             ix->profiling ? ix->prof_rows : nullptr, st));
-        CU(launch_exclusive_scan_i64(ix->s_pairpages.as<int64_t>(), npairs, ix->s_pageoff.as<int64_t>(),
-                                     ix->s_scan.as<int64_t>(), st));
+        if (((ix->plan_epoch + 1) & 0x3fffffu) == 0) {  // epochs 1 .. 2^22 - 2, then start over on zeroed words
+            CU(cudaMemsetAsync(ix->s_scan.p, 0, ix->s_scan.cap, st));
+            ix->plan_epoch = 0;
+        }
+        CU(launch_plan_pairs(probe, npairs, ix->list_len, ix->nlist, ix->s_pageoff.as<int64_t>(),
+                             ix->s_scan.as<unsigned long long>(), ++ix->plan_epoch, ix->profiling ? ix->prof_rows : nullptr, st));
         SC(prof_mark(ix, st));
         ScanArgs a;
         memset(&a, 0, sizeof(a));
@@ -720,7 +731,8 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
                                  (ix->scan_mode == 0 && long_lists && 4 * npairs >= 3 * (int64_t)ix->nlist));
         if (list_major) {
             const size_t nl = (size_t)ix->nlist;
-            const size_t words = 3 * nl + 4 + 4 * (nl + 1) + (size_t)npairs + 16;
+            const size_t agg_words = (size_t)list_plan_ctas(ix->nlist) * 8;  // 4 x u64 per plan CTA
+            const size_t words = 3 * nl + 4 + agg_words + 4 * (nl + 1) + (size_t)npairs + 16;
             CU(ix->s_lplan.reserve(words * 4));
             int32_t *w = ix->s_lplan.as<int32_t>();
             ListPlan lp;
@@ -737,7 +749,8 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
             lp.cnt = w;
             lp.cursor = w + nl;
             lp.counters = w + 2 * nl;
-            lp.n32 = lp.counters + 4;
+            lp.agg = reinterpret_cast<unsigned long long *>(lp.counters + 4);
+            lp.n32 = lp.counters + 4 + agg_words;
             lp.lq_off = lp.n32 + nl;
             lp.off32 = lp.lq_off + nl + 1;
             lp.pg8off = lp.off32 + nl + 1;
@@ -774,7 +787,7 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
             CU(launch_select_candidates(a, m, k, od, oi, st));
         }
         SC(prof_mark(ix, st));
-        ix->prof_total_launches += 4;
+        ix->prof_total_launches += 2;  // pair plan, top-k (the scan launchers count their own)
         if (!outd_dev) CU(cudaMemcpyAsync(out_dist + s * k, od, (size_t)m * k * 4, cudaMemcpyDeviceToHost, st));
         if (!outi_dev) CU(cudaMemcpyAsync(out_ids + s * k, oi, (size_t)m * k * 8, cudaMemcpyDeviceToHost, st));
     }
@@ -882,7 +895,7 @@ int sc_index_destroy(sc_index_t *ix) {
     cudaDeviceSynchronize();
     free_lists(ix);
     clear_prof(ix);
-    for (DevBuf *b : {&ix->s_q, &ix->s_scores, &ix->s_probe, &ix->s_pairpages, &ix->s_pageoff, &ix->s_cand, &ix->s_outd,
+    for (DevBuf *b : {&ix->s_q, &ix->s_scores, &ix->s_probe, &ix->s_pageoff, &ix->s_cand, &ix->s_outd,
                       &ix->s_outi, &ix->s_repobits, &ix->s_x, &ix->s_xpad, &ix->s_ids, &ix->s_repo, &ix->s_lang,
                       &ix->s_assign, &ix->s_best, &ix->s_pos, &ix->s_lenold, &ix->s_need, &ix->s_npg, &ix->s_needoff,
                       &ix->s_bad, &ix->s_sums, &ix->s_counts, &ix->s_obj, &ix->s_rows, &ix->s_rm, &ix->s_cnt, &ix->s_ahi, &ix->s_alo, &ix->s_lplan, &ix->s_scan, &ix->s_packed, &ix->s_qsplit})
@@ -1354,7 +1367,7 @@ int sc_index_stats(sc_index_t *ix, sc_stats_t *out) {
     const int64_t rows = ((int64_t)ix->slabs.size() << ix->slab_shift) * kPageRows;
     out->bytes_lists = rows * ((int64_t)ix->ds * 4 + 12);
     int64_t sb = 0;
-    for (const DevBuf *b : {&ix->s_q, &ix->s_scores, &ix->s_probe, &ix->s_pairpages, &ix->s_pageoff, &ix->s_cand,
+    for (const DevBuf *b : {&ix->s_q, &ix->s_scores, &ix->s_probe, &ix->s_pageoff, &ix->s_cand,
                             &ix->s_outd, &ix->s_outi, &ix->s_repobits, &ix->s_x, &ix->s_xpad, &ix->s_ids, &ix->s_repo,
                             &ix->s_lang, &ix->s_assign, &ix->s_best, &ix->s_pos, &ix->s_lenold, &ix->s_need, &ix->s_npg,
                             &ix->s_needoff, &ix->s_bad, &ix->s_sums, &ix->s_counts, &ix->s_obj, &ix->s_rows, &ix->s_rm,
@@ -1456,7 +1469,7 @@ int sc_index_last_search_times(sc_index_t *ix, sc_search_times_t *out) {
     out->scanned_rows = (int64_t)rows[0];
     out->unique_rows = (int64_t)rows[1];
     out->scan_launches = ix->prof_scan_launches;
-    out->total_launches = ix->prof_total_launches;
+    out->total_launches = ix->prof_total_launches + ix->prof_scan_launches;
     return SC_OK;
 }
 

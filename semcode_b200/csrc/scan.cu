@@ -22,19 +22,118 @@ namespace sc {
 
 namespace {
 
-__global__ void plan_pairs_kernel(const int32_t *__restrict__ probe, int64_t npairs,
-                                  const int32_t *__restrict__ list_len, int32_t nlist,
-                                  int64_t *__restrict__ pair_pages, unsigned long long *__restrict__ rows_total) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npairs) return;
-    const int32_t l = probe[i];
-    int64_t pages = 0;
-    if (l >= 0 && l < nlist) {
-        const int32_t len = list_len[l];
-        pages = (len + kPageRows - 1) / kPageRows;
-        if (rows_total != nullptr && len > 0) atomicAdd(rows_total, (unsigned long long)len);
+// ---- pair plan: pages per (query, list) pair and their exclusive prefix in ONE launch -------------------
+// (first version: one kernel for the page counts + a three-launch two-level scan.)  Single-pass scan with
+// decoupled look-back: a CTA takes a ticket (its position in scheduling order, so a CTA only ever waits for CTAs
+// that are already running), publishes the total of its 1024 pairs, adds up its predecessors' words until it
+// meets one that already carries an inclusive prefix, and publishes its own inclusive prefix.  One 64-bit word
+// per CTA holds value, state and the launch's epoch together -- [epoch:22 | state:2 | pages:40] -- so a word is
+// valid on its own: no fence, no flag array, and no memset between launches (the epoch changes; the host zeroes
+// the words when the epoch wraps).  The CTA holding the last ticket writes the grand total and resets the ticket.
+constexpr int PP_T = 256, PP_IPT = 4, PP_BLK = PP_T * PP_IPT;
+constexpr int PP_VAL_BITS = 40;  // pages of a batch: the candidate array (128 B per page) must fit in HBM
+
+__device__ __forceinline__ unsigned long long pp_pack(uint32_t epoch, uint32_t state, int64_t v) {
+    return ((unsigned long long)epoch << (PP_VAL_BITS + 2)) | ((unsigned long long)state << PP_VAL_BITS) | (unsigned long long)v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(PP_T) plan_pairs_kernel(const int32_t *__restrict__ probe, int64_t npairs,
+                                                          const int32_t *__restrict__ list_len, int32_t nlist,
+                                                          int64_t *__restrict__ page_off, unsigned long long *__restrict__ look,
+                                                          uint32_t epoch, unsigned long long *__restrict__ rows_total) {
+    __shared__ int64_t warp_tot[PP_T / 32];
+    __shared__ int64_t s_pre;
+    __shared__ uint32_t s_ticket;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(look);  // word 0: ticket counter; words 1..: CTA states
+    unsigned long long *state = look + 1;
+    if (tid == 0) s_ticket = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t b = s_ticket;
+    const int64_t i0 = (int64_t)b * PP_BLK + (int64_t)tid * PP_IPT;
+    int32_t v[PP_IPT];
+    int64_t local = 0;
+    unsigned long long rows = 0;
+#pragma unroll
+    for (int j = 0; j < PP_IPT; ++j) {
+        int32_t pages = 0;
+        if (i0 + j < npairs) {
+            const int32_t l = probe[i0 + j];
+            if (l >= 0 && l < nlist) {
+                const int32_t len = __ldg(list_len + l);
+                pages = (len + kPageRows - 1) / kPageRows;
+                rows += (unsigned long long)len;
+            }
+        }
+        v[j] = pages;
+        local += pages;
     }
-    pair_pages[i] = pages;
+    int64_t incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int64_t wpre = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < PP_T / 32; ++w) {
+        const int64_t t = warp_tot[w];
+        if (w < warp) wpre += t;
+        total += t;
+    }
+    if (warp == 0) {
+        int64_t pre = 0;
+        if (b == 0) {
+            if (lane == 0) st_relaxed_u64(state, pp_pack(epoch, 2, total));
+        } else {
+            if (lane == 0) st_relaxed_u64(state + b, pp_pack(epoch, 1, total));
+            const unsigned long long vmask = (1ull << PP_VAL_BITS) - 1;
+            for (int64_t j = (int64_t)b - 1;; j -= 32) {  // lane 0 looks at the nearest predecessor
+                const int64_t idx = j - lane;
+                unsigned long long s = pp_pack(epoch, 2, 0);  // before CTA 0: an inclusive prefix of 0
+                if (idx >= 0) {
+                    do {
+                        s = ld_relaxed_u64(state + idx);
+                    } while ((uint32_t)(s >> (PP_VAL_BITS + 2)) != epoch || ((s >> PP_VAL_BITS) & 3) == 0);
+                }
+                const uint32_t inc = __ballot_sync(0xffffffffu, ((s >> PP_VAL_BITS) & 3) == 2);
+                const int stop = inc ? (__ffs(inc) - 1) : 31;  // nearest word that is an inclusive prefix
+                int64_t val = lane <= stop ? (int64_t)(s & vmask) : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+                pre += val;
+                if (inc) break;
+            }
+            if (lane == 0) st_relaxed_u64(state + b, pp_pack(epoch, 2, pre + total));
+        }
+        if (lane == 0) s_pre = pre;
+    }
+    __syncthreads();
+    int64_t run = s_pre + wpre + incl - local;
+#pragma unroll
+    for (int j = 0; j < PP_IPT; ++j) {
+        if (i0 + j < npairs) page_off[i0 + j] = run;
+        run += v[j];
+    }
+    if (b == gridDim.x - 1 && tid == PP_T - 1) {
+        page_off[npairs] = s_pre + total;
+        *ticket = 0;  // every ticket of this launch has been taken
+    }
+    if (rows_total != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rows += __shfl_xor_sync(0xffffffffu, rows, o);
+        if (lane == 0 && rows) atomicAdd(rows_total, rows);
+    }
 }
 
 template <bool L2>
@@ -199,11 +298,17 @@ cudaError_t launch_rum(const ScanArgs &a, int num_sms, cudaStream_t st) {
 
 }  // namespace
 
+// page_off [npairs + 1]: exclusive prefix of the pages of each (query, list) pair; look: plan_pairs_look_words(npairs)
+// 64-bit words of device scratch that were zero when first used, epoch: a 22-bit value that differs from the last
+// launches on the same scratch (the caller counts up and zeroes the scratch when it wraps)
+size_t plan_pairs_look_words(int64_t npairs) { return (size_t)((npairs + PP_BLK - 1) / PP_BLK) + 1; }
+
 cudaError_t launch_plan_pairs(const int32_t *probe, int64_t npairs, const int32_t *list_len, int32_t nlist,
-                              int64_t *pair_pages, unsigned long long *rows_total, cudaStream_t st) {
-    if (npairs <= 0) return cudaSuccess;
-    plan_pairs_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(probe, npairs, list_len, nlist, pair_pages,
-                                                                         rows_total);
+                              int64_t *page_off, unsigned long long *look, uint32_t epoch,
+                              unsigned long long *rows_total, cudaStream_t st) {
+    if (npairs <= 0) return cudaMemsetAsync(page_off, 0, sizeof(int64_t), st);
+    plan_pairs_kernel<<<(unsigned)((npairs + PP_BLK - 1) / PP_BLK), PP_T, 0, st>>>(probe, npairs, list_len, nlist, page_off,
+                                                                                  look, epoch & 0x3fffffu, rows_total);
     return cudaGetLastError();
 }
 

@@ -44,104 +44,141 @@ __global__ void count_list_pairs_kernel(const int32_t *__restrict__ probe, int64
     }
 }
 
-// One CTA plans every list.  A list probed by c queries becomes c / chunk tile items of `chunk` queries (32 for the
+// Plans every list.  A list probed by c queries becomes c / chunk tile items of `chunk` queries (32 for the
 // FFMA tiles, 64 for the tcgen05 tiles) plus a remainder:
 //   rem > T      one more (ragged) tile item; T = 16 for the FFMA tiles, 8 for the tcgen05 tiles
 //   rem 5..T     ceil(rem / 8) passes of the 8-query page scan
 //   rem 1..4     one pass of the 4-query page scan
 // and four exclusive prefix sums are produced in the same sweep: lq_off (queries per list), off32 (tile items; for
 // the tcgen05 tiles: items x 128-row tiles, the unit its CTAs share out in equal ranges),
-// pg8off / pg4off (page x pass units of the two page scans).  (Seven launches in the first version.)
-__global__ void __launch_bounds__(1024) plan_lists_kernel(const int32_t *__restrict__ cnt, const int32_t *__restrict__ list_len,
+// pg8off / pg4off (page x pass units of the two page scans).
+// (First version: seven launches; second: ONE CTA for all lists -- 64k warp instructions on a single SM, 47 us at
+// 16384 lists.)  Now 1024 lists per CTA and a single-pass scan: a CTA takes a ticket (its position in scheduling
+// order, so it only waits for CTAs that are already running), publishes its four totals as self-validating words
+// (1 << 32 | total) in `agg` (zeroed by the plan's one memset) and adds up the words of ALL its predecessors (16
+// CTAs at 16384 lists: one load per lane; no chaining, every CTA publishes before it waits).  9 us at 16384 lists.
+constexpr int PL_T = 256, PL_IPT = 4, PL_BLK = PL_T * PL_IPT;
+
+__device__ __forceinline__ unsigned long long pl_ld(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(PL_T) plan_lists_kernel(const int32_t *__restrict__ cnt, const int32_t *__restrict__ list_len,
                                                           int32_t nlist, int32_t chunk, int32_t min_items,
-                                                          const int32_t *__restrict__ over8, int32_t *__restrict__ n32, int32_t *__restrict__ lq_off,
+                                                          int32_t *__restrict__ counters, unsigned long long *__restrict__ agg,
+                                                          int32_t *__restrict__ n32, int32_t *__restrict__ lq_off,
                                                           int32_t *__restrict__ off32, int32_t *__restrict__ pg8off,
                                                           int32_t *__restrict__ pg4off,
                                                           unsigned long long *__restrict__ unique_rows) {
-    __shared__ int32_t warp_tot[4][32];
-    __shared__ int32_t blk_tot[4];
+    __shared__ int32_t warp_tot[4][PL_T / 32];
+    __shared__ int32_t s_pre[4];
+    __shared__ int32_t s_ticket;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int IPT = 8;  // 16384 lists in two sweeps of the CTA
+    if (tid == 0) s_ticket = atomicAdd(counters + 2, 1);
+    __syncthreads();
+    const int32_t b = s_ticket;
     // a ragged tile item costs ~2.8 list reads of time on the FFMA tiles (two passes of 8 are cheaper up to 16
     // queries) but about 1.6 on the tcgen05 tiles (cheaper than two passes from 9 queries on) -- provided there are
     // enough items to fill the GPU: an item is walked by ONE CTA (~100 us), so a handful of them is a pure tail
-    const int32_t rem_tile = (chunk == 64 && *over8 >= min_items) ? 8 : 16;
-    int32_t carry[4] = {0, 0, 0, 0};
+    const int32_t rem_tile = (chunk == 64 && counters[1] >= min_items) ? 8 : 16;
+    const int32_t i0 = b * PL_BLK + tid * PL_IPT;
+    int32_t v[4][PL_IPT];
+    int32_t local[4] = {0, 0, 0, 0};
     unsigned long long rows = 0;
-    for (int32_t base = 0; base < nlist; base += 1024 * IPT) {
-        const int32_t i0 = base + tid * IPT;
-        int32_t v[4][IPT];
-        int32_t local[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int j = 0; j < IPT; ++j) {
-            const int32_t l = i0 + j;
-            int32_t c = 0, a = 0, u8 = 0, u4 = 0, tiles = 1;
-            if (l < nlist) {
-                c = cnt[l];
-                const int32_t len = list_len[l];
-                const int32_t pages = (len + kPageRows - 1) / kPageRows;
-                if (chunk == 64) tiles = (len + 127) / 128;
-                if (c > 0) rows += (unsigned long long)len;
-                a = c / chunk;
-                const int32_t rem = c - a * chunk;
-                if (rem > rem_tile)
-                    ++a;
-                else if (rem > 4)
-                    u8 = ((rem + 7) / 8) * pages;
-                else if (rem > 0)
-                    u4 = pages;
-                n32[l] = a;
-            }
-            v[0][j] = c;
-            v[1][j] = a * tiles;  // FFMA tiles: items; tcgen05 tiles: (item, 128-row tile) units
-            v[2][j] = u8;
-            v[3][j] = u4;
-#pragma unroll
-            for (int t = 0; t < 4; ++t) local[t] += v[t][j];
+    for (int j = 0; j < PL_IPT; ++j) {
+        const int32_t l = i0 + j;
+        int32_t c = 0, a = 0, u8 = 0, u4 = 0, tiles = 1;
+        if (l < nlist) {
+            c = cnt[l];
+            const int32_t len = list_len[l];
+            const int32_t pages = (len + kPageRows - 1) / kPageRows;
+            if (chunk == 64) tiles = (len + 127) / 128;
+            if (c > 0) rows += (unsigned long long)len;
+            a = c / chunk;
+            const int32_t rem = c - a * chunk;
+            if (rem > rem_tile)
+                ++a;
+            else if (rem > 4)
+                u8 = ((rem + 7) / 8) * pages;
+            else if (rem > 0)
+                u4 = pages;
+            n32[l] = a;
         }
-        int32_t incl[4];
+        v[0][j] = c;
+        v[1][j] = a * tiles;  // FFMA tiles: items; tcgen05 tiles: (item, 128-row tile) units
+        v[2][j] = u8;
+        v[3][j] = u4;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            int32_t x = local[t];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
-                if (lane >= o) x += y;
-            }
-            incl[t] = x;
-            if (lane == 31) warp_tot[t][warp] = x;
-        }
-        __syncthreads();
-        if (warp < 4) {  // warp t scans the 32 warp totals of quantity t
-            const int32_t t0 = warp_tot[warp][lane];
-            int32_t x = t0;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
-                if (lane >= o) x += y;
-            }
-            warp_tot[warp][lane] = x - t0;
-            if (lane == 31) blk_tot[warp] = x;
-        }
-        __syncthreads();
-        int32_t *const outs[4] = {lq_off, off32, pg8off, pg4off};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            int32_t run = carry[t] + warp_tot[t][warp] + incl[t] - local[t];
-#pragma unroll
-            for (int j = 0; j < IPT; ++j) {
-                if (i0 + j < nlist) outs[t][i0 + j] = run;
-                run += v[t][j];
-            }
-            carry[t] += blk_tot[t];
-        }
-        __syncthreads();
+        for (int t = 0; t < 4; ++t) local[t] += v[t][j];
     }
-    if (tid == 0) {
-        lq_off[nlist] = carry[0];
-        off32[nlist] = carry[1];
-        pg8off[nlist] = carry[2];
-        pg4off[nlist] = carry[3];
+    int32_t incl[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        int32_t x = local[t];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        incl[t] = x;
+        if (lane == 31) warp_tot[t][warp] = x;
+    }
+    __syncthreads();
+    int32_t wpre[4], total[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        wpre[t] = 0;
+        total[t] = 0;
+#pragma unroll
+        for (int w = 0; w < PL_T / 32; ++w) {
+            const int32_t x = warp_tot[t][w];
+            if (w < warp) wpre[t] += x;
+            total[t] += x;
+        }
+    }
+    if (warp == 0) {
+        if (lane < 4) {
+            int32_t mine = total[0];
+#pragma unroll
+            for (int t = 1; t < 4; ++t)
+                if (lane == t) mine = total[t];
+            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(agg + 4 * (size_t)b + lane),
+                         "l"((1ull << 32) | (unsigned long long)(uint32_t)mine)
+                         : "memory");
+        }
+        int32_t pre[4] = {0, 0, 0, 0};
+        for (int32_t j = lane; j < b; j += 32) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                unsigned long long w;
+                do {
+                    w = pl_ld(agg + 4 * (size_t)j + t);
+                } while ((w >> 32) == 0);
+                pre[t] += (int32_t)(uint32_t)w;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) pre[t] += __shfl_xor_sync(0xffffffffu, pre[t], o);
+            if (lane == 0) s_pre[t] = pre[t];
+        }
+    }
+    __syncthreads();
+    int32_t *const outs[4] = {lq_off, off32, pg8off, pg4off};
+    const bool last = b == (int32_t)gridDim.x - 1 && tid == PL_T - 1;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        int32_t run = s_pre[t] + wpre[t] + incl[t] - local[t];
+#pragma unroll
+        for (int j = 0; j < PL_IPT; ++j) {
+            if (i0 + j < nlist) outs[t][i0 + j] = run;
+            run += v[t][j];
+        }
+        if (last) outs[t][nlist] = s_pre[t] + total[t];
     }
     if (unique_rows != nullptr) {
 #pragma unroll
@@ -437,17 +474,20 @@ cudaError_t launch_lists_variant(const ScanArgs &a, const ListPlan &p, int num_s
 
 cudaError_t launch_scan_mq(const ScanArgs &a, const ListPlan &p, int bucket, const int32_t *pgoff, int num_sms, cudaStream_t st);
 
+int list_plan_ctas(int32_t nlist) { return (nlist + PL_BLK - 1) / PL_BLK; }
+
 // p.chunk == 64 (set by the caller): tcgen05 tiles; else FFMA tiles, cfg 2 = their 32-float-stage variant
 cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int num_sms, int *launches, cudaStream_t st) {
     if (a.npairs <= 0) return cudaSuccess;
     if (a.npairs > (int64_t)INT32_MAX) return cudaErrorInvalidValue;
     cudaError_t e;
     const unsigned pb = (unsigned)((a.npairs + 255) / 256);
-    // cnt | cursor | counters are adjacent: one memset
-    if ((e = cudaMemsetAsync(p.cnt, 0, (size_t)(2 * p.nlist + 4) * 4, st)) != cudaSuccess) return e;
+    // cnt | cursor | counters | agg are adjacent: one memset
+    const unsigned plan_ctas = (unsigned)list_plan_ctas(p.nlist);
+    if ((e = cudaMemsetAsync(p.cnt, 0, (size_t)(2 * p.nlist + 4) * 4 + (size_t)plan_ctas * 32, st)) != cudaSuccess) return e;
     count_list_pairs_kernel<<<pb, 256, 0, st>>>(a.probe, a.npairs, a.list_len, p.nlist, p.cnt, p.counters + 1);
-    plan_lists_kernel<<<1, 1024, 0, st>>>(p.cnt, a.list_len, p.nlist, p.chunk, 2 * num_sms, p.counters + 1, p.n32, p.lq_off, p.off32, p.pg8off, p.pg4off,
-                                          p.unique_rows);
+    plan_lists_kernel<<<plan_ctas, PL_T, 0, st>>>(p.cnt, a.list_len, p.nlist, p.chunk, 2 * num_sms, p.counters, p.agg, p.n32, p.lq_off, p.off32,
+                                                  p.pg8off, p.pg4off, p.unique_rows);
     fill_list_pairs_kernel<<<pb, 256, 0, st>>>(a.probe, a.npairs, a.list_len, p.nlist, p.lq_off, p.cursor, p.lq);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     // Three consumers of the plan.  The 32-query tile kernel holds the FP32-bound items (lists probed by many

@@ -10,11 +10,13 @@
 //
 // The vector dimension is cut into SLICES of 32*U float4 (<= 768 floats for MQ = 4, <= 384 for MQ = 8), so the
 // per-warp query stage is MQ * 32*U * 16 B <= 12 KB whatever the dimension is (16 warps per SM at dim 3072 as
-// at dim 768).  Per (page, slice) the warp stages the MQ query slices from L2, streams the slice of every live
-// row of the page, reduces the R*MQ partial sums with one transposing butterfly (31 shuffles for 32 sums
-// instead of 160) and adds them into a per-warp [MQ][32] shared-memory page accumulator; the finished page is
-// written to the candidate array with coalesced 128-byte stores.  A single-slice dimension (768 with MQ = 4)
-// stages its queries once per list.
+// at dim 768).  A warp walks its pages in groups (consecutive pages of one list and pass): per (group, slice) it
+// stages the MQ query slices from L2 once, streams that slice of every live row of every page of the group, reduces
+// the R*MQ partial sums (MQ = 8: one transposing butterfly, 31 shuffles for 32 sums instead of 160, into a per-warp
+// [MQ][32] shared-memory page accumulator) and writes the page's 32 x MQ values to the candidate array with
+// coalesced 128-byte stores -- adding the earlier slices' partial sums, which it left there itself.
+// Tried for MQ = 8 (4.3 TB/s: 47 % issue-active): packed fp32 pairs (fma.rn.f32x2) with R = 2 and a register
+// prefetch of the next rows -- half the FMA issue slots but twice the query LDS per byte: the same 460 us.
 // Replaces the same FAISS IVFFlatScanner::scan_codes loop (reference src/semcode/storage/milvus_store.py:141-147).
 // Algorithmic bytes: rows of each list x 4 x dim, once per pass (compulsory for one pass).
 #include "common.cuh"
@@ -112,38 +114,36 @@ __global__ void __launch_bounds__(256, 2)
     }
     int32_t l = lo;
     int32_t l_start = pgoff[l], l_end = pgoff[l + 1];
-    int32_t len = 0, ptbase = 0, npg = 1, cur_pass = -1;
-    bool new_list = true;
     const int slab_mask = (1 << a.slab_shift) - 1;
     // which (row, query) total this lane receives from reduce_transpose
     const int my_idx = lane / (32 / N);
     const int my_r = my_idx / MQ, my_j = my_idx % MQ;
     const bool my_owner = (lane % (32 / N)) == 0;
 
-    for (int32_t w = w0; w < w1; ++w) {
+    // The warp's units are walked in GROUPS: the run of consecutive pages of one (list, pass) inside [w0, w1).
+    // Per group the query slices are staged ONCE per slice and every page of the group is streamed against them
+    // (slice-outer, page-inner); with more than one slice the per-row partial sums of a page travel through the
+    // candidate array itself (4 B per row and query, L2-resident, re-read by the lane that wrote them) instead of
+    // restaging 12 KB of queries per (page, slice) as the first version did.
+    int32_t w = w0;
+    while (w < w1) {
         while (w >= l_end) {
             ++l;
             l_start = l_end;
             l_end = pgoff[l + 1];
-            new_list = true;
         }
-        if (new_list) {
-            new_list = false;
-            len = a.list_len[l];
-            ptbase = a.pt_off[l];
-            npg = (len + kPageRows - 1) / kPageRows;
-            cur_pass = -1;
-        }
+        const int32_t len = a.list_len[l];
+        const int32_t ptbase = a.pt_off[l];
+        const int32_t npg = (len + kPageRows - 1) / kPageRows;
         const int32_t ul = w - l_start;
         const int32_t pass = ul / npg;
-        const int32_t jpage = ul - pass * npg;
-        bool restage = nslices > 1;
-        if (pass != cur_pass) {
-            cur_pass = pass;
-            restage = true;
+        const int32_t jpage0 = ul - pass * npg;
+        const int32_t wend = min(w1, l_start + (pass + 1) * npg);
+        const int32_t G = wend - w;
+        {
             const int32_t qbase = p.lq_off[l] + p.chunk * p.n32[l] + MQ * pass;
             const int nqi = min(MQ, p.lq_off[l + 1] - qbase);
-            __syncwarp();  // the previous pass's readers are done with cbs / qgs
+            __syncwarp();  // the previous group's readers are done with cbs / qgs
             if (lane < MQ) {
                 int64_t cb = -1;
                 const float4 *qg = nullptr;
@@ -157,100 +157,104 @@ __global__ void __launch_bounds__(256, 2)
             }
             __syncwarp();
         }
-        const int32_t page = __ldg(a.pt + ptbase + jpage);
-        const int slab = page >> a.slab_shift;
-        const int64_t slot0 = (int64_t)(page & slab_mask) * kPageRows;
-        const int rows = min(kPageRows, len - jpage * kPageRows);
-        const uint32_t tag = __ldg(a.slabs->tags[slab] + slot0 + lane);
-        const bool live = lane < rows && filter_pass(a.filt, tag);
-        const uint32_t live_mask = __ballot_sync(0xffffffffu, live);
-        const int64_t poff = (int64_t)jpage * kPageRows;
-        const float4 *vbase = reinterpret_cast<const float4 *>(a.slabs->vec[slab]) + slot0 * ds4;
-        float treg[MQ];  // MQ = 4: this lane's row of the page, one total per query
-#pragma unroll
-        for (int j = 0; j < MQ; ++j) {
-            treg[j] = 0.f;
-            if (SMEM_TOT) tot[j * kTotLd + lane] = 0.f;
-        }
-
         for (int s = 0; s < nslices; ++s) {
             const int c0 = s * SL4;
-            if (restage) {
-                __syncwarp();  // the previous slice's readers are done with qs
+            __syncwarp();  // the previous slice's readers are done with qs
 #pragma unroll
-                for (int j = 0; j < MQ; ++j) {
-                    const float4 *qg = qgs[j];
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const int c = c0 + lane + 32 * u;
-                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (qg != nullptr && (EXACT || c < ds4)) v = __ldg(qg + c);
-                        qs[j * SL4 + lane + 32 * u] = v;
-                    }
-                }
-            }
-            __syncwarp();  // qs and the zeroed / partial tot visible to the whole warp
-            uint32_t m = live_mask;
-            while (m) {
-                int row[R];
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    row[r] = m ? (__ffs(m) - 1) : -1;
-                    m &= m - 1;
-                }
-                float4 x[R][U];
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const float4 *rp = vbase + (int64_t)(row[r] < 0 ? row[0] : row[r]) * ds4 + c0 + lane;
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        if (row[r] >= 0 && (EXACT || c0 + lane + 32 * u < ds4))
-                            x[r][u] = ld_stream_f4(rp + 32 * u);
-                        else
-                            x[r][u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                }
-                float acc[N];
-#pragma unroll
-                for (int i = 0; i < N; ++i) acc[i] = 0.f;
+            for (int j = 0; j < MQ; ++j) {
+                const float4 *qg = qgs[j];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-#pragma unroll
-                    for (int j = 0; j < MQ; ++j) {
-                        const float4 qv = qs[j * SL4 + lane + 32 * u];
-#pragma unroll
-                        for (int r = 0; r < R; ++r) acc[r * MQ + j] = mq_accum4<L2>(acc[r * MQ + j], x[r][u], qv);
-                    }
+                    const int c = c0 + lane + 32 * u;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (qg != nullptr && (EXACT || c < ds4)) v = __ldg(qg + c);
+                    qs[j * SL4 + lane + 32 * u] = v;
                 }
-                if (SMEM_TOT) {
-                    const float t = reduce_transpose<N>(acc, lane);
-                    int myrow = row[0];
+            }
+            for (int32_t g = 0; g < G; ++g) {
+                const int32_t jpage = jpage0 + g;
+                const int32_t page = __ldg(a.pt + ptbase + jpage);
+                const int slab = page >> a.slab_shift;
+                const int64_t slot0 = (int64_t)(page & slab_mask) * kPageRows;
+                const int rows = min(kPageRows, len - jpage * kPageRows);
+                const uint32_t tag = __ldg(a.slabs->tags[slab] + slot0 + lane);
+                const bool live = lane < rows && filter_pass(a.filt, tag);
+                const uint32_t live_mask = __ballot_sync(0xffffffffu, live);
+                const int64_t poff = (int64_t)jpage * kPageRows;
+                const float4 *vbase = reinterpret_cast<const float4 *>(a.slabs->vec[slab]) + slot0 * ds4;
+                float treg[MQ];  // MQ = 4: this lane's row of the page, one total per query
 #pragma unroll
-                    for (int r = 1; r < R; ++r)
-                        if (my_r == r) myrow = row[r];
-                    if (my_owner && myrow >= 0) tot[my_j * kTotLd + myrow] += t;  // one owner per (row, query): no race
-                } else {
+                for (int j = 0; j < MQ; ++j) {
+                    treg[j] = 0.f;
+                    if (SMEM_TOT) tot[j * kTotLd + lane] = 0.f;
+                }
+                __syncwarp();  // qs and the zeroed tot visible to the whole warp
+                uint32_t m = live_mask;
+                while (m) {
+                    int row[R];
 #pragma unroll
-                    for (int r = 0; r < R; ++r)
+                    for (int r = 0; r < R; ++r) {
+                        row[r] = m ? (__ffs(m) - 1) : -1;
+                        m &= m - 1;
+                    }
+                    float4 x[R][U];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const float4 *rp = vbase + (int64_t)(row[r] < 0 ? row[0] : row[r]) * ds4 + c0 + lane;
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            if (row[r] >= 0 && (EXACT || c0 + lane + 32 * u < ds4))
+                                x[r][u] = ld_stream_f4(rp + 32 * u);
+                            else
+                                x[r][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                    float acc[N];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) acc[i] = 0.f;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
 #pragma unroll
                         for (int j = 0; j < MQ; ++j) {
-                            const float t = warp_sum(acc[r * MQ + j]);
-                            if (lane == row[r]) treg[j] += t;
-                        }
-                }
-            }
-            restage = nslices > 1;
-        }
-        __syncwarp();
+                            const float4 qv = qs[j * SL4 + lane + 32 * u];
 #pragma unroll
-        for (int j = 0; j < MQ; ++j) {
-            const int64_t cb = cbs[j];
-            if (cb >= 0) {
-                const float v = SMEM_TOT ? tot[j * kTotLd + lane] : treg[j];
-                a.cand[cb + poff + lane] = live ? (L2 ? -v : v) : -INFINITY;
+                            for (int r = 0; r < R; ++r) acc[r * MQ + j] = mq_accum4<L2>(acc[r * MQ + j], x[r][u], qv);
+                        }
+                    }
+                    if (SMEM_TOT) {
+                        const float t = reduce_transpose<N>(acc, lane);
+                        int myrow = row[0];
+#pragma unroll
+                        for (int r = 1; r < R; ++r)
+                            if (my_r == r) myrow = row[r];
+                        if (my_owner && myrow >= 0) tot[my_j * kTotLd + myrow] += t;  // one owner per (row, query): no race
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < R; ++r)
+#pragma unroll
+                            for (int j = 0; j < MQ; ++j) {
+                                const float t = warp_sum(acc[r * MQ + j]);
+                                if (lane == row[r]) treg[j] += t;
+                            }
+                    }
+                }
+                if (SMEM_TOT) __syncwarp();  // the page's totals are complete
+                const bool first = s == 0, final = s == nslices - 1;
+#pragma unroll
+                for (int j = 0; j < MQ; ++j) {
+                    const int64_t cb = cbs[j];
+                    if (cb >= 0) {
+                        float v = SMEM_TOT ? tot[j * kTotLd + lane] : treg[j];
+                        float *dst = a.cand + cb + poff + lane;
+                        if (!first) v += *dst;  // this lane's own partial sum of the earlier slices
+                        if (final) v = live ? (L2 ? -v : v) : -INFINITY;
+                        *dst = v;
+                    }
+                }
+                if (SMEM_TOT) __syncwarp();  // tot is re-zeroed for the next page
             }
         }
-        __syncwarp();  // tot is re-zeroed for the next page
+        w = wend;
     }
 }
 

@@ -391,43 +391,6 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const T *__restric
     if (tid == 0) out[n] = carry;
 }
 
-constexpr int SCAN_BLK = 4096;  // elements per block of the two-level scan
-
-// APPLY = false: sums[b] = total of block b.  APPLY = true: out = exclusive scan of the block + offs[b];
-// the last block also writes out[n] = offs[nb].
-template <typename T, bool APPLY>
-__global__ void __launch_bounds__(1024) scan_block_kernel(const T *__restrict__ in, int64_t n, T *__restrict__ out,
-                                                          T *__restrict__ sums, const T *__restrict__ offs) {
-    __shared__ T warp_tot[32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t i0 = (int64_t)blockIdx.x * SCAN_BLK + (int64_t)tid * 4;
-    T v[4];
-    T local = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        v[j] = (i0 + j < n) ? in[i0 + j] : (T)0;
-        local += v[j];
-    }
-    const T incl = warp_incl_scan(local, lane);
-    if (lane == 31) warp_tot[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        const T t = warp_tot[lane];
-        const T ti = warp_incl_scan(t, lane);
-        warp_tot[lane] = ti - t;
-        if (!APPLY && lane == 31) sums[blockIdx.x] = ti;
-    }
-    if (!APPLY) return;
-    __syncthreads();
-    T run = offs[blockIdx.x] + warp_tot[warp] + incl - local;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        if (i0 + j < n) out[i0 + j] = run;
-        run += v[j];
-    }
-    if (blockIdx.x == gridDim.x - 1 && tid == 0) out[n] = offs[gridDim.x];
-}
-
 }  // namespace
 
 cudaError_t launch_select_rows(const float *scores, int64_t M, int N, int k, int32_t *out_idx, float *out_val,
@@ -486,30 +449,6 @@ cudaError_t launch_merge_topk_wait(const float *part_dist, const int64_t *part_i
     MergeSrc src{part_dist, part_ids, parts, nq, kin, k, metric, out_dist, out_ids};
     select_topk_kernel<MergeSrc><<<(unsigned)nq, SEL_T, 0, st>>>(src, k, wait, PeerSignal{});
     return cudaGetLastError();
-}
-
-namespace {
-
-// n > 8192: three short launches (per-block totals, scan of the totals, per-block rescan + offset) instead
-// of one CTA walking the whole array; `scratch` holds 2 * (n / 4096 + 2) elements.
-template <typename T>
-cudaError_t exclusive_scan_any(const T *in, int64_t n, T *out, T *scratch, cudaStream_t st) {
-    if (n <= 8192 || scratch == nullptr) {
-        exclusive_scan_kernel<T><<<1, 1024, 0, st>>>(in, n, out);
-        return cudaGetLastError();
-    }
-    const int64_t nb = (n + SCAN_BLK - 1) / SCAN_BLK;
-    T *sums = scratch, *sums_off = scratch + nb + 1;
-    scan_block_kernel<T, false><<<(unsigned)nb, 1024, 0, st>>>(in, n, nullptr, sums, nullptr);
-    exclusive_scan_kernel<T><<<1, 1024, 0, st>>>(sums, nb, sums_off);
-    scan_block_kernel<T, true><<<(unsigned)nb, 1024, 0, st>>>(in, n, out, nullptr, sums_off);
-    return cudaGetLastError();
-}
-
-}  // namespace
-
-cudaError_t launch_exclusive_scan_i64(const int64_t *in, int64_t n, int64_t *out, int64_t *scratch, cudaStream_t st) {
-    return exclusive_scan_any<int64_t>(in, n, out, scratch, st);
 }
 
 cudaError_t launch_exclusive_scan_i32(const int32_t *in, int64_t n, int32_t *out, cudaStream_t st) {
