@@ -205,7 +205,7 @@ struct ListPlan {
 int list_plan_ctas(int32_t nlist);
 cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int num_sms, int *launches, cudaStream_t st);
 // tile items on the tensor cores (scan_lists_tc.cu): inner product, ds % 32 == 0, p.chunk == 64
-cudaError_t launch_scan_lists_tc(const ScanArgs &a, const ListPlan &p, int num_sms, cudaStream_t st);
+cudaError_t launch_scan_lists_tc(const ScanArgs &a, const ListPlan &p, int variant, int num_sms, cudaStream_t st);
 // final top-k over the candidates of each query + id translation
 cudaError_t launch_select_candidates(const ScanArgs &a, int64_t nq, int k, float *out_dist, int64_t *out_ids,
                                      cudaStream_t st);

@@ -1500,6 +1500,11 @@ int sc_index_set_param(sc_index_t *ix, const char *name, int64_t value) {
         ix->scan_mode = (int)value;
         return SC_OK;
     }
+    if (strcmp(name, "plan_epoch") == 0) {  // tests: put the pair plan's launch counter next to its 22-bit wrap
+        if (value < 0 || value >= (1 << 22)) return fail(SC_ERR_INVALID, "plan_epoch must be in [0, 2^22)");
+        ix->plan_epoch = (uint32_t)value;
+        return SC_OK;
+    }
     if (strcmp(name, "small_coarse") == 0) {
         ix->small_coarse = value != 0;
         return SC_OK;

@@ -221,6 +221,13 @@ struct UnitCursor {
     }
 };
 
+// V2 (default): the raw fp32 k-block IS the hi operand (the tensor core reads the top 19 bits of a tf32 operand, i.e.
+// hi = x with the low 13 mantissa bits dropped; the splitter only writes lo = tf32(x - hi)), and hi.hi + hi.lo are ONE
+// 128-column MMA against the query tile [B_hi ; B_lo] (64 + 64 rows, contiguous in the B ring).  Per 32-float stage the
+// shared-memory traffic drops from 152 KB to 120 KB and the MMA count from 12 to 8.  Two issuers, one per k-step
+// parity, each the only writer of its accumulator set [hh | cross] (fold MMA, then lo.hi into the cross columns):
+// the order of additions into every accumulator is fixed, so results are reproducible run to run.
+template <bool V2>
 __global__ void __launch_bounds__(NT_TC2, 1) scan_lists_tc_kernel(const ScanArgs a, const ListPlan p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -246,11 +253,12 @@ __global__ void __launch_bounds__(NT_TC2, 1) scan_lists_tc_kernel(const ScanArgs
     };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NR; ++s) mbar_init(done_bar(s), NMW);
+        constexpr int NISS = V2 ? 2 : NMW;  // issuers that commit per stage / per tile
+        for (int s = 0; s < NR; ++s) mbar_init(done_bar(s), NISS);
         for (int s = 0; s < NL; ++s) mbar_init(aready_bar(s), NAW);
         for (int s = 0; s < NB; ++s) mbar_init(bready_bar(s), 1);
         for (int acc = 0; acc < 2; ++acc) {
-            mbar_init(tfull_bar(acc), NMW);
+            mbar_init(tfull_bar(acc), NISS);
             mbar_init(tempty_bar(acc), 4);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -334,10 +342,17 @@ __global__ void __launch_bounds__(NT_TC2, 1) scan_lists_tc_kernel(const ScanArgs
                 asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "r"(sr + cell[i]));
 #pragma unroll
             for (int i = 0; i < CPT; ++i) {
-                h[i].x = to_tf32(v[i].x);
-                h[i].y = to_tf32(v[i].y);
-                h[i].z = to_tf32(v[i].z);
-                h[i].w = to_tf32(v[i].w);
+                if (V2) {  // hi = what the tensor core reads of the raw word
+                    h[i].x = __uint_as_float(__float_as_uint(v[i].x) & 0xffffe000u);
+                    h[i].y = __uint_as_float(__float_as_uint(v[i].y) & 0xffffe000u);
+                    h[i].z = __uint_as_float(__float_as_uint(v[i].z) & 0xffffe000u);
+                    h[i].w = __uint_as_float(__float_as_uint(v[i].w) & 0xffffe000u);
+                } else {
+                    h[i].x = to_tf32(v[i].x);
+                    h[i].y = to_tf32(v[i].y);
+                    h[i].z = to_tf32(v[i].z);
+                    h[i].w = to_tf32(v[i].w);
+                }
                 l[i].x = to_tf32(v[i].x - h[i].x);
                 l[i].y = to_tf32(v[i].y - h[i].y);
                 l[i].z = to_tf32(v[i].z - h[i].z);
@@ -345,7 +360,8 @@ __global__ void __launch_bounds__(NT_TC2, 1) scan_lists_tc_kernel(const ScanArgs
             }
 #pragma unroll
             for (int i = 0; i < CPT; ++i) {
-                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sr + cell[i]), "f"(h[i].x), "f"(h[i].y), "f"(h[i].z), "f"(h[i].w) : "memory");
+                if (!V2)
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sr + cell[i]), "f"(h[i].x), "f"(h[i].y), "f"(h[i].z), "f"(h[i].w) : "memory");
                 asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sl + cell[i]), "f"(l[i].x), "f"(l[i].y), "f"(l[i].z), "f"(l[i].w) : "memory");
             }
             fence_async_smem();  // generic-proxy writes (cp.async + the stores above) -> visible to the MMA's async proxy
@@ -411,9 +427,10 @@ __global__ void __launch_bounds__(NT_TC2, 1) scan_lists_tc_kernel(const ScanArgs
     } else if (warp <= NAW + NMW) {
         // ---------------- MMA issuers: term 0 = hi.hi -> accumulators 2 / 3 (even / odd k-steps), term 1 = hi.lo -> 0,
         //                  term 2 = lo.hi -> 1 ----------------
-        if (lane == 0) {
-            const int term = warp - (NAW + 1);
+        const int term = warp - (NAW + 1);
+        if (lane == 0 && (!V2 || term < 2)) {
             constexpr uint32_t idesc = umma_idesc_tf32(TM, TN);
+            constexpr uint32_t idesc_fold = umma_idesc_tf32(TM, 2 * TN);
             int sc = 0, acc = 0, sR = 0, sL = 0, sB = 0;
             uint32_t acc_phase = 0, phL = 0, phB = 0;
             {
@@ -425,6 +442,20 @@ __global__ void __launch_bounds__(NT_TC2, 1) scan_lists_tc_kernel(const ScanArgs
                         mbar_wait(aready_bar(sL), phL);
                         mbar_wait(bready_bar(sB), phB);
                         tc_fence_after();
+                        if (V2) {
+                            // issuer `term` owns the k-steps of parity `term` and the accumulator set [hh | cross] at
+                            // columns term * 128: fold MMA (N = 128: hi.hi | hi.lo), then lo.hi into the cross half
+                            const uint64_t dah = umma_desc_sw128(smem_u32(ringR + sR * A_TILE));
+                            const uint64_t dal = umma_desc_sw128(smem_u32(ringL + sL * A_TILE));
+                            const uint64_t db = umma_desc_sw128(smem_u32(ringB + sB * 2 * B_TILE));
+                            const uint32_t tmem_d = tmem_t + (uint32_t)(term * 2 * TN);
+#pragma unroll
+                            for (int ks = 0; ks < TK / 8; ks += 2) {
+                                const uint64_t off = (uint64_t)(((ks + term) * 8 * 4) >> 4);
+                                umma_tf32(tmem_d, dah + off, db + off, idesc_fold, (kb | ks) != 0 ? 1u : 0u);
+                                umma_tf32(tmem_d + (uint32_t)TN, dal + off, db + off, idesc, 1u);
+                            }
+                        } else {
                         const uint32_t aop = term == 2 ? smem_u32(ringL + sL * A_TILE) : smem_u32(ringR + sR * A_TILE);
                         const uint32_t bop = smem_u32(ringB + sB * 2 * B_TILE) + (term == 1 ? B_TILE : 0);
                         const uint64_t da = umma_desc_sw128(aop), db = umma_desc_sw128(bop);
@@ -441,6 +472,7 @@ __global__ void __launch_bounds__(NT_TC2, 1) scan_lists_tc_kernel(const ScanArgs
                                 const uint64_t off = (uint64_t)((ks * 8 * 4) >> 4);
                                 umma_tf32(tmem_d, da + off, db + off, idesc, (kb | ks) != 0 ? 1u : 0u);
                             }
+                        }
                         }
                         umma_commit(done_bar(sR));
                         if (++sR == NR) sR = 0;
@@ -492,12 +524,14 @@ __global__ void __launch_bounds__(NT_TC2, 1) scan_lists_tc_kernel(const ScanArgs
                 for (int h = 0; h < TN / 32; ++h) {
                     float v[32], w[32];
                     float x[32];
-                    tmem_ld32(taddr + (uint32_t)(0 * TN + h * 32), v);  // the two cross terms
-                    tmem_ld32(taddr + (uint32_t)(1 * TN + h * 32), w);
+                    // V1: 0, 1 = the two cross terms, 2, 3 = hi.hi of the even / odd k-steps
+                    // V2: 1, 3 = cross terms (hi.lo + lo.hi) of the even / odd k-steps, 0, 2 = hi.hi
+                    tmem_ld32(taddr + (uint32_t)((V2 ? 1 : 0) * TN + h * 32), v);
+                    tmem_ld32(taddr + (uint32_t)((V2 ? 3 : 1) * TN + h * 32), w);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) x[j] = v[j] + w[j];
-                    tmem_ld32(taddr + (uint32_t)(2 * TN + h * 32), v);  // hi.hi, even and odd k-steps
-                    tmem_ld32(taddr + (uint32_t)(3 * TN + h * 32), w);
+                    tmem_ld32(taddr + (uint32_t)((V2 ? 0 : 2) * TN + h * 32), v);
+                    tmem_ld32(taddr + (uint32_t)((V2 ? 2 : 3) * TN + h * 32), w);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = (v[j] + w[j]) + x[j];
                     if (r < slots) {
@@ -530,15 +564,17 @@ __global__ void __launch_bounds__(NT_TC2, 1) scan_lists_tc_kernel(const ScanArgs
 }  // namespace
 
 // items: (list, chunk of 64 queries) from p.off32 (plan_lists_kernel with chunk = 64); p.qsplit holds 2 x [nq, ds]
-cudaError_t launch_scan_lists_tc(const ScanArgs &a, const ListPlan &p, int num_sms, cudaStream_t st) {
+// variant 1: the first version (rounded hi stored in place, three 64-column MMAs per k-step, three issuers)
+cudaError_t launch_scan_lists_tc(const ScanArgs &a, const ListPlan &p, int variant, int num_sms, cudaStream_t st) {
     if (a.metric != 0 || (a.ds % TK) != 0 || p.chunk != TN || p.qsplit == nullptr) return cudaErrorNotSupported;
     const int64_t n4 = (a.npairs / a.nprobe) * (int64_t)a.ds / 4;
     const int64_t want = (n4 + 255) / 256;
     split_rows_kernel<<<(unsigned)(want < num_sms * 8 ? want : num_sms * 8), 256, 0, st>>>(
         reinterpret_cast<const float4 *>(a.q), n4, reinterpret_cast<float4 *>(p.qsplit));
-    cudaError_t e = cudaFuncSetAttribute(scan_lists_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TC);
+    auto kern = variant == 1 ? scan_lists_tc_kernel<false> : scan_lists_tc_kernel<true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TC);
     if (e != cudaSuccess) return e;
-    scan_lists_tc_kernel<<<num_sms, NT_TC2, SMEM_TC, st>>>(a, p);
+    kern<<<num_sms, NT_TC2, SMEM_TC, st>>>(a, p);
     return cudaGetLastError();
 }
 

@@ -495,6 +495,52 @@ def test_list_major_scan_matches_query_major_and_oracle(sb, orc, metric, d, nlis
     np.testing.assert_array_equal(out[1][1], out[2][1])
 
 
+@pytest.mark.parametrize("metric", ["IP", "L2"])
+def test_plan_scans_across_many_ctas(sb, metric):
+    # The pair plan (1024 pairs per CTA) and the list plan (1024 lists per CTA) are single-pass scans with a
+    # look-back over the preceding CTAs: 140800 pairs -> 138 CTAs (look-back windows of 32), 40000 lists -> 40 CTAs.
+    # Query-major and list-major must agree, and both must match a brute-force scan of the probed lists.
+    n, d, nlist, nq, nprobe, k = 120_000, 128, 40_000, 2200, 64, 10
+    rng = np.random.default_rng(99)
+    x = unit_rows(rng, n, d)
+    q = unit_rows(rng, nq, d)
+    ids = np.arange(n, dtype=np.int64) * 3 + 1
+    assign = rng.integers(0, nlist, n).astype(np.int32)
+    g = sb.IVFFlatIndex(d, nlist=nlist, metric=metric)
+    g.set_centroids(unit_rows(rng, nlist, d))
+    g.add(x, ids, lists=assign)
+    start = rng.integers(0, nlist, nq)
+    probes = ((start[:, None] + np.arange(nprobe)[None, :] * 617) % nlist).astype(np.int32)  # distinct per query
+    out = {}
+    for mode in (1, 2):
+        g.set_param("scan_mode", mode)
+        for rep in range(3):  # the look-back words are reused from launch to launch (epochs)
+            out[mode] = g.search(q, k, lists=probes)
+    g.set_param("plan_epoch", (1 << 22) - 3)  # ... and zeroed when the 22-bit epoch wraps
+    for rep in range(4):
+        wd, wi = g.search(q, k, lists=probes)
+        np.testing.assert_array_equal(wi, out[2][1])
+    np.testing.assert_array_equal(out[1][1], out[2][1])
+    assert_topk_parity(out[2][0], out[2][1], out[1][0], out[1][1], f"list-major vs query-major {metric}")
+    order = np.argsort(assign, kind="stable")
+    bounds = np.searchsorted(assign[order], np.arange(nlist + 1))
+    for qi in list(range(0, nq, 97)) + [nq - 1]:
+        rows = np.concatenate([order[bounds[l] : bounds[l + 1]] for l in probes[qi]])
+        xr = x[rows].astype(np.float64)
+        if metric == "IP":
+            sc = xr @ q[qi].astype(np.float64)
+            best = np.argsort(-sc, kind="stable")[:k]
+        else:
+            sc = ((xr - q[qi].astype(np.float64)) ** 2).sum(axis=1)
+            best = np.argsort(sc, kind="stable")[:k]
+        rd = np.full(k, FMAX if metric == "L2" else -FMAX, dtype=np.float64)
+        ri = np.full(k, -1, dtype=np.int64)
+        rd[: best.size] = sc[best]
+        ri[: best.size] = ids[rows[best]]
+        assert_topk_parity(out[1][0][qi : qi + 1], out[1][1][qi : qi + 1], rd[None, :].astype(np.float32), ri[None, :],
+                           f"query {qi} vs brute force {metric}")
+
+
 def probes_valid(orc, probes):
     """The NumPy oracle indexes list_off with every probe: map the skipped (-1) slots to an empty
     trailing list by handing it a ragged Python structure instead."""
