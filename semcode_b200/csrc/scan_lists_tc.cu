@@ -53,8 +53,8 @@ constexpr int TMEM_COLS_TC = 512;  // two tiles x NACC 64-column accumulators
 //   L   2 x 16 KB  lo operand of A
 //   B  NB x 16 KB  hi | lo k-blocks of the (pre-split) queries, loaded by their own warp
 // NR - 2 = 5 raw stages (80 KB per SM, 11.8 MB per GPU) are in flight while one is split and one is multiplied.
-constexpr int NR = 7, NL = 2, NB = 4;
-constexpr int SMEM_TC = NR * A_TILE + NL * A_TILE + NB * 2 * B_TILE + 1024 /*align*/ + 1024 /*barriers, tables*/;
+// (ring depths are template parameters of the kernel: NR raw, NL lo, NB query stages)
+constexpr int smem_tc(int nr, int nl, int nb) { return nr * A_TILE + nl * A_TILE + nb * 2 * B_TILE + 1024 /*align*/ + 1024 /*barriers, tables*/; }
 constexpr int NAW = 8;        // A loader/splitter warps
 constexpr int NMW = 3;        // MMA issuer warps (one lane each), one per product term
 constexpr int NT_TC2 = (NAW + 1 + NMW + 4) * 32;  // + 1 B loader warp, 4 epilogue warps
@@ -227,7 +227,7 @@ struct UnitCursor {
 // shared-memory traffic drops from 152 KB to 120 KB and the MMA count from 12 to 8.  Two issuers, one per k-step
 // parity, each the only writer of its accumulator set [hh | cross] (fold MMA, then lo.hi into the cross columns):
 // the order of additions into every accumulator is fixed, so results are reproducible run to run.
-template <bool V2>
+template <bool V2, int NR, int NL, int NB>
 __global__ void __launch_bounds__(NT_TC2, 1) scan_lists_tc_kernel(const ScanArgs a, const ListPlan p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -571,10 +571,14 @@ cudaError_t launch_scan_lists_tc(const ScanArgs &a, const ListPlan &p, int varia
     const int64_t want = (n4 + 255) / 256;
     split_rows_kernel<<<(unsigned)(want < num_sms * 8 ? want : num_sms * 8), 256, 0, st>>>(
         reinterpret_cast<const float4 *>(a.q), n4, reinterpret_cast<float4 *>(p.qsplit));
-    auto kern = variant == 1 ? scan_lists_tc_kernel<false> : scan_lists_tc_kernel<true>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TC);
+    // ring depths 7 / 2 / 4 (raw, lo, query stages); 7/3/3, 6/3/4 and 8/2/3 measured the same 13.0 ms per batch at
+    // nq 4096 / nprobe 128: the kernel is bound by shared-memory bandwidth (ncu: LSU + tensor-core wavefronts = 71 % of
+    // the data pipe, tensor pipe 26 %, DRAM 38 %), not by the depth of its pipeline
+    auto kern = variant == 1 ? scan_lists_tc_kernel<false, 7, 2, 4> : scan_lists_tc_kernel<true, 7, 2, 4>;
+    const int smem = smem_tc(7, 2, 4);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    kern<<<num_sms, NT_TC2, SMEM_TC, st>>>(a, p);
+    kern<<<num_sms, NT_TC2, smem, st>>>(a, p);
     return cudaGetLastError();
 }
 
