@@ -295,6 +295,55 @@ def test_exact_ties_keep_both(sb):
         assert sorted(ii[r].tolist()) == [r, 100 + r] and dd[r, 0] == dd[r, 1]
 
 
+@pytest.mark.parametrize("metric", ["IP", "L2"])
+def test_one_pass_selection_and_its_fallbacks(sb, orc, metric):
+    # >= 8192 candidates and k <= 128: the top-k kernel keeps 4 pairs per thread in ONE pass over the candidates;
+    # k = 129 and 300 take the radix select.  One list, so candidate index == insertion order.
+    n, d = 50_000, 32
+    rng = np.random.default_rng(5)
+    x = unit_rows(rng, n, d)
+    q = unit_rows(rng, 24, d)
+    # queries 0..3: their ten best rows sit 512 slots apart -> one thread of the selection CTA meets them all,
+    # keeps four, and the CTA must notice and fall back
+    for qi in range(4):
+        for j in range(10):
+            x[(7 + 31 * qi) + 512 * j] = (q[qi] + 0.01 * (j + 1) * unit_rows(rng, 1, d)[0])
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    # query 4: sixty exact duplicates of its best row -> ties across the k-th position
+    x[1000:1060] = x[999]
+    q[4] = x[999]
+    ids = np.arange(n, dtype=np.int64) + 11
+    g = sb.IVFFlatIndex(d, nlist=1, metric=metric)
+    g.set_centroids(np.zeros((1, d), np.float32))
+    g.add(x, ids)
+    for k in (1, 10, 50, 128, 129, 300):
+        bd, bi = orc.brute_force(x, ids, q, k, metric)
+        gd, gi = g.search(q, k, nprobe=1)
+        assert_topk_parity(gd, gi, bd.astype(np.float32), bi, f"one list, k={k} {metric}")
+    gd, gi = g.search(q[4:5], 10, nprobe=1)
+    assert gi[0].tolist() == (np.arange(999, 1009) + 11).tolist()  # ties in candidate (insertion) order
+
+
+def test_one_pass_selection_of_probes(sb, orc):
+    # the same kernel ranks the centroids: 12000 lists >= 8192 -> one pass for nprobe <= 128
+    d, nlist = 64, 12_000
+    rng = np.random.default_rng(6)
+    cent = unit_rows(rng, nlist, d)
+    q = unit_rows(rng, 200, d)
+    g = sb.IVFFlatIndex(d, nlist=nlist, metric="IP")
+    g.set_centroids(cent)
+    sim = orc.coarse_similarity(q, cent, "IP", dtype=np.float64)
+    for nprobe in (1, 8, 32, 128, 200):
+        want = orc.top_desc(sim, nprobe)
+        got, sc = g.probe(q, nprobe, with_scores=True)
+        for r in range(q.shape[0]):
+            assert len(set(got[r].tolist())) == nprobe
+            assert close(sc[r], sim[r][got[r]].astype(np.float32)).all()
+            assert (np.diff(sc[r]) <= 0).all()
+            if not np.array_equal(got[r], want[r]):  # only near-ties (fp32 rounding of the contraction) may reorder
+                assert np.allclose(np.sort(sim[r][got[r]]), np.sort(sim[r][want[r]]), rtol=1e-5, atol=1e-6), (nprobe, r)
+
+
 def test_chunked_search_equals_single_pass(sb, orc):
     x, q, cent, ids = make_case(orc, 20000, 64, 128, 700, "IP", seed=41)
     g, _, _ = build_pair(sb, orc, x, ids, cent, "IP")
