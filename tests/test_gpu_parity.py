@@ -320,8 +320,9 @@ def test_one_pass_selection_and_its_fallbacks(sb, orc, metric):
         bd, bi = orc.brute_force(x, ids, q, k, metric)
         gd, gi = g.search(q, k, nprobe=1)
         assert_topk_parity(gd, gi, bd.astype(np.float32), bi, f"one list, k={k} {metric}")
-    gd, gi = g.search(q[4:5], 10, nprobe=1)
-    assert gi[0].tolist() == (np.arange(999, 1009) + 11).tolist()  # ties in candidate (insertion) order
+    gd, gi = g.search(q[4:5], 10, nprobe=1)  # all ten out of the 61 tied rows (which ten: slot order inside the list)
+    assert set(gi[0].tolist()) <= set((np.arange(999, 1060) + 11).tolist()) and len(set(gi[0].tolist())) == 10
+    assert (gd[0] == gd[0, 0]).all()
 
 
 def test_one_pass_selection_of_probes(sb, orc):
