@@ -244,7 +244,7 @@ def run_reference(args):
     from oracle import ivf_c
 
     ivf_c.build()
-    cores = ivf_c.num_threads()
+    cores = ivf_c.use_all_cores()  # torchrun exports OMP_NUM_THREADS=1; rank 0 runs alone and takes every core it may use
     # A bounded sample of the workload that needs no GPU: the same synthetic rows for the lists a
     # query sample probes.  The CPU arm builds its own (smaller) slice of the index: nlist and
     # nprobe as configured, rows = n, but only the probed lists are materialised.
@@ -648,6 +648,7 @@ def run_ours(args):
         from oracle import ivf_c
 
         ivf_c.build()
+        ivf_c.use_all_cores()
         cq = min(args.cpu_queries, nq)
         qs = qb[0][:cq].cpu().numpy()
         probes = g.probe(qs, nprobe)

@@ -34,6 +34,8 @@ def lib():
         L = C.CDLL(_LIB_PATH)
         f32p, i32p, i64p, u8p = (C.POINTER(t) for t in (C.c_float, C.c_int32, C.c_int64, C.c_uint8))
         L.orc_num_threads.restype = C.c_int
+        L.orc_set_num_threads.argtypes = [C.c_int]
+        L.orc_set_num_threads.restype = None
         L.orc_gemm_nt.argtypes = [f32p, C.c_int64, f32p, C.c_int, C.c_int, f32p]
         L.orc_coarse_scores.argtypes = [f32p, C.c_int64, f32p, C.c_int, C.c_int, C.c_int, f32p]
         L.orc_top_probes.argtypes = [f32p, C.c_int64, C.c_int, C.c_int, i32p]
@@ -61,6 +63,16 @@ def _f32(a):
 
 def num_threads() -> int:
     return int(lib().orc_num_threads())
+
+
+def use_all_cores() -> int:
+    """OpenMP threads = the cores this process may run on (a launcher such as torchrun sets OMP_NUM_THREADS=1)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().orc_set_num_threads(n)
+    return num_threads()
 
 
 def coarse_scores(q, centroids, metric: int) -> np.ndarray:

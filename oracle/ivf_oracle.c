@@ -66,6 +66,15 @@ float orc_l2sqr(const float *a, const float *b, int d) {
     return s;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the timed CPU arm asks for the cores it may run on instead */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
