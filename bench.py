@@ -62,6 +62,7 @@ def parse_args():
     p.add_argument("--train-rows", type=int, default=1_000_000)
     p.add_argument("--train-iters", type=int, default=4)
     p.add_argument("--sweep", action="store_true", help="also time an nprobe x nq grid (extra key 'sweep')")
+    p.add_argument("--sweep-nq", default="1,16,256,4096", help="batch sizes of --sweep")
     p.add_argument("--recall-queries", type=int, default=128)
     p.add_argument("--cpu-queries", type=int, default=96, help="queries in the CPU baseline sample")
     p.add_argument("--cpu-reps", type=int, default=120, help="timed repetitions of the CPU baseline sample")
@@ -610,7 +611,7 @@ def run_ours(args):
     # ---- optional nprobe x nq sweep --------------------------------------------------------------------
     if args.sweep and world == 1:
         sweep = []
-        for nq_ in (1, 16, 256, 4096):
+        for nq_ in [int(v) for v in args.sweep_nq.split(",")]:
             qs = gen_rows(torch, 0, nq_, d, 777 + nq_, dev, args.dataset)
             exact_ids = None
             if nq_ == 256:  # recall@10 per nprobe on this batch (exact = exhaustive probe)
