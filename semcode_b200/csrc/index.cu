@@ -723,14 +723,16 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
         a.cand = ix->s_cand.as<float>();
         a.filt = fdev;
         // large batches re-probe the same lists: read each list once and score it against all its queries
-        // (auto: when a list is probed 0.25x or more on average -- 88 % or fewer of the pair passes hit a distinct
-        //  list -- and lists hold at least a page.  Measured on C2, list-major / query-major step time at 0.125x /
-        //  0.25x / 0.5x / 1x / 2x / 4x: 1.01 / 0.95 / 0.85 / 0.69 / 0.48 / 0.32, profiles/r1_scan_mode_crossover.md;
-        //  the threshold was 0.75x while the list plan cost 0.1 ms)
+        // (auto: when a list is probed 0.5x or more on average -- 79 % or fewer of the pair passes hit a distinct
+        //  list -- and lists hold at least a page.  Measured list-major / query-major step time at 0.125x / 0.25x /
+        //  0.5x / 1x / 2x / 4x on C2 (dim 768): 1.01 / 0.95 / 0.85 / 0.69 / 0.48 / 0.32
+        //  (profiles/r1_scan_mode_crossover.md); at dim 2048, where the 4-query page scan needs four slices, 0.25x is
+        //  a loss (1.11) and 0.5x a gain (0.82).  With a scalar filter the scans are short and the plan's launches
+        //  weigh more: 0.75x, the threshold of the first version)
         const bool long_lists = ix->ntotal + ix->nremoved >= (int64_t)kPageRows * ix->nlist;
+        const int64_t lm_min_pairs = fdev.flags != 0 ? (3 * (int64_t)ix->nlist + 3) / 4 : ((int64_t)ix->nlist + 1) / 2;
         const bool list_major = ix->ds >= 128 && npairs <= (int64_t)INT32_MAX &&
-                                (ix->scan_mode == 2 ||
-                                 (ix->scan_mode == 0 && long_lists && 4 * npairs >= (int64_t)ix->nlist));
+                                (ix->scan_mode == 2 || (ix->scan_mode == 0 && long_lists && npairs >= lm_min_pairs));
         if (list_major) {
             const size_t nl = (size_t)ix->nlist;
             const size_t agg_words = (size_t)list_plan_ctas(ix->nlist) * 8;  // 4 x u64 per plan CTA
