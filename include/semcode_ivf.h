@@ -182,7 +182,17 @@ int sc_index_export_list(sc_index_t *idx, int32_t list, int64_t cap, float *vecs
                          int64_t *len_out, void *stream);
 int sc_index_set_profiling(sc_index_t *idx, int32_t enabled);
 int sc_index_last_search_times(sc_index_t *idx, sc_search_times_t *out);
-/* tuning knobs (tests/bench): scratch budget in bytes for candidate distances; scan variant */
+/* tuning knobs (tests / bench; the defaults are the measured best):
+ *   "scratch_bytes"  search scratch ceiling (>= 1 MiB, default 8 GiB): larger batches run in equal passes
+ *   "scan_mode"      0 = automatic (list-major from nq*nprobe >= nlist/2, 3/4 nlist with a filter), 1 = query-major,
+ *                    2 = list-major
+ *   "scan_variant"   0..4 rows x loads in flight of the query-major scan
+ *   "lists_cfg"      tile items of the list-major scan: 0 = tcgen05 where it applies (inner product, dim % 32 == 0),
+ *                    1 / 2 = exact-fp32 FFMA tiles (64- / 32-float stages), 3 = the first tcgen05 tile kernel
+ *   "lists_fork"     1 = tile items on a side stream next to the page scans
+ *   "coarse_impl"    0 = tcgen05 3xTF32 contraction, 1 = fp32 SIMT;  "tc_variant" 0 = 256x256, 1 = 128x256 tiles
+ *   "small_coarse"   1 (default) = streamed fp32 coarse kernel for batches of <= 16 queries
+ *   "plan_epoch"     tests: launch counter of the pair plan's look-back words (22-bit wrap) */
 int sc_index_set_param(sc_index_t *idx, const char *name, int64_t value);
 
 #ifdef __cplusplus
