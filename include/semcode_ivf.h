@@ -188,7 +188,8 @@ int sc_index_last_search_times(sc_index_t *idx, sc_search_times_t *out);
  *                    2 = list-major
  *   "scan_variant"   0..4 rows x loads in flight of the query-major scan
  *   "lists_cfg"      tile items of the list-major scan: 0 = tcgen05 where it applies (inner product, dim % 32 == 0),
- *                    1 / 2 = exact-fp32 FFMA tiles (64- / 32-float stages), 3 = the first tcgen05 tile kernel
+ *                    1 / 2 = exact-fp32 FFMA tiles (64- / 32-float stages), 3 = the first tcgen05 tile kernel,
+ *                    4 = 0 with the 8-query page scan on mma.sync (parity-green, measured slower)
  *   "lists_fork"     1 = tile items on a side stream next to the page scans
  *   "coarse_impl"    0 = tcgen05 3xTF32 contraction, 1 = fp32 SIMT;  "tc_variant" 0 = 256x256, 1 = 128x256 tiles
  *   "small_coarse"   1 (default) = streamed fp32 coarse kernel for batches of <= 16 queries

@@ -174,7 +174,7 @@ struct sc_index {
     DevBuf s_sums, s_counts, s_obj, s_rows, s_rm, s_cnt, s_ahi, s_alo, s_lplan, s_scan, s_packed, s_qsplit;
     int64_t scratch_budget = (int64_t)8 << 30;  // search scratch ceiling (candidates dominate); sc_index_set_param("scratch_bytes")
     int scan_variant = 0;
-    int lists_cfg = 0;  // list-major tile items: 0 = tcgen05 where it applies, 1 = FFMA tiles, 2 = FFMA tiles with 32-float stages, 3 = the first tcgen05 tile kernel (scan_lists_tc.cu, variant 1)
+    int lists_cfg = 0;  // list-major tile items: 0 = tcgen05 where it applies, 1 = FFMA tiles, 2 = FFMA tiles with 32-float stages, 3 = the first tcgen05 tile kernel (scan_lists_tc.cu, variant 1), 4 = 0 with the 8-query page scan on mma.sync
     int scan_mode = 0;  // 0 = auto, 1 = query-major (scan.cu), 2 = list-major (scan_lists.cu)
     cudaEvent_t ev_done = nullptr;
     cudaStream_t side[2] = {nullptr, nullptr};  // fork/join streams of the list-major scan
@@ -1496,7 +1496,7 @@ int sc_index_set_param(sc_index_t *ix, const char *name, int64_t value) {
         return SC_OK;
     }
     if (strcmp(name, "lists_cfg") == 0) {
-        if (value < 0 || value > 3) return fail(SC_ERR_INVALID, "lists_cfg must be in [0,3]");
+        if (value < 0 || value > 4) return fail(SC_ERR_INVALID, "lists_cfg must be in [0,4]");
         ix->lists_cfg = (int)value;
         return SC_OK;
     }

@@ -309,6 +309,209 @@ __global__ void __launch_bounds__(256, 2)
     }
 }
 
+// ---- 8-query page scan on the (legacy) warp-level tensor cores (lists_cfg = 4; measured slower, see launch_scan_mq) ----
+// The scalar 8-query scan above is issue-bound (47 % issue-active at 4.3 TB/s: 384 FMAs, 24 LDS.128 and a 31-shuffle
+// butterfly per 6 KB).  Here a page is two 16-row MMA tiles and the 8 queries are exactly one n-tile of
+// mma.sync.m16n8k8 (tf32 x tf32 -> fp32): the A fragments come straight from global memory in the fragment layout
+// (lane (g, t) loads the float4 at row g / g + 8, columns 16*kc + 4t of each tile: 8 rows x 64 B per instruction,
+// every 32-byte sector used once), the k index of the MMA is a permutation of those 16 columns that A and B share,
+// and the MMA does the reduction over the dimension -- no shuffles.  fp32 accuracy as in the tcgen05 tiles:
+// x = hi + lo with hi = x & 0xffffe000 (exact in tf32) and lo = x - hi, product = hi.hi + hi.lo + lo.hi, hi.hi in
+// separate accumulators for the two k-steps of a chunk; the split of both operands happens in registers.
+// Inner product, dim % 16 == 0, no scalar filter (a filtered page has few live rows: the scalar kernel streams
+// only those).  Same units, groups, candidate layout and slice-outer order as scan_mq_kernel.
+constexpr int MM_SLF = 384;            // floats per slice
+constexpr int MM_QLD = MM_SLF + 16;    // padded query row (floats): consecutive queries shift by 64 B -> the
+                                       // quarter-warp's two query rows of an LDS.128 hit disjoint banks
+constexpr size_t MM_WARP_BYTES = (size_t)8 * MM_QLD * 4 + 8 * 8 + 8 * 8;
+
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                                uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xffffe000u; }
+__device__ __forceinline__ uint32_t tf32_lo(float x, uint32_t hi) { return __float_as_uint(x - __uint_as_float(hi)); }
+
+__global__ void __launch_bounds__(256, 2)
+    scan_mq8_mma_kernel(const ScanArgs a, const ListPlan p, const int32_t *__restrict__ pgoff) {
+    extern __shared__ __align__(16) float4 qsmem[];
+    constexpr int MQ = 8;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int wpb = blockDim.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int ds4 = a.ds >> 2;
+    const int nslices = (a.ds + MM_SLF - 1) / MM_SLF;
+    float4 *qs = reinterpret_cast<float4 *>(reinterpret_cast<char *>(qsmem) + (size_t)warp * MM_WARP_BYTES);  // [8][MM_QLD / 4]
+    int64_t *cbs = reinterpret_cast<int64_t *>(qs + MQ * (MM_QLD / 4));
+    const float4 **qgs = reinterpret_cast<const float4 **>(cbs + MQ);
+
+    const int32_t W = pgoff[p.nlist];
+    const int64_t nwarps = (int64_t)gridDim.x * wpb;
+    const int64_t gw = (int64_t)blockIdx.x * wpb + warp;
+    const int32_t per = (int32_t)((W + nwarps - 1) / nwarps);
+    const int64_t w0l = gw * per;
+    if (w0l >= W) return;
+    const int32_t w0 = (int32_t)w0l;
+    const int32_t w1 = (w0 + per < W) ? (w0 + per) : W;
+    int32_t lo = 0, hi = p.nlist;  // list that owns unit w0: last l with pgoff[l] <= w0
+    while (hi - lo > 1) {
+        const int32_t mid = (lo + hi) >> 1;
+        if (pgoff[mid] <= w0)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    int32_t l = lo;
+    int32_t l_start = pgoff[l], l_end = pgoff[l + 1];
+    const int slab_mask = (1 << a.slab_shift) - 1;
+
+    int32_t w = w0;
+    while (w < w1) {
+        while (w >= l_end) {
+            ++l;
+            l_start = l_end;
+            l_end = pgoff[l + 1];
+        }
+        const int32_t len = a.list_len[l];
+        const int32_t ptbase = a.pt_off[l];
+        const int32_t npg = (len + kPageRows - 1) / kPageRows;
+        const int32_t ul = w - l_start;
+        const int32_t pass = ul / npg;
+        const int32_t jpage0 = ul - pass * npg;
+        const int32_t wend = min(w1, l_start + (pass + 1) * npg);
+        const int32_t G = wend - w;
+        {
+            const int32_t qbase = p.lq_off[l] + p.chunk * p.n32[l] + MQ * pass;
+            const int nqi = min(MQ, p.lq_off[l + 1] - qbase);
+            __syncwarp();  // the previous group's readers are done with cbs / qgs
+            if (lane < MQ) {
+                int64_t cb = -1;
+                const float4 *qg = nullptr;
+                if (lane < nqi) {
+                    const int32_t pair = p.lq[qbase + lane];
+                    cb = a.page_off[pair] * kPageRows;
+                    qg = reinterpret_cast<const float4 *>(a.q + (int64_t)(pair / a.nprobe) * a.ds);
+                }
+                cbs[lane] = cb;
+                qgs[lane] = qg;
+            }
+            __syncwarp();
+        }
+        const int64_t cb0 = cbs[2 * t], cb1 = cbs[2 * t + 1];  // this lane's two queries (C fragment columns 2t, 2t + 1)
+        for (int s = 0; s < nslices; ++s) {
+            const int c0f = s * MM_SLF;                              // first float of the slice
+            const int nkc = (min(MM_SLF, a.ds - c0f)) >> 4;         // 16-column chunks in the slice
+            __syncwarp();  // the previous slice's readers are done with qs
+#pragma unroll
+            for (int j = 0; j < MQ; ++j) {
+                const float4 *qg = qgs[j];
+                for (int c = lane; c < 4 * nkc; c += 32)
+                    qs[j * (MM_QLD / 4) + c] = qg != nullptr ? __ldg(qg + (c0f >> 2) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __syncwarp();
+            const float4 *qrow = qs + g * (MM_QLD / 4) + t;  // query g, float4 t of every chunk
+            for (int32_t gi = 0; gi < G; ++gi) {
+                const int32_t jpage = jpage0 + gi;
+                const int32_t page = __ldg(a.pt + ptbase + jpage);
+                const int slab = page >> a.slab_shift;
+                const int64_t slot0 = (int64_t)(page & slab_mask) * kPageRows;
+                const int rows = min(kPageRows, len - jpage * kPageRows);
+                const uint32_t tag = __ldg(a.slabs->tags[slab] + slot0 + lane);
+                const bool live = lane < rows && filter_pass(a.filt, tag);
+                const uint32_t live_mask = __ballot_sync(0xffffffffu, live);
+                const int64_t poff = (int64_t)jpage * kPageRows;
+                // rows g, g + 8 (tile 0) and g + 16, g + 24 (tile 1), float4 t of chunk kc
+                const float4 *rp = reinterpret_cast<const float4 *>(a.slabs->vec[slab]) + (slot0 + g) * ds4 + (c0f >> 2) + t;
+                bool rl[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rl[i] = (live_mask >> (g + 8 * i)) & 1u;
+                float acc[2][3][4];  // [tile][hh of k-step 0, hh of k-step 1, cross][C fragment]
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[mt][k][i] = 0.f;
+#pragma unroll 1
+                for (int kc = 0; kc < nkc; kc += 2) {
+                    float4 x[2][4];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (rl[i] && kc + u < nkc)
+                                x[u][i] = ld_stream_f4(rp + (int64_t)(8 * i) * ds4 + 4 * (kc + u));
+                            else
+                                x[u][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        if (kc + u < nkc) {
+                            const float4 qv = qrow[4 * (kc + u)];
+                            const float qf[4] = {qv.x, qv.y, qv.z, qv.w};
+                            uint32_t qh[4], ql[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                qh[e] = tf32_hi(qf[e]);
+                                ql[e] = tf32_lo(qf[e], qh[e]);
+                            }
+#pragma unroll
+                            for (int mt = 0; mt < 2; ++mt) {
+                                const float4 xa = x[u][2 * mt], xb = x[u][2 * mt + 1];  // rows g + 16 mt, g + 8 + 16 mt
+                                const float fa[4] = {xa.x, xa.y, xa.z, xa.w}, fb[4] = {xb.x, xb.y, xb.z, xb.w};
+                                uint32_t ah[4], al[4], bh[4], bl[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    ah[e] = tf32_hi(fa[e]);
+                                    al[e] = tf32_lo(fa[e], ah[e]);
+                                    bh[e] = tf32_hi(fb[e]);
+                                    bl[e] = tf32_lo(fb[e], bh[e]);
+                                }
+#pragma unroll
+                                for (int st = 0; st < 2; ++st) {  // k-step st: k = t <-> column 4t + 2 st, k = t + 4 <-> column 4t + 2 st + 1
+                                    const int e0 = 2 * st, e1 = 2 * st + 1;
+                                    mma_tf32_16x8x8(acc[mt][st], ah[e0], bh[e0], ah[e1], bh[e1], qh[e0], qh[e1]);
+                                    mma_tf32_16x8x8(acc[mt][2], ah[e0], bh[e0], ah[e1], bh[e1], ql[e0], ql[e1]);
+                                    mma_tf32_16x8x8(acc[mt][2], al[e0], bl[e0], al[e1], bl[e1], qh[e0], qh[e1]);
+                                }
+                            }
+                        }
+                    }
+                }
+                const bool first = s == 0, final = s == nslices - 1;
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {  // C fragment: i = 0, 1 -> row g, queries 2t, 2t + 1; i = 2, 3 -> row g + 8
+                        const int64_t cb = (i & 1) ? cb1 : cb0;
+                        if (cb >= 0) {
+                            const int ri = 2 * mt + (i >> 1);  // index into rl: rows g + 8 ri
+                            float v = (acc[mt][0][i] + acc[mt][1][i]) + acc[mt][2][i];
+                            float *dst = a.cand + cb + poff + (g + 8 * ri);
+                            if (!first) v += *dst;  // this lane's own partial sum of the earlier slices
+                            if (final) v = rl[ri] ? v : -INFINITY;
+                            *dst = v;
+                        }
+                    }
+            }
+        }
+        w = wend;
+    }
+}
+
+cudaError_t launch_mq8_mma(const ScanArgs &a, const ListPlan &p, const int32_t *pgoff, int num_sms, cudaStream_t st) {
+    constexpr int wpb = 8;
+    constexpr size_t smem = MM_WARP_BYTES * wpb;
+    static_assert(MM_WARP_BYTES % 16 == 0 && 2 * (smem + 1024) <= 227 * 1024, "two CTAs per SM must fit");
+    cudaError_t e = cudaFuncSetAttribute(scan_mq8_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    scan_mq8_mma_kernel<<<num_sms * 2, wpb * 32, smem, st>>>(a, p, pgoff);
+    return cudaGetLastError();
+}
+
 template <int MQ, int R, int U, bool L2, bool EXACT, bool SO>
 cudaError_t launch_mq_order(const ScanArgs &a, const ListPlan &p, const int32_t *pgoff, int num_sms, cudaStream_t st) {
     auto kern = scan_mq_kernel<MQ, R, U, L2, EXACT, SO>;
@@ -339,13 +542,18 @@ cudaError_t launch_mq_metric(const ScanArgs &a, const ListPlan &p, const int32_t
 
 // bucket 0: remainders of 1..4 queries (one pass); bucket 1: remainders of 5..16 queries (passes of 8).
 // pgoff [nlist+1]: exclusive prefix of the bucket's page x pass units (plan_lists_kernel)
-cudaError_t launch_scan_mq(const ScanArgs &a, const ListPlan &p, int bucket, const int32_t *pgoff, int num_sms, cudaStream_t st) {
+// cfg 4: the 8-query bucket on mma.sync where it applies (inner product, dim % 16 == 0, no filter).  Parity-green but
+// SLOWER than the scalar scan on B200 -- headline step 4.79 vs 4.43 ms (profiles/r1_bench40_mq8_mma.json vs
+// r1_bench40_mq8_scalar.json): 12 legacy-path MMAs + 40 split instructions per 16 columns do not beat 96 FMAs -- so
+// it stays an option
+cudaError_t launch_scan_mq(const ScanArgs &a, const ListPlan &p, int bucket, int cfg, const int32_t *pgoff, int num_sms, cudaStream_t st) {
     const int ds4 = a.ds >> 2;
     if (bucket == 0) {
         if (ds4 % 192 == 0) return launch_mq_metric<4, 2, 6, true>(a, p, pgoff, num_sms, st);
         if (ds4 % 128 == 0) return launch_mq_metric<4, 2, 4, true>(a, p, pgoff, num_sms, st);
         return launch_mq_metric<4, 2, 4, false>(a, p, pgoff, num_sms, st);
     }
+    if (cfg == 4 && a.metric == 0 && a.ds % 16 == 0 && a.filt.flags == 0) return launch_mq8_mma(a, p, pgoff, num_sms, st);
     if (ds4 % 96 == 0) return launch_mq_metric<8, 4, 3, true>(a, p, pgoff, num_sms, st);
     if (ds4 % 64 == 0) return launch_mq_metric<8, 4, 2, true>(a, p, pgoff, num_sms, st);
     return launch_mq_metric<8, 4, 3, false>(a, p, pgoff, num_sms, st);

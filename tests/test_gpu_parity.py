@@ -639,7 +639,7 @@ def test_multi_query_page_scan_buckets_and_slices(sb, orc, metric, per_list):
         g.set_param("scan_mode", 1)
         d1, i1 = g.search(q, 10, lists=probes)
         rd, ri = orc.search(oidx, q, 10, 2, mask=orc.row_mask(oidx, removed_ids=ids[::13]), probes=probes)
-        for cfg in (0, 2):
+        for cfg in (0, 2, 4):  # 4: the 8-query bucket on mma.sync (inner product, dim % 16 == 0)
             g.set_param("scan_mode", 2)
             g.set_param("lists_cfg", cfg)
             d3, i3 = g.search(q, 10, lists=probes)
