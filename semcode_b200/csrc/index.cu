@@ -343,13 +343,6 @@ int stage_rows(sc_index *ix, const float *x, int64_t n, DevBuf &raw, DevBuf &pad
     return SC_OK;
 }
 
-int copy_out(sc_index *ix, void *dst, const void *src_dev, size_t bytes, cudaStream_t st) {
-    if (dst == src_dev || bytes == 0) return SC_OK;
-    const bool dev = is_device_ptr(dst, ix->device);
-    CU(cudaMemcpyAsync(dst, src_dev, bytes, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
-    return SC_OK;
-}
-
 int begin_call(sc_index *ix, cudaStream_t st) {
     // scratch is shared by all calls on the handle: order this call after the previous one even
     // when the caller switched streams
