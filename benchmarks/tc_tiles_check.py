@@ -1,4 +1,5 @@
-"""Accuracy / parity probe for the tcgen05 list-major tiles (lists_cfg 3 = 2 tf32 terms, 4 = 3 terms) against the
+"""Accuracy / parity probe for the tcgen05 list-major tiles (lists_cfg 0 / 3: operands from shared memory, v2 / v1;
+5: list rows from tensor memory) against the
 query-major fp32 scan on the same probes.  Prints the error statistics the default choice is based on."""
 import os
 import sys
@@ -25,7 +26,7 @@ def main():
         g.set_param("scan_mode", 1)
         d0, i0 = g.search(qd, 10, nprobe=nprobe)
         torch.cuda.synchronize()
-        for cfg in (0, 3):
+        for cfg in (0, 3, 5):
             g.set_param("scan_mode", 2)
             g.set_param("lists_cfg", cfg)
             d1, i1 = g.search(qd, 10, nprobe=nprobe)

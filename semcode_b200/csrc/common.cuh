@@ -138,6 +138,7 @@ struct ScanArgs {
     int slab_shift;
     float *cand;  // [page_off[npairs]*32] similarity to maximise, -inf for dead slots
     FilterDev filt;
+    const void *slab_maps;  // one 128-byte TMA tensor map per slab (encode_slab_map), or nullptr
 };
 
 // ---- cross-GPU exchange over peer-mapped memory (NVLink / NVSwitch), one process per GPU -------------------
@@ -206,6 +207,12 @@ int list_plan_ctas(int32_t nlist);
 cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int num_sms, int *launches, cudaStream_t st);
 // tile items on the tensor cores (scan_lists_tc.cu): inner product, ds % 32 == 0, p.chunk == 64
 cudaError_t launch_scan_lists_tc(const ScanArgs &a, const ListPlan &p, int variant, int num_sms, cudaStream_t st);
+// the same items with the list rows as a tensor-memory operand (scan_lists_ts.cu); needs a.slab_maps
+cudaError_t launch_scan_lists_ts(const ScanArgs &a, const ListPlan &p, int num_sms, cudaStream_t st);
+// out = 2 x [n4] float4: the tf32 terms hi = tf32(q), lo = tf32(q - hi) of the query rows
+cudaError_t launch_split_queries(const float *q, int64_t n4, float *out, int num_sms, cudaStream_t st);
+// TMA tensor map (128 bytes, host memory) of one list slab: fp32 [rows, ds], boxes of one page x 32 floats, 128 B swizzle
+cudaError_t encode_slab_map(void *map128, const float *base, int64_t rows, int ds);
 // final top-k over the candidates of each query + id translation
 cudaError_t launch_select_candidates(const ScanArgs &a, int64_t nq, int k, float *out_dist, int64_t *out_ids,
                                      cudaStream_t st);
@@ -222,13 +229,26 @@ cudaError_t launch_peer_signal(const PeerSignal &sig, cudaStream_t st);  // a ra
 cudaError_t launch_peer_wait(const PeerWait &wait, cudaStream_t st);     // orders the stream after the peers' stores
 
 // list maintenance
-cudaError_t launch_count_positions(const int32_t *assign, int64_t n, int32_t nlist, int32_t *list_len, int32_t *pos,
-                                   int32_t *bad, cudaStream_t st);
+// bad[0] += rows with a list id outside [0, nlist), bad[1] += rows with a repo tag above kTagRepoMax (repo nullable)
+cudaError_t launch_count_positions(const int32_t *assign, const uint32_t *repo, int64_t n, int32_t nlist, int32_t *list_len,
+                                   int32_t *pos, int32_t *bad, cudaStream_t st);
 cudaError_t launch_page_need(const int32_t *len_old, const int32_t *len_new, int32_t nlist, int32_t *need,
                              int32_t *npg_new, cudaStream_t st);
+// the batch's new pages: numbers < nfree come from free_pages[] (returned by compaction), the rest from pool_top up
 cudaError_t launch_rebuild_pt(const int32_t *pt_off_old, const int32_t *pt_old, const int32_t *pt_off_new,
-                              int32_t *pt_new, const int32_t *need_off, int32_t pool_top, int32_t nlist,
-                              cudaStream_t st);
+                              int32_t *pt_new, const int32_t *need_off, int32_t pool_top, const int32_t *free_pages,
+                              int32_t nfree, int32_t nlist, cudaStream_t st);
+// compaction: squeeze the tombstoned slots out of every list in place (list_len shrinks), then rebuild the page
+// table keeping ceil(len / 32) pages per list and appending the others to free_pages at *free_cursor
+cudaError_t launch_compact_lists(int32_t nlist, int32_t *list_len, const int32_t *pt_off, const int32_t *pt,
+                                 const SlabTable *slabs, int slab_shift, int ds, int num_sms, cudaStream_t st);
+cudaError_t launch_pages_of_len(const int32_t *len, int32_t nlist, int32_t *npg, cudaStream_t st);
+cudaError_t launch_compact_pt(const int32_t *pt_off_old, const int32_t *pt_old, const int32_t *pt_off_new, int32_t *pt_new,
+                              int32_t nlist, int32_t *free_pages, int32_t *free_cursor, cudaStream_t st);
+// lists [l0, l0 + nl) back to back into vecs / ids / tags (nullable); off [nl + 1] device exclusive prefix of their slots
+cudaError_t launch_export_range(const int32_t *pt_off, const int32_t *pt, int32_t l0, int32_t nl, const int64_t *off, int64_t rows,
+                                int ds, int d_out, const SlabTable *slabs, int slab_shift, float *vecs, int64_t *ids, uint32_t *tags,
+                                int num_sms, cudaStream_t st);
 cudaError_t launch_scatter_rows(const float *x, const int64_t *ids, const uint32_t *repo, const uint8_t *lang,
                                 const int32_t *assign, const int32_t *pos, int64_t n, int ds, const int32_t *pt_off,
                                 const int32_t *pt, const SlabTable *slabs, int slab_shift, cudaStream_t st);

@@ -8,6 +8,7 @@
 #include <float.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -156,7 +157,12 @@ struct sc_index {
     std::vector<Slab> slabs;
     SlabTable *h_tab = nullptr;  // host mirror
     SlabTable *d_tab = nullptr;
+    uint8_t *d_maps = nullptr;   // [kMaxSlabs][128] TMA tensor maps of the slabs' vectors (scan_lists_ts.cu); nullptr = unavailable
     int32_t pool_top = 0;          // pages handed out
+    int32_t *free_pages = nullptr; // pages returned by compaction; the LAST nfree entries are free (taken from the end)
+    int32_t nfree = 0, free_cap = 0;
+    int64_t add_chunk_rows = 0;    // tests: rows per add chunk (0 = automatic)
+    int32_t fail_add_after = 0;    // tests: the n-th add chunk from now fails after its slots were claimed
     int32_t *list_len = nullptr;   // [nlist] slots used (incl. tombstones)
     int32_t *pt_off = nullptr;     // [nlist+1]
     int32_t *pt_off_alt = nullptr; // double buffer
@@ -280,6 +286,17 @@ int ensure_slabs(sc_index *ix, int64_t pages_needed, cudaStream_t st) {
         ix->h_tab->tags[i] = s.tags;
         ix->slabs.push_back(s);
         grew = true;
+        if (ix->d_maps && ix->ds % 32 == 0) {  // tensor map of the slab for the TMA-fed tile kernel
+            alignas(64) uint8_t m[128];
+            if (encode_slab_map(m, s.vec, rows, ix->ds) == cudaSuccess) {
+                CU(cudaMemcpyAsync(ix->d_maps + (size_t)i * 128, m, 128, cudaMemcpyHostToDevice, st));
+                CU(cudaStreamSynchronize(st));  // `m` dies at scope exit
+            } else {
+                cudaGetLastError();
+                cudaFree(ix->d_maps);  // no driver entry point: the shared-memory tile kernel keeps serving
+                ix->d_maps = nullptr;
+            }
+        }
     }
     if (grew) CU(cudaMemcpyAsync(ix->d_tab, ix->h_tab, sizeof(SlabTable), cudaMemcpyHostToDevice, st));
     return SC_OK;
@@ -442,8 +459,8 @@ int coarse_assign(sc_index *ix, const float *xd, int64_t n, int32_t *assign, flo
 }
 
 // append rows that already sit on the device ([n, ds] rows, device ids/tags/lists)
-int add_device_rows(sc_index *ix, const float *xd, const int64_t *ids_d, const uint32_t *repo_d,
-                    const uint8_t *lang_d, const int32_t *lists_d, int64_t n, cudaStream_t st) {
+int add_device_rows_unguarded(sc_index *ix, const float *xd, const int64_t *ids_d, const uint32_t *repo_d, const uint8_t *lang_d,
+                              const int32_t *lists_d, int64_t n, cudaStream_t st, bool *bumped) {
     const int nlist = ix->nlist;
     CU(ix->s_pos.reserve((size_t)n * 4));
     CU(ix->s_lenold.reserve((size_t)nlist * 4));
@@ -453,24 +470,26 @@ int add_device_rows(sc_index *ix, const float *xd, const int64_t *ids_d, const u
     CU(ix->s_bad.reserve(16));
     CU(cudaMemcpyAsync(ix->s_lenold.p, ix->list_len, (size_t)nlist * 4, cudaMemcpyDeviceToDevice, st));
     CU(cudaMemsetAsync(ix->s_bad.p, 0, 16, st));
-    CU(launch_count_positions(lists_d, n, nlist, ix->list_len, ix->s_pos.as<int32_t>(), ix->s_bad.as<int32_t>(), st));
+    *bumped = true;  // from here on the device list lengths are ahead of the page table until the scatter is queued
+    CU(launch_count_positions(lists_d, repo_d, n, nlist, ix->list_len, ix->s_pos.as<int32_t>(), ix->s_bad.as<int32_t>(), st));
     CU(launch_page_need(ix->s_lenold.as<int32_t>(), ix->list_len, nlist, ix->s_need.as<int32_t>(),
                         ix->s_npg.as<int32_t>(), st));
     CU(launch_exclusive_scan_i32(ix->s_need.as<int32_t>(), nlist, ix->s_needoff.as<int32_t>(), st));
     CU(launch_exclusive_scan_i32(ix->s_npg.as<int32_t>(), nlist, ix->pt_off_alt, st));
-    int32_t h_new = 0, h_total = 0, h_bad = 0;
+    int32_t h_new = 0, h_total = 0, h_bad[2] = {0, 0};
     CU(cudaMemcpyAsync(&h_new, ix->s_needoff.as<int32_t>() + nlist, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&h_total, ix->pt_off_alt + nlist, 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(&h_bad, ix->s_bad.p, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_bad, ix->s_bad.p, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    if (h_bad != 0) {
-        // undo the length bumps of the valid rows so that the index stays consistent
-        CU(cudaMemcpyAsync(ix->list_len, ix->s_lenold.p, (size_t)nlist * 4, cudaMemcpyDeviceToDevice, st));
-        CU(cudaStreamSynchronize(st));
-        return fail(SC_ERR_INVALID, "%d rows carry a list id outside [0, %d)", h_bad, nlist);
-    }
-    if ((int64_t)ix->pool_top + h_new > (int64_t)INT32_MAX / 2) return fail(SC_ERR_OOM, "page id space exhausted");
-    SC(ensure_slabs(ix, (int64_t)ix->pool_top + h_new, st));
+    if (h_bad[0] != 0) return fail(SC_ERR_INVALID, "%d rows carry a list id outside [0, %d)", h_bad[0], nlist);
+    if (h_bad[1] != 0) return fail(SC_ERR_INVALID, "%d rows carry a repo tag above %u", h_bad[1], kTagRepoMax);
+    if (ix->fail_add_after > 0 && --ix->fail_add_after == 0)  // tests: a device allocation failure in a later chunk
+        return fail(SC_ERR_OOM, "injected allocation failure (fail_add_after)");
+    // pages come from the free list first (compaction returns pages there), then from the top of the pool
+    const int32_t from_free = std::min<int32_t>(h_new, ix->nfree);
+    const int32_t from_top = h_new - from_free;
+    if ((int64_t)ix->pool_top + from_top > (int64_t)INT32_MAX / 2) return fail(SC_ERR_OOM, "page id space exhausted");
+    SC(ensure_slabs(ix, (int64_t)ix->pool_top + from_top, st));
     if (h_total > ix->pt_alt_cap) {
         const int64_t want = std::max<int64_t>((int64_t)h_total + h_total / 2, 1024);
         if (ix->pt_alt) cudaFree(ix->pt_alt);
@@ -480,15 +499,38 @@ int add_device_rows(sc_index *ix, const float *xd, const int64_t *ids_d, const u
         ix->pt_alt_cap = want;
     }
     CU(launch_rebuild_pt(ix->pt_off, ix->pt, ix->pt_off_alt, ix->pt_alt, ix->s_needoff.as<int32_t>(), ix->pool_top,
-                         nlist, st));
+                         ix->free_pages ? ix->free_pages + (ix->nfree - from_free) : nullptr, from_free, nlist, st));
+    CU(launch_scatter_rows(xd, ids_d, repo_d, lang_d, lists_d, ix->s_pos.as<int32_t>(), n, ix->ds, ix->pt_off_alt, ix->pt_alt,
+                           ix->d_tab, ix->slab_shift, st));
+    // committed: every launch is queued, only now does the host state move
     std::swap(ix->pt, ix->pt_alt);
     std::swap(ix->pt_cap, ix->pt_alt_cap);
     std::swap(ix->pt_off, ix->pt_off_alt);
-    ix->pool_top += h_new;
-    CU(launch_scatter_rows(xd, ids_d, repo_d, lang_d, lists_d, ix->s_pos.as<int32_t>(), n, ix->ds, ix->pt_off, ix->pt,
-                           ix->d_tab, ix->slab_shift, st));
+    ix->pool_top += from_top;
+    ix->nfree -= from_free;
     ix->ntotal += n;
+    *bumped = false;
     return SC_OK;
+}
+
+// A failure between the slot claim (count_positions bumps the device list lengths) and the scatter must not leave
+// the lengths ahead of the page table: plan_pairs sizes the scan from the DEVICE lengths, so candidates would be
+// written past the scratch the host sized from its own mirror.  Roll the lengths back on every such exit.
+int add_device_rows(sc_index *ix, const float *xd, const int64_t *ids_d, const uint32_t *repo_d, const uint8_t *lang_d,
+                    const int32_t *lists_d, int64_t n, cudaStream_t st) {
+    bool bumped = false;
+    const int rc = add_device_rows_unguarded(ix, xd, ids_d, repo_d, lang_d, lists_d, n, st, &bumped);
+    if (rc != SC_OK && bumped) {
+        const std::string why = g_err;
+        cudaGetLastError();
+        if (cudaMemcpyAsync(ix->list_len, ix->s_lenold.p, (size_t)ix->nlist * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(rc, "%s; AND the list lengths could not be restored: reset the index", why.c_str());
+        }
+        g_err = why;
+    }
+    return rc;
 }
 
 int sync_host_lengths(sc_index *ix, cudaStream_t st) {
@@ -498,16 +540,12 @@ int sync_host_lengths(sc_index *ix, cudaStream_t st) {
     return SC_OK;
 }
 
-int add_impl(sc_index *ix, const float *x, const int64_t *ids, const uint32_t *repo, const uint8_t *lang,
-             const int32_t *lists, int64_t n, cudaStream_t st) {
-    if (n < 0) return fail(SC_ERR_INVALID, "n < 0");
-    if (n == 0) return SC_OK;
-    if (x == nullptr || ids == nullptr) return fail(SC_ERR_INVALID, "x and ids must not be NULL");
-    SC(require_trained(ix));
-    CU(cudaDeviceSynchronize());  // no search may still be reading the page table we are about to swap
+int add_chunks(sc_index *ix, const float *x, const int64_t *ids, const uint32_t *repo, const uint8_t *lang,
+               const int32_t *lists, int64_t n, cudaStream_t st) {
     // bounded staging: ~256 MB of rows per pass
     int64_t chunk = std::max<int64_t>(1024, ((int64_t)256 << 20) / ((int64_t)ix->ds * 4));
     if (is_device_ptr(x, ix->device)) chunk = std::max<int64_t>(chunk, (int64_t)1 << 18);
+    if (ix->add_chunk_rows > 0) chunk = ix->add_chunk_rows;
     chunk = std::min(chunk, n);
     for (int64_t s = 0; s < n; s += chunk) {
         const int64_t m = std::min(chunk, n - s);
@@ -529,8 +567,26 @@ int add_impl(sc_index *ix, const float *x, const int64_t *ids, const uint32_t *r
         }
         SC(add_device_rows(ix, xd, ids_d, repo_d, lang_d, lists_d, m, st));
     }
-    SC(sync_host_lengths(ix, st));
     return SC_OK;
+}
+
+int add_impl(sc_index *ix, const float *x, const int64_t *ids, const uint32_t *repo, const uint8_t *lang,
+             const int32_t *lists, int64_t n, cudaStream_t st) {
+    if (n < 0) return fail(SC_ERR_INVALID, "n < 0");
+    if (n == 0) return SC_OK;
+    if (x == nullptr || ids == nullptr) return fail(SC_ERR_INVALID, "x and ids must not be NULL");
+    SC(require_trained(ix));
+    CU(cudaDeviceSynchronize());  // no search may still be reading the page table we are about to swap
+    const int rc = add_chunks(ix, x, ids, repo, lang, lists, n, st);
+    // the chunks that went in before a failure stay committed: the host mirror of the list lengths (scratch sizing of
+    // the searches) must follow them on EVERY exit
+    const std::string why = g_err;
+    const int rs = sync_host_lengths(ix, st);
+    if (rc != SC_OK) {
+        g_err = why;
+        return rc;
+    }
+    return rs;
 }
 
 int build_filter(sc_index *ix, const sc_filter_t *filt, cudaStream_t st, FilterDev *out) {
@@ -715,6 +771,7 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
         a.slab_shift = ix->slab_shift;
         a.cand = ix->s_cand.as<float>();
         a.filt = fdev;
+        a.slab_maps = ix->d_maps;
         // large batches re-probe the same lists: read each list once and score it against all its queries
         // (auto: when a list is probed 0.5x or more on average -- 79 % or fewer of the pair passes hit a distinct
         //  list -- and lists hold at least a page.  Measured list-major / query-major step time at 0.125x / 0.25x /
@@ -848,6 +905,10 @@ int sc_index_create(int32_t dim, int32_t metric, int32_t nlist, int32_t device, 
     // slab = ~256 MB of vectors, at least 64 pages, at most 2^16 pages
     int shift = 6;
     while (shift < 16 && ((size_t)2 << shift) * page_bytes(ix) <= ((size_t)256 << 20)) ++shift;
+    if (const char *env = getenv("SEMCODE_SLAB_SHIFT")) {  // experiments: pages per slab = 2^shift
+        const int v = atoi(env);
+        if (v >= 6 && v <= 16) shift = v;
+    }
     ix->slab_shift = shift;
     ix->h_tab = new SlabTable();
     memset(ix->h_tab, 0, sizeof(SlabTable));
@@ -862,6 +923,7 @@ int sc_index_create(int32_t dim, int32_t metric, int32_t nlist, int32_t device, 
     if (e == cudaSuccess) e = cudaMalloc(&ix->cent_hi, (size_t)nlist * ix->ds * 4);
     if (e == cudaSuccess) e = cudaMalloc(&ix->cent_lo, (size_t)nlist * ix->ds * 4);
     if (e == cudaSuccess) e = cudaMalloc(&ix->d_tab, sizeof(SlabTable));
+    if (e == cudaSuccess) e = cudaMalloc(&ix->d_maps, (size_t)kMaxSlabs * 128);
     if (e == cudaSuccess) e = cudaMalloc(&ix->list_len, (size_t)nlist * 4);
     if (e == cudaSuccess) e = cudaMalloc(&ix->pt_off, (size_t)(nlist + 1) * 4);
     if (e == cudaSuccess) e = cudaMalloc(&ix->pt_off_alt, (size_t)(nlist + 1) * 4);
@@ -898,7 +960,7 @@ int sc_index_destroy(sc_index_t *ix) {
                       &ix->s_assign, &ix->s_best, &ix->s_pos, &ix->s_lenold, &ix->s_need, &ix->s_npg, &ix->s_needoff,
                       &ix->s_bad, &ix->s_sums, &ix->s_counts, &ix->s_obj, &ix->s_rows, &ix->s_rm, &ix->s_cnt, &ix->s_ahi, &ix->s_alo, &ix->s_lplan, &ix->s_scan, &ix->s_packed, &ix->s_qsplit})
         b->release();
-    for (void *p : {(void *)ix->centroids, (void *)ix->cnorm, (void *)ix->cent_hi, (void *)ix->cent_lo, (void *)ix->d_tab, (void *)ix->list_len, (void *)ix->pt_off,
+    for (void *p : {(void *)ix->centroids, (void *)ix->cnorm, (void *)ix->cent_hi, (void *)ix->cent_lo, (void *)ix->d_tab, (void *)ix->d_maps, (void *)ix->list_len, (void *)ix->pt_off,
                     (void *)ix->pt_off_alt, (void *)ix->pt, (void *)ix->pt_alt, (void *)ix->prof_rows})
         if (p) cudaFree(p);
     if (ix->ev_done) cudaEventDestroy(ix->ev_done);
@@ -1489,7 +1551,7 @@ int sc_index_set_param(sc_index_t *ix, const char *name, int64_t value) {
         return SC_OK;
     }
     if (strcmp(name, "lists_cfg") == 0) {
-        if (value < 0 || value > 4) return fail(SC_ERR_INVALID, "lists_cfg must be in [0,4]");
+        if (value < 0 || value > 5) return fail(SC_ERR_INVALID, "lists_cfg must be in [0,5]");
         ix->lists_cfg = (int)value;
         return SC_OK;
     }

@@ -501,7 +501,12 @@ cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int
         if ((e = cudaStreamWaitEvent(s32, p.ev_fork, 0)) != cudaSuccess) return e;
     }
     if (p.chunk == 64) {  // tcgen05 tiles (index.cu picked chunk = 64 only when the kernel applies)
-        if ((e = launch_scan_lists_tc(a, p, cfg == 3 ? 1 : 0, num_sms, s32)) != cudaSuccess) return e;
+        // cfg 5: list rows as a tensor-memory operand (scan_lists_ts.cu)
+        if (cfg == 5 && a.slab_maps != nullptr)
+            e = launch_scan_lists_ts(a, p, num_sms, s32);
+        else
+            e = launch_scan_lists_tc(a, p, cfg == 3 ? 1 : 0, num_sms, s32);
+        if (e != cudaSuccess) return e;
     } else if (cfg == 2) {
         if ((e = launch_lists_variant<32, 32, 3, 128, 4>(a, p, num_sms, s32)) != cudaSuccess) return e;
     } else {

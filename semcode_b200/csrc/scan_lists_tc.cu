@@ -29,13 +29,14 @@
 //              the other scans
 // Replaces the same FAISS IVFFlatScanner::scan_codes loop (reference src/semcode/storage/milvus_store.py:141-147).
 // Bound: HBM (each list once per 64 queries) once the tensor pipe has >= 6x headroom over FFMA.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace sc {
 
 namespace {
 
-constexpr int TM = 128, TN = 64, TK = 32;
+using namespace tcu;
+
 constexpr int A_TILE = TM * TK * 4;  // 16 KB
 constexpr int B_TILE = TN * TK * 4;  // 8 KB
 // The tensor core adds every 128x64x8 product block into the fp32 accumulator with truncation, so ONE accumulation
@@ -59,90 +60,6 @@ constexpr int NAW = 8;        // A loader/splitter warps
 constexpr int NMW = 3;        // MMA issuer warps (one lane each), one per product term
 constexpr int NT_TC2 = (NAW + 1 + NMW + 4) * 32;  // + 1 B loader warp, 4 epilogue warps
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row atoms 1024 B apart (same as gemm_tc.cu)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)(1024u >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ void cp_async16_zfill(uint32_t smem_dst, const void *gmem, bool valid) {
-    const int sz = valid ? 16 : 0;  // src-size 0 => 16 bytes of zeros
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait_group() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-__device__ __forceinline__ float to_tf32(float x) {
-    uint32_t b;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(x));
-    return __uint_as_float(b);
-}
-
-// byte offset of 16-byte chunk c (0..7) of row r inside a 128-byte-swizzled K-major tile
-__device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)); }
-
 // out[s][i] = s-th tf32 term of x[i]
 constexpr int NSPLIT = 2;
 __global__ void split_rows_kernel(const float4 *__restrict__ x, int64_t n4, float4 *__restrict__ out) {
@@ -163,63 +80,6 @@ __global__ void split_rows_kernel(const float4 *__restrict__ x, int64_t n4, floa
         for (int s = 0; s < NSPLIT; ++s) out[(int64_t)s * n4 + i] = make_float4(t[s][0], t[s][1], t[s][2], t[s][3]);
     }
 }
-
-__device__ __forceinline__ int32_t owner_of_tc(const int32_t *__restrict__ off, int32_t n, int32_t v) {
-    int32_t lo = 0, hi = n;
-    while (hi - lo > 1) {
-        const int32_t mid = (lo + hi) >> 1;
-        if (off[mid] <= v)
-            lo = mid;
-        else
-            hi = mid;
-    }
-    return lo;
-}
-
-// Work unit = (list, chunk of 64 queries, 128-row tile); p.off32 is the exclusive prefix of chunks(l) * tiles(l)
-// (plan_lists_kernel with chunk = 64).  Every CTA owns an equal, contiguous range of units -- a list of any length
-// or multiplicity is spread over as many CTAs as it has tiles, so skewed lists neither queue behind one CTA nor
-// leave a tail -- and every warp role walks the same range with its own cursor.
-struct UnitCursor {
-    int32_t u = 0, u1 = 0;
-    int32_t l = 0, len = 0, ptbase = 0, ntiles = 1, nchunks = 0, chunk = 0, tile = 0, qbase = 0, nqi = 0;
-    bool valid = false, new_chunk = false;
-    __device__ __forceinline__ void set_chunk(const ListPlan &p) {
-        qbase = p.lq_off[l] + TN * chunk;
-        nqi = min(TN, p.lq_off[l + 1] - qbase);
-        new_chunk = true;
-    }
-    __device__ __forceinline__ void locate(const ScanArgs &a, const ListPlan &p) {
-        l = owner_of_tc(p.off32, p.nlist, u);
-        len = a.list_len[l];
-        ptbase = a.pt_off[l];
-        ntiles = (len + TM - 1) / TM;
-        nchunks = p.n32[l];
-        const int32_t local = u - p.off32[l];
-        chunk = local / ntiles;
-        tile = local - chunk * ntiles;
-        set_chunk(p);
-    }
-    __device__ __forceinline__ void start(const ScanArgs &a, const ListPlan &p, int32_t u0_, int32_t u1_) {
-        u = u0_;
-        u1 = u1_;
-        valid = u < u1;
-        if (valid) locate(a, p);
-    }
-    __device__ __forceinline__ void next_unit(const ScanArgs &a, const ListPlan &p) {
-        if (++u >= u1) {
-            valid = false;
-            return;
-        }
-        if (++tile == ntiles) {
-            tile = 0;
-            if (++chunk == nchunks)
-                locate(a, p);
-            else
-                set_chunk(p);
-        }
-    }
-};
 
 // V2 (default): the raw fp32 k-block IS the hi operand (the tensor core reads the top 19 bits of a tf32 operand, i.e.
 // hi = x with the low 13 mantissa bits dropped; the splitter only writes lo = tf32(x - hi)), and hi.hi + hi.lo are ONE
@@ -563,20 +423,26 @@ __global__ void __launch_bounds__(NT_TC2, 1) scan_lists_tc_kernel(const ScanArgs
 
 }  // namespace
 
+cudaError_t launch_split_queries(const float *q, int64_t n4, float *out, int num_sms, cudaStream_t st) {
+    if (n4 <= 0) return cudaSuccess;
+    const int64_t want = (n4 + 255) / 256;
+    split_rows_kernel<<<(unsigned)(want < num_sms * 8 ? want : num_sms * 8), 256, 0, st>>>(reinterpret_cast<const float4 *>(q), n4,
+                                                                                          reinterpret_cast<float4 *>(out));
+    return cudaGetLastError();
+}
+
 // items: (list, chunk of 64 queries) from p.off32 (plan_lists_kernel with chunk = 64); p.qsplit holds 2 x [nq, ds]
 // variant 1: the first version (rounded hi stored in place, three 64-column MMAs per k-step, three issuers)
 cudaError_t launch_scan_lists_tc(const ScanArgs &a, const ListPlan &p, int variant, int num_sms, cudaStream_t st) {
     if (a.metric != 0 || (a.ds % TK) != 0 || p.chunk != TN || p.qsplit == nullptr) return cudaErrorNotSupported;
-    const int64_t n4 = (a.npairs / a.nprobe) * (int64_t)a.ds / 4;
-    const int64_t want = (n4 + 255) / 256;
-    split_rows_kernel<<<(unsigned)(want < num_sms * 8 ? want : num_sms * 8), 256, 0, st>>>(
-        reinterpret_cast<const float4 *>(a.q), n4, reinterpret_cast<float4 *>(p.qsplit));
+    cudaError_t e = launch_split_queries(a.q, (a.npairs / a.nprobe) * (int64_t)a.ds / 4, p.qsplit, num_sms, st);
+    if (e != cudaSuccess) return e;
     // ring depths 7 / 2 / 4 (raw, lo, query stages); 7/3/3, 6/3/4 and 8/2/3 measured the same 13.0 ms per batch at
     // nq 4096 / nprobe 128: the kernel is bound by shared-memory bandwidth (ncu: LSU + tensor-core wavefronts = 71 % of
     // the data pipe, tensor pipe 26 %, DRAM 38 %), not by the depth of its pipeline
     auto kern = variant == 1 ? scan_lists_tc_kernel<false, 7, 2, 4> : scan_lists_tc_kernel<true, 7, 2, 4>;
     const int smem = smem_tc(7, 2, 4);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     kern<<<num_sms, NT_TC2, smem, st>>>(a, p);
     return cudaGetLastError();

@@ -670,7 +670,7 @@ def test_tensor_core_tiles_match_ffma_tiles_and_oracle(sb, orc, d, nlist, nq, np
         g.set_param("scan_mode", 1)
         d1, i1 = g.search(q, k, lists=probes, langs=langs)
         assert_topk_parity(d1, i1, rd, ri, f"query-major d={d} langs={langs}")
-        for cfg in (0, 1):
+        for cfg in (0, 1, 5):  # 5: list rows as a tensor-memory operand (scan_lists_ts.cu)
             g.set_param("scan_mode", 2)
             g.set_param("lists_cfg", cfg)
             d2, i2 = g.search(q, k, lists=probes, langs=langs)
