@@ -194,6 +194,7 @@ struct ListPlan {
     unsigned long long *agg;           // [list_plan_ctas(nlist)][4] (directly after counters) per-CTA totals of the plan's four prefix sums
     int32_t chunk;                     // queries per tile item: 32 (FFMA tiles) or 64 (tcgen05 tiles)
     float *qsplit;                     // tcgen05 tiles: 2 x [nq, ds] tf32 terms (hi, lo) of the queries (scratch)
+    float *bstage;                     // scan_lists_ts.cu: per-CTA query staging slots (scan_lists_ts_stage_bytes), or nullptr
     int32_t *n32;                      // [nlist] tile items (of `chunk` queries) per list
     int32_t *lq_off, *off32;           // [nlist+1] exclusive prefixes of cnt / n32 (chunk == 64: of n32 x 128-row tiles)
     int32_t *pg8off, *pg4off;          // [nlist+1] exclusive prefixes of the page x pass units of the two page scans
@@ -209,6 +210,7 @@ cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int
 cudaError_t launch_scan_lists_tc(const ScanArgs &a, const ListPlan &p, int variant, int num_sms, cudaStream_t st);
 // the same items with the list rows as a tensor-memory operand (scan_lists_ts.cu); needs a.slab_maps
 cudaError_t launch_scan_lists_ts(const ScanArgs &a, const ListPlan &p, int num_sms, cudaStream_t st);
+size_t scan_lists_ts_stage_bytes(int ds, int num_sms);
 // out = 2 x [n4] float4: the tf32 terms hi = tf32(q), lo = tf32(q - hi) of the query rows
 cudaError_t launch_split_queries(const float *q, int64_t n4, float *out, int num_sms, cudaStream_t st);
 // TMA tensor map (128 bytes, host memory) of one list slab: fp32 [rows, ds], boxes of one page x 32 floats, 128 B swizzle

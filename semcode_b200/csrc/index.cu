@@ -177,7 +177,7 @@ struct sc_index {
     // scratch (stream ordered; ev_done chains calls made on different streams)
     DevBuf s_q, s_scores, s_probe, s_pageoff, s_cand, s_outd, s_outi, s_repobits;
     DevBuf s_x, s_xpad, s_ids, s_repo, s_lang, s_assign, s_best, s_pos, s_lenold, s_need, s_npg, s_needoff, s_bad;
-    DevBuf s_sums, s_counts, s_obj, s_rows, s_rm, s_cnt, s_ahi, s_alo, s_lplan, s_scan, s_packed, s_qsplit;
+    DevBuf s_sums, s_counts, s_obj, s_rows, s_rm, s_cnt, s_ahi, s_alo, s_lplan, s_scan, s_packed, s_qsplit, s_bstage;
     int64_t scratch_budget = (int64_t)8 << 30;  // search scratch ceiling (candidates dominate); sc_index_set_param("scratch_bytes")
     int scan_variant = 0;
     int lists_cfg = 0;  // list-major tile items: 0 = tcgen05 where it applies, 1 = FFMA tiles, 2 = FFMA tiles with 32-float stages, 3 = the first tcgen05 tile kernel (scan_lists_tc.cu, variant 1), 4 = 0 with the 8-query page scan on mma.sync
@@ -797,9 +797,16 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
             const bool tc_tiles = ix->lists_cfg != 1 && ix->lists_cfg != 2 && ix->metric == SC_METRIC_IP && ix->ds % 32 == 0;
             lp.chunk = tc_tiles ? 64 : 32;
             lp.qsplit = nullptr;
+            lp.bstage = nullptr;
             if (tc_tiles) {
                 CU(ix->s_qsplit.reserve((size_t)m * ix->ds * 4 * 2));
                 lp.qsplit = ix->s_qsplit.as<float>();
+                if (ix->lists_cfg == 5 && ix->d_maps) {
+                    const void *before = ix->s_bstage.p;
+                    CU(ix->s_bstage.reserve(scan_lists_ts_stage_bytes(ix->ds, ix->num_sms)));
+                    if (ix->s_bstage.p != before) CU(cudaMemsetAsync(ix->s_bstage.p, 0, ix->s_bstage.cap, st));  // padded rows are read (never stored): keep them finite
+                    lp.bstage = ix->s_bstage.as<float>();
+                }
             }
             lp.cnt = w;
             lp.cursor = w + nl;
@@ -958,7 +965,7 @@ int sc_index_destroy(sc_index_t *ix) {
     for (DevBuf *b : {&ix->s_q, &ix->s_scores, &ix->s_probe, &ix->s_pageoff, &ix->s_cand, &ix->s_outd,
                       &ix->s_outi, &ix->s_repobits, &ix->s_x, &ix->s_xpad, &ix->s_ids, &ix->s_repo, &ix->s_lang,
                       &ix->s_assign, &ix->s_best, &ix->s_pos, &ix->s_lenold, &ix->s_need, &ix->s_npg, &ix->s_needoff,
-                      &ix->s_bad, &ix->s_sums, &ix->s_counts, &ix->s_obj, &ix->s_rows, &ix->s_rm, &ix->s_cnt, &ix->s_ahi, &ix->s_alo, &ix->s_lplan, &ix->s_scan, &ix->s_packed, &ix->s_qsplit})
+                      &ix->s_bad, &ix->s_sums, &ix->s_counts, &ix->s_obj, &ix->s_rows, &ix->s_rm, &ix->s_cnt, &ix->s_ahi, &ix->s_alo, &ix->s_lplan, &ix->s_scan, &ix->s_packed, &ix->s_qsplit, &ix->s_bstage})
         b->release();
     for (void *p : {(void *)ix->centroids, (void *)ix->cnorm, (void *)ix->cent_hi, (void *)ix->cent_lo, (void *)ix->d_tab, (void *)ix->d_maps, (void *)ix->list_len, (void *)ix->pt_off,
                     (void *)ix->pt_off_alt, (void *)ix->pt, (void *)ix->pt_alt, (void *)ix->prof_rows})
@@ -1431,7 +1438,7 @@ int sc_index_stats(sc_index_t *ix, sc_stats_t *out) {
                             &ix->s_outd, &ix->s_outi, &ix->s_repobits, &ix->s_x, &ix->s_xpad, &ix->s_ids, &ix->s_repo,
                             &ix->s_lang, &ix->s_assign, &ix->s_best, &ix->s_pos, &ix->s_lenold, &ix->s_need, &ix->s_npg,
                             &ix->s_needoff, &ix->s_bad, &ix->s_sums, &ix->s_counts, &ix->s_obj, &ix->s_rows, &ix->s_rm,
-                            &ix->s_cnt, &ix->s_ahi, &ix->s_alo, &ix->s_lplan, &ix->s_scan, &ix->s_packed, &ix->s_qsplit})
+                            &ix->s_cnt, &ix->s_ahi, &ix->s_alo, &ix->s_lplan, &ix->s_scan, &ix->s_packed, &ix->s_qsplit, &ix->s_bstage})
         sb += (int64_t)b->cap;
     out->bytes_scratch = sb;
     int32_t mx = 0, mn = ix->nlist > 0 ? INT32_MAX : 0;

@@ -502,7 +502,7 @@ cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int
     }
     if (p.chunk == 64) {  // tcgen05 tiles (index.cu picked chunk = 64 only when the kernel applies)
         // cfg 5: list rows as a tensor-memory operand (scan_lists_ts.cu)
-        if (cfg == 5 && a.slab_maps != nullptr)
+        if (cfg == 5 && a.slab_maps != nullptr && p.bstage != nullptr)
             e = launch_scan_lists_ts(a, p, num_sms, s32);
         else
             e = launch_scan_lists_tc(a, p, cfg == 3 ? 1 : 0, num_sms, s32);

@@ -1,17 +1,24 @@
 // K5e: list-major tile items on the tensor cores with the LIST ROWS AS A TENSOR-MEMORY OPERAND (inner product).
 //
-// scan_lists_tc.cu (K5d) is bound by shared-memory bandwidth: per 16 KB k-block of list rows it moves 120 KB through
-// the shared-memory data pipe (cp.async fill 16, query fill 16, splitter read + lo write 32, MMA operand reads 56) and
-// stops at 3.1 TB/s of HBM.  Here the row operand never goes back to shared memory:
+// scan_lists_tc.cu (K5d) moves 120 KB through the shared-memory / LSU data path per 16 KB k-block of list rows (cp.async
+// fill 16, query fill 16, splitter read + lo write 32, MMA operand reads 56) and stops at 3.1 TB/s of HBM; its real
+// pace-setter turned out to be the LSU: cp.async.128 sustains ~16-20 B/cycle/SM, and one warp issued every query
+// copy of a stage.  Here nothing on the streaming path goes through the LSU and the row operand never returns to
+// shared memory:
 //
 //   HBM --TMA box (32 rows x 128 B, 128-byte swizzle, one per list page)--> raw ring in shared memory        16 KB
 //       --converter warps: LDS.128 row-per-lane (conflict-free under the swizzle)--> registers                16 KB
 //       --hi = x & ~0x1fff, lo = tf32(x - hi)--> tcgen05.st into a TMEM operand slot (lane = row)              0
 //   D[128 rows, queries] += A[TMEM] . B[shared]^T    (tcgen05.mma, A from tensor memory: only B is read)
 //
-// and the query tile is only as wide as the item needs (N = queries rounded up to 16, not 64):
-//   B fill 2 x N x 128 B + B reads 3 x N x 128 B  =  40 KB at N = 64, 20 KB at the N = 32 of nq 4096 / nprobe 128.
-// Shared-memory traffic per 16 KB of list rows: 72 KB (N = 64) / 52 KB (N = 32) instead of 120 KB.
+// The query tile is only as wide as the item needs (N = queries rounded up to 16, not 64) and arrives as ONE TMA box per
+// k-block: a stager warp gathers the item's query rows once (splitting them into tf32 hi / lo terms on the way) into a
+// per-CTA staging slot in global memory (L2-resident: 2 x 128 rows x dim per CTA), laid out [hi rows ; lo rows], so a
+// k-block of the tile is a plain 2-D box of 2 N rows x 128 B.  (Tried for the query rows: a cp.async warp -- 1800
+// cycles per stage with naive addressing, 970 with everything hoisted, still the slowest role; TMA tile::gather4, four
+// arbitrary rows per instruction, parity-green -- but a TMA instruction costs its issuing thread ~70 cycles, so 2 N / 4
+// of them per stage are slower still.)
+// Shared-memory traffic per 16 KB of list rows: 72 KB (N = 64) / 52 KB (N = 32) instead of 120 KB, none of it LSU stores.
 //
 // fp32 accuracy as in K5d: three tf32 terms (hi.hi + hi.lo + lo.hi), the first two as ONE MMA against the query tile
 // [B_hi ; B_lo] (N doubled), and per tile two accumulator sets by k-step parity ([hh | cross] each), summed by the
@@ -20,12 +27,13 @@
 // CTA = 16 warps, one per SM; every role walks the same contiguous range of (list, chunk, 128-row tile) units.  The
 // warp scheduler prefers the highest warp id of a sub-partition, so the roles on the critical path come last:
 //   warps 0-7   converters: warp w serves TMEM lane quarter w % 4 (= page w % 4 of the tile); the two sets alternate
-//               k-blocks, 4 TMEM operand slots of 64 columns (hi | lo)
+//               k-blocks, 4 TMEM operand slots of 64 columns (hi | lo); each warp also requests its own page boxes
+//               (TMA, 32 rows x 128 B, NR k-blocks ahead), so the row stream has eight issuers and no producer warp
 //   warps 8-11  epilogue: tcgen05.ld, fused tag predicate, coalesced candidate stores (same layout as the other scans)
-//   warp 12     TMA producer (one lane): per k-block one box per page of the tile into the raw ring (NR x 16 KB)
+//   warp 12     query producer (one lane): per k-block one TMA box [2 N rows x 32 floats] from the item's staging slot
 //   warps 13-14 MMA issuers by k-step parity (one lane each); each owns its accumulator set, so the order of the
 //               additions into every accumulator is fixed and results are reproducible
-//   warp 15     query loader: cp.async of the pre-split query k-blocks, hi rows then lo rows, 4 slots
+//   warp 15     stager: gathers + splits the NEXT item's query rows into the other staging slot
 // TMEM: columns [0, 256) accumulators (2 parities x [hh | cross] x 64), [256, 512) four operand slots.
 // Replaces the same FAISS IVFFlatScanner::scan_codes loop (reference src/semcode/storage/milvus_store.py:141-147).
 // Bound: HBM (each list once per 64 queries).
@@ -59,34 +67,37 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void *map, uint3
 }
 
 // wait-time profile (SEMCODE_TS_PROF=1): cycles summed over all CTAs, one warp (lane 0) per role
-//   0 producer: raw empty   1 converter (set 0, quarter 0): raw full   2 converter: slot free   3 converter: total
-//   4 issuer 0: accumulators empty   5 issuer 0: A ready   6 issuer 0: B ready   7 issuer 0: total
-//   8 query loader: slot free   9 query loader: total
-//   12 epilogue warp 0: accumulators full   13 epilogue warp 0: total   14 kernel total (thread 0)
+//   0-2 query producer: operand slot free, staging slot filled, total     4-6 converter (warp 0): raw full, slot free, total
+//   7-10 issuer 0: accumulators empty, A ready, B ready, total     11-12 stager: staging slot consumed, total
+//   13-14 epilogue warp 0: accumulators full, total     15 kernel total (thread 0)
 __device__ unsigned long long g_ts_prof[16];
 
-// (TMA tile::gather4 was tried for the query rows -- four arbitrary rows per instruction, parity-green -- but a TMA
-//  instruction costs its issuing thread ~70 cycles: 2 x N / 4 of them per stage are slower than the cp.async warp.)
+struct BMaps {
+    CUtensorMap m[4];  // the staging area as a [rows, ds] tensor with boxes of 32 / 64 / 96 / 128 rows x 32 floats
+};
+
 template <bool PROF>
-__global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const ScanArgs a, const ListPlan p, const int ablate) {
+__global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const __grid_constant__ BMaps bmaps, const ScanArgs a, const ListPlan p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *ringR = smem;                      // NR x RAW_TILE
     uint8_t *ringB = ringR + NR * RAW_TILE;     // NS x B_SLOT
     uint64_t *bars = reinterpret_cast<uint64_t *>(ringB + NS * B_SLOT);
-    // bars: [0,NR) raw full (TMA tx)   [NR,2NR) raw empty (4 converter warps)   then per slot: A ready (4 converter warps),
-    //       B ready (query loader), slot free (one commit per issuer); then accumulators full (2 commits), empty (4 warps)
-    constexpr int NBARS = 2 * NR + 3 * NS + 2;
+    // bars: [0,NR) raw full (4 converter warps + TMA tx)   [NR,2NR) unused   then per slot: A ready (4 converter warps),
+    //       B ready (TMA tx), slot free (one commit per issuer); then accumulators full (2 commits), empty (4 warps),
+    //       staging slot filled x 2 (stager), staging slot consumed x 2 (issuer 0)
+    constexpr int NBARS = 2 * NR + 3 * NS + 2 + 4;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + NBARS);
     int64_t *cbE = reinterpret_cast<int64_t *>(bars + NBARS + 2);  // [TN] candidate bases of the epilogue's current item
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = smem_u32(bars);
     auto rfull_bar = [&](int s) { return bar0 + 8u * s; };
-    auto rempty_bar = [&](int s) { return bar0 + 8u * (NR + s); };
     auto aready_bar = [&](int s) { return bar0 + 8u * (2 * NR + s); };
     auto bready_bar = [&](int s) { return bar0 + 8u * (2 * NR + NS + s); };
     auto sfree_bar = [&](int s) { return bar0 + 8u * (2 * NR + 2 * NS + s); };
     const uint32_t accfull_bar = bar0 + 8u * (2 * NR + 3 * NS), accempty_bar = accfull_bar + 8u;
+    auto staged_bar = [&](int s) { return accfull_bar + 16u + 8u * s; };
+    auto bfree_bar = [&](int s) { return accfull_bar + 32u + 8u * s; };
 
     unsigned long long pw[3] = {0, 0, 0};
     const long long t_start = PROF ? clock64() : 0;
@@ -107,8 +118,7 @@ __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const ScanArgs 
     };
     if (threadIdx.x == 0) {
         for (int s = 0; s < NR; ++s) {
-            mbar_init(rfull_bar(s), 1);
-            mbar_init(rempty_bar(s), 4);
+            mbar_init(rfull_bar(s), 4);  // one arrival (+ 4 KB of TMA bytes) per converter warp of the set
         }
         for (int s = 0; s < NS; ++s) {
             mbar_init(aready_bar(s), 4);
@@ -117,6 +127,10 @@ __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const ScanArgs 
         }
         mbar_init(accfull_bar, 2);
         mbar_init(accempty_bar, 4);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(staged_bar(s), 1);
+            mbar_init(bfree_bar(s), 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
     }
@@ -137,116 +151,100 @@ __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const ScanArgs 
     const int slab_mask = (1 << a.slab_shift) - 1;
 
     if (warp == 12) {
-        // ---------------- TMA producer ----------------
+        // ---------------- query producer (one lane): per k-block one box [2 N rows x 32 floats] from the item's staging slot ----------------
         if (lane == 0) {
-            const uint8_t *maps = reinterpret_cast<const uint8_t *>(a.slab_maps);
-            int s = 0;
+            int s = 0, n = -1, npad = 16, row0 = 0;
+            const CUtensorMap *bm = &bmaps.m[0];
             UnitCursor cur;
             for (cur.start(a, p, u0, u1); cur.valid; cur.next_unit(a, p)) {
-                const int32_t npages = (cur.len + kPageRows - 1) / kPageRows;
-                const int nbox = min(4, npages - cur.tile * 4);
-                const void *map[4];
-                int row[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    map[j] = maps;
-                    row[j] = 0;
-                    if (j < nbox) {
-                        const int32_t page = __ldg(a.pt + cur.ptbase + cur.tile * 4 + j);
-                        map[j] = maps + (size_t)(page >> a.slab_shift) * 128;
-                        row[j] = (page & slab_mask) * kPageRows;
-                    }
+                if (cur.new_chunk) {
+                    cur.new_chunk = false;
+                    ++n;
+                    npad = (cur.nqi + 15) & ~15;
+                    bm = &bmaps.m[(npad >> 4) - 1];
+                    row0 = ((int)blockIdx.x * 2 + (n & 1)) * (2 * TN);
+                    pwait(staged_bar(n & 1), ((uint32_t)(n >> 1)) & 1u, 1);
                 }
                 for (int kb = 0; kb < KB; ++kb, ++s) {
-                    const int slot = s % NR;
-                    pwait(rempty_bar(slot), (((uint32_t)(s / NR)) & 1u) ^ 1u, 0);
-                    const uint32_t dst = smem_u32(ringR + slot * RAW_TILE);
-                    if (ablate & 1) {  // timing experiments only: no row stream
-                        mbar_arrive(rfull_bar(slot));
-                        continue;
-                    }
-                    mbar_expect_tx(rfull_bar(slot), (uint32_t)nbox * 4096u);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (j < nbox) tma_load_2d(dst + j * 4096, map[j], rfull_bar(slot), kb * TK, row[j]);
+                    const int slot = s % NS;
+                    pwait(sfree_bar(slot), (((uint32_t)(s / NS)) & 1u) ^ 1u, 0);
+                    mbar_expect_tx(bready_bar(slot), (uint32_t)npad * 256u);
+                    tma_load_2d(smem_u32(ringB + slot * B_SLOT), bm, bready_bar(slot), kb * TK, row0);
                 }
             }
-            if (PROF) atomicAdd(&g_ts_prof[0], pw[0]);
+            pflush(0, 2);
         }
     } else if (warp == 15) {
-        // ---------------- query loader (cp.async): lane (r0, c) copies chunk c of rows r0 + 4 i, hi part then lo part ----------------
-        // One warp issues every copy of a stage, so its instruction count per stage IS the kernel's pace when it is the
-        // slowest role (first version: ~25 dependent instructions per copy pair, 1800 cycles per stage -- the whole kernel
-        // ran at the speed of this loop, and so did scan_lists_tc.cu).  Everything that does not depend on the k-block is
-        // hoisted to the item: 32-bit element offsets of the lane's 16 rows, the validity mask, the two swizzled
-        // destination offsets (rows r0 + 4 i alternate between two swizzle phases, 1 KB apart per pair).
-        const int c = lane & 7, r0 = lane >> 3;
-        const float *qhi = p.qsplit;
-        const float *qlo = p.qsplit + (a.npairs / a.nprobe) * (int64_t)a.ds;
-        const uint32_t so_e = swz(r0, c), so_o = swz(r0 + 4, c);
+        // ---------------- stager: the next item's query rows, split into tf32 terms, [hi rows ; lo rows] ----------------
+        // three rows in flight per pass (12 x 512 bytes per warp): the copy of an item (<= 64 rows) takes a few thousand
+        // cycles, an item lasts tens of thousands
+        const int ds4 = a.ds >> 2;
+        float4 *slot_base = reinterpret_cast<float4 *>(p.bstage) + (size_t)blockIdx.x * 2 * (2 * TN) * ds4;
+        const float4 *q4 = reinterpret_cast<const float4 *>(a.q);
+        int n = 0;
         UnitCursor cur;
         cur.start(a, p, u0, u1);
-        int kb = 0, npad = 0;
-        uint32_t goff[16];
-        uint32_t vmask = 0;
-        int issued = 0, done = 0;
-        constexpr int BAHEAD = NS - 1;
-        auto issue = [&]() {
-            if (cur.new_chunk) {
-                cur.new_chunk = false;
-                npad = (cur.nqi + 15) & ~15;
-                vmask = 0;
+        while (cur.valid) {
+            const int npad = (cur.nqi + 15) & ~15;
+            // lane l keeps the query rows of columns l and l + 32 of the item
+            int32_t qa = 0, qb = 0;
+            if (lane < cur.nqi) qa = p.lq[cur.qbase + lane] / a.nprobe;
+            if (lane + 32 < cur.nqi) qb = p.lq[cur.qbase + lane + 32] / a.nprobe;
+            if (n >= 2) pwait(bfree_bar(n & 1), (((uint32_t)(n >> 1)) & 1u) ^ 1u, 0);  // the item two back has been consumed
+            float4 *hi_rows = slot_base + (size_t)(n & 1) * (2 * TN) * ds4;
+            float4 *lo_rows = hi_rows + (size_t)npad * ds4;
+            for (int j0 = 0; j0 < cur.nqi; j0 += 3) {  // rows past the item keep stale (finite) values: their columns are never stored
+                const float4 *src[3];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int j = r0 + 4 * i;
-                    goff[i] = 0;
-                    if (j < cur.nqi) {
-                        goff[i] = (uint32_t)(p.lq[cur.qbase + j] / a.nprobe) * (uint32_t)a.ds + (uint32_t)(c * 4);
-                        vmask |= 1u << i;
+                for (int r = 0; r < 3; ++r) {
+                    const int j = min(j0 + r, cur.nqi - 1);
+                    const int32_t qi = __shfl_sync(0xffffffffu, j < 32 ? qa : qb, j & 31);
+                    src[r] = q4 + (size_t)qi * ds4;
+                }
+                for (int c0 = 0; c0 < ds4; c0 += 128) {
+                    float4 v[3][4];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const int c = c0 + t * 32 + lane;
+                            if (c < ds4) v[r][t] = __ldg(src[r] + c);
+                        }
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        const int j = j0 + r;
+                        if (j >= cur.nqi) break;
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const int c = c0 + t * 32 + lane;
+                            if (c < ds4) {
+                                float4 h, l;
+                                h.x = to_tf32(v[r][t].x);
+                                h.y = to_tf32(v[r][t].y);
+                                h.z = to_tf32(v[r][t].z);
+                                h.w = to_tf32(v[r][t].w);
+                                l.x = to_tf32(v[r][t].x - h.x);
+                                l.y = to_tf32(v[r][t].y - h.y);
+                                l.z = to_tf32(v[r][t].z - h.z);
+                                l.w = to_tf32(v[r][t].w - h.w);
+                                hi_rows[(size_t)j * ds4 + c] = h;
+                                lo_rows[(size_t)j * ds4 + c] = l;
+                            }
+                        }
                     }
                 }
             }
-            const int slot = issued % NS;
-            pwait(sfree_bar(slot), (((uint32_t)(issued / NS)) & 1u) ^ 1u, 0);
-            const uint32_t sbase = smem_u32(ringB + slot * B_SLOT);
-            const uint32_t lo_base = sbase + (uint32_t)npad * 128u;
-            const uint32_t koff = (uint32_t)(kb * TK);
-            const int ni = npad >> 2;  // rows r0 + 4 i < npad  <=>  i < npad / 4 (npad is a multiple of 16)
-            if (!(ablate & 4)) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    if (i < ni) {
-                        const uint32_t o = ((i & 1) ? so_o : so_e) + (uint32_t)((i >> 1) * 1024);
-                        const bool ok = (vmask >> i) & 1u;
-                        const uint32_t off = goff[i] + koff;
-                        cp_async16_zfill(sbase + o, qhi + off, ok);
-                        cp_async16_zfill(lo_base + o, qlo + off, ok);
-                    }
-                }
-            }
-            ++issued;
-            if (++kb == KB) {
-                kb = 0;
-                cur.next_unit(a, p);
-            }
-        };
-#pragma unroll 1
-        for (int s = 0; s < BAHEAD; ++s) {
-            if (cur.valid) issue();
-            cp_async_commit_group();
-        }
-#pragma unroll 1
-        while (done < issued) {
-            cp_async_wait_group<BAHEAD - 1>();
-            fence_async_smem();
+            __threadfence();
+            asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy global writes -> visible to the TMA reads
             __syncwarp();
-            if (lane == 0) mbar_arrive(bready_bar(done % NS));
-            ++done;
-            if (cur.valid) issue();
-            cp_async_commit_group();
+            if (lane == 0) mbar_arrive(staged_bar(n & 1));
+            ++n;
+            cur.new_chunk = false;  // skip the remaining tiles of this item
+            do {
+                cur.next_unit(a, p);
+            } while (cur.valid && !cur.new_chunk);
         }
-        cp_async_wait_group<0>();
-        if (lane == 0) pflush(8, 1);
+        if (lane == 0) pflush(11, 1);
     } else if (warp >= 13) {
         // ---------------- MMA issuers: warp 2 = even k-steps -> accumulators [0, 128), warp 3 = odd -> [128, 256) ----------------
         const int par = warp - 13;
@@ -254,7 +252,13 @@ __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const ScanArgs 
             int s = 0;
             uint32_t acc_phase = 0;
             UnitCursor cur;
+            int n = -1;
             for (cur.start(a, p, u0, u1); cur.valid; cur.next_unit(a, p)) {
+                if (cur.new_chunk) {  // every k-block of the previous item has landed (its B-ready waits are behind us)
+                    cur.new_chunk = false;
+                    if (par == 0 && n >= 0) mbar_arrive(bfree_bar(n & 1));
+                    ++n;
+                }
                 const int npad = (cur.nqi + 15) & ~15;
                 const uint32_t idesc_fold = umma_idesc_tf32(TM, 2 * npad);
                 const uint32_t idesc_lo = umma_idesc_tf32(TM, npad);
@@ -271,7 +275,6 @@ __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const ScanArgs 
                     const uint64_t db = umma_desc_sw128(smem_u32(ringB + slot * B_SLOT));
 #pragma unroll
                     for (int ks = 0; ks < TK / 8; ks += 2) {
-                        if (ablate & 8) break;
                         const int k8 = ks + par;
                         const uint64_t off = (uint64_t)((k8 * 8 * 4) >> 4);
                         umma_tf32_ts(tmem_d, a_hi + (uint32_t)(k8 * 8), db + off, idesc_fold, (kb | ks) != 0 ? 1u : 0u);
@@ -282,18 +285,57 @@ __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const ScanArgs 
                 umma_commit(accfull_bar);
                 acc_phase ^= 1u;
             }
-            if (par == 0) pflush(4, 3);
+            if (par == 0) pflush(7, 3);
         }
     } else if (warp <= 7) {
-        // ---------------- converters ----------------
+        // ---------------- converters: warp (set, quarter) converts page `quarter` of the k-blocks s = set (mod 2) and, as soon as
+        // it holds a k-block in registers, refills that quarter of the raw slot with the k-block NR further on (lane 0: one TMA
+        // box).  The row stream is thus issued by eight warps -- a single producer thread needs ~1100 cycles for the five TMA
+        // boxes, two barrier waits and the bookkeeping of a stage -- and needs no "slot empty" handshake. ----------------
         const int set = warp >> 2, quarter = warp & 3;
         const uint32_t lane_off = (uint32_t)(quarter * 4096 + lane * 128);
         const uint32_t x7 = (uint32_t)(lane & 7);
         const uint32_t tq = ((uint32_t)(quarter * 32) << 16);
-        int64_t nstages = 0;
-        {   // stages of this CTA = units x KB
-            nstages = (int64_t)(u1 - u0) * KB;
+        const uint8_t *maps = reinterpret_cast<const uint8_t *>(a.slab_maps);
+        const int64_t nstages = (int64_t)(u1 - u0) * KB;
+        // load cursor: (unit, k-block) of the next k-block this warp has to request
+        UnitCursor cl;
+        cl.start(a, p, u0, u1);
+        int kbl = set;
+        while (cl.valid && kbl >= KB) {
+            kbl -= KB;
+            cl.next_unit(a, p);
         }
+        int32_t l_unit = -1;
+        const void *l_map = maps;
+        int l_row = -1;
+        auto request = [&](int64_t s) {  // k-block s (this warp's parity) into raw slot s % NR, quarter `quarter`
+            if (cl.u != l_unit) {        // new tile: where does its page `quarter` live?
+                l_unit = cl.u;
+                l_row = -1;
+                const int32_t npages = (cl.len + kPageRows - 1) / kPageRows;
+                if (cl.tile * 4 + quarter < npages) {
+                    const int32_t page = __ldg(a.pt + cl.ptbase + cl.tile * 4 + quarter);
+                    l_map = maps + (size_t)(page >> a.slab_shift) * 128;
+                    l_row = (page & slab_mask) * kPageRows;
+                }
+            }
+            if (lane == 0) {
+                const int rslot = (int)(s % NR);
+                if (l_row >= 0) {
+                    mbar_expect_tx(rfull_bar(rslot), 4096u);
+                    tma_load_2d(smem_u32(ringR + rslot * RAW_TILE) + quarter * 4096, l_map, rfull_bar(rslot), kbl * TK, l_row);
+                } else {
+                    mbar_arrive(rfull_bar(rslot));  // the tile ends before this page: nothing to load
+                }
+            }
+            kbl += 2;
+            while (cl.valid && kbl >= KB) {
+                kbl -= KB;
+                cl.next_unit(a, p);
+            }
+        };
+        for (int64_t s = set; s < nstages && s < set + NR; s += 2) request(s);
         for (int64_t s = set; s < nstages; s += 2) {
             const int rslot = (int)(s % NR);
             pwait(rfull_bar(rslot), ((uint32_t)(s / NR)) & 1u, 0);
@@ -309,23 +351,20 @@ __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const ScanArgs 
             for (int i = 0; i < 32; ++i) h[i] = v[i] & 0xffffe000u;
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(to_tf32(__uint_as_float(v[i]) - __uint_as_float(h[i])));
+            __syncwarp();  // every lane holds its row: the quarter may be overwritten
+            if (s + NR < nstages) request(s + NR);
             const int slot = (int)(s % NS);
             pwait(sfree_bar(slot), (((uint32_t)(s / NS)) & 1u) ^ 1u, 1);
             tc_fence_after();
             const uint32_t ta = tmem_base + tq + (uint32_t)(ACC_COLS + slot * A_SLOT_COLS);
-            if (!(ablate & 2)) {
-                tmem_st32(ta, h);
-                tmem_st32(ta + 32u, v);
-                tmem_wait_st();
-            }
+            tmem_st32(ta, h);
+            tmem_st32(ta + 32u, v);
+            tmem_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(rempty_bar(rslot));
-                mbar_arrive(aready_bar(slot));
-            }
+            if (lane == 0) mbar_arrive(aready_bar(slot));
         }
-        if (warp == 0 && lane == 0) pflush(1, 2);
+        if (warp == 0 && lane == 0) pflush(4, 2);
     } else {
         // ---------------- epilogue (the last four warps) ----------------
         const int quarter = warp & 3;
@@ -375,12 +414,12 @@ __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const ScanArgs 
             if (lane == 0) mbar_arrive(accempty_bar);
             acc_phase ^= 1u;
         }
-        if (warp == 8 && lane == 0) pflush(12, 1);
+        if (warp == 8 && lane == 0) pflush(13, 1);
     }
 
     tc_fence_before();
     __syncthreads();
-    if (PROF && threadIdx.x == 0) atomicAdd(&g_ts_prof[14], (unsigned long long)(clock64() - t_start));
+    if (PROF && threadIdx.x == 0) atomicAdd(&g_ts_prof[15], (unsigned long long)(clock64() - t_start));
     if (warp == 13) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS_TS) : "memory");
@@ -424,19 +463,29 @@ cudaError_t encode_slab_map(void *map128, const float *base, int64_t rows, int d
     return cudaSuccess;
 }
 
-// items: (list, chunk of 64 queries) from p.off32 (plan_lists_kernel with chunk = 64); p.qsplit holds 2 x [nq, ds];
-// a.slab_maps: one tensor map per slab (encode_slab_map)
+// items: (list, chunk of 64 queries) from p.off32 (plan_lists_kernel with chunk = 64); p.bstage: num_sms x 2 staging
+// slots of 128 rows x ds floats; a.slab_maps: one tensor map per slab (encode_slab_map)
+size_t scan_lists_ts_stage_bytes(int ds, int num_sms) { return (size_t)num_sms * 2 * (2 * TN) * ds * sizeof(float); }
+
 cudaError_t launch_scan_lists_ts(const ScanArgs &a, const ListPlan &p, int num_sms, cudaStream_t st) {
-    if (a.metric != 0 || (a.ds % TK) != 0 || p.chunk != TN || p.qsplit == nullptr || a.slab_maps == nullptr) return cudaErrorNotSupported;
-    if ((a.npairs / a.nprobe) * (int64_t)a.ds >= ((int64_t)1 << 31)) return cudaErrorNotSupported;  // 32-bit query offsets
-    cudaError_t e = launch_split_queries(a.q, (a.npairs / a.nprobe) * (int64_t)a.ds / 4, p.qsplit, num_sms, st);
-    if (e != cudaSuccess) return e;
+    if (a.metric != 0 || (a.ds % TK) != 0 || p.chunk != TN || p.bstage == nullptr || a.slab_maps == nullptr) return cudaErrorNotSupported;
+    EncodeTiledFn fn = encode_fn_ts();
+    if (!fn) return cudaErrorNotSupported;
+    BMaps bm;
+    const cuuint64_t dims[2] = {(cuuint64_t)a.ds, (cuuint64_t)num_sms * 2 * (2 * TN)};
+    const cuuint64_t strides[1] = {(cuuint64_t)a.ds * 4};
+    const cuuint32_t estr[2] = {1, 1};
+    for (int i = 0; i < 4; ++i) {
+        const cuuint32_t box[2] = {(cuuint32_t)TK, (cuuint32_t)(32 * (i + 1))};
+        if (fn(&bm.m[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, p.bstage, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return cudaErrorInvalidValue;
+    }
     static const bool prof = getenv("SEMCODE_TS_PROF") != nullptr;
     auto kern = prof ? scan_lists_ts_kernel<true> : scan_lists_ts_kernel<false>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TS);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TS);
     if (e != cudaSuccess) return e;
-    static const int ablate = getenv("SEMCODE_TS_ABLATE") ? atoi(getenv("SEMCODE_TS_ABLATE")) : 0;
-    kern<<<num_sms, NT_TS, SMEM_TS, st>>>(a, p, ablate);
+    kern<<<num_sms, NT_TS, SMEM_TS, st>>>(bm, a, p);
     return cudaGetLastError();
 }
 
@@ -450,7 +499,3 @@ extern "C" int scdbg_ts_prof(unsigned long long *out16) {
     if (cudaMemcpyToSymbol(sc::g_ts_prof, zero, sizeof(zero)) != cudaSuccess) return -2;
     return 0;
 }
-
-namespace sc {
-
-}  // namespace sc

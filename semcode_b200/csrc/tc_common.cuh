@@ -170,10 +170,22 @@ struct UnitCursor {
         }
         if (++tile == ntiles) {
             tile = 0;
-            if (++chunk == nchunks)
-                locate(a, p);
-            else
+            if (++chunk == nchunks) {
+                // the owner of the next unit is usually the next list: one probe instead of a binary search
+                if (l + 2 <= p.nlist && p.off32[l + 1] <= u && u < p.off32[l + 2]) {
+                    ++l;
+                    len = a.list_len[l];
+                    ptbase = a.pt_off[l];
+                    ntiles = (len + TM - 1) / TM;
+                    nchunks = p.n32[l];
+                    chunk = 0;
+                    set_chunk(p);
+                } else {
+                    locate(a, p);
+                }
+            } else {
                 set_chunk(p);
+            }
         }
     }
 };
