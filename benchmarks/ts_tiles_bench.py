@@ -53,7 +53,7 @@ def main():
                 _capi.lib().scdbg_ts_prof(buf)  # reset
                 g.search(q[:nq], k, nprobe=nprobe)
                 _capi.lib().scdbg_ts_prof(buf)
-                names = ["qprod.sfree", "qprod.staged", "qprod.total", "-", "conv.rfull", "conv.sfree", "conv.total", "iss.accempty",
+                names = ["qprod.qfree", "qprod.staged", "qprod.total", "-", "conv.rfull", "conv.sfree", "conv.total", "iss.accempty",
                          "iss.aready", "iss.bready", "iss.total", "stager.bfree", "stager.total", "epi.accfull", "epi.total", "kernel"]
                 prof = {n: round(buf[i] / 148 / 1e3, 1) for i, n in enumerate(names)}  # kcycles per CTA
             print(json.dumps({"dataset": dataset, "prof_kcyc_per_cta": prof, "nq": nq, "nprobe": nprobe, "cfg": cfg, "scan_ms": round(best.scan_ms, 3),

@@ -24,17 +24,17 @@
 // [B_hi ; B_lo] (N doubled), and per tile two accumulator sets by k-step parity ([hh | cross] each), summed by the
 // epilogue in fp32 -- the tensor core's truncating accumulation stays two short chains (see scan_lists_tc.cu, NACC).
 //
-// CTA = 16 warps, one per SM; every role walks the same contiguous range of (list, chunk, 128-row tile) units.  The
+// CTA = 20 warps, one per SM; every role walks the same contiguous range of (list, chunk, 128-row tile) units.  The
 // warp scheduler prefers the highest warp id of a sub-partition, so the roles on the critical path come last:
-//   warps 0-7   converters: warp w serves TMEM lane quarter w % 4 (= page w % 4 of the tile); the two sets alternate
-//               k-blocks, 4 TMEM operand slots of 64 columns (hi | lo); each warp also requests its own page boxes
-//               (TMA, 32 rows x 128 B, NR k-blocks ahead), so the row stream has eight issuers and no producer warp
-//   warps 8-11  epilogue: tcgen05.ld, fused tag predicate, coalesced candidate stores (same layout as the other scans)
-//   warp 12     query producer (one lane): per k-block one TMA box [2 N rows x 32 floats] from the item's staging slot
-//   warps 13-14 MMA issuers by k-step parity (one lane each); each owns its accumulator set, so the order of the
-//               additions into every accumulator is fixed and results are reproducible
-//   warp 15     stager: gathers + splits the NEXT item's query rows into the other staging slot
-// TMEM: columns [0, 256) accumulators (2 parities x [hh | cross] x 64), [256, 512) four operand slots.
+//   warps 0-11  converters: warp w serves TMEM lane quarter w % 4 (= page w % 4 of the tile); three sets take the k-blocks
+//               round-robin, 4 TMEM operand slots of 64 columns (hi | lo); each warp also requests its own page boxes
+//               (TMA, 32 rows x 128 B, NR k-blocks ahead): the row stream has twelve issuers and no producer warp
+//   warps 12-15 epilogue: tcgen05.ld, fused tag predicate, coalesced candidate stores (same layout as the other scans)
+//   warp 16     query producer (one elected lane): per k-block one TMA box [2 N rows x 32 floats] from the staging slot
+//   warps 17-18 MMA issuers (one elected lane each): issuer p owns the k-blocks of parity p of every tile and ITS
+//               accumulator set, so the order of the additions into every accumulator is fixed and results are reproducible
+//   warp 19     stager: gathers + splits the NEXT item's query rows into the other staging slot
+// TMEM: columns [0, 256) accumulators (2 k-block parities x [hh | cross]; two buffers when N <= 32), [256, 512) four operand slots.
 // Replaces the same FAISS IVFFlatScanner::scan_codes loop (reference src/semcode/storage/milvus_store.py:141-147).
 // Bound: HBM (each list once per 64 queries).
 #include <cuda.h>
@@ -51,13 +51,17 @@ using namespace tcu;
 
 constexpr int RAW_TILE = TM * TK * 4;       // 16 KB: four 4 KB boxes (one per page of the tile)
 constexpr int B_SLOT = 2 * TN * TK * 4;     // 16 KB: up to 64 hi rows + 64 lo rows
-constexpr int NR = 8;                       // raw stages (128 KB in flight per SM at most)
-constexpr int NS = 4;                       // operand slots: TMEM A slots and shared-memory B slots advance together
+constexpr int NSETS = 3;                    // converter sets (4 warps each), k-blocks dealt round-robin
+constexpr int NR = 6;                       // raw stages (96 KB in flight per SM), a multiple of NSETS
+constexpr int NS = 4;                       // TMEM operand slots (hi | lo, 64 columns each)
+constexpr int NB = 6;                       // query ring slots
+constexpr int ND = 12;                      // k-block-done barriers: a multiple of NS and NB
 constexpr int ACC_COLS = 256;
 constexpr int A_SLOT_COLS = 64;
 constexpr int TMEM_COLS_TS = 512;
-constexpr int NT_TS = 16 * 32;
-constexpr int SMEM_TS = NR * RAW_TILE + NS * B_SLOT + 1024 /*align*/ + 2048 /*barriers, tables*/;
+constexpr int W_EPI = 4 * NSETS, W_QPROD = W_EPI + 4, W_ISSUE = W_QPROD + 1, W_STAGER = W_ISSUE + 2;  // first warp of each role
+constexpr int NT_TS = (W_STAGER + 1) * 32;  // 20 warps: <= 96 registers per thread
+constexpr int SMEM_TS = NR * RAW_TILE + NB * B_SLOT + 1024 /*align*/ + 2048 /*barriers, tables*/;
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void *map, uint32_t bar, int c0, int c1) {
     asm volatile(
@@ -67,7 +71,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void *map, uint3
 }
 
 // wait-time profile (SEMCODE_TS_PROF=1): cycles summed over all CTAs, one warp (lane 0) per role
-//   0-2 query producer: operand slot free, staging slot filled, total     4-6 converter (warp 0): raw full, slot free, total
+//   0-2 query producer: query slot free, staging slot filled, total     4-6 converter (warp 0): raw full, slot free, total
 //   7-10 issuer 0: accumulators empty, A ready, B ready, total     11-12 stager: staging slot consumed, total
 //   13-14 epilogue warp 0: accumulators full, total     15 kernel total (thread 0)
 __device__ unsigned long long g_ts_prof[16];
@@ -76,28 +80,46 @@ struct BMaps {
     CUtensorMap m[4];  // the staging area as a [rows, ds] tensor with boxes of 32 / 64 / 96 / 128 rows x 32 floats
 };
 
+// Which accumulator buffer(s) a tile uses -- every role steps through the same sequence.  A tile of N <= 32 queries needs
+// 2 sets x [hh | cross] x 32 = 128 columns and alternates between the two halves of the accumulator region, so its
+// epilogue overlaps the next tile's MMAs; a wider tile takes both halves.
+struct AccSched {
+    int next = 0;
+    uint32_t uses[2] = {0u, 0u};
+    __device__ __forceinline__ int pick(int npad) {
+        if (npad > 32) return 3;
+        const int m = 1 << next;
+        next ^= 1;
+        return m;
+    }
+    // first column of accumulator set `set` (k-block parity) of the tile that owns buffer mask m
+    __device__ __forceinline__ static uint32_t col(int m, int set) { return m == 3 ? (uint32_t)(set * 128) : (uint32_t)((m >> 1) * 128 + set * 64); }
+};
+
 template <bool PROF>
 __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const __grid_constant__ BMaps bmaps, const ScanArgs a, const ListPlan p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *ringR = smem;                      // NR x RAW_TILE
-    uint8_t *ringB = ringR + NR * RAW_TILE;     // NS x B_SLOT
-    uint64_t *bars = reinterpret_cast<uint64_t *>(ringB + NS * B_SLOT);
-    // bars: [0,NR) raw full (4 converter warps + TMA tx)   [NR,2NR) unused   then per slot: A ready (4 converter warps),
-    //       B ready (TMA tx), slot free (one commit per issuer); then accumulators full (2 commits), empty (4 warps),
-    //       staging slot filled x 2 (stager), staging slot consumed x 2 (issuer 0)
-    constexpr int NBARS = 2 * NR + 3 * NS + 2 + 4;
+    uint8_t *ringB = ringR + NR * RAW_TILE;     // NB x B_SLOT
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ringB + NB * B_SLOT);
+    // bars: raw full [NR] (4 converter warps + TMA bytes) | A ready [NS] (4 converter warps) | B ready [NB] (TMA bytes) |
+    //       k-block done [ND] (commit of the issuer that owns it: frees TMEM slot s % NS and query slot s % NB) |
+    //       accumulators full [2] (2 commits), empty [2] (4 epilogue warps) | staging slot filled [2] (stager), consumed [2]
+    //       (both issuers)
+    constexpr int NBARS = NR + NS + NB + ND + 8;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + NBARS);
     int64_t *cbE = reinterpret_cast<int64_t *>(bars + NBARS + 2);  // [TN] candidate bases of the epilogue's current item
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = smem_u32(bars);
     auto rfull_bar = [&](int s) { return bar0 + 8u * s; };
-    auto aready_bar = [&](int s) { return bar0 + 8u * (2 * NR + s); };
-    auto bready_bar = [&](int s) { return bar0 + 8u * (2 * NR + NS + s); };
-    auto sfree_bar = [&](int s) { return bar0 + 8u * (2 * NR + 2 * NS + s); };
-    const uint32_t accfull_bar = bar0 + 8u * (2 * NR + 3 * NS), accempty_bar = accfull_bar + 8u;
-    auto staged_bar = [&](int s) { return accfull_bar + 16u + 8u * s; };
-    auto bfree_bar = [&](int s) { return accfull_bar + 32u + 8u * s; };
+    auto aready_bar = [&](int s) { return bar0 + 8u * (NR + s); };
+    auto bready_bar = [&](int s) { return bar0 + 8u * (NR + NS + s); };
+    auto done_bar = [&](int s) { return bar0 + 8u * (NR + NS + NB + s); };
+    auto accfull_bar = [&](int s) { return bar0 + 8u * (NR + NS + NB + ND + s); };
+    auto accempty_bar = [&](int s) { return bar0 + 8u * (NR + NS + NB + ND + 2 + s); };
+    auto staged_bar = [&](int s) { return bar0 + 8u * (NR + NS + NB + ND + 4 + s); };
+    auto bfree_bar = [&](int s) { return bar0 + 8u * (NR + NS + NB + ND + 6 + s); };
 
     unsigned long long pw[3] = {0, 0, 0};
     const long long t_start = PROF ? clock64() : 0;
@@ -116,25 +138,25 @@ __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const __grid_co
             atomicAdd(&g_ts_prof[base + n], (unsigned long long)(clock64() - t_start));
         }
     };
+    // k-block s may overwrite a slot of a ring of depth D once k-block s - D has been multiplied
+    auto wait_done = [&](int32_t s, int depth, int which) {
+        if (s >= depth) pwait(done_bar((s - depth) % ND), ((uint32_t)((s - depth) / ND)) & 1u, which);
+    };
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NR; ++s) {
-            mbar_init(rfull_bar(s), 4);  // one arrival (+ 4 KB of TMA bytes) per converter warp of the set
-        }
-        for (int s = 0; s < NS; ++s) {
-            mbar_init(aready_bar(s), 4);
-            mbar_init(bready_bar(s), 1);
-            mbar_init(sfree_bar(s), 2);
-        }
-        mbar_init(accfull_bar, 2);
-        mbar_init(accempty_bar, 4);
+        for (int s = 0; s < NR; ++s) mbar_init(rfull_bar(s), 4);
+        for (int s = 0; s < NS; ++s) mbar_init(aready_bar(s), 4);
+        for (int s = 0; s < NB; ++s) mbar_init(bready_bar(s), 1);
+        for (int s = 0; s < ND; ++s) mbar_init(done_bar(s), 1);
         for (int s = 0; s < 2; ++s) {
+            mbar_init(accfull_bar(s), 2);
+            mbar_init(accempty_bar(s), 4);
             mbar_init(staged_bar(s), 1);
-            mbar_init(bfree_bar(s), 1);
+            mbar_init(bfree_bar(s), 2);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_smem();
     }
-    if (warp == 13) {
+    if (warp == W_ISSUE) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS_TS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -147,13 +169,14 @@ __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const __grid_co
     const int32_t per_cta = (int32_t)(((int64_t)total + gridDim.x - 1) / gridDim.x);
     const int32_t u0 = (int32_t)min((int64_t)total, (int64_t)blockIdx.x * per_cta);
     const int32_t u1 = (int32_t)min((int64_t)total, (int64_t)u0 + per_cta);
-    const int KB = a.ds / TK;  // launcher guarantees ds % 32 == 0
+    const int KB = a.ds / TK;  // launcher guarantees ds % 32 == 0 and (u1 - u0) * KB < 2^31
     const int slab_mask = (1 << a.slab_shift) - 1;
 
-    if (warp == 12) {
-        // ---------------- query producer (one lane): per k-block one box [2 N rows x 32 floats] from the item's staging slot ----------------
-        if (lane == 0) {
-            int s = 0, n = -1, npad = 16, row0 = 0;
+    if (warp == W_QPROD) {
+        // ---------------- query producer (one elected lane): per k-block one box [2 N rows x 32 floats] from the item's staging slot ----------------
+        if (elect_one()) {
+            int32_t s = 0;
+            int n = -1, npad = 16, row0 = 0;
             const CUtensorMap *bm = &bmaps.m[0];
             UnitCursor cur;
             for (cur.start(a, p, u0, u1); cur.valid; cur.next_unit(a, p)) {
@@ -166,18 +189,17 @@ __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const __grid_co
                     pwait(staged_bar(n & 1), ((uint32_t)(n >> 1)) & 1u, 1);
                 }
                 for (int kb = 0; kb < KB; ++kb, ++s) {
-                    const int slot = s % NS;
-                    pwait(sfree_bar(slot), (((uint32_t)(s / NS)) & 1u) ^ 1u, 0);
+                    const int slot = s % NB;
+                    wait_done(s, NB, 0);
                     mbar_expect_tx(bready_bar(slot), (uint32_t)npad * 256u);
                     tma_load_2d(smem_u32(ringB + slot * B_SLOT), bm, bready_bar(slot), kb * TK, row0);
                 }
             }
             pflush(0, 2);
         }
-    } else if (warp == 15) {
+    } else if (warp == W_STAGER) {
         // ---------------- stager: the next item's query rows, split into tf32 terms, [hi rows ; lo rows] ----------------
-        // three rows in flight per pass (12 x 512 bytes per warp): the copy of an item (<= 64 rows) takes a few thousand
-        // cycles, an item lasts tens of thousands
+        // three rows in flight per pass (12 x 512 bytes per warp); the copy of an item runs one item ahead of its use
         const int ds4 = a.ds >> 2;
         float4 *slot_base = reinterpret_cast<float4 *>(p.bstage) + (size_t)blockIdx.x * 2 * (2 * TN) * ds4;
         const float4 *q4 = reinterpret_cast<const float4 *>(a.q);
@@ -245,59 +267,70 @@ __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const __grid_co
             } while (cur.valid && !cur.new_chunk);
         }
         if (lane == 0) pflush(11, 1);
-    } else if (warp >= 13) {
-        // ---------------- MMA issuers: warp 2 = even k-steps -> accumulators [0, 128), warp 3 = odd -> [128, 256) ----------------
-        const int par = warp - 13;
-        if (lane == 0) {
-            int s = 0;
-            uint32_t acc_phase = 0;
+    } else if (warp >= W_ISSUE) {
+        // ---------------- MMA issuers: issuer `par` multiplies the k-blocks of parity `par` of every tile (all four k-steps, all
+        // three terms) into ITS accumulator set, so the order of the additions into every accumulator is fixed ----------------
+        const int par = warp - W_ISSUE;
+        if (elect_one()) {
+            int32_t sbase = 0;
+            AccSched acc;
             UnitCursor cur;
             int n = -1;
-            for (cur.start(a, p, u0, u1); cur.valid; cur.next_unit(a, p)) {
-                if (cur.new_chunk) {  // every k-block of the previous item has landed (its B-ready waits are behind us)
+            for (cur.start(a, p, u0, u1); cur.valid; cur.next_unit(a, p), sbase += KB) {
+                if (cur.new_chunk) {
+                    // this issuer is past the B-ready wait of every k-block of its parity of the previous item: once both
+                    // issuers say so, every TMA read of that item's staging slot has completed and the slot may be rewritten
                     cur.new_chunk = false;
-                    if (par == 0 && n >= 0) mbar_arrive(bfree_bar(n & 1));
+                    if (n >= 0) mbar_arrive(bfree_bar(n & 1));
                     ++n;
                 }
                 const int npad = (cur.nqi + 15) & ~15;
                 const uint32_t idesc_fold = umma_idesc_tf32(TM, 2 * npad);
                 const uint32_t idesc_lo = umma_idesc_tf32(TM, npad);
-                pwait(accempty_bar, acc_phase ^ 1u, 0);
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(par * 128);
-                for (int kb = 0; kb < KB; ++kb, ++s) {
-                    const int slot = s % NS;
-                    const uint32_t ph = ((uint32_t)(s / NS)) & 1u;
-                    pwait(aready_bar(slot), ph, 1);
-                    pwait(bready_bar(slot), ph, 2);
-                    tc_fence_after();
-                    const uint32_t a_hi = tmem_base + (uint32_t)(ACC_COLS + slot * A_SLOT_COLS);
-                    const uint64_t db = umma_desc_sw128(smem_u32(ringB + slot * B_SLOT));
+                const int m = acc.pick(npad);
 #pragma unroll
-                    for (int ks = 0; ks < TK / 8; ks += 2) {
-                        const int k8 = ks + par;
+                for (int i = 0; i < 2; ++i)
+                    if ((m >> i) & 1) pwait(accempty_bar(i), (acc.uses[i] & 1u) ^ 1u, 0);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + AccSched::col(m, par);
+                for (int kb = par; kb < KB; kb += 2) {
+                    const int32_t s = sbase + kb;
+                    const int aslot = s % NS, bslot = s % NB;
+                    pwait(aready_bar(aslot), ((uint32_t)(s / NS)) & 1u, 1);
+                    pwait(bready_bar(bslot), ((uint32_t)(s / NB)) & 1u, 2);
+                    tc_fence_after();
+                    const uint32_t a_hi = tmem_base + (uint32_t)(ACC_COLS + aslot * A_SLOT_COLS);
+                    const uint64_t db = umma_desc_sw128(smem_u32(ringB + bslot * B_SLOT));
+#pragma unroll
+                    for (int k8 = 0; k8 < TK / 8; ++k8) {
                         const uint64_t off = (uint64_t)((k8 * 8 * 4) >> 4);
-                        umma_tf32_ts(tmem_d, a_hi + (uint32_t)(k8 * 8), db + off, idesc_fold, (kb | ks) != 0 ? 1u : 0u);
+                        umma_tf32_ts(tmem_d, a_hi + (uint32_t)(k8 * 8), db + off, idesc_fold, (kb != par || k8 != 0) ? 1u : 0u);
                         umma_tf32_ts(tmem_d + (uint32_t)npad, a_hi + (uint32_t)(32 + k8 * 8), db + off, idesc_lo, 1u);
                     }
-                    umma_commit(sfree_bar(slot));
+                    umma_commit(done_bar(s % ND));
                 }
-                umma_commit(accfull_bar);
-                acc_phase ^= 1u;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    if ((m >> i) & 1) {
+                        umma_commit(accfull_bar(i));
+                        acc.uses[i] += 1;
+                    }
+                }
             }
             if (par == 0) pflush(7, 3);
         }
-    } else if (warp <= 7) {
-        // ---------------- converters: warp (set, quarter) converts page `quarter` of the k-blocks s = set (mod 2) and, as soon as
-        // it holds a k-block in registers, refills that quarter of the raw slot with the k-block NR further on (lane 0: one TMA
-        // box).  The row stream is thus issued by eight warps -- a single producer thread needs ~1100 cycles for the five TMA
-        // boxes, two barrier waits and the bookkeeping of a stage -- and needs no "slot empty" handshake. ----------------
+    } else if (warp < W_EPI) {
+        // ---------------- converters: warp (set, quarter) converts page `quarter` of the k-blocks s = set (mod NSETS) and, while
+        // its TMEM stores drain, refills that quarter of the raw slot with the k-block NR further on (one elected lane: one TMA
+        // box).  An asynchronous-copy or mbarrier instruction costs its issuing thread ~80-100 cycles, so a single producer
+        // thread (5 boxes, 2 waits, 2 expect_tx per k-block) cannot feed the ring -- twelve warps can, and no "slot empty"
+        // handshake is needed. ----------------
         const int set = warp >> 2, quarter = warp & 3;
         const uint32_t lane_off = (uint32_t)(quarter * 4096 + lane * 128);
         const uint32_t x7 = (uint32_t)(lane & 7);
         const uint32_t tq = ((uint32_t)(quarter * 32) << 16);
         const uint8_t *maps = reinterpret_cast<const uint8_t *>(a.slab_maps);
-        const int64_t nstages = (int64_t)(u1 - u0) * KB;
+        const int32_t nstages = (u1 - u0) * KB;
         // load cursor: (unit, k-block) of the next k-block this warp has to request
         UnitCursor cl;
         cl.start(a, p, u0, u1);
@@ -309,7 +342,7 @@ __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const __grid_co
         int32_t l_unit = -1;
         const void *l_map = maps;
         int l_row = -1;
-        auto request = [&](int64_t s) {  // k-block s (this warp's parity) into raw slot s % NR, quarter `quarter`
+        auto request = [&](int32_t s) {  // k-block s (this warp's set) into raw slot s % NR, quarter `quarter`
             if (cl.u != l_unit) {        // new tile: where does its page `quarter` live?
                 l_unit = cl.u;
                 l_row = -1;
@@ -320,8 +353,8 @@ __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const __grid_co
                     l_row = (page & slab_mask) * kPageRows;
                 }
             }
-            if (lane == 0) {
-                const int rslot = (int)(s % NR);
+            if (elect_one()) {
+                const int rslot = s % NR;
                 if (l_row >= 0) {
                     mbar_expect_tx(rfull_bar(rslot), 4096u);
                     tma_load_2d(smem_u32(ringR + rslot * RAW_TILE) + quarter * 4096, l_map, rfull_bar(rslot), kbl * TK, l_row);
@@ -329,36 +362,41 @@ __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const __grid_co
                     mbar_arrive(rfull_bar(rslot));  // the tile ends before this page: nothing to load
                 }
             }
-            kbl += 2;
+            kbl += NSETS;
             while (cl.valid && kbl >= KB) {
                 kbl -= KB;
                 cl.next_unit(a, p);
             }
         };
-        for (int64_t s = set; s < nstages && s < set + NR; s += 2) request(s);
-        for (int64_t s = set; s < nstages; s += 2) {
-            const int rslot = (int)(s % NR);
-            pwait(rfull_bar(rslot), ((uint32_t)(s / NR)) & 1u, 0);
-            const uint32_t src = smem_u32(ringR + rslot * RAW_TILE) + lane_off;
-            uint32_t v[32];
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
-                             : "=r"(v[4 * c]), "=r"(v[4 * c + 1]), "=r"(v[4 * c + 2]), "=r"(v[4 * c + 3])
-                             : "r"(src + (((uint32_t)c ^ x7) << 4)));
-            uint32_t h[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) h[i] = v[i] & 0xffffe000u;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(to_tf32(__uint_as_float(v[i]) - __uint_as_float(h[i])));
-            __syncwarp();  // every lane holds its row: the quarter may be overwritten
-            if (s + NR < nstages) request(s + NR);
-            const int slot = (int)(s % NS);
-            pwait(sfree_bar(slot), (((uint32_t)(s / NS)) & 1u) ^ 1u, 1);
-            tc_fence_after();
+        static_assert(NR % NSETS == 0, "the warp that converts k-block s refills its slot with k-block s + NR");
+        for (int32_t s = set; s < nstages && s < set + NR; s += NSETS) request(s);
+        for (int32_t s = set; s < nstages; s += NSETS) {
+            const int rslot = s % NR;
+            const int slot = s % NS;
             const uint32_t ta = tmem_base + tq + (uint32_t)(ACC_COLS + slot * A_SLOT_COLS);
-            tmem_st32(ta, h);
-            tmem_st32(ta + 32u, v);
+            pwait(rfull_bar(rslot), ((uint32_t)(s / NR)) & 1u, 0);
+            wait_done(s, NS, 1);
+            tc_fence_after();
+            const uint32_t src = smem_u32(ringR + rslot * RAW_TILE) + lane_off;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {  // 16 columns at a time: 32 live registers
+                uint32_t v[16], h[16];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(v[4 * c]), "=r"(v[4 * c + 1]), "=r"(v[4 * c + 2]), "=r"(v[4 * c + 3])
+                                 : "r"(src + (((uint32_t)(half * 4 + c) ^ x7) << 4)));
+#pragma unroll
+                for (int i = 0; i < 16; ++i) h[i] = v[i] & 0xffffe000u;
+                // lo = x - hi, exact in fp32 and at most 2^-10 |x|; the tensor core reads its upper 19 bits, so what is lost
+                // is below 2^-20 |x| -- two ALU instructions per element on the sub-partition that owns the quarter
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) - __uint_as_float(h[i]));
+                tmem_st16(ta + (uint32_t)(half * 16), h);
+                tmem_st16(ta + (uint32_t)(32 + half * 16), v);
+            }
+            __syncwarp();  // every lane has consumed its row: refill the quarter while the stores drain
+            if (s + NR < nstages) request(s + NR);
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
@@ -366,11 +404,11 @@ __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const __grid_co
         }
         if (warp == 0 && lane == 0) pflush(4, 2);
     } else {
-        // ---------------- epilogue (the last four warps) ----------------
+        // ---------------- epilogue (warps W_EPI .. W_EPI + 3) ----------------
         const int quarter = warp & 3;
-        const int et = threadIdx.x - 8 * 32;  // 0..127
+        const int et = threadIdx.x - W_EPI * 32;  // 0..127
         const int row = quarter * 32 + lane;
-        uint32_t acc_phase = 0;
+        AccSched acc;
         UnitCursor I;
         for (I.start(a, p, u0, u1); I.valid; I.next_unit(a, p)) {
             if (I.new_chunk) {  // same decision in all four warps
@@ -387,40 +425,50 @@ __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const __grid_co
                 const int32_t page = __ldg(a.pt + I.ptbase + (r >> 5));
                 live = filter_pass(a.filt, __ldg(a.slabs->tags[page >> a.slab_shift] + (int64_t)(page & slab_mask) * kPageRows + (r & 31)));
             }
-            pwait(accfull_bar, acc_phase, 0);
+            const int m = acc.pick(npad);
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                if ((m >> i) & 1) pwait(accfull_bar(i), acc.uses[i] & 1u, 0);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+            const uint32_t t0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + AccSched::col(m, 0);
+            const uint32_t t1 = tmem_base + ((uint32_t)(quarter * 32) << 16) + AccSched::col(m, 1);
 #pragma unroll 1
-            for (int h = 0; h * 32 < I.nqi; ++h) {
-                float v[32], w[32], x[32];
-                tmem_ld32(taddr + (uint32_t)(npad + h * 32), v);        // cross terms, even k-steps
-                tmem_ld32(taddr + (uint32_t)(128 + npad + h * 32), w);  // cross terms, odd k-steps
-#pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] = v[j] + w[j];
-                tmem_ld32(taddr + (uint32_t)(h * 32), v);               // hi.hi, even
-                tmem_ld32(taddr + (uint32_t)(128 + h * 32), w);         // hi.hi, odd
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = (v[j] + w[j]) + x[j];
+            for (int g = 0; g * 16 < I.nqi; ++g) {  // 16 queries at a time
+                uint32_t c0[16], h0[16], c1[16], h1[16];
+                tmem_ld16_nowait(t0 + (uint32_t)(npad + g * 16), c0);  // cross terms, even k-blocks
+                tmem_ld16_nowait(t0 + (uint32_t)(g * 16), h0);         // hi.hi, even k-blocks
+                if (KB > 1) {  // (a one-k-block tile never touches the odd set)
+                    tmem_ld16_nowait(t1 + (uint32_t)(npad + g * 16), c1);
+                    tmem_ld16_nowait(t1 + (uint32_t)(g * 16), h1);
+                }
+                tmem_wait_ld();
                 if (r < slots) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int jj = h * 32 + j;
-                        if (jj < I.nqi) a.cand[cbE[jj] + r] = live ? v[j] : -INFINITY;
+                    for (int j = 0; j < 16; ++j) {
+                        const int jj = g * 16 + j;
+                        float v = __uint_as_float(c0[j]) + __uint_as_float(h0[j]);
+                        if (KB > 1) v += __uint_as_float(c1[j]) + __uint_as_float(h1[j]);
+                        if (jj < I.nqi) a.cand[cbE[jj] + r] = live ? v : -INFINITY;
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(accempty_bar);
-            acc_phase ^= 1u;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                if ((m >> i) & 1) {
+                    if (lane == 0) mbar_arrive(accempty_bar(i));
+                    acc.uses[i] += 1;
+                }
+            }
         }
-        if (warp == 8 && lane == 0) pflush(13, 1);
+        if (warp == W_EPI && lane == 0) pflush(13, 1);
     }
 
     tc_fence_before();
     __syncthreads();
     if (PROF && threadIdx.x == 0) atomicAdd(&g_ts_prof[15], (unsigned long long)(clock64() - t_start));
-    if (warp == 13) {
+    if (warp == W_ISSUE) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS_TS) : "memory");
     }
@@ -469,6 +517,7 @@ size_t scan_lists_ts_stage_bytes(int ds, int num_sms) { return (size_t)num_sms *
 
 cudaError_t launch_scan_lists_ts(const ScanArgs &a, const ListPlan &p, int num_sms, cudaStream_t st) {
     if (a.metric != 0 || (a.ds % TK) != 0 || p.chunk != TN || p.bstage == nullptr || a.slab_maps == nullptr) return cudaErrorNotSupported;
+    if (a.npairs * (int64_t)(a.ds / TK) >= ((int64_t)1 << 30)) return cudaErrorNotSupported;  // 32-bit k-block counters per CTA
     EncodeTiledFn fn = encode_fn_ts();
     if (!fn) return cudaErrorNotSupported;
     BMaps bm;
