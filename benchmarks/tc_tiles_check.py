@@ -1,5 +1,5 @@
-"""Accuracy / parity probe for the tcgen05 list-major tiles (lists_cfg 0 / 3: operands from shared memory, v2 / v1;
-5: list rows from tensor memory) against the
+"""Accuracy / parity probe for the tcgen05 list-major tiles (lists_cfg 0: list rows from tensor memory;
+3 / 5: operands from shared memory, v1 / v2) against the
 query-major fp32 scan on the same probes.  Prints the error statistics the default choice is based on."""
 import os
 import sys

@@ -1,5 +1,5 @@
-"""List-major tile kernels on the C2 index (10M x 768, nlist 16384): shared-memory operands (lists_cfg 0) against list
-rows from tensor memory (lists_cfg 5) at large batches.  Prints one JSON line per (nq, nprobe, cfg)."""
+"""List-major tile kernels on the C2 index (10M x 768, nlist 16384): shared-memory operands (lists_cfg 5) against list
+rows from tensor memory (lists_cfg 0, the default) at large batches.  Prints one JSON line per (nq, nprobe, cfg)."""
 import json
 import os
 import sys
@@ -13,7 +13,7 @@ import semcode_b200 as sb  # noqa: E402
 
 def main():
     dataset = sys.argv[1] if len(sys.argv) > 1 else "iid"
-    cfgs = [int(v) for v in (sys.argv[2] if len(sys.argv) > 2 else "0,5").split(",")]
+    cfgs = [int(v) for v in (sys.argv[2] if len(sys.argv) > 2 else "5,0").split(",")]
     dev = torch.device("cuda", 0)
     n, d, nlist, k = 10_000_000, 768, 16384, 10
     g = sb.IVFFlatIndex(d, nlist=nlist, metric="IP")
@@ -44,7 +44,7 @@ def main():
             same = float((ii == ref[1]).all(dim=1).float().mean())
             err = float((dd - ref[0]).abs().max())
             prof = None
-            if cfg == 5 and os.environ.get("SEMCODE_TS_PROF"):
+            if cfg == 0 and os.environ.get("SEMCODE_TS_PROF"):
                 import ctypes as C
 
                 from semcode_b200 import _capi

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SC_ABI_VERSION 2
+#define SC_ABI_VERSION 3
 
 typedef enum sc_status {
     SC_OK = 0,
@@ -60,7 +60,8 @@ typedef struct sc_stats {
     int32_t dim, dim_padded, metric, nlist, device, trained;
     int64_t ntotal;        /* live rows (added - removed) */
     int64_t nremoved;      /* tombstoned rows still occupying list slots */
-    int64_t npages;        /* allocated 32-row list pages */
+    int64_t npages;        /* 32-row list pages handed out so far (including the free ones) */
+    int64_t nfree_pages;   /* pages returned by sc_index_compact and not yet reused */
     int64_t bytes_lists;   /* device bytes held by list slabs (vectors + ids + tags) */
     int64_t bytes_scratch; /* device bytes held by scratch */
     int32_t max_list_len, min_list_len;
@@ -131,6 +132,11 @@ int sc_index_add_preassigned(sc_index_t *idx, const float *x, const int64_t *ids
  * milvus_store.py:128).  n_removed_out (host, nullable) receives how many rows matched. */
 int sc_index_remove_ids(sc_index_t *idx, const int64_t *ids, int64_t n, int64_t *n_removed_out, void *stream);
 
+/* drop the tombstoned slots of every list in place (row order inside a list is kept) and return the emptied pages to
+ * the index's free list; pages_freed_out (host, nullable).  Replaces Milvus' background segment compaction [EXT]
+ * behind the same Collection.upsert calls (milvus_store.py:128-130). */
+int sc_index_compact(sc_index_t *idx, int64_t *pages_freed_out, void *stream);
+
 /* -- search.  Replaces Collection.search(data=[vector], param={"metric_type":"IP","params":
  *    {"nprobe":16}}, limit=top_k) at milvus_store.py:141-147 [FAISS IndexIVFFlat::search].
  *    out_dist [nq,k] raw inner product or squared L2, best first; out_ids [nq,k], -1 = no result
@@ -180,6 +186,11 @@ int sc_index_list_sizes(sc_index_t *idx, int32_t *out_host /* [nlist], slots inc
  * buffers can hold. */
 int sc_index_export_list(sc_index_t *idx, int32_t list, int64_t cap, float *vecs, int64_t *ids, uint32_t *tags,
                          int64_t *len_out, void *stream);
+/* lists [list_begin, list_end) back to back in slot order (tombstoned slots included, see tags); off_out
+ * [list_end - list_begin + 1] (host, nullable) = exclusive prefix of the slot counts; cap = rows the buffers hold.
+ * One call per ~GB instead of one per list: snapshots, re-training, the CPU baseline. */
+int sc_index_export_lists(sc_index_t *idx, int32_t list_begin, int32_t list_end, int64_t cap, float *vecs, int64_t *ids,
+                          uint32_t *tags, int64_t *off_out, void *stream);
 int sc_index_set_profiling(sc_index_t *idx, int32_t enabled);
 int sc_index_last_search_times(sc_index_t *idx, sc_search_times_t *out);
 /* tuning knobs (tests / bench; the defaults are the measured best):
@@ -187,13 +198,16 @@ int sc_index_last_search_times(sc_index_t *idx, sc_search_times_t *out);
  *   "scan_mode"      0 = automatic (list-major from nq*nprobe >= nlist/2, 3/4 nlist with a filter), 1 = query-major,
  *                    2 = list-major
  *   "scan_variant"   0..4 rows x loads in flight of the query-major scan
- *   "lists_cfg"      tile items of the list-major scan: 0 = tcgen05 where it applies (inner product, dim % 32 == 0),
- *                    1 / 2 = exact-fp32 FFMA tiles (64- / 32-float stages), 3 = the first tcgen05 tile kernel,
+ *   "lists_cfg"      tile items of the list-major scan: 0 = tcgen05 where it applies (inner product, dim % 32 == 0; list
+ *                    rows as a tensor-memory operand), 1 / 2 = exact-fp32 FFMA tiles (64- / 32-float stages), 3 / 5 = the
+ *                    earlier tcgen05 tile kernels with both operands in shared memory (v1 / v2),
  *                    4 = 0 with the 8-query page scan on mma.sync (parity-green, measured slower)
  *   "lists_fork"     1 = tile items on a side stream next to the page scans
  *   "coarse_impl"    0 = tcgen05 3xTF32 contraction, 1 = fp32 SIMT;  "tc_variant" 0 = 256x256, 1 = 128x256 tiles
  *   "small_coarse"   1 (default) = streamed fp32 coarse kernel for batches of <= 16 queries
- *   "plan_epoch"     tests: launch counter of the pair plan's look-back words (22-bit wrap) */
+ *   "plan_epoch"     tests: launch counter of the pair plan's look-back words (22-bit wrap)
+ *   "add_chunk_rows" tests: rows per insert chunk (0 = automatic);  "fail_add_after" tests: the n-th insert chunk from
+ *                    now fails after its slots were claimed (the index must stay consistent) */
 int sc_index_set_param(sc_index_t *idx, const char *name, int64_t value);
 
 #ifdef __cplusplus

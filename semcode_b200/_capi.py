@@ -31,7 +31,8 @@ SYMBOLS = [
     "sc_index_train", "sc_index_kmeans_init", "sc_index_kmeans_step", "sc_index_kmeans_update",
     "sc_index_set_centroids", "sc_index_get_centroids", "sc_index_assign", "sc_index_probe", "sc_index_add",
     "sc_index_add_preassigned", "sc_index_remove_ids", "sc_index_search", "sc_index_search_preassigned",
-    "sc_merge_topk", "sc_index_stats", "sc_index_list_sizes", "sc_index_export_list", "sc_index_set_profiling",
+    "sc_merge_topk", "sc_index_stats", "sc_index_list_sizes", "sc_index_export_list", "sc_index_export_lists",
+    "sc_index_compact", "sc_index_set_profiling",
     "sc_index_last_search_times", "sc_index_set_param",
     "sc_exchange_create", "sc_exchange_destroy", "sc_exchange_status", "sc_index_search_sharded",
 ]
@@ -56,7 +57,8 @@ class ScStats(C.Structure):
     _fields_ = [
         ("dim", C.c_int32), ("dim_padded", C.c_int32), ("metric", C.c_int32), ("nlist", C.c_int32),
         ("device", C.c_int32), ("trained", C.c_int32),
-        ("ntotal", C.c_int64), ("nremoved", C.c_int64), ("npages", C.c_int64), ("bytes_lists", C.c_int64),
+        ("ntotal", C.c_int64), ("nremoved", C.c_int64), ("npages", C.c_int64), ("nfree_pages", C.c_int64),
+        ("bytes_lists", C.c_int64),
         ("bytes_scratch", C.c_int64),
         ("max_list_len", C.c_int32), ("min_list_len", C.c_int32),
     ]
@@ -111,6 +113,8 @@ def lib():
         "sc_index_stats": [vp, C.POINTER(ScStats)],
         "sc_index_list_sizes": [vp, vp],
         "sc_index_export_list": [vp, i32, i64, vp, vp, vp, vp, vp],
+        "sc_index_export_lists": [vp, i32, i32, i64, vp, vp, vp, vp, vp],
+        "sc_index_compact": [vp, vp, vp],
         "sc_index_set_profiling": [vp, i32],
         "sc_index_last_search_times": [vp, C.POINTER(ScSearchTimes)],
         "sc_index_set_param": [vp, C.c_char_p, i64],

@@ -180,7 +180,7 @@ struct sc_index {
     DevBuf s_sums, s_counts, s_obj, s_rows, s_rm, s_cnt, s_ahi, s_alo, s_lplan, s_scan, s_packed, s_qsplit, s_bstage;
     int64_t scratch_budget = (int64_t)8 << 30;  // search scratch ceiling (candidates dominate); sc_index_set_param("scratch_bytes")
     int scan_variant = 0;
-    int lists_cfg = 0;  // list-major tile items: 0 = tcgen05 where it applies, 1 = FFMA tiles, 2 = FFMA tiles with 32-float stages, 3 = the first tcgen05 tile kernel (scan_lists_tc.cu, variant 1), 4 = 0 with the 8-query page scan on mma.sync
+    int lists_cfg = 0;  // list-major tile items: 0 = tcgen05 where it applies (scan_lists_ts.cu: list rows from tensor memory), 1 = FFMA tiles, 2 = FFMA tiles with 32-float stages, 3 / 5 = the shared-memory-operand tcgen05 kernels (scan_lists_tc.cu v1 / v2), 4 = 0 with the 8-query page scan on mma.sync
     int scan_mode = 0;  // 0 = auto, 1 = query-major (scan.cu), 2 = list-major (scan_lists.cu)
     cudaEvent_t ev_done = nullptr;
     cudaStream_t side[2] = {nullptr, nullptr};  // fork/join streams of the list-major scan
@@ -310,6 +310,7 @@ void free_lists(sc_index *ix) {
     }
     ix->slabs.clear();
     ix->pool_top = 0;
+    ix->nfree = 0;
     ix->ntotal = 0;
     ix->nremoved = 0;
 }
@@ -799,9 +800,13 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
             lp.qsplit = nullptr;
             lp.bstage = nullptr;
             if (tc_tiles) {
-                CU(ix->s_qsplit.reserve((size_t)m * ix->ds * 4 * 2));
-                lp.qsplit = ix->s_qsplit.as<float>();
-                if (ix->lists_cfg == 5 && ix->d_maps) {
+                const bool ts = ix->lists_cfg != 5 && ix->lists_cfg != 3 && ix->d_maps != nullptr &&
+                                npairs * (int64_t)(ix->ds / 32) < ((int64_t)1 << 30);
+                if (!ts) {
+                    CU(ix->s_qsplit.reserve((size_t)m * ix->ds * 4 * 2));
+                    lp.qsplit = ix->s_qsplit.as<float>();
+                }
+                if (ts) {
                     const void *before = ix->s_bstage.p;
                     CU(ix->s_bstage.reserve(scan_lists_ts_stage_bytes(ix->ds, ix->num_sms)));
                     if (ix->s_bstage.p != before) CU(cudaMemsetAsync(ix->s_bstage.p, 0, ix->s_bstage.cap, st));  // padded rows are read (never stored): keep them finite
@@ -968,7 +973,7 @@ int sc_index_destroy(sc_index_t *ix) {
                       &ix->s_bad, &ix->s_sums, &ix->s_counts, &ix->s_obj, &ix->s_rows, &ix->s_rm, &ix->s_cnt, &ix->s_ahi, &ix->s_alo, &ix->s_lplan, &ix->s_scan, &ix->s_packed, &ix->s_qsplit, &ix->s_bstage})
         b->release();
     for (void *p : {(void *)ix->centroids, (void *)ix->cnorm, (void *)ix->cent_hi, (void *)ix->cent_lo, (void *)ix->d_tab, (void *)ix->d_maps, (void *)ix->list_len, (void *)ix->pt_off,
-                    (void *)ix->pt_off_alt, (void *)ix->pt, (void *)ix->pt_alt, (void *)ix->prof_rows})
+                    (void *)ix->pt_off_alt, (void *)ix->pt, (void *)ix->pt_alt, (void *)ix->prof_rows, (void *)ix->free_pages})
         if (p) cudaFree(p);
     if (ix->ev_done) cudaEventDestroy(ix->ev_done);
     if (ix->ev_fork) cudaEventDestroy(ix->ev_fork);
@@ -1109,6 +1114,8 @@ int sc_index_kmeans_update(sc_index_t *ix, const double *sums, const int32_t *co
     DeviceGuard g(ix->device);
     cudaStream_t st = (cudaStream_t)stream;
     SC(require_trained(ix));
+    if (ix->ntotal + ix->nremoved > 0)  // the lists were assigned under the current centroids (as kmeans_init / set_centroids refuse)
+        return fail(SC_ERR_STATE, "cannot move the centroids of a non-empty index (reset it first)");
     if (!is_device_ptr(sums, ix->device) || !is_device_ptr(counts, ix->device))
         return fail(SC_ERR_INVALID, "sums / counts must be device buffers");
     SC(begin_call(ix, st));
@@ -1417,6 +1424,59 @@ int sc_merge_topk(const float *part_dist, const int64_t *part_ids, int32_t parts
     return SC_OK;
 }
 
+// ---- compaction -------------------------------------------------------------------------------------
+// Squeeze the tombstoned slots out of every list in place and hand the emptied pages to the free list (the next
+// inserts take them before the pool grows).  Milvus compacts segments in the background [EXT]; here the host wrapper
+// calls this when nremoved / (ntotal + nremoved) passes its threshold.  Searches return the same rows before and after
+// (slot order inside a list is kept, so exact-tie order does not change either).
+int sc_index_compact(sc_index_t *ix, int64_t *pages_freed_out, void *stream) {
+    if (!ix) return fail(SC_ERR_INVALID, "idx is NULL");
+    if (pages_freed_out) *pages_freed_out = 0;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ix->nremoved == 0) return SC_OK;
+    CU(cudaDeviceSynchronize());  // no search may still be reading the lists we are about to rewrite
+    const int nlist = ix->nlist;
+    int32_t h_old = 0;
+    CU(cudaMemcpy(&h_old, ix->pt_off + nlist, 4, cudaMemcpyDeviceToHost));
+    // free list: room for every page that may come back, the current entries kept at the front
+    if (ix->nfree + h_old > ix->free_cap) {
+        const int32_t want = ix->nfree + h_old + 1024;
+        int32_t *nf = nullptr;
+        CU(cudaMalloc(&nf, (size_t)want * 4));
+        if (ix->nfree) CU(cudaMemcpy(nf, ix->free_pages, (size_t)ix->nfree * 4, cudaMemcpyDeviceToDevice));
+        if (ix->free_pages) cudaFree(ix->free_pages);
+        ix->free_pages = nf;
+        ix->free_cap = want;
+    }
+    if (h_old > ix->pt_alt_cap) {
+        if (ix->pt_alt) cudaFree(ix->pt_alt);
+        ix->pt_alt = nullptr;
+        ix->pt_alt_cap = 0;
+        CU(cudaMalloc(&ix->pt_alt, (size_t)std::max<int32_t>(h_old, 1024) * 4));
+        ix->pt_alt_cap = std::max<int32_t>(h_old, 1024);
+    }
+    CU(ix->s_npg.reserve((size_t)nlist * 4));
+    CU(ix->s_bad.reserve(16));
+    CU(launch_compact_lists(nlist, ix->list_len, ix->pt_off, ix->pt, ix->d_tab, ix->slab_shift, ix->ds, ix->num_sms, st));
+    CU(launch_pages_of_len(ix->list_len, nlist, ix->s_npg.as<int32_t>(), st));
+    CU(launch_exclusive_scan_i32(ix->s_npg.as<int32_t>(), nlist, ix->pt_off_alt, st));
+    CU(cudaMemcpyAsync(ix->s_bad.p, &ix->nfree, 4, cudaMemcpyHostToDevice, st));  // cursor starts behind the current entries
+    CU(launch_compact_pt(ix->pt_off, ix->pt, ix->pt_off_alt, ix->pt_alt, nlist, ix->free_pages, ix->s_bad.as<int32_t>(), st));
+    int32_t h_free = 0;
+    CU(cudaMemcpyAsync(&h_free, ix->s_bad.p, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    std::swap(ix->pt, ix->pt_alt);
+    std::swap(ix->pt_cap, ix->pt_alt_cap);
+    std::swap(ix->pt_off, ix->pt_off_alt);
+    if (pages_freed_out) *pages_freed_out = h_free - ix->nfree;
+    ix->nfree = h_free;
+    ix->nremoved = 0;
+    SC(sync_host_lengths(ix, st));
+    return SC_OK;
+}
+
 // ---- introspection ----------------------------------------------------------------------------------
 int sc_index_stats(sc_index_t *ix, sc_stats_t *out) {
     if (!ix || !out) return fail(SC_ERR_INVALID, "NULL argument");
@@ -1431,6 +1491,7 @@ int sc_index_stats(sc_index_t *ix, sc_stats_t *out) {
     out->ntotal = ix->ntotal;
     out->nremoved = ix->nremoved;
     out->npages = ix->pool_top;
+    out->nfree_pages = ix->nfree;
     const int64_t rows = ((int64_t)ix->slabs.size() << ix->slab_shift) * kPageRows;
     out->bytes_lists = rows * ((int64_t)ix->ds * 4 + 12);
     int64_t sb = 0;
@@ -1497,6 +1558,54 @@ int sc_index_export_list(sc_index_t *ix, int32_t list, int64_t cap, float *vecs,
     if (tags && !tdev) CU(cudaMemcpyAsync(tags, td, (size_t)len * 4, cudaMemcpyDeviceToHost, st));
     SC(end_call(ix, st));
     CU(cudaStreamSynchronize(st));
+    return SC_OK;
+}
+
+// lists [list_begin, list_end) back to back, slot order (tombstoned slots included: the caller reads the tags):
+// off_out [list_end - list_begin + 1] (host) = exclusive prefix of the slot counts; buffers host or device, nullable
+int sc_index_export_lists(sc_index_t *ix, int32_t list_begin, int32_t list_end, int64_t cap, float *vecs, int64_t *ids,
+                          uint32_t *tags, int64_t *off_out, void *stream) {
+    if (!ix) return fail(SC_ERR_INVALID, "idx is NULL");
+    if (list_begin < 0 || list_end > ix->nlist || list_begin > list_end)
+        return fail(SC_ERR_INVALID, "list range [%d, %d) outside [0, %d]", list_begin, list_end, ix->nlist);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int32_t nl = list_end - list_begin;
+    std::vector<int64_t> off((size_t)nl + 1, 0);
+    for (int32_t i = 0; i < nl; ++i) off[i + 1] = off[i] + ix->h_len[list_begin + i];
+    if (off_out) memcpy(off_out, off.data(), off.size() * 8);
+    const int64_t rows = off[nl];
+    if (rows == 0 || (!vecs && !ids && !tags)) return SC_OK;
+    if (cap < rows) return fail(SC_ERR_INVALID, "lists [%d, %d) hold %lld rows, buffers hold %lld", list_begin, list_end, (long long)rows, (long long)cap);
+    SC(begin_call(ix, st));
+    const bool vdev = vecs ? is_device_ptr(vecs, ix->device) : true;
+    const bool idev = ids ? is_device_ptr(ids, ix->device) : true;
+    const bool tdev = tags ? is_device_ptr(tags, ix->device) : true;
+    float *vd = vecs;
+    int64_t *idd = ids;
+    uint32_t *td = tags;
+    if (vecs && !vdev) {
+        CU(ix->s_x.reserve((size_t)rows * ix->dim * 4));
+        vd = ix->s_x.as<float>();
+    }
+    if (ids && !idev) {
+        CU(ix->s_ids.reserve((size_t)rows * 8));
+        idd = ix->s_ids.as<int64_t>();
+    }
+    if (tags && !tdev) {
+        CU(ix->s_repo.reserve((size_t)rows * 4));
+        td = ix->s_repo.as<uint32_t>();
+    }
+    CU(ix->s_rows.reserve(off.size() * 8));
+    CU(cudaMemcpyAsync(ix->s_rows.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, st));
+    CU(launch_export_range(ix->pt_off, ix->pt, list_begin, nl, ix->s_rows.as<int64_t>(), rows, ix->ds, ix->dim, ix->d_tab, ix->slab_shift,
+                           vd, idd, td, ix->num_sms, st));
+    if (vecs && !vdev) CU(cudaMemcpyAsync(vecs, vd, (size_t)rows * ix->dim * 4, cudaMemcpyDeviceToHost, st));
+    if (ids && !idev) CU(cudaMemcpyAsync(ids, idd, (size_t)rows * 8, cudaMemcpyDeviceToHost, st));
+    if (tags && !tdev) CU(cudaMemcpyAsync(tags, td, (size_t)rows * 4, cudaMemcpyDeviceToHost, st));
+    SC(end_call(ix, st));
+    CU(cudaStreamSynchronize(st));  // `off` dies at scope exit
     return SC_OK;
 }
 
@@ -1570,6 +1679,16 @@ int sc_index_set_param(sc_index_t *ix, const char *name, int64_t value) {
     if (strcmp(name, "plan_epoch") == 0) {  // tests: put the pair plan's launch counter next to its 22-bit wrap
         if (value < 0 || value >= (1 << 22)) return fail(SC_ERR_INVALID, "plan_epoch must be in [0, 2^22)");
         ix->plan_epoch = (uint32_t)value;
+        return SC_OK;
+    }
+    if (strcmp(name, "add_chunk_rows") == 0) {  // tests: rows per add chunk (0 = automatic)
+        if (value < 0) return fail(SC_ERR_INVALID, "add_chunk_rows must be >= 0");
+        ix->add_chunk_rows = value;
+        return SC_OK;
+    }
+    if (strcmp(name, "fail_add_after") == 0) {  // tests: the value-th add chunk from now fails after claiming its slots
+        if (value < 0 || value > INT32_MAX) return fail(SC_ERR_INVALID, "fail_add_after must be >= 0");
+        ix->fail_add_after = (int32_t)value;
         return SC_OK;
     }
     if (strcmp(name, "small_coarse") == 0) {

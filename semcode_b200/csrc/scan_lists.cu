@@ -501,8 +501,9 @@ cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int
         if ((e = cudaStreamWaitEvent(s32, p.ev_fork, 0)) != cudaSuccess) return e;
     }
     if (p.chunk == 64) {  // tcgen05 tiles (index.cu picked chunk = 64 only when the kernel applies)
-        // cfg 5: list rows as a tensor-memory operand (scan_lists_ts.cu)
-        if (cfg == 5 && a.slab_maps != nullptr && p.bstage != nullptr)
+        // default: list rows as a tensor-memory operand (scan_lists_ts.cu; index.cu hands over the staging area when
+        // it applies); cfg 5 / 3: the shared-memory-operand kernels (scan_lists_tc.cu v2 / v1)
+        if (p.bstage != nullptr && a.slab_maps != nullptr)
             e = launch_scan_lists_ts(a, p, num_sms, s32);
         else
             e = launch_scan_lists_tc(a, p, cfg == 3 ? 1 : 0, num_sms, s32);
@@ -516,7 +517,7 @@ cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int
     if ((e = launch_scan_mq(a, p, 1, cfg, p.pg8off, num_sms, st)) != cudaSuccess) return e;
     if ((e = launch_scan_mq(a, p, 0, cfg, p.pg4off, num_sms, st)) != cudaSuccess) return e;
     if (fork && (e = cudaStreamWaitEvent(st, p.ev_join[0], 0)) != cudaSuccess) return e;
-    if (launches) *launches += p.chunk == 64 ? 7 : 6;
+    if (launches) *launches += p.chunk == 64 && p.bstage == nullptr ? 7 : 6;  // the shared-memory-operand kernel splits the queries first
     return cudaSuccess;
 }
 

@@ -24,16 +24,16 @@
 // [B_hi ; B_lo] (N doubled), and per tile two accumulator sets by k-step parity ([hh | cross] each), summed by the
 // epilogue in fp32 -- the tensor core's truncating accumulation stays two short chains (see scan_lists_tc.cu, NACC).
 //
-// CTA = 20 warps, one per SM; every role walks the same contiguous range of (list, chunk, 128-row tile) units.  The
+// CTA = 16 warps, one per SM; every role walks the same contiguous range of (list, chunk, 128-row tile) units.  The
 // warp scheduler prefers the highest warp id of a sub-partition, so the roles on the critical path come last:
-//   warps 0-11  converters: warp w serves TMEM lane quarter w % 4 (= page w % 4 of the tile); three sets take the k-blocks
+//   warps 0-7   converters: warp w serves TMEM lane quarter w % 4 (= page w % 4 of the tile); two sets take the k-blocks
 //               round-robin, 4 TMEM operand slots of 64 columns (hi | lo); each warp also requests its own page boxes
-//               (TMA, 32 rows x 128 B, NR k-blocks ahead): the row stream has twelve issuers and no producer warp
-//   warps 12-15 epilogue: tcgen05.ld, fused tag predicate, coalesced candidate stores (same layout as the other scans)
-//   warp 16     query producer (one elected lane): per k-block one TMA box [2 N rows x 32 floats] from the staging slot
-//   warps 17-18 MMA issuers (one elected lane each): issuer p owns the k-blocks of parity p of every tile and ITS
+//               (TMA, 32 rows x 128 B, NR k-blocks ahead): the row stream has eight issuers and no producer warp
+//   warps 8-11  epilogue: tcgen05.ld, fused tag predicate, coalesced candidate stores (same layout as the other scans)
+//   warp 12     query producer (one elected lane): per k-block one TMA box [2 N rows x 32 floats] from the staging slot
+//   warps 13-14 MMA issuers (one elected lane each): issuer p owns the k-blocks of parity p of every tile and ITS
 //               accumulator set, so the order of the additions into every accumulator is fixed and results are reproducible
-//   warp 19     stager: gathers + splits the NEXT item's query rows into the other staging slot
+//   warp 15     stager: gathers + splits the NEXT item's query rows into the other staging slot
 // TMEM: columns [0, 256) accumulators (2 k-block parities x [hh | cross]; two buffers when N <= 32), [256, 512) four operand slots.
 // Replaces the same FAISS IVFFlatScanner::scan_codes loop (reference src/semcode/storage/milvus_store.py:141-147).
 // Bound: HBM (each list once per 64 queries).
@@ -51,7 +51,7 @@ using namespace tcu;
 
 constexpr int RAW_TILE = TM * TK * 4;       // 16 KB: four 4 KB boxes (one per page of the tile)
 constexpr int B_SLOT = 2 * TN * TK * 4;     // 16 KB: up to 64 hi rows + 64 lo rows
-constexpr int NSETS = 3;                    // converter sets (4 warps each), k-blocks dealt round-robin
+constexpr int NSETS = 2;                    // converter sets (4 warps each), k-blocks dealt round-robin
 constexpr int NR = 6;                       // raw stages (96 KB in flight per SM), a multiple of NSETS
 constexpr int NS = 4;                       // TMEM operand slots (hi | lo, 64 columns each)
 constexpr int NB = 6;                       // query ring slots
@@ -60,13 +60,17 @@ constexpr int ACC_COLS = 256;
 constexpr int A_SLOT_COLS = 64;
 constexpr int TMEM_COLS_TS = 512;
 constexpr int W_EPI = 4 * NSETS, W_QPROD = W_EPI + 4, W_ISSUE = W_QPROD + 1, W_STAGER = W_ISSUE + 2;  // first warp of each role
-constexpr int NT_TS = (W_STAGER + 1) * 32;  // 20 warps: <= 96 registers per thread
+constexpr int NSTAGERS = 1;
+constexpr int NT_TS = (W_STAGER + NSTAGERS) * 32;  // 16 warps: 128 registers per thread
 constexpr int SMEM_TS = NR * RAW_TILE + NB * B_SLOT + 1024 /*align*/ + 2048 /*barriers, tables*/;
 
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void *map, uint32_t bar, int c0, int c1) {
+// L2 policies of the two streams (the encodings CUTLASS passes as TMA cache hints): the list rows are read once, the
+// query tiles once per tile of the item
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull, kEvictLast = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void *map, uint32_t bar, int c0, int c1, uint64_t policy) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
         : "memory");
 }
 
@@ -150,7 +154,7 @@ __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const __grid_co
         for (int s = 0; s < 2; ++s) {
             mbar_init(accfull_bar(s), 2);
             mbar_init(accempty_bar(s), 4);
-            mbar_init(staged_bar(s), 1);
+            mbar_init(staged_bar(s), NSTAGERS);
             mbar_init(bfree_bar(s), 2);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -192,17 +196,21 @@ __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const __grid_co
                     const int slot = s % NB;
                     wait_done(s, NB, 0);
                     mbar_expect_tx(bready_bar(slot), (uint32_t)npad * 256u);
-                    tma_load_2d(smem_u32(ringB + slot * B_SLOT), bm, bready_bar(slot), kb * TK, row0);
+                    tma_load_2d(smem_u32(ringB + slot * B_SLOT), bm, bready_bar(slot), kb * TK, row0, kEvictLast);
                 }
             }
             pflush(0, 2);
         }
-    } else if (warp == W_STAGER) {
+    } else if (warp >= W_STAGER) {
         // ---------------- stager: the next item's query rows, split into tf32 terms, [hi rows ; lo rows] ----------------
-        // three rows in flight per pass (12 x 512 bytes per warp); the copy of an item runs one item ahead of its use
+        // 3 rows x 6 float4 per lane in flight per pass (9 KB per warp); the copy of an item runs one item ahead of its use.
+        // Loads and stores carry the L2 evict_last policy: the queries and the staging slots (~0.4 MB per CTA) are re-read for
+        // every tile of the item while ~100 MB of list rows stream through the L2 between two uses.
         const int ds4 = a.ds >> 2;
         float4 *slot_base = reinterpret_cast<float4 *>(p.bstage) + (size_t)blockIdx.x * 2 * (2 * TN) * ds4;
         const float4 *q4 = reinterpret_cast<const float4 *>(a.q);
+        uint64_t keep;
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
         int n = 0;
         UnitCursor cur;
         cur.start(a, p, u0, u1);
@@ -223,21 +231,24 @@ __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const __grid_co
                     const int32_t qi = __shfl_sync(0xffffffffu, j < 32 ? qa : qb, j & 31);
                     src[r] = q4 + (size_t)qi * ds4;
                 }
-                for (int c0 = 0; c0 < ds4; c0 += 128) {
-                    float4 v[3][4];
+                for (int c0 = 0; c0 < ds4; c0 += 192) {
+                    float4 v[3][6];
 #pragma unroll
                     for (int r = 0; r < 3; ++r)
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) {
+                        for (int t = 0; t < 6; ++t) {
                             const int c = c0 + t * 32 + lane;
-                            if (c < ds4) v[r][t] = __ldg(src[r] + c);
+                            if (c < ds4)
+                                asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                                             : "=f"(v[r][t].x), "=f"(v[r][t].y), "=f"(v[r][t].z), "=f"(v[r][t].w)
+                                             : "l"(src[r] + c), "l"(keep));
                         }
 #pragma unroll
                     for (int r = 0; r < 3; ++r) {
                         const int j = j0 + r;
                         if (j >= cur.nqi) break;
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) {
+                        for (int t = 0; t < 6; ++t) {
                             const int c = c0 + t * 32 + lane;
                             if (c < ds4) {
                                 float4 h, l;
@@ -249,8 +260,12 @@ __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const __grid_co
                                 l.y = to_tf32(v[r][t].y - h.y);
                                 l.z = to_tf32(v[r][t].z - h.z);
                                 l.w = to_tf32(v[r][t].w - h.w);
-                                hi_rows[(size_t)j * ds4 + c] = h;
-                                lo_rows[(size_t)j * ds4 + c] = l;
+                                asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(hi_rows + (size_t)j * ds4 + c),
+                                             "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w), "l"(keep)
+                                             : "memory");
+                                asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(lo_rows + (size_t)j * ds4 + c),
+                                             "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w), "l"(keep)
+                                             : "memory");
                             }
                         }
                     }
@@ -266,7 +281,7 @@ __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const __grid_co
                 cur.next_unit(a, p);
             } while (cur.valid && !cur.new_chunk);
         }
-        if (lane == 0) pflush(11, 1);
+        if (warp == W_STAGER && lane == 0) pflush(11, 1);
     } else if (warp >= W_ISSUE) {
         // ---------------- MMA issuers: issuer `par` multiplies the k-blocks of parity `par` of every tile (all four k-steps, all
         // three terms) into ITS accumulator set, so the order of the additions into every accumulator is fixed ----------------
@@ -342,7 +357,11 @@ __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const __grid_co
         int32_t l_unit = -1;
         const void *l_map = maps;
         int l_row = -1;
-        auto request = [&](int32_t s) {  // k-block s (this warp's set) into raw slot s % NR, quarter `quarter`
+        // `dep` is 0 at run time but computed from the words the caller has just read out of the slot: the copy's
+        // destination address depends on it, so the TMA instruction cannot be issued before those LDS have returned
+        // (ptxas is free to sink the arithmetic that consumes them below the copy otherwise -- seen as a few wrong rows per
+        // thousand queries)
+        auto request = [&](int32_t s, uint32_t dep) {  // k-block s (this warp's set) into raw slot s % NR, quarter `quarter`
             if (cl.u != l_unit) {        // new tile: where does its page `quarter` live?
                 l_unit = cl.u;
                 l_row = -1;
@@ -357,7 +376,7 @@ __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const __grid_co
                 const int rslot = s % NR;
                 if (l_row >= 0) {
                     mbar_expect_tx(rfull_bar(rslot), 4096u);
-                    tma_load_2d(smem_u32(ringR + rslot * RAW_TILE) + quarter * 4096, l_map, rfull_bar(rslot), kbl * TK, l_row);
+                    tma_load_2d(smem_u32(ringR + rslot * RAW_TILE) + quarter * 4096 + dep, l_map, rfull_bar(rslot), kbl * TK, l_row, kEvictFirst);
                 } else {
                     mbar_arrive(rfull_bar(rslot));  // the tile ends before this page: nothing to load
                 }
@@ -369,34 +388,37 @@ __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const __grid_co
             }
         };
         static_assert(NR % NSETS == 0, "the warp that converts k-block s refills its slot with k-block s + NR");
-        for (int32_t s = set; s < nstages && s < set + NR; s += NSETS) request(s);
+        const uint32_t rt_zero = (uint32_t)(p.nlist >> 31);  // 0, but not to the compiler
+        for (int32_t s = set; s < nstages && s < set + NR; s += NSETS) request(s, 0u);
         for (int32_t s = set; s < nstages; s += NSETS) {
             const int rslot = s % NR;
             const int slot = s % NS;
             const uint32_t ta = tmem_base + tq + (uint32_t)(ACC_COLS + slot * A_SLOT_COLS);
             pwait(rfull_bar(rslot), ((uint32_t)(s / NR)) & 1u, 0);
+            const uint32_t src = smem_u32(ringR + rslot * RAW_TILE) + lane_off;
+            uint32_t v[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(v[4 * c]), "=r"(v[4 * c + 1]), "=r"(v[4 * c + 2]), "=r"(v[4 * c + 3])
+                             : "r"(src + (((uint32_t)c ^ x7) << 4)));
+            // hi = the 19 bits the tensor core reads of x; lo = x - hi, exact in fp32 and at most 2^-10 |x| (the tensor core
+            // reads its upper 19 bits, so what is lost is below 2^-20 |x|): two ALU instructions per element on the
+            // sub-partition that owns the quarter
+            uint32_t h[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) h[i] = v[i] & 0xffffe000u;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) - __uint_as_float(h[i]));
+            // every word of the raw quarter has been consumed by an instruction (not merely loaded): refill the quarter now --
+            // the row stream must not wait for the MMAs -- then wait for the TMEM operand slot
+            __syncwarp();
+            if (s + NR < nstages)
+                request(s + NR, (v[0] | v[4] | v[8] | v[12] | v[16] | v[20] | v[24] | v[28]) & rt_zero);
             wait_done(s, NS, 1);
             tc_fence_after();
-            const uint32_t src = smem_u32(ringR + rslot * RAW_TILE) + lane_off;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {  // 16 columns at a time: 32 live registers
-                uint32_t v[16], h[16];
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
-                                 : "=r"(v[4 * c]), "=r"(v[4 * c + 1]), "=r"(v[4 * c + 2]), "=r"(v[4 * c + 3])
-                                 : "r"(src + (((uint32_t)(half * 4 + c) ^ x7) << 4)));
-#pragma unroll
-                for (int i = 0; i < 16; ++i) h[i] = v[i] & 0xffffe000u;
-                // lo = x - hi, exact in fp32 and at most 2^-10 |x|; the tensor core reads its upper 19 bits, so what is lost
-                // is below 2^-20 |x| -- two ALU instructions per element on the sub-partition that owns the quarter
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) - __uint_as_float(h[i]));
-                tmem_st16(ta + (uint32_t)(half * 16), h);
-                tmem_st16(ta + (uint32_t)(32 + half * 16), v);
-            }
-            __syncwarp();  // every lane has consumed its row: refill the quarter while the stores drain
-            if (s + NR < nstages) request(s + NR);
+            tmem_st32(ta, h);
+            tmem_st32(ta + 32u, v);
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
@@ -432,23 +454,30 @@ __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const __grid_co
             tc_fence_after();
             const uint32_t t0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + AccSched::col(m, 0);
             const uint32_t t1 = tmem_base + ((uint32_t)(quarter * 32) << 16) + AccSched::col(m, 1);
-#pragma unroll 1
-            for (int g = 0; g * 16 < I.nqi; ++g) {  // 16 queries at a time
-                uint32_t c0[16], h0[16], c1[16], h1[16];
-                tmem_ld16_nowait(t0 + (uint32_t)(npad + g * 16), c0);  // cross terms, even k-blocks
-                tmem_ld16_nowait(t0 + (uint32_t)(g * 16), h0);         // hi.hi, even k-blocks
-                if (KB > 1) {  // (a one-k-block tile never touches the odd set)
-                    tmem_ld16_nowait(t1 + (uint32_t)(npad + g * 16), c1);
-                    tmem_ld16_nowait(t1 + (uint32_t)(g * 16), h1);
-                }
-                tmem_wait_ld();
-                if (r < slots) {
+            // drain the accumulators into registers first (one row x up to 64 queries per thread) and hand them back to the
+            // issuers; the candidate stores that follow go to one region per query -- a TLB miss each, ~10k cycles per tile
+            float res[TN];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int jj = g * 16 + j;
-                        float v = __uint_as_float(c0[j]) + __uint_as_float(h0[j]);
-                        if (KB > 1) v += __uint_as_float(c1[j]) + __uint_as_float(h1[j]);
-                        if (jj < I.nqi) a.cand[cbE[jj] + r] = live ? v : -INFINITY;
+            for (int g = 0; g < TN / 16; ++g) {
+                if (g * 16 < I.nqi) {
+                    uint32_t t[16];
+                    tmem_ld16_nowait(t0 + (uint32_t)(npad + g * 16), t);  // cross terms, even k-blocks
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) res[g * 16 + j] = __uint_as_float(t[j]);
+                    tmem_ld16_nowait(t0 + (uint32_t)(g * 16), t);         // hi.hi, even k-blocks
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) res[g * 16 + j] += __uint_as_float(t[j]);
+                    if (KB > 1) {  // (a one-k-block tile never touches the odd set)
+                        tmem_ld16_nowait(t1 + (uint32_t)(npad + g * 16), t);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) res[g * 16 + j] += __uint_as_float(t[j]);
+                        tmem_ld16_nowait(t1 + (uint32_t)(g * 16), t);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) res[g * 16 + j] += __uint_as_float(t[j]);
                     }
                 }
             }
@@ -460,6 +489,11 @@ __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const __grid_co
                     if (lane == 0) mbar_arrive(accempty_bar(i));
                     acc.uses[i] += 1;
                 }
+            }
+            if (r < slots) {
+#pragma unroll
+                for (int jj = 0; jj < TN; ++jj)
+                    if (jj < I.nqi) a.cand[cbE[jj] + r] = live ? res[jj] : -INFINITY;
             }
         }
         if (warp == W_EPI && lane == 0) pflush(13, 1);
@@ -517,7 +551,7 @@ size_t scan_lists_ts_stage_bytes(int ds, int num_sms) { return (size_t)num_sms *
 
 cudaError_t launch_scan_lists_ts(const ScanArgs &a, const ListPlan &p, int num_sms, cudaStream_t st) {
     if (a.metric != 0 || (a.ds % TK) != 0 || p.chunk != TN || p.bstage == nullptr || a.slab_maps == nullptr) return cudaErrorNotSupported;
-    if (a.npairs * (int64_t)(a.ds / TK) >= ((int64_t)1 << 30)) return cudaErrorNotSupported;  // 32-bit k-block counters per CTA
+    if (a.npairs * (int64_t)(a.ds / TK) >= ((int64_t)1 << 30)) return cudaErrorNotSupported;  // 32-bit k-block counters per CTA (index.cu checks first)
     EncodeTiledFn fn = encode_fn_ts();
     if (!fn) return cudaErrorNotSupported;
     BMaps bm;

@@ -399,9 +399,47 @@ class IVFFlatIndex:
         )
         return vec, ids, tags
 
+    def export_lists(self, list_begin: int, list_end: int, device: bool = False):
+        """Lists [list_begin, list_end) back to back in slot order, ONE call (sc_index_export_lists):
+        (off [n + 1] int64, vecs [rows, dim], ids [rows], tags [rows]) as numpy arrays, or CUDA tensors with
+        ``device=True`` (tags as int32 bits).  Tombstoned slots are included (tag bit 31)."""
+        n = int(list_end) - int(list_begin)
+        off = np.zeros(n + 1, dtype=np.int64)
+        _capi.check(self._L.sc_index_export_lists(self._h, int(list_begin), int(list_end), 0, None, None, None,
+                                                  _capi.ptr(off, "i64"), self._stream()))
+        rows = int(off[-1])
+        if device:
+            dev = self._dev()
+            vecs = torch.empty((rows, self.dim), dtype=torch.float32, device=dev)
+            ids = torch.empty(rows, dtype=torch.int64, device=dev)
+            tags = torch.empty(rows, dtype=torch.int32, device=dev)
+        else:
+            vecs = np.empty((rows, self.dim), dtype=np.float32)
+            ids = np.empty(rows, dtype=np.int64)
+            tags = np.empty(rows, dtype=np.uint32)
+        if rows:
+            _capi.check(self._L.sc_index_export_lists(self._h, int(list_begin), int(list_end), rows, _capi.ptr(vecs, "f32"),
+                                                      _capi.ptr(ids, "i64"), _capi.ptr(tags, "u32"), None, self._stream()))
+        return off, vecs, ids, tags
+
+    def list_ranges(self, max_bytes: int = 512 << 20):
+        """Consecutive list ranges of at most ~max_bytes of vectors each (bulk export / re-insert in bounded steps)."""
+        sizes = self.list_sizes().astype(np.int64)
+        per_row = self.dim * 4 + 12
+        out, lo, acc = [], 0, 0
+        for l in range(self.nlist):
+            b = int(sizes[l]) * per_row
+            if acc and acc + b > max_bytes:
+                out.append((lo, l))
+                lo, acc = l, 0
+            acc += b
+        out.append((lo, self.nlist))
+        return out
+
     def export_csr(self, live_only: bool = True):
         """Whole index as CSR on the host: (list_off [nlist+1], vecs [n,dim], ids [n], tags [n]).
-        Used by persistence and to hand the same lists to the CPU baseline."""
+        Used by persistence and to hand the same lists to the CPU baseline.  A few bulk calls
+        (sc_index_export_lists over ~512 MB ranges), not one call per list."""
         sizes = self.list_sizes().astype(np.int64)
         total = int(sizes.sum())
         vecs = np.empty((total, self.dim), dtype=np.float32)
@@ -409,17 +447,14 @@ class IVFFlatIndex:
         tags = np.empty(total, dtype=np.uint32)
         off = np.zeros(self.nlist + 1, dtype=np.int64)
         np.cumsum(sizes, out=off[1:])
-        ln = C.c_int64(0)
         st = self._stream()
-        for l in range(self.nlist):
-            n = int(sizes[l])
-            if n == 0:
+        for lo, hi in self.list_ranges():
+            a, b = int(off[lo]), int(off[hi])
+            if b == a:
                 continue
-            lo = int(off[l])
             _capi.check(
-                self._L.sc_index_export_list(
-                    self._h, l, n, vecs[lo:].ctypes.data, ids[lo:].ctypes.data, tags[lo:].ctypes.data,
-                    C.addressof(ln), st,
+                self._L.sc_index_export_lists(
+                    self._h, lo, hi, b - a, vecs[a:b].ctypes.data, ids[a:b].ctypes.data, tags[a:b].ctypes.data, None, st,
                 )
             )
         if live_only and total:
@@ -431,6 +466,12 @@ class IVFFlatIndex:
                 off = np.zeros(self.nlist + 1, dtype=np.int64)
                 np.cumsum(new_sizes, out=off[1:])
         return off, vecs, ids, tags
+
+    def compact(self) -> int:
+        """Drop the tombstoned slots of every list in place (sc_index_compact); returns the pages freed."""
+        out = C.c_int64(0)
+        _capi.check(self._L.sc_index_compact(self._h, C.addressof(out), self._stream()))
+        return int(out.value)
 
     # -- persistence ----------------------------------------------------------------------------------
     def save(self, path: str) -> None:

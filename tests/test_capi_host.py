@@ -21,8 +21,8 @@ def test_header_symbols_are_exported(native_lib):
     assert declared == set(_capi.SYMBOLS), declared ^ set(_capi.SYMBOLS)
     for name in declared:
         assert hasattr(native_lib, name), f"{name} is declared in the header but not exported"
-    assert native_lib.sc_abi_version() == 2
-    assert re.search(r"#define SC_ABI_VERSION 2\b", hdr)
+    assert native_lib.sc_abi_version() == 3
+    assert re.search(r"#define SC_ABI_VERSION 3\b", hdr)
 
 
 def test_struct_layouts_match_header():
@@ -31,7 +31,7 @@ def test_struct_layouts_match_header():
     from semcode_b200 import _capi
 
     assert C.sizeof(_capi.ScFilter) == 32
-    assert C.sizeof(_capi.ScStats) == 6 * 4 + 5 * 8 + 2 * 4
+    assert C.sizeof(_capi.ScStats) == 6 * 4 + 6 * 8 + 2 * 4
     assert C.sizeof(_capi.ScSearchTimes) == 6 * 4 + 2 * 8 + 2 * 4
 
 

@@ -670,7 +670,7 @@ def test_tensor_core_tiles_match_ffma_tiles_and_oracle(sb, orc, d, nlist, nq, np
         g.set_param("scan_mode", 1)
         d1, i1 = g.search(q, k, lists=probes, langs=langs)
         assert_topk_parity(d1, i1, rd, ri, f"query-major d={d} langs={langs}")
-        for cfg in (0, 1, 5):  # 5: list rows as a tensor-memory operand (scan_lists_ts.cu)
+        for cfg in (0, 1, 5):  # 0: list rows as a tensor-memory operand (scan_lists_ts.cu), 5: both operands in shared memory
             g.set_param("scan_mode", 2)
             g.set_param("lists_cfg", cfg)
             d2, i2 = g.search(q, k, lists=probes, langs=langs)
@@ -780,3 +780,113 @@ def test_small_batch_path(sb, orc, metric, d, nq):
         assert_topk_parity(gd2, gi2, rd, ri, "all rows carry repo tag 0")
         gd3, gi3 = g.search(q, 10, lists=probes, repos=[7])
         assert (gi3 == -1).all()
+
+
+# ---- failure atomicity of inserts, tag validation ---------------------------------------------------
+def test_failed_add_chunk_leaves_a_consistent_index(sb, orc):
+    """A multi-chunk add whose third chunk fails AFTER its slots were claimed: chunks 1-2 stay committed, the list
+    lengths of the failed chunk are rolled back on the device and the host mirror follows, so the next search sizes its
+    scratch from the truth; later inserts work.  Same for a bad list id and an oversize repo tag in a later chunk."""
+    n, d, nlist = 6000, 64, 8
+    x, q, cent, ids = make_case(orc, n, d, nlist, 40, "IP", seed=3)
+    assign = orc.assign(x, cent, "IP")
+    g = sb.IVFFlatIndex(d, nlist=nlist, metric="IP")
+    g.set_centroids(cent)
+    g.set_param("add_chunk_rows", 1500)
+    g.set_param("fail_add_after", 3)
+    with pytest.raises(sb.NativeError, match="injected"):
+        g.add(x, ids, lists=assign)
+    assert g.ntotal == 3000
+    np.testing.assert_array_equal(g.list_sizes(), np.bincount(assign[:3000], minlength=nlist))
+    oidx = orc.build_index(x[:3000], ids[:3000], cent, "IP", assignment=assign[:3000])
+    rd, ri = orc.search(oidx, q, 10, 3)
+    for mode in (1, 2):
+        g.set_param("scan_mode", mode)
+        gd, gi = g.search(q, 10, nprobe=3)
+        assert_topk_parity(gd, gi, rd, ri, f"after a failed chunk, mode {mode}")
+    bad = assign[3000:].copy()
+    bad[1600] = 99  # second chunk of this call
+    with pytest.raises(sb.NativeError, match="list id outside"):
+        g.add(x[3000:], ids[3000:], lists=bad)
+    assert g.ntotal == 4500
+    np.testing.assert_array_equal(g.list_sizes(), np.bincount(assign[:4500], minlength=nlist))
+    tags = np.zeros(1500, dtype=np.uint32)
+    tags[7] = 1 << 23  # does not fit the 23-bit repo field: must be refused, not aliased to repo 0
+    with pytest.raises(sb.NativeError, match="repo tag"):
+        g.add(x[4500:], ids[4500:], repo_tags=tags, lists=assign[4500:])
+    assert g.ntotal == 4500
+    g.add(x[4500:], ids[4500:], lists=assign[4500:])
+    oidx = orc.build_index(x, ids, cent, "IP", assignment=assign)
+    rd, ri = orc.search(oidx, q, 10, 3)
+    for mode in (1, 2):
+        g.set_param("scan_mode", mode)
+        gd, gi = g.search(q, 10, nprobe=3)
+        assert_topk_parity(gd, gi, rd, ri, f"after the retries, mode {mode}")
+    sums, counts, obj = g.kmeans_buffers()
+    with pytest.raises(sb.NativeError, match="non-empty"):
+        g.kmeans_update(sums, counts)  # would re-centre lists that were assigned under the old centroids
+
+
+# ---- compaction (SURVEY 8f rank 2) + bulk export ----------------------------------------------------------------
+@pytest.mark.parametrize("metric", ["IP", "L2"])
+def test_compaction_keeps_results_and_recycles_pages(sb, orc, metric):
+    rng = np.random.default_rng(17)
+    n, d, nlist, nq = 20000, 96, 12, 60
+    x, q, cent, ids = make_case(orc, n, d, nlist, nq, metric, seed=11)
+    repo = rng.integers(0, 5, n).astype(np.uint32)
+    lang = rng.integers(0, 3, n).astype(np.uint8)
+    g, oidx, assign = build_pair(sb, orc, x, ids, cent, metric, repo, lang)
+    gone = rng.random(n) < 0.4
+    gone[assign == 3] = True  # one list loses every row
+    assert g.remove_ids(ids[gone]) == int(gone.sum())
+    before = {}
+    for mode in (1, 2):
+        g.set_param("scan_mode", mode)
+        before[mode] = (g.search(q, 10, nprobe=5), g.search(q, 10, nprobe=5, repos=[1, 3], langs=[0, 2]))
+    pages0 = g.stats().npages
+    freed = g.compact()
+    st = g.stats()
+    assert freed > 0 and st.nfree_pages == freed and st.nremoved == 0 and st.ntotal == n - int(gone.sum()) and st.npages == pages0
+    np.testing.assert_array_equal(g.list_sizes(), np.bincount(assign[~gone], minlength=nlist))
+    live = orc.build_index(x[~gone], ids[~gone], cent, metric, repo[~gone], lang[~gone], assignment=assign[~gone])
+    rd, ri = orc.search(live, q, 10, 5)
+    fd, fi = orc.search(live, q, 10, 5, mask=orc.row_mask(live, repos=[1, 3], langs=[0, 2]))
+    for mode in (1, 2):
+        g.set_param("scan_mode", mode)
+        (d0, i0), (d1, i1) = g.search(q, 10, nprobe=5), g.search(q, 10, nprobe=5, repos=[1, 3], langs=[0, 2])
+        np.testing.assert_array_equal(i0, before[mode][0][1])  # slot order inside a list is kept: even ties stay put
+        np.testing.assert_array_equal(d0, before[mode][0][0])
+        np.testing.assert_array_equal(i1, before[mode][1][1])
+        assert_topk_parity(d0, i0, rd, ri, f"compacted vs oracle rebuilt from the live rows, mode {mode} {metric}")
+        assert_topk_parity(d1, i1, fd, fi, f"compacted + filter vs oracle, mode {mode} {metric}")
+    assert g.compact() == 0  # nothing left to drop
+    # new rows take the freed pages before the pool grows
+    m = 3000
+    xn = unit_rows(rng, m, d)
+    idn = np.arange(m, dtype=np.int64) + 10**7
+    an = orc.assign(xn, cent, metric)
+    g.add(xn, idn, repo[:m], lang[:m], lists=an)
+    st2 = g.stats()
+    assert st2.npages == pages0 and st2.nfree_pages < freed and st2.ntotal == st.ntotal + m
+    both = orc.build_index(np.concatenate([x[~gone], xn]), np.concatenate([ids[~gone], idn]), cent, metric,
+                           np.concatenate([repo[~gone], repo[:m]]), np.concatenate([lang[~gone], lang[:m]]),
+                           assignment=np.concatenate([assign[~gone], an]))
+    rd, ri = orc.search(both, q, 10, 5)
+    for mode in (1, 2):
+        g.set_param("scan_mode", mode)
+        d0, i0 = g.search(q, 10, nprobe=5)
+        assert_topk_parity(d0, i0, rd, ri, f"after re-filling the freed pages, mode {mode} {metric}")
+    # bulk export == per-list export, host and device
+    off, vecs, eids, tags = g.export_lists(2, 9)
+    _, dv, di, dt = g.export_lists(2, 9, device=True)
+    np.testing.assert_array_equal(dv.cpu().numpy(), vecs)
+    np.testing.assert_array_equal(di.cpu().numpy(), eids)
+    np.testing.assert_array_equal(dt.cpu().numpy().view(np.uint32), tags)
+    for l in range(2, 9):
+        v1, i1, t1 = g.export_list(l)
+        a, b = int(off[l - 2]), int(off[l - 1])
+        np.testing.assert_array_equal(vecs[a:b], v1)
+        np.testing.assert_array_equal(eids[a:b], i1)
+        np.testing.assert_array_equal(tags[a:b], t1)
+    coff, cv, ci, ct = g.export_csr()
+    assert coff[-1] == st2.ntotal and set(ci.tolist()) == set(ids[~gone].tolist()) | set(idn.tolist())
