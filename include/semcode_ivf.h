@@ -169,6 +169,12 @@ int sc_exchange_destroy(sc_exchange_t *ex);
 /* timed_out (host, nullable): 1 when a wait for a peer gave up (results of that step are invalid);
  * epoch (host, nullable): number of exchange steps issued.  Synchronises the device. */
 int sc_exchange_status(sc_exchange_t *ex, int32_t *timed_out, int64_t *epoch);
+/* the same flag WITHOUT synchronising (a pinned host word the waiting kernel stores to): 1 once a finished step of this
+ * rank gave up waiting for a peer, or a step failed after its epoch had moved.  sc_index_search_sharded refuses to run
+ * on such an exchange (SC_ERR_STATE): destroy it on every rank, barrier, create a new one. */
+int sc_exchange_poll(sc_exchange_t *ex, int32_t *timed_out);
+/* how long the waiting kernels spin for a peer before giving up (default 10 s) */
+int sc_exchange_set_timeout_ms(sc_exchange_t *ex, int64_t ms);
 /* One search step of a row-sharded index: `idx` holds this rank's rows, every rank passes the same queries.
  * lists == NULL: the coarse pass is split over the ranks (rank r ranks the centroids for its 1/world of the
  * batch and STORES the probe rows into every peer's table); the top-k epilogue STORES this rank's partial

@@ -34,7 +34,8 @@ SYMBOLS = [
     "sc_merge_topk", "sc_index_stats", "sc_index_list_sizes", "sc_index_export_list", "sc_index_export_lists",
     "sc_index_compact", "sc_index_set_profiling",
     "sc_index_last_search_times", "sc_index_set_param",
-    "sc_exchange_create", "sc_exchange_destroy", "sc_exchange_status", "sc_index_search_sharded",
+    "sc_exchange_create", "sc_exchange_destroy", "sc_exchange_status", "sc_exchange_poll", "sc_exchange_set_timeout_ms",
+    "sc_index_search_sharded",
 ]
 
 
@@ -121,6 +122,8 @@ def lib():
         "sc_exchange_create": [i32, i32, C.POINTER(vp), i64, i32, C.POINTER(vp)],
         "sc_exchange_destroy": [vp],
         "sc_exchange_status": [vp, C.POINTER(i32), C.POINTER(i64)],
+        "sc_exchange_poll": [vp, C.POINTER(i32)],
+        "sc_exchange_set_timeout_ms": [vp, i64],
         "sc_index_search_sharded": [vp, vp, vp, i64, i32, i32, vp, C.POINTER(ScFilter), vp, vp, vp],
     }
     for name, args in sig.items():

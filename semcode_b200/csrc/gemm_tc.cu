@@ -53,6 +53,21 @@ struct TcArgs {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of the (converged) warp.  Unlike `lane == 0`, ptxas knows that exactly one thread runs the guarded region,
+// so every tcgen05.mma / TMA instruction in it takes its operands with plain R2UR moves; under `lane == 0` each one is
+// wrapped in an ELECT / R2UR.BROADCAST / branch loop (~100 cycles per MMA -- as long as a 128x256x8 tf32 MMA runs).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -184,7 +199,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
     const int kblocks = (a.K + BK - 1) / BK;
 
     if (warp == 0) {
-        if (lane == 0) {  // ---- TMA producer ----
+        if (elect_one()) {  // ---- TMA producer ----
             int stage = 0;
             uint32_t phase = 0;
             int mt, nt;
@@ -205,7 +220,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {  // ---- MMA issuer ----
+        if (elect_one()) {  // ---- MMA issuer ----
             constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
@@ -398,7 +413,7 @@ gemm_tc256_argmax_kernel(const __grid_constant__ CUtensorMap map_ahi, const __gr
     };
 
     if (warp == 0) {
-        if (lane == 0) {  // ---- TMA producer ----
+        if (elect_one()) {  // ---- TMA producer ----
             int stage = 0;
             uint32_t phase = 0;
             int mt, nt;
@@ -419,7 +434,7 @@ gemm_tc256_argmax_kernel(const __grid_constant__ CUtensorMap map_ahi, const __gr
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {  // ---- MMA issuer ----
+        if (elect_one()) {  // ---- MMA issuer ----
             constexpr uint32_t idesc = umma_idesc_tf32(128, BN2);
             int stage = 0;
             uint32_t phase = 0, acc_phase = 0;

@@ -213,8 +213,11 @@ struct sc_exchange {
     char *peer[kMaxPeers] = {nullptr};
     size_t bytes = 0;
     unsigned long long epoch = 0;
-    unsigned int *done = nullptr;    // [2] CTA counters (probe select, top-k select)
-    unsigned int *status = nullptr;  // [1] 1 = a wait timed out
+    unsigned int *done = nullptr;      // [2] CTA counters (probe select, top-k select)
+    unsigned int *status = nullptr;    // device view of h_status
+    unsigned int *h_status = nullptr;  // [1] pinned, mapped: 1 = a wait timed out (the waiting kernel stores it; the host
+                                       //     reads it without synchronising anything)
+    bool broken = false;               // a step failed after its epoch moved: ranks no longer agree
     unsigned long long timeout_ns = 10ull * 1000 * 1000 * 1000;
 };
 constexpr size_t kExHeader = 4096;
@@ -683,8 +686,6 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
         if (exl.end > ex->bytes)  // depends on (nq, nprobe, k, world) only: every rank fails alike, before the epoch moves
             return fail(SC_ERR_INVALID, "exchange buffer of %zu bytes is too small for nq=%lld nprobe=%d k=%d world=%d",
                         ex->bytes, (long long)nq, np, k, ex->world);
-        ex->epoch += 1;  // every rank makes the same calls, so the epochs agree
-        exl = exchange_layout(ex, nq, np, k);
     }
     if (nqc >= nq) {
         nqc = nq;  // one pass
@@ -710,6 +711,13 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
     CU(ix->s_cand.reserve((size_t)nqc * pb * kPageRows * 4));
     if (!outd_dev) CU(ix->s_outd.reserve((size_t)nqc * k * 4));
     if (!outi_dev) CU(ix->s_outi.reserve((size_t)nqc * k * 8));
+    if (ex) {
+        // The step's epoch moves only now, after the large scratch reservations: a rank that fails above (out of memory)
+        // has not published anything and its peers time out cleanly.  A failure further down leaves this rank's epoch ahead
+        // of what it published: sc_index_search_sharded marks the exchange broken so that the next call fails loudly.
+        ex->epoch += 1;  // every rank makes the same calls, so the epochs agree
+        exl = exchange_layout(ex, nq, np, k);
+    }
 
     for (int64_t s = 0; s < nq; s += nqc) {
         const int64_t m = std::min(nqc, nq - s);
@@ -1372,13 +1380,19 @@ int sc_exchange_create(int32_t rank, int32_t world, const void *const *peer_buff
     unsigned int *w = nullptr;
     cudaError_t e = cudaMalloc(&w, 16);
     if (e == cudaSuccess) e = cudaMemset(w, 0, 16);
+    if (e == cudaSuccess) e = cudaHostAlloc(&ex->h_status, 64, cudaHostAllocMapped | cudaHostAllocPortable);
+    if (e == cudaSuccess) {
+        *ex->h_status = 0;
+        e = cudaHostGetDevicePointer(&ex->status, ex->h_status, 0);
+    }
     if (e != cudaSuccess) {
         cudaGetLastError();
+        if (w) cudaFree(w);
+        if (ex->h_status) cudaFreeHost(ex->h_status);
         delete ex;
         return fail(SC_ERR_CUDA, "exchange counters: %s", cudaGetErrorString(e));
     }
     ex->done = w;
-    ex->status = w + 2;
     *out = ex;
     return SC_OK;
 }
@@ -1387,6 +1401,7 @@ int sc_exchange_destroy(sc_exchange_t *ex) {
     if (!ex) return SC_OK;
     DeviceGuard g(ex->device);
     if (ex->done) cudaFree(ex->done);
+    if (ex->h_status) cudaFreeHost(ex->h_status);
     delete ex;
     return SC_OK;
 }
@@ -1394,10 +1409,24 @@ int sc_exchange_destroy(sc_exchange_t *ex) {
 int sc_exchange_status(sc_exchange_t *ex, int32_t *timed_out, int64_t *epoch) {
     if (!ex) return fail(SC_ERR_INVALID, "exchange is NULL");
     DeviceGuard g(ex->device);
-    unsigned int st = 0;
-    CU(cudaMemcpy(&st, ex->status, 4, cudaMemcpyDeviceToHost));  // synchronises the device's prior work
-    if (timed_out) *timed_out = (int32_t)st;
+    CU(cudaDeviceSynchronize());  // every step issued so far has finished: the word is final
+    if (timed_out) *timed_out = (*(volatile unsigned int *)ex->h_status != 0 || ex->broken) ? 1 : 0;
     if (epoch) *epoch = (int64_t)ex->epoch;
+    return SC_OK;
+}
+
+// the same word WITHOUT synchronising: 1 as soon as a finished step of this rank gave up waiting for a peer (or a step
+// failed midway).  Cheap enough to call before every step.
+int sc_exchange_poll(sc_exchange_t *ex, int32_t *timed_out) {
+    if (!ex || !timed_out) return fail(SC_ERR_INVALID, "NULL argument");
+    *timed_out = (*(volatile unsigned int *)ex->h_status != 0 || ex->broken) ? 1 : 0;
+    return SC_OK;
+}
+
+int sc_exchange_set_timeout_ms(sc_exchange_t *ex, int64_t ms) {
+    if (!ex) return fail(SC_ERR_INVALID, "exchange is NULL");
+    if (ms < 1) return fail(SC_ERR_INVALID, "timeout must be >= 1 ms");
+    ex->timeout_ns = (unsigned long long)ms * 1000000ull;
     return SC_OK;
 }
 
@@ -1407,7 +1436,14 @@ int sc_index_search_sharded(sc_index_t *ix, sc_exchange_t *ex, const float *q, i
     if (!ex) return fail(SC_ERR_INVALID, "exchange is NULL");
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
-    return search_impl(ix, q, nq, k, nprobe, lists, filter, out_dist, out_ids, (cudaStream_t)stream, ex);
+    if (ex->broken || *(volatile unsigned int *)ex->h_status != 0)
+        return fail(SC_ERR_STATE, "the exchange is unusable: %s.  Results since then are invalid; destroy the exchange on every "
+                                  "rank, barrier, and create a new one", ex->broken ? "an earlier step failed midway on this rank"
+                                                                                    : "a peer did not arrive within the timeout");
+    const unsigned long long epoch0 = ex->epoch;
+    const int rc = search_impl(ix, q, nq, k, nprobe, lists, filter, out_dist, out_ids, (cudaStream_t)stream, ex);
+    if (rc != SC_OK && ex->epoch != epoch0) ex->broken = true;  // this rank's epoch is ahead of what it published
+    return rc;
 }
 
 int sc_merge_topk(const float *part_dist, const int64_t *part_ids, int32_t parts, int64_t nq, int32_t kin, int32_t k,

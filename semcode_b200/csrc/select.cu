@@ -79,7 +79,7 @@ __device__ __forceinline__ void peer_wait(const PeerWait &w) {
         const unsigned long long t0 = global_timer_ns();
         while (ld_acquire_sys_u64(w.flags + threadIdx.x) < w.epoch) {
             if (global_timer_ns() - t0 > w.timeout_ns) {
-                atomicExch(w.status, 1u);
+                *(volatile unsigned int *)w.status = 1u;  // pinned host word (zero-copy): the host polls it without a sync
                 break;
             }
             __nanosleep(64);

@@ -512,6 +512,9 @@ class IVFFlatIndex:
         vecs = np.load(os.path.join(path, "vecs.npy"), mmap_mode="r")
         ids = np.load(os.path.join(path, "ids.npy"), mmap_mode="r")
         tags = np.load(os.path.join(path, "tags.npy"), mmap_mode="r")
+        if not (int(off[-1]) == vecs.shape[0] == ids.shape[0] == tags.shape[0] == int(meta["ntotal"])) or off.shape[0] != meta["nlist"] + 1:
+            raise ValueError(f"snapshot {path!r} is inconsistent: list_off ends at {int(off[-1])}, vecs {vecs.shape[0]}, "
+                             f"ids {ids.shape[0]}, tags {tags.shape[0]}, meta {meta['ntotal']}")
         lists = np.repeat(np.arange(meta["nlist"], dtype=np.int32), np.diff(off))
         for s in range(0, int(off[-1]), chunk_rows):
             e = min(int(off[-1]), s + chunk_rows)
@@ -572,6 +575,15 @@ class PeerExchange:
         t, e = C.c_int32(0), C.c_int64(0)
         _capi.check(_capi.lib().sc_exchange_status(self.handle, C.byref(t), C.byref(e)))
         return bool(t.value), int(e.value)
+
+    def poll(self) -> bool:
+        """True once a finished step gave up waiting for a peer (or failed midway); does NOT synchronise."""
+        t = C.c_int32(0)
+        _capi.check(_capi.lib().sc_exchange_poll(self.handle, C.byref(t)))
+        return bool(t.value)
+
+    def set_timeout_ms(self, ms: int) -> None:
+        _capi.check(_capi.lib().sc_exchange_set_timeout_ms(self.handle, int(ms)))
 
     def close(self) -> None:
         if getattr(self, "handle", None):

@@ -152,6 +152,12 @@ class ShardedIVFFlat:
         """The caller has already partitioned the rows (ids must be globally unique)."""
         self.local.add(x_local, ids_local, repo_tags, lang_tags)
 
+    def check_exchange(self) -> None:
+        """Synchronise and raise if any fused step issued so far timed out waiting for a peer."""
+        if self.exchange is not None and self.exchange.status()[0]:
+            raise RuntimeError("sharded search: a peer did not arrive within the exchange timeout; the results of that step "
+                               "and the ones after it are invalid -- rebuild the exchange after a barrier")
+
     @property
     def ntotal(self) -> int:
         t = torch.tensor([self.local.ntotal], dtype=torch.int64, device=self.local.tensor_device())
@@ -183,6 +189,11 @@ class ShardedIVFFlat:
         if self.world == 1:
             return self.local.search(q, k, nprobe=nprobe, repos=repos, langs=langs)
         if self.exchange is not None and self.shard_by == "rows" and q.shape[0] >= 1:
+            # A step whose merge gave up waiting for a peer returned garbage, and the late peer now writes into buffers
+            # of later steps: never continue silently.  (The C ABI refuses as well; this gives the Python-level reason.)
+            if self.exchange.poll():
+                raise RuntimeError("sharded search: a peer did not arrive within the exchange timeout (or a step failed "
+                                   "midway); results since then are invalid -- rebuild the exchange after a barrier")
             # fused steps of at most 8192 queries: split coarse pass, probe rows and partial top-k stored into the
             # peers' buffers by the kernels that produce them, merge kernel waiting on the peers' flags
             np_ = min(int(nprobe), self.nlist)

@@ -27,9 +27,14 @@ languages on search(); search_batch(); search_arrays(); upsert_arrays(); build_i
 
 from __future__ import annotations
 
+import atexit
 import json
 import os
+import shutil
 import threading
+import time
+import weakref
+from contextlib import contextmanager
 from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence
 
 import numpy as np
@@ -162,6 +167,77 @@ class SearchResult(list):
     """list of Hits, one per query vector (pymilvus SearchResult shape)."""
 
 
+def _merge_parts(parts, top_k: int, metric: int, device: int):
+    """Reduce the partial results of the sealed index and the growing segment ([(dist, ids), ...], each [nq, k]) on the
+    device (sc_merge_topk): what the Milvus proxy does across segments [EXT].  numpy in -> numpy out."""
+    (d0, i0), (d1, i1) = parts
+    if isinstance(d0, np.ndarray):
+        dev = torch.device("cuda", device)
+        pd = torch.stack([torch.from_numpy(d0), torch.from_numpy(d1)]).to(dev)
+        pi = torch.stack([torch.from_numpy(i0), torch.from_numpy(i1)]).to(dev)
+        d, i = merge_topk(pd, pi, top_k, metric, device)
+        return d.cpu().numpy(), i.cpu().numpy()
+    return merge_topk(torch.stack([d0, d1]), torch.stack([i0, i1]), top_k, metric, device)
+
+
+class _RWLock:
+    """Many searches or one writer (FastAPI serves /query from a thread pool, api/main.py:202, next to
+    BackgroundTasks ingestion, api/main.py:160).  Writers are preferred so that a stream of queries cannot starve an
+    upsert; re-entrant for the thread that holds the write side (seal -> build_index -> add)."""
+
+    def __init__(self):
+        self._cv = threading.Condition(threading.Lock())
+        self._readers = 0
+        self._writer = None
+        self._depth = 0
+        self._waiting_writers = 0
+
+    @contextmanager
+    def read(self):
+        me = threading.get_ident()
+        with self._cv:
+            if self._writer == me:  # the writer may read its own state
+                self._depth += 1
+                nested = True
+            else:
+                nested = False
+                while self._writer is not None or self._waiting_writers:
+                    self._cv.wait()
+                self._readers += 1
+        try:
+            yield
+        finally:
+            with self._cv:
+                if nested:
+                    self._depth -= 1
+                else:
+                    self._readers -= 1
+                    if self._readers == 0:
+                        self._cv.notify_all()
+
+    @contextmanager
+    def write(self):
+        me = threading.get_ident()
+        with self._cv:
+            if self._writer == me:
+                self._depth += 1
+            else:
+                self._waiting_writers += 1
+                while self._writer is not None or self._readers:
+                    self._cv.wait()
+                self._waiting_writers -= 1
+                self._writer = me
+                self._depth = 1
+        try:
+            yield
+        finally:
+            with self._cv:
+                self._depth -= 1
+                if self._depth == 0:
+                    self._writer = None
+                    self._cv.notify_all()
+
+
 # --------------------------------------------------------------------------------------------------
 # the in-process collection
 # --------------------------------------------------------------------------------------------------
@@ -169,16 +245,24 @@ class GpuCollection:
     """What `Collection(name)` is to the reference wrapper: schema + index + rows."""
 
     def __init__(self, name: str, dim: int, nlist: int = 128, metric: str = "IP", device: int = 0,
-                 seal_rows: Optional[int] = None, train_niter: int = 25):
+                 seal_rows: Optional[int] = None, train_niter: int = 25, devices: Optional[Sequence[int]] = None,
+                 compact_ratio: float = 0.2, retrain_factor: float = 0.0):
         self.name = name
         self.dim = int(dim)
         self.nlist = int(nlist)
         self.metric = metric_code(metric)
-        self.device = int(device)
+        self.devices = [int(d) for d in devices] if devices else [int(device)]
+        self.device = self.devices[0]
         self.seal_rows = int(seal_rows) if seal_rows else KMEANS_MIN_POINTS_PER_CENTROID * self.nlist
         self.train_niter = int(train_niter)
+        # maintenance Milvus does in the background [EXT]: drop tombstoned slots once they are this fraction of a sealed
+        # index's slots; re-cluster once the index holds retrain_factor x the rows it was trained on (0 = never)
+        self.compact_ratio = float(compact_ratio)
+        self.retrain_factor = float(retrain_factor)
         self.persist_dir: Optional[str] = None
-        self._lock = threading.RLock()
+        self._generation = 0
+        self._dirty = False
+        self._lock = _RWLock()
         # host scalar columns, indexed by row number (== the int64 id stored next to the vector)
         self._pk: List[Optional[str]] = []
         self._repo: List[str] = []
@@ -193,7 +277,23 @@ class GpuCollection:
         self._growing = IVFFlatIndex(self.dim, nlist=1, metric=self.metric, device=self.device)
         self._growing.set_centroids(np.zeros((1, self.dim), dtype=np.float32))
         self._growing_rows = 0
-        self._ivf: Optional[IVFFlatIndex] = None
+        self._ivf = None  # IVFFlatIndex, or MultiDeviceIVFFlat when several devices are configured
+        self._trained_rows = 0
+        self.maintenance = {"compactions": 0, "retrains": 0}
+
+    def _new_index(self, nlist: int):
+        if len(self.devices) > 1:
+            from ..multidevice import MultiDeviceIVFFlat
+
+            return MultiDeviceIVFFlat(self.dim, nlist=nlist, metric=self.metric, devices=self.devices)
+        return IVFFlatIndex(self.dim, nlist=nlist, metric=self.metric, device=self.device)
+
+    def _load_index(self, path: str):
+        if os.path.exists(os.path.join(path, "shards.json")):
+            from ..multidevice import MultiDeviceIVFFlat
+
+            return MultiDeviceIVFFlat.load(path, devices=self.devices)
+        return IVFFlatIndex.load(path, device=self.device)
 
     # -- pymilvus-compatible no-ops --------------------------------------------------------------
     def load(self) -> None:
@@ -207,40 +307,74 @@ class GpuCollection:
     # -- persistence (connect() on an existing collection just loads,
     #    milvus_store.py:51-54; Milvus keeps its data in a volume, docker-compose.yml:13-14) -----------
     def save(self, path: str) -> None:
-        with self._lock:
+        """Write a complete snapshot into a fresh generation directory and publish it by replacing `CURRENT`:
+        a crash at any point leaves the previous generation loadable, never a mix of old and new files."""
+        with self._lock.write():
             os.makedirs(path, exist_ok=True)
-            self._growing.save(os.path.join(path, "growing"))
+            gen = self._generation + 1
+            name = f"gen-{gen:08d}"
+            tmp = os.path.join(path, name + ".tmp")
+            shutil.rmtree(tmp, ignore_errors=True)
+            os.makedirs(tmp)
+            self._growing.save(os.path.join(tmp, "growing"))
             if self._ivf is not None:
-                self._ivf.save(os.path.join(path, "ivf"))
-            with open(os.path.join(path, "columns.jsonl.tmp"), "w") as f:
+                self._ivf.save(os.path.join(tmp, "ivf"))
+            with open(os.path.join(tmp, "columns.jsonl"), "w") as f:
                 for r, pk in enumerate(self._pk):
                     if pk is None:
                         f.write("null\n")
                     else:
                         f.write(json.dumps([pk, self._repo[r], self._path[r], self._language[r], self._text[r],
                                             self._metadata[r]]) + "\n")
-            os.replace(os.path.join(path, "columns.jsonl.tmp"), os.path.join(path, "columns.jsonl"))
-            meta = {"format": 1, "name": self.name, "dim": self.dim, "nlist": self.nlist, "metric": self.metric,
+            meta = {"format": 2, "generation": gen, "name": self.name, "dim": self.dim, "nlist": self.nlist, "metric": self.metric,
                     "seal_rows": self.seal_rows, "train_niter": self.train_niter, "has_ivf": self._ivf is not None,
-                    "growing_rows": self._growing_rows, "repo_vocab": self._repo_vocab, "lang_vocab": self._lang_vocab}
-            with open(os.path.join(path, "collection.json.tmp"), "w") as f:
+                    "growing_rows": self._growing_rows, "rows": len(self._pk), "trained_rows": self._trained_rows,
+                    "compact_ratio": self.compact_ratio, "retrain_factor": self.retrain_factor,
+                    "repo_vocab": self._repo_vocab, "lang_vocab": self._lang_vocab}
+            with open(os.path.join(tmp, "collection.json"), "w") as f:
                 json.dump(meta, f)
-            os.replace(os.path.join(path, "collection.json.tmp"), os.path.join(path, "collection.json"))
+            final = os.path.join(path, name)
+            shutil.rmtree(final, ignore_errors=True)
+            os.replace(tmp, final)
+            with open(os.path.join(path, "CURRENT.tmp"), "w") as f:
+                f.write(name)
+            os.replace(os.path.join(path, "CURRENT.tmp"), os.path.join(path, "CURRENT"))  # the publication point
+            self._generation = gen
+            self._dirty = False
+            for old in os.listdir(path):
+                if old.startswith("gen-") and old != name:
+                    shutil.rmtree(os.path.join(path, old), ignore_errors=True)
+
+    @staticmethod
+    def snapshot_dir(path: str) -> Optional[str]:
+        """Directory of the published generation under `path` (or `path` itself for a round-1 flat snapshot)."""
+        cur = os.path.join(path, "CURRENT")
+        if os.path.exists(cur):
+            with open(cur) as f:
+                d = os.path.join(path, f.read().strip())
+            return d if os.path.exists(os.path.join(d, "collection.json")) else None
+        return path if os.path.exists(os.path.join(path, "collection.json")) else None
 
     @classmethod
-    def from_snapshot(cls, path: str, device: int = 0) -> "GpuCollection":
-        with open(os.path.join(path, "collection.json")) as f:
+    def from_snapshot(cls, path: str, device: int = 0, devices: Optional[Sequence[int]] = None) -> "GpuCollection":
+        snap = cls.snapshot_dir(path)
+        if snap is None:
+            raise FileNotFoundError(f"no published snapshot under {path!r}")
+        with open(os.path.join(snap, "collection.json")) as f:
             meta = json.load(f)
-        col = cls(meta["name"], meta["dim"], nlist=meta["nlist"], metric=meta["metric"], device=device,
-                  seal_rows=meta["seal_rows"], train_niter=meta["train_niter"])
+        col = cls(meta["name"], meta["dim"], nlist=meta["nlist"], metric=meta["metric"], device=device, devices=devices,
+                  seal_rows=meta["seal_rows"], train_niter=meta["train_niter"],
+                  compact_ratio=meta.get("compact_ratio", 0.2), retrain_factor=meta.get("retrain_factor", 0.0))
+        col._generation = int(meta.get("generation", 0))
         col._growing.close()
-        col._growing = IVFFlatIndex.load(os.path.join(path, "growing"), device=device)
+        col._growing = IVFFlatIndex.load(os.path.join(snap, "growing"), device=col.device)
         col._growing_rows = int(meta["growing_rows"])
+        col._trained_rows = int(meta.get("trained_rows", 0))
         if meta["has_ivf"]:
-            col._ivf = IVFFlatIndex.load(os.path.join(path, "ivf"), device=device)
+            col._ivf = col._load_index(os.path.join(snap, "ivf"))
         col._repo_vocab = {k: int(v) for k, v in meta["repo_vocab"].items()}
         col._lang_vocab = {k: int(v) for k, v in meta["lang_vocab"].items()}
-        with open(os.path.join(path, "columns.jsonl")) as f:
+        with open(os.path.join(snap, "columns.jsonl")) as f:
             for r, line in enumerate(f):
                 row = json.loads(line)
                 if row is None:
@@ -254,19 +388,23 @@ class GpuCollection:
                 col._metadata.append(md)
                 if pk is not None:
                     col._row_of[pk] = r
+        live = col._growing.ntotal + (col._ivf.ntotal if col._ivf is not None else 0)
+        if "rows" in meta and len(col._pk) != int(meta["rows"]) or live != len(col._row_of):
+            raise ValueError(f"snapshot {snap!r} is inconsistent: {len(col._pk)} column rows, {len(col._row_of)} live keys, "
+                             f"{live} live vectors")
         return col
 
     @property
     def num_entities(self) -> int:
-        with self._lock:
+        with self._lock.read():
             return len(self._row_of)
 
     @property
-    def index(self) -> Optional[IVFFlatIndex]:
+    def index(self):
         return self._ivf
 
     def close(self) -> None:
-        with self._lock:
+        with self._lock.write():
             self._growing.close()
             if self._ivf is not None:
                 self._ivf.close()
@@ -314,7 +452,7 @@ class GpuCollection:
 
         repos, paths, languages, texts = col(repos, ""), col(paths, ""), col(languages, ""), col(texts, "")
         metadata = col(metadata, None)
-        with self._lock:
+        with self._lock.write():
             # last occurrence of a primary key inside the batch wins
             last: Dict[str, int] = {}
             for i, pk in enumerate(ids):
@@ -341,8 +479,10 @@ class GpuCollection:
                 ltags[j] = self._tag(self._lang_vocab, l, 255)
             if len(keep) != n:
                 vec = vec[torch.as_tensor(keep, device=vec.device)] if not isinstance(vec, np.ndarray) else vec[keep]
+            self._dirty = True
             if self._ivf is not None:
                 self._ivf.add(vec, row_ids, rtags, ltags)
+                self._maintain()
             else:
                 self._growing.add(vec, row_ids, rtags, ltags, lists=np.zeros(len(keep), dtype=np.int32))
                 self._growing_rows += len(keep)
@@ -363,19 +503,75 @@ class GpuCollection:
             self._pk[r] = None
             self._text[r] = ""
             self._metadata[r] = None
+        self._dirty = True
 
     def delete(self, ids: Sequence[str]) -> int:
-        with self._lock:
+        with self._lock.write():
             rows = [self._row_of[str(pk)] for pk in ids if str(pk) in self._row_of]
             if rows:
                 self._remove_rows(rows)
+                self._maintain()
             return len(rows)
 
+    # -- maintenance: what Milvus' compaction / index rebuild do behind the reference's back [EXT] -------------
+    def _maintain(self) -> None:
+        if self._ivf is None:
+            return
+        st = self._ivf.stats()
+        slots = st.ntotal + st.nremoved
+        if self.compact_ratio > 0 and st.nremoved > 0 and st.nremoved >= self.compact_ratio * slots:
+            self.compact()
+        if self.retrain_factor > 0 and self._trained_rows > 0 and st.ntotal >= self.retrain_factor * self._trained_rows:
+            self.retrain()
+
+    def compact(self) -> int:
+        """Drop the tombstoned slots of the sealed index in place (sc_index_compact); returns the pages freed."""
+        with self._lock.write():
+            if self._ivf is None:
+                return 0
+            freed = self._ivf.compact()
+            self.maintenance["compactions"] += 1
+            log.info("index_compacted", collection=self.name, pages_freed=freed)
+            return freed
+
+    def retrain(self, niter: Optional[int] = None) -> None:
+        """Re-cluster the sealed index on the rows it holds NOW and move every live row to its new list: the centroids of
+        the first seal stop describing a collection that has grown several-fold (FAISS itself never re-trains; Milvus
+        builds a fresh index per sealed segment [EXT])."""
+        with self._lock.write():
+            old = self._ivf
+            if old is None or old.ntotal == 0:
+                return
+            n = old.ntotal
+            nlist = self.nlist if self.nlist * KMEANS_MIN_POINTS_PER_CENTROID <= n else max(1, n // KMEANS_MIN_POINTS_PER_CENTROID)
+            new = self._new_index(nlist)
+            ranges = old.list_ranges()
+            # train on a sample spread over all lists (FAISS caps the training set at 256 rows per centroid [EXT])
+            cap = 256 * nlist
+            stride = max(1, n // cap)
+            sample = []
+            for lo, hi in ranges:
+                _, v, _, t = old.export_lists(lo, hi)
+                livev = v[(t & np.uint32(0x80000000)) == 0]
+                sample.append(livev[::stride])
+            new.train(np.concatenate(sample), niter=self.train_niter if niter is None else niter, max_points_per_centroid=0)
+            for lo, hi in ranges:
+                _, v, i, t = old.export_lists(lo, hi)
+                live = (t & np.uint32(0x80000000)) == 0
+                if live.any():
+                    new.add(v[live], i[live], (t[live] >> np.uint32(8)) & np.uint32((1 << 23) - 1), (t[live] & np.uint32(0xFF)).astype(np.uint8))
+            self._ivf = new
+            old.close()
+            self._trained_rows = n
+            self._dirty = True
+            self.maintenance["retrains"] += 1
+            log.info("index_retrained", collection=self.name, nlist=nlist, rows=n)
+
     # -- index build ----------------------------------------------------------------------------------
-    def build_index(self, niter: Optional[int] = None, centroids=None) -> Optional[IVFFlatIndex]:
+    def build_index(self, niter: Optional[int] = None, centroids=None):
         """Seal the growing segment: k-means (or the supplied centroids), then move its rows into
         the inverted lists.  With fewer than 39 rows per list nlist shrinks as knowhere does [EXT]."""
-        with self._lock:
+        with self._lock.write():
             if self._growing_rows == 0:
                 return self._ivf
             vec, rid, tags = self._growing.export_list(0)
@@ -389,23 +585,26 @@ class GpuCollection:
                     nlist = self.nlist
                     if nlist * KMEANS_MIN_POINTS_PER_CENTROID > n:
                         nlist = max(1, n // KMEANS_MIN_POINTS_PER_CENTROID)
-                ivf = IVFFlatIndex(self.dim, nlist=nlist, metric=self.metric, device=self.device)
+                ivf = self._new_index(nlist)
                 if centroids is not None:
                     ivf.set_centroids(centroids)
                 else:
                     ivf.train(vec, niter=self.train_niter if niter is None else niter)
                 log.info("index_trained", collection=self.name, nlist=nlist, rows=n)
                 self._ivf = ivf
+                self._trained_rows = n
             self._ivf.add(vec, rid, (tags >> np.uint32(8)) & np.uint32((1 << 23) - 1), (tags & np.uint32(0xFF)).astype(np.uint8))
             self._growing.reset()
             self._growing_rows = 0
+            self._dirty = True
             return self._ivf
 
     # -- search ---------------------------------------------------------------------------------------
     def search_arrays(self, vectors, top_k: int, nprobe: int = 16, repos: Optional[Iterable[str]] = None,
                       languages: Optional[Iterable[str]] = None):
-        """Raw tensor path: (dist [nq,k] fp32, row ids [nq,k] int64, -1 = none).  CUDA in -> CUDA out."""
-        with self._lock:
+        """Raw tensor path: (dist [nq,k] fp32, row ids [nq,k] int64, -1 = none).  CUDA in -> CUDA out.
+        Searches hold the READ side of the collection lock: they run concurrently with each other."""
+        with self._lock.read():
             rt = lt = None
             if repos is not None:
                 rt = self.repo_tags(repos)
@@ -422,14 +621,7 @@ class GpuCollection:
                 parts.append(self._growing.search(vectors, top_k, nprobe=1, repos=rt, langs=lt))
             if len(parts) == 1:
                 return parts[0]
-            (d0, i0), (d1, i1) = parts
-            if isinstance(d0, np.ndarray):
-                dev = torch.device("cuda", self.device)
-                pd = torch.stack([torch.from_numpy(d0), torch.from_numpy(d1)]).to(dev)
-                pi = torch.stack([torch.from_numpy(i0), torch.from_numpy(i1)]).to(dev)
-                d, i = merge_topk(pd, pi, top_k, self.metric, self.device)
-                return d.cpu().numpy(), i.cpu().numpy()
-            return merge_topk(torch.stack([d0, d1]), torch.stack([i0, i1]), top_k, self.metric, self.device)
+            return _merge_parts(parts, top_k, self.metric, self.device)
 
     def _empty(self, vectors, top_k: int):
         nq = len(vectors) if not hasattr(vectors, "shape") else (1 if len(vectors.shape) == 1 else vectors.shape[0])
@@ -455,7 +647,7 @@ class GpuCollection:
         if q.ndim != 2 or q.shape[1] != self.dim:
             raise ValueError(f"vector dimension mismatch: expected {self.dim}, got {q.shape[-1]}")
         fields = tuple(output_fields) if output_fields is not None else ()
-        with self._lock:
+        with self._lock.read():
             dist, rows = self.search_arrays(q, int(limit), nprobe=nprobe, repos=repos, languages=languages)
             if not isinstance(dist, np.ndarray):
                 dist, rows = dist.cpu().numpy(), rows.cpu().numpy()
@@ -504,6 +696,31 @@ def drop_collection(name: str) -> None:
         c.close()
 
 
+def _parse_devices(value) -> Optional[List[int]]:
+    """`ivf_devices`: "0,1,2,3" / [0, 1] / "all" -> CUDA ordinals of the row-sharded collection; empty = single device."""
+    if value in (None, "", [], ()):
+        return None
+    if isinstance(value, str):
+        if value.strip().lower() == "all":
+            return list(range(torch.cuda.device_count())) if torch is not None else None
+        return [int(v) for v in value.replace(";", ",").split(",") if v.strip() != ""]
+    return [int(v) for v in value]
+
+
+def _flush_all_at_exit() -> None:
+    # Milvus persists server-side; the reference never calls flush() (its milvus_store.py:128-133).  Collections with a
+    # persist directory are therefore written after every upsert_embeddings call and, as a last resort, here.
+    for c in list(_REGISTRY.values()):
+        try:
+            if c.persist_dir and c._dirty:
+                c.flush()
+        except Exception:  # pragma: no cover - interpreter teardown
+            pass
+
+
+atexit.register(_flush_all_at_exit)
+
+
 # --------------------------------------------------------------------------------------------------
 # the drop-in wrapper
 # --------------------------------------------------------------------------------------------------
@@ -532,8 +749,9 @@ class MilvusVectorStore:
                 return existing
             persist = _setting("ivf_persist_dir", "")
             snap = os.path.join(persist, self.collection_name) if persist else ""
-            if snap and os.path.exists(os.path.join(snap, "collection.json")):
-                collection = GpuCollection.from_snapshot(snap, device=_setting("ivf_device", 0))
+            devices = _parse_devices(_setting("ivf_devices", ""))
+            if snap and GpuCollection.snapshot_dir(snap) is not None:
+                collection = GpuCollection.from_snapshot(snap, device=_setting("ivf_device", 0), devices=devices)
                 if collection.dim != self.dim:
                     collection.close()
                     raise ValueError(f"snapshot {snap!r} has dim {collection.dim}, requested {self.dim}")
@@ -541,14 +759,22 @@ class MilvusVectorStore:
                 _REGISTRY[self.collection_name] = collection
                 return collection
             log.info("creating_milvus_collection", collection=self.collection_name, dim=self.dim)
+            if not snap:
+                # one-process limitation: without a persist directory the rows live and die with this process (a Milvus
+                # server would keep them for the next CLI / API process)
+                log.warning("collection_not_persisted", collection=self.collection_name,
+                            hint="set SEMCODE_IVF_PERSIST_DIR to keep the collection across processes")
             collection = GpuCollection(
                 self.collection_name,
                 self.dim,
                 nlist=_setting("ivf_nlist", 128),  # milvus_store.py:81
                 metric=_setting("ivf_metric", "IP"),  # milvus_store.py:79
                 device=_setting("ivf_device", 0),
+                devices=devices,
                 seal_rows=_setting("ivf_seal_rows", 0) or None,
                 train_niter=_setting("ivf_train_niter", 25),
+                compact_ratio=_setting("ivf_compact_ratio", 0.2),
+                retrain_factor=_setting("ivf_retrain_factor", 0.0),
             )
             collection.persist_dir = snap or None
             collection.load()
@@ -587,6 +813,8 @@ class MilvusVectorStore:
             inserted += len(batch)
             if progress:
                 progress(inserted, total)
+        if collection.persist_dir:  # what the Milvus server does without being asked: the rows survive this process
+            collection.flush()
 
     def search(self, vector: "list[float]", top_k: int = 10, *, nprobe: int = 16,
                repos: Optional[Iterable[str]] = None, languages: Optional[Iterable[str]] = None) -> list:
@@ -622,7 +850,19 @@ class MilvusVectorStore:
         return self._require().upsert_columns(ids, vectors, repos, paths, languages, texts, metadata)
 
     def build_index(self, niter: Optional[int] = None, centroids=None):
-        return self._require().build_index(niter=niter, centroids=centroids)
+        collection = self._require()
+        out = collection.build_index(niter=niter, centroids=centroids)
+        if collection.persist_dir:
+            collection.flush()
+        return out
+
+    def compact(self) -> int:
+        """Drop tombstoned slots now (done automatically once they pass `ivf_compact_ratio` of the sealed index)."""
+        return self._require().compact()
+
+    def retrain(self, niter: Optional[int] = None) -> None:
+        """Re-cluster the sealed index on its current rows (automatic at `ivf_retrain_factor` x the trained size)."""
+        self._require().retrain(niter=niter)
 
     def flush(self) -> None:
         """Persist the collection when `ivf_persist_dir` (SEMCODE_IVF_PERSIST_DIR) is configured."""

@@ -890,3 +890,47 @@ def test_compaction_keeps_results_and_recycles_pages(sb, orc, metric):
         np.testing.assert_array_equal(tags[a:b], t1)
     coff, cv, ci, ct = g.export_csr()
     assert coff[-1] == st2.ntotal and set(ci.tolist()) == set(ids[~gone].tolist()) | set(idn.tolist())
+
+
+def test_exchange_timeout_is_surfaced(sb, orc):
+    """a peer that never arrives must not yield a silently wrong result.  Rank 0 of a 2-rank exchange whose peer
+    never calls: the waiting kernels give up after the (shortened) timeout and set the pinned status word; poll() sees it
+    without a sync, status() after one, and the next step is refused."""
+    import ctypes as C
+
+    import torch
+
+    from semcode_b200 import _capi
+
+    x, q, cent, ids = make_case(orc, 3000, 64, 8, 20, "IP", seed=9)
+    g, _, _ = build_pair(sb, orc, x, ids, cent, "IP")
+    nbytes = 4 << 20
+    mine = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    peer = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")  # stands in for the absent rank 1
+    arr = (C.c_void_p * 2)(mine.data_ptr(), peer.data_ptr())
+    h = C.c_void_p()
+    L = _capi.lib()
+    _capi.check(L.sc_exchange_create(0, 2, arr, nbytes, 0, C.byref(h)))
+
+    class Ex:
+        handle = h
+
+    try:
+        _capi.check(L.sc_exchange_set_timeout_ms(h, 30))
+        t = C.c_int32(0)
+        _capi.check(L.sc_exchange_poll(h, C.byref(t)))
+        assert t.value == 0
+        g.search(torch.from_numpy(q).cuda(), 5, nprobe=4, exchange=Ex)  # issues; the waits time out on the device
+        torch.cuda.synchronize()
+        _capi.check(L.sc_exchange_poll(h, C.byref(t)))
+        assert t.value == 1
+        e = C.c_int64(0)
+        _capi.check(L.sc_exchange_status(h, C.byref(t), C.byref(e)))
+        assert t.value == 1 and e.value == 1
+        with pytest.raises(_capi.NativeError, match="unusable"):
+            g.search(torch.from_numpy(q).cuda(), 5, nprobe=4, exchange=Ex)
+        d0, i0 = g.search(q, 5, nprobe=4)  # the index itself is fine
+        rd, ri = orc.search(orc.build_index(x, ids, cent, "IP"), q, 5, 4)
+        assert_topk_parity(d0, i0, rd, ri, "plain search after a timed-out exchange step")
+    finally:
+        L.sc_exchange_destroy(h)

@@ -213,3 +213,129 @@ def test_snapshot_round_trip(store_mod, monkeypatch, tmp_path):
     # upserts keep working on the reloaded collection (primary-key map restored)
     again.upsert_arrays(["k5"], x[5:6], repos=["a"], languages=["python"])
     assert col.num_entities == n
+
+
+# ---- the host-logic scenarios of tests/test_store_host.py, with the real engine ------------------------------------
+@pytest.fixture()
+def real_store(native_lib):
+    import semcode_b200.storage.milvus_store as ms
+
+    yield ms
+    for name in list(ms._REGISTRY):
+        ms.drop_collection(name)
+
+
+def test_persist_without_flush_on_the_gpu(real_store, monkeypatch, tmp_path):
+    from test_store_host import scenario_persist_without_flush
+
+    scenario_persist_without_flush(real_store, monkeypatch, tmp_path)
+
+
+def test_compaction_and_retrain_on_the_gpu(real_store, monkeypatch):
+    from test_store_host import scenario_compaction_and_retrain
+
+    scenario_compaction_and_retrain(real_store, monkeypatch)
+
+
+def test_concurrent_searches_on_the_gpu(real_store, monkeypatch):
+    from test_store_host import scenario_concurrent_searches
+
+    scenario_concurrent_searches(real_store, monkeypatch)
+
+
+def test_reference_caller_traffic_replayed_on_the_gpu(real_store):
+    """tests/golden/callers.json was recorded in the build container by running the reference's OWN IndexerService and
+    SemanticSearchPipeline (unmodified, /root/reference) against the drop-in store with the oracle-backed engine double
+    (tests/golden/make_callers_golden.py).  Here the same payloads go through the same wrapper with the CUDA engine; the
+    documents the reference's `_hit_to_document` built there must be the hits returned here."""
+    import json
+
+    with open(os.path.join(GOLD, "callers.json")) as f:
+        gold = json.load(f)
+    store = real_store.MilvusVectorStore("callers_replay", dim=gold["dim"])
+    store.connect()
+    store.upsert_embeddings([EmbeddingPayload(p["id"], p["text"], p["vector"], p["metadata"]) for p in gold["payloads"]])
+    assert store._collection.num_entities == len(gold["payloads"])
+    for case in gold["queries"]:
+        hits = next(iter(store.search(case["vector"], top_k=case["top_k"])))
+        docs = case["documents"]
+        assert len(hits) == len(docs)
+        for h, d in zip(hits, docs):
+            assert abs(h.distance - d["score"]) <= 1e-5 * abs(d["score"]) + 1e-6
+        # ids identical except inside exact-score ties
+        got, want = [h.entity.get("text") for h in hits], [d["snippet"] for d in docs]
+        for j, (g, w) in enumerate(zip(got, want)):
+            if g != w:
+                assert abs(docs[j]["score"] - hits[j].distance) <= 1e-6 and g in want, (j, g[:40], w[:40])
+        assert hits[0].entity.get("repo") == docs[0]["repo"] and hits[0].entity.get("metadata") == docs[0]["metadata"]
+
+
+# ---- one collection over several devices, one process (ivf_devices) ----------------------------------------------
+def test_multi_device_collection_behind_the_wrapper(real_store, monkeypatch, tmp_path):
+    """`ivf_devices` gives the collection a row-sharded backend (semcode_b200/multidevice.py): upsert deals the rows, seal
+    trains data-parallel, search reduces the shards' partial top-k on the first device, flush / connect persist and reload
+    the shards.  With one visible GPU both shards live on cuda:0 -- same code path, same checks."""
+    import torch
+
+    ms = real_store
+    ngpu = torch.cuda.device_count()
+    devs = "0,1" if ngpu >= 2 else "0,0"
+    print(f"multi-device collection on devices {devs} ({ngpu} visible GPU(s))")
+    rng = np.random.default_rng(5)
+    n, d = 6000, 96
+    x = unit_rows(rng, n, d)
+    repos = ["alpha" if i % 4 else "beta" for i in range(n)]
+    langs = ["python" if i % 3 else "cpp" for i in range(n)]
+    ids = [f"k{i:06d}" for i in range(n)]
+    monkeypatch.setenv("SEMCODE_IVF_NLIST", "16")
+    monkeypatch.setenv("SEMCODE_IVF_SEAL_ROWS", "100000")  # sealed explicitly below, with given centroids
+    single = ms.MilvusVectorStore("md_single", dim=d)
+    single.connect()
+    monkeypatch.setenv("SEMCODE_IVF_DEVICES", devs)
+    monkeypatch.setenv("SEMCODE_IVF_PERSIST_DIR", str(tmp_path / "p"))
+    multi = ms.MilvusVectorStore("md_multi", dim=d)
+    multi.connect()
+    assert multi._collection.devices == [int(v) for v in devs.split(",")]
+    cent = x[rng.choice(n, 16, replace=False)].copy()
+    for st in (single, multi):
+        for a in range(0, n, 1700):  # uneven batches exercise the global round-robin cursor
+            st.upsert_arrays(ids[a:a + 1700], x[a:a + 1700], repos=repos[a:a + 1700], languages=langs[a:a + 1700])
+        st.build_index(centroids=cent)
+    from semcode_b200.multidevice import MultiDeviceIVFFlat
+
+    mi = multi._collection.index
+    assert isinstance(mi, MultiDeviceIVFFlat) and mi.ntotal == n and abs(mi.shards[0].ntotal - mi.shards[1].ntotal) <= 1
+    q = unit_rows(rng, 70, d)
+    for kw in ({}, {"repos": ["beta"]}, {"languages": ["cpp"], "repos": ["alpha"]}):
+        d1, r1 = single.search_arrays(q, 10, nprobe=5, **kw)
+        d2, r2 = multi.search_arrays(q, 10, nprobe=5, **kw)
+        assert_topk_parity(d2, r2, d1, r1, f"two shards vs one index {kw}")
+    # later rows go straight to the shards; replaced keys are tombstoned on whichever shard holds them
+    extra = unit_rows(rng, 501, d)
+    for st in (single, multi):
+        st.upsert_arrays(ids[:501], extra, repos=repos[:501], languages=langs[:501])
+    d1, r1 = single.search_arrays(extra[:40], 5, nprobe=16)
+    d2, r2 = multi.search_arrays(extra[:40], 5, nprobe=16)
+    assert_topk_parity(d2, r2, d1, r1, "after an upsert-replace")
+    # device tensors in -> device tensors out
+    dq = torch.from_numpy(q).cuda()
+    d3, r3 = multi.search_arrays(dq, 10, nprobe=5)
+    d1, r1 = single.search_arrays(q, 10, nprobe=5)
+    assert d3.is_cuda and r3.is_cuda
+    assert_topk_parity(d3.cpu().numpy(), r3.cpu().numpy(), d1, r1, "device tensors")
+    # persisted by the upserts above (no flush() call); a new 'process' reloads both shards
+    hits_before = multi.search(q[3].tolist(), top_k=4, nprobe=5)[0]
+    multi.flush()
+    ms._REGISTRY.pop("md_multi").close()
+    again = ms.MilvusVectorStore("md_multi", dim=d)
+    again.connect()
+    assert isinstance(again._collection.index, MultiDeviceIVFFlat) and again._collection.num_entities == n
+    hits_after = again.search(q[3].tolist(), top_k=4, nprobe=5)[0]
+    assert [h.id for h in hits_after] == [h.id for h in hits_before]
+    # data-parallel k-means over the shards tracks the single-device Lloyd iterations
+    one = ms.IVFFlatIndex(d, nlist=16, metric="IP")
+    two = MultiDeviceIVFFlat(d, nlist=16, metric="IP", devices=[int(v) for v in devs.split(",")])
+    o1 = one.train(x, niter=4, seed=9, max_points_per_centroid=0)
+    o2 = two.train(x, niter=4, seed=9, max_points_per_centroid=0)
+    np.testing.assert_allclose(o2, o1, rtol=1e-6)
+    np.testing.assert_allclose(two.get_centroids(), one.get_centroids(), rtol=1e-4, atol=1e-6)
