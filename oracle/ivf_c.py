@@ -18,12 +18,48 @@ _LIB_PATH = os.path.join(_HERE, "liborc.so")
 _lib = None
 
 
-def build(force: bool = False) -> str:
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(
-        os.path.join(_HERE, "ivf_oracle.c")
-    ):
+def _cpu_key() -> str:
+    """Identifies the host CPU (model + ISA flags): a -march=native build is only valid on the CPU it was made on."""
+    import hashlib
+
+    try:
+        with open("/proc/cpuinfo") as f:
+            txt = f.read()
+        model = next((l for l in txt.splitlines() if l.startswith("model name")), "")
+        flags = next((l for l in txt.splitlines() if l.startswith("flags")), "")
+    except OSError:
+        model, flags = "unknown", ""
+    return hashlib.sha1((model + flags).encode()).hexdigest()[:12]
+
+
+def build(force: bool = False, native: bool = False) -> str:
+    """Compile oracle/liborc.so (portable x86-64-v3).  native=True (bench.py's CPU arm): compile for THIS host with
+    -march=native into oracle/_native/ (git- and gpurun-ignored, keyed by the CPU, never shipped) and bind that instead;
+    falls back to the portable build if the compile fails."""
+    global _LIB_PATH, _lib
+    src = os.path.join(_HERE, "ivf_oracle.c")
+    if native:
+        out = os.path.join(_HERE, "_native", f"liborc-{_cpu_key()}.so")
+        try:
+            if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+                os.makedirs(os.path.dirname(out), exist_ok=True)
+                cc = "/usr/bin/gcc" if os.access("/usr/bin/gcc", os.X_OK) else "gcc"
+                subprocess.run([cc, "-O3", "-march=native", "-fopenmp", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas",
+                                "-o", out + ".tmp", src, "-lm"], check=True, capture_output=True)
+                os.replace(out + ".tmp", out)
+            if _LIB_PATH != out:
+                _LIB_PATH, _lib = out, None
+            return out
+        except (subprocess.CalledProcessError, OSError):
+            pass
+    portable = os.path.join(_HERE, "liborc.so")
+    if force or not os.path.exists(portable) or os.path.getmtime(portable) < os.path.getmtime(src):
         subprocess.run(["make", "-C", _HERE, "-B", "liborc.so"], check=True, capture_output=True)
     return _LIB_PATH
+
+
+def is_native() -> bool:
+    return os.sep + "_native" + os.sep in _LIB_PATH
 
 
 def lib():

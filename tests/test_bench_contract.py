@@ -29,9 +29,11 @@ def test_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 1
     assert d["unit"] == "queries/s" and d["higher_is_better"] is True and d["value"] > 0 and d["ms_per_step"] > 0
     assert d["vs_baseline"] is None and d["data"] == "synthetic" and d["dtype"] == "f32"
-    assert "workload" in d["config"] and d["config"]["nq"] == 8
+    # the config is the product arm's (the driver compares the two lines' configs); the bounded sample is described beside it
+    assert "workload" in d["config"] and d["config"]["nq"] == 1024 and d["config"]["nprobe"] == 4 and d["config"]["n"] == 20000
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["value"] == d["value"] and cb["unit"] == d["unit"] and cb["sample"]
+    assert cb["kind"] == "port" and cb["value"] == d["value"] and cb["unit"] == d["unit"] and "8 of the 1024" in cb["sample"]
+    assert 0 < cb["coarse_share"] < 1 and cb["scan_host_GBps"] > 0
     want = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     assert cb["cores"] == want  # not the launcher's OMP_NUM_THREADS=1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -103,7 +103,7 @@ def test_probe_and_assign_match_oracle(sb, orc, metric, d):
         if not np.array_equal(got[r], want[r]):
             # only near-ties (fp32 rounding of the contraction) may reorder
             assert sorted(got[r]) == sorted(want[r]) or np.allclose(
-                np.sort(sim[r][got[r]]), np.sort(sim[r][want[r]]), rtol=1e-5, atol=1e-6
+                np.sort(sim[r][got[r]]), np.sort(sim[r][want[r]]), rtol=1e-5, atol=2e-7
             ), f"query {r}: probes differ beyond rounding"
         assert close(sc[r], sim[r][got[r]].astype(np.float32)).all()
     a = g.assign(x)
@@ -342,7 +342,7 @@ def test_one_pass_selection_of_probes(sb, orc):
             assert close(sc[r], sim[r][got[r]].astype(np.float32)).all()
             assert (np.diff(sc[r]) <= 0).all()
             if not np.array_equal(got[r], want[r]):  # only near-ties (fp32 rounding of the contraction) may reorder
-                assert np.allclose(np.sort(sim[r][got[r]]), np.sort(sim[r][want[r]]), rtol=1e-5, atol=1e-6), (nprobe, r)
+                assert np.allclose(np.sort(sim[r][got[r]]), np.sort(sim[r][want[r]]), rtol=1e-5, atol=2e-7), (nprobe, r)
 
 
 def test_chunked_search_equals_single_pass(sb, orc):
@@ -394,7 +394,7 @@ def test_kmeans_tracks_oracle(sb, orc, metric):
     g2 = sb.IVFFlatIndex(40, nlist=24, metric=metric)
     obj2 = g2.train(x, niter=8, init_centroids=x[orc.kmeans_init_rows(6000, 24, 5)])
     np.testing.assert_allclose(obj2, obj, rtol=1e-6)
-    np.testing.assert_allclose(g2.get_centroids(), g.get_centroids(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(g2.get_centroids(), g.get_centroids(), rtol=1e-5, atol=2e-7)
 
 
 def test_kmeans_empty_cluster_split(sb, orc):
@@ -764,7 +764,7 @@ def test_small_batch_path(sb, orc, metric, d, nq):
     want = orc.top_desc(exact, 11)
     for r in range(nq):
         if not np.array_equal(lists[r], want[r]):
-            assert np.allclose(np.sort(exact[r][lists[r]]), np.sort(exact[r][want[r]]), rtol=1e-5, atol=1e-6)
+            assert np.allclose(np.sort(exact[r][lists[r]]), np.sort(exact[r][want[r]]), rtol=1e-5, atol=2e-7)
         assert close(sc[r], exact[r][lists[r]].astype(np.float32)).all()
     g.set_param("small_coarse", 0)
     lists_tc = g.probe(q, 11)
@@ -934,3 +934,64 @@ def test_exchange_timeout_is_surfaced(sb, orc):
         assert_topk_parity(d0, i0, rd, ri, "plain search after a timed-out exchange step")
     finally:
         L.sc_exchange_destroy(h)
+
+
+# ---- the headline regime: nlist 16384, thousands of queries, every list-major consumer at once -------------------
+@pytest.mark.parametrize("metric", ["IP", "L2"])
+def test_headline_regime_list_major_against_oracle(sb, orc_c, metric):
+    """BASELINE.json configs[1]'s shape at a quarter of its rows: 2.5M x 768, nlist 16384, nq 2048, nprobe 32, top-10 on a
+    Zipf-clustered set, so one batch holds lists probed once, a few times (scan_mq<4>, scan_mq<8>) and hundreds of times
+    (tile items), and the one-pass top-k reads candidates from all of them.  The whole batch is compared with the
+    query-major kernel (ids identical), a random slice of it with the C oracle on the same lists."""
+    import torch
+
+    n, d, nlist, nq, nprobe, k = 2_500_000, 768, 16384, 2048, 32, 10
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator(device=dev).manual_seed(2024)
+    centres = torch.randn((2048, d), generator=gen, device=dev)
+    w = 1.0 / torch.arange(1, 2049, device=dev, dtype=torch.float32) ** 1.1
+
+    def rows(m):
+        c = torch.multinomial(w / w.sum(), m, replacement=True, generator=gen)
+        return torch.nn.functional.normalize(centres[c] + 0.3 * torch.randn((m, d), generator=gen, device=dev), dim=1)
+
+    g = sb.IVFFlatIndex(d, nlist=nlist, metric=metric)
+    g.train(rows(300_000), niter=2, max_points_per_centroid=0)
+    for s in range(0, n, 500_000):
+        g.add(rows(500_000), torch.arange(s, s + 500_000, device=dev, dtype=torch.int64) * 3 + 1)
+    assert g.ntotal == n
+    q = rows(nq)
+
+    g.set_profiling(True)
+    d0, i0 = g.search(q, k, nprobe=nprobe)  # automatic switch: nq * nprobe = 4 * nlist -> list-major
+    torch.cuda.synchronize()
+    t = g.last_search_times()
+    assert t.unique_rows > 0 and t.scanned_rows > 2 * t.unique_rows, "the batch must have gone list-major with real sharing"
+    assert t.scan_launches >= 6, t.scan_launches  # count, plan, fill, tile items (+ split) and both multi-query page scans
+    g.set_profiling(False)
+    g.set_param("scan_mode", 1)
+    d1, i1 = g.search(q, k, nprobe=nprobe)
+    g.set_param("scan_mode", 0)
+    d0, i0, d1, i1 = (a.cpu().numpy() for a in (d0, i0, d1, i1))
+    assert_sorted(d0, i0, metric == "IP")
+    assert_topk_parity(d0, i0, d1, i1, "list-major vs query-major, whole batch")
+    # the clustered set is dense near the top: a handful of 1e-5-relative near-ties order differently under the tile
+    # kernel's 3xTF32 sums and the page scan's FFMA sums (assert_topk_parity has just checked that is all they are)
+    assert (i0 == i1).mean() > 0.998
+
+    # C oracle on a random slice of the SAME output, over the lists those queries probe
+    rng = np.random.default_rng(5)
+    pick = np.sort(rng.choice(nq, 128, replace=False))
+    qs = q[torch.from_numpy(pick).to(dev)].cpu().numpy()
+    probes = g.probe(qs, nprobe)
+    used = np.unique(probes)
+    remap = -np.ones(nlist, dtype=np.int32)
+    remap[used] = np.arange(used.size, dtype=np.int32)
+    parts = [g.export_list(int(l)) for l in used]
+    off = np.zeros(used.size + 1, dtype=np.int64)
+    np.cumsum([p[0].shape[0] for p in parts], out=off[1:])
+    vecs = np.concatenate([p[0] for p in parts])
+    ids = np.concatenate([p[1] for p in parts])
+    od, oi = orc_c.scan_search(qs, g.metric, remap[probes], off, vecs, ids, k)
+    assert_topk_parity(d0[pick], i0[pick], od, oi, "list-major vs C oracle")
+    g.close()
