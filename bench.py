@@ -86,6 +86,8 @@ def parse_args():
     p.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
                    help="N > 1: p2p = probe rows and partial top-k stored straight into the peers' buffers by the kernels "
                         "that produce them (NVLink peer memory), merge kernel waits on flags; nccl = all-gathers + merge")
+    p.add_argument("--inflight", type=int, default=2,
+                   help="N > 1, p2p exchange: fused steps in flight per rank (one stream + one exchange + one scratch slot each)")
     p.add_argument("--shard-by", default="rows", choices=["rows", "lists"],
                    help="N > 1: deal every list's rows round-robin (rows) or whole lists (list l on rank l %% N)")
     return p.parse_args()
@@ -419,6 +421,11 @@ def build_index(c, n, d, nlist, dataset, metric="IP", tags=None):
             keep = torch.nonzero(lists % c.world == c.rank).squeeze(1)
             g.add(x[keep].contiguous(), ids[keep].contiguous(), lists=lists[keep].contiguous())
             del lists, keep
+        elif args.shard_sim > 1 and args.shard_by == "lists":  # rank 0 of a G-way LIST-sharded index: lists l with l % G == 0
+            lists = g.assign(x)
+            keep = torch.nonzero(lists % args.shard_sim == 0).squeeze(1)
+            g.add(x[keep].contiguous(), ids[keep].contiguous(), lists=lists[keep].contiguous())
+            del lists, keep
         elif args.shard_sim > 1:
             g.add(x[0::args.shard_sim].contiguous(), ids[0::args.shard_sim].contiguous())
         else:
@@ -706,8 +713,7 @@ def run_ours(args):
     c.want_cpu_baseline = world == 1 and not args.no_cpu_baseline
     c.last_list_major = False
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own log (NCCL_DEBUG as the launcher set it) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL_DEBUG is left as the launcher set it; NCCL logs on fd 1, which main() has pointed at stderr for the run
         dist.init_process_group("nccl", device_id=dev)
     n, d, nlist, k, nprobe, nq = args.n, args.dim, args.nlist, args.k, args.nprobe, args.nq
 
@@ -730,21 +736,27 @@ def run_ours(args):
     probe_mine = torch.full((per, min(nprobe, nlist)), -1, dtype=torch.int32, device=dev)
     probe_all = torch.empty((world * per, min(nprobe, nlist)), dtype=torch.int32, device=dev)
 
-    ex, ex_err = None, None
+    ex, ex_err, exs, lanes, lane_out = None, None, [], [], []
     if world > 1 and args.exchange != "nccl" and args.shard_by == "rows":
         ok = torch.zeros(1, dtype=torch.int32, device=dev)
         try:
             from semcode_b200.index import PeerExchange
 
-            ex = PeerExchange(local, None, 64 << 20)
+            exs = [PeerExchange(local, None, 64 << 20) for _ in range(max(1, args.inflight))]
             ok += 1
         except Exception as e:
             ex_err = f"{type(e).__name__}: {e}"
         dist.all_reduce(ok)
         if int(ok.item()) != world:
-            ex = None
+            exs = []
             if args.exchange == "p2p":
                 raise SystemExit(f"--exchange p2p: peer-memory exchange unavailable ({ex_err})")
+        if exs:
+            ex = exs[0]
+            lanes = [torch.cuda.Stream(device=dev) for _ in exs]
+            lane_out = [(torch.empty((nq, k), dtype=torch.float32, device=dev), torch.empty((nq, k), dtype=torch.int64, device=dev))
+                        for _ in exs]
+    nl = len(lanes)
 
     def search_sharded(qs):
         if ex is not None:  # ONE C-ABI call: split coarse pass + probe scatter + scan + top-k scatter + waiting merge
@@ -763,16 +775,44 @@ def run_ours(args):
         dist.all_gather_into_tensor(gat_i, out_i)
         return sb.merge_topk(gat_d, gat_i, k, args.metric, local)
 
+    sim_lists = None
+    if world == 1 and args.shard_sim > 1 and args.shard_by == "lists":  # probe tables of the simulated rank, computed up front
+        sim_lists = []
+        for t in qb:
+            pl = g.probe(t, nprobe)
+            sim_lists.append(torch.where(pl % args.shard_sim == 0, pl, torch.full_like(pl, -1)).contiguous())
+
     def step_device(i):
+        if nl > 1:  # lane i % nl: its own stream, exchange and (inside the library) scratch slot
+            j = i % nl
+            with torch.cuda.stream(lanes[j]):
+                g.search(qb[i % nb], k, nprobe=nprobe, out=lane_out[j], exchange=exs[j])
+            return lane_out[j]
         if world > 1:
             return search_sharded(qb[i % nb])
+        if sim_lists is not None:
+            g.search(qb[i % nb], k, lists=sim_lists[i % nb], out=(out_d, out_i))
+            return out_d, out_i
         g.search(qb[i % nb], k, nprobe=nprobe, out=(out_d, out_i))
         return out_d, out_i
+
+    host_lane = [(torch.empty((nq, k), dtype=torch.float32).pin_memory(), torch.empty((nq, k), dtype=torch.int64).pin_memory())
+                 for _ in lanes]
 
     def step_e2e(i):
         if world == 1:
             g.search(qhost[i % nb], k, nprobe=nprobe, out=(host_d, host_i))  # C ABI, host buffers
             return host_d, host_i
+        if nl > 1:
+            # the same pipeline end to end: lane j's previous step (i - nl) is read back to the host before the lane is reused
+            j = i % nl
+            lanes[j].synchronize()
+            with torch.cuda.stream(lanes[j]):
+                qd = qhost[i % nb].to(dev, non_blocking=True)
+                g.search(qd, k, nprobe=nprobe, out=lane_out[j], exchange=exs[j])
+                host_lane[j][0].copy_(lane_out[j][0], non_blocking=True)
+                host_lane[j][1].copy_(lane_out[j][1], non_blocking=True)
+            return host_lane[j]
         qd = qhost[i % nb].to(dev, non_blocking=True)
         md, mi = search_sharded(qd)
         host_d.copy_(md, non_blocking=True)
@@ -785,13 +825,25 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def fork():
+        cur = torch.cuda.current_stream()
+        for st in lanes:
+            st.wait_stream(cur)
+
+    def join():
+        cur = torch.cuda.current_stream()
+        for st in lanes:
+            cur.wait_stream(st)
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0 = time.time()
         e0.record()
+        fork()
         for i in range(steps):
             fn(i)
+        join()
         e1.record()
         barrier()
         w1 = time.time()
@@ -802,9 +854,11 @@ def run_ours(args):
 
     # under `ncu --profile-from-start off` only the search steps are captured, not the index build
     torch.cuda.cudart().cudaProfilerStart()
+    fork()
     for i in range(args.warmup):
         step_device(i)
         step_e2e(i)
+    join()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -818,7 +872,9 @@ def run_ours(args):
     step_ms = ms_total / args.steps
 
     # ---- the timed path, checked: step 0's output ----------------------------------------------------
+    fork()
     d0, i0 = step_device(0)
+    join()
     d0, i0 = d0.clone(), i0.clone()
     torch.cuda.synchronize()
     # per-phase CUDA events (recorded by the library on the launching stream): a separate pass over the same inputs
@@ -826,7 +882,9 @@ def run_ours(args):
     prof_acc = None
     nprof = min(args.steps, 8)
     for i in range(nprof):
+        fork()
         step_device(i)
+        join()
         torch.cuda.synchronize()
         t = g.last_search_times()
         vals = [t.coarse_ms, t.probe_select_ms, t.plan_ms, t.scan_ms, t.topk_ms, t.total_ms, t.scanned_rows, t.unique_rows,
@@ -839,7 +897,9 @@ def run_ours(args):
     launches_per_step = int(round(prof["total_launches"])) + (4 if world > 1 and ex is None else 0)
 
     parity = None
-    if world == 1:
+    if sim_lists is not None:
+        parity = {"path": "shard simulation (lists)", "ok": None}
+    elif world == 1:
         parity = check_parity(c, g, qb[0], k, nprobe, d0, i0, min(args.cpu_queries, nq), with_oracle=True,
                               cpu_budget_s=args.cpu_seconds if c.want_cpu_baseline else 0.0)
     else:
@@ -867,14 +927,14 @@ def run_ours(args):
     # the query-major kernel on the same workload (the regime the HBM-fraction claim of SURVEY.md 8d is made in:
     # it streams every probed list once per (query, list) pair, so logical bytes == DRAM bytes)
     qm = None
-    if list_major and not args.scan_mode and world == 1:
+    if list_major and not args.scan_mode and world == 1 and sim_lists is None:
         g.set_param("scan_mode", 1)
         qm_ms, _ = time_search(c, g, qb[1], k, nprobe, 4)
         qm_prof = profiled(c, g, qb[1], k, nprobe, reps=2)
         g.set_param("scan_mode", 0)
         qm = (qm_ms, qm_prof)
 
-    recall = recall_at_k(c, g, qb[0], k, i0[: min(args.recall_queries, nq)])
+    recall = recall_at_k(c, g, qb[0], k, i0[: min(args.recall_queries, nq)]) if sim_lists is None else None
 
     if rank != 0:
         if world > 1 and world == 8 and not args.no_extras:
@@ -922,10 +982,10 @@ def run_ours(args):
         "build_s": build_s,
     }
     if world > 1:
-        line["config"]["exchange"] = "p2p-fused (peer-memory stores + flags, no collective call)" if ex is not None else \
-            f"nccl all-gather + merge ({ex_err or 'requested'})"
+        line["config"]["exchange"] = (f"p2p-fused (peer-memory stores + flags, no collective call), {nl} steps in flight per rank"
+                                      if ex is not None else f"nccl all-gather + merge ({ex_err or 'requested'})")
         if ex is not None:
-            line["exchange_timed_out"] = ex.status()[0]
+            line["exchange_timed_out"] = any(e.status()[0] for e in exs)
 
     # ---- CPU baseline: timed inside check_parity on the same lists (bounded sample) ----------------------
     if world == 1:
@@ -969,7 +1029,7 @@ def run_ours(args):
                 line["c3"] = run_c3(c)
             except Exception as e:  # noqa: BLE001
                 line["c3"] = {"error": f"{type(e).__name__}: {e}"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -1009,12 +1069,32 @@ def run_c3(c):
             "exchange_timed_out": timed_out, "build_s": build_s}
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The one JSON line goes to the process's ORIGINAL stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
-    else:
-        run_ours(args)
+        return
+    # stdout carries exactly one JSON line.  Libraries underneath write to fd 1 on their own (NCCL prints its version and, with
+    # NCCL_DEBUG=INFO, its whole log there): keep the original stdout for the line and point fd 1 at stderr for the run, so
+    # NCCL_DEBUG stays whatever the launcher chose and its output stays visible.
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+    run_ours(args)
 
 
 if __name__ == "__main__":

@@ -225,8 +225,6 @@ cudaError_t launch_select_rows_peers(const float *scores, int64_t M, int N, int 
                                      const PeerSignal &sig, cudaStream_t st);
 cudaError_t launch_select_candidates_peers(const ScanArgs &a, int64_t nq, int k, const PeerTopk &out, const PeerSignal &sig,
                                            cudaStream_t st);
-cudaError_t launch_merge_topk_wait(const float *part_dist, const int64_t *part_ids, int parts, int64_t nq, int kin, int k,
-                                   int metric, float *out_dist, int64_t *out_ids, const PeerWait &wait, cudaStream_t st);
 cudaError_t launch_peer_signal(const PeerSignal &sig, cudaStream_t st);  // a rank with an empty slice still publishes
 cudaError_t launch_peer_wait(const PeerWait &wait, cudaStream_t st);     // orders the stream after the peers' stores
 

@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <mutex>
 #include <queue>
 #include <string>
@@ -138,6 +139,40 @@ __global__ void fill_u32_kernel(uint32_t *p, int64_t n, uint32_t v) {
 
 }  // namespace
 
+// Scratch of ONE call in flight.  Stream ordered: ev_done marks the end of the slot's last user, so the next user may be on
+// another stream.
+constexpr int kSlots = 2;
+struct Scratch {
+    DevBuf s_q, s_scores, s_probe, s_pageoff, s_cand, s_outd, s_outi, s_repobits;
+    DevBuf s_x, s_xpad, s_ids, s_repo, s_lang, s_assign, s_best, s_pos, s_lenold, s_need, s_npg, s_needoff, s_bad;
+    DevBuf s_sums, s_counts, s_obj, s_rows, s_rm, s_cnt, s_ahi, s_alo, s_lplan, s_scan, s_packed, s_qsplit, s_bstage;
+    cudaEvent_t ev_done = nullptr;
+    cudaStream_t side[2] = {nullptr, nullptr};  // fork/join streams of the list-major scan
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    uint32_t plan_epoch = 0;  // launch counter of the pair plan's look-back words (s_scan)
+    bool busy = false, used = false;
+    void *last_stream = nullptr;  // stream of the slot's last search
+    unsigned long long last_use = 0;
+
+    // profiling of the last search that ran in this slot
+    std::vector<cudaEvent_t> prof_ev;  // 6 events per chunk: t0 coarse | select | plan | scan | topk t5
+    unsigned long long *prof_rows = nullptr;  // device counter
+    int64_t prof_pages = 0;
+    int prof_scan_launches = 0, prof_total_launches = 0;
+
+    template <class F>
+    void each_buf(F f) {
+        for (DevBuf *b : {&s_q, &s_scores, &s_probe, &s_pageoff, &s_cand, &s_outd, &s_outi, &s_repobits, &s_x, &s_xpad, &s_ids, &s_repo,
+                          &s_lang, &s_assign, &s_best, &s_pos, &s_lenold, &s_need, &s_npg, &s_needoff, &s_bad, &s_sums, &s_counts, &s_obj,
+                          &s_rows, &s_rm, &s_cnt, &s_ahi, &s_alo, &s_lplan, &s_scan, &s_packed, &s_qsplit, &s_bstage})
+            f(b);
+    }
+};
+
+// the slot of the call running on this host thread (set by ReadGuard / WriteGuard for the duration of a C-ABI call)
+static thread_local Scratch *tl_scr = nullptr;
+static thread_local bool tl_writer = false;
+
 // ------------------------------------------------------------------------------------------------
 // the index object
 // ------------------------------------------------------------------------------------------------
@@ -174,28 +209,99 @@ struct sc_index {
     int32_t h_max_pages = 0;
     int64_t ntotal = 0, nremoved = 0;
 
-    // scratch (stream ordered; ev_done chains calls made on different streams)
-    DevBuf s_q, s_scores, s_probe, s_pageoff, s_cand, s_outd, s_outi, s_repobits;
-    DevBuf s_x, s_xpad, s_ids, s_repo, s_lang, s_assign, s_best, s_pos, s_lenold, s_need, s_npg, s_needoff, s_bad;
-    DevBuf s_sums, s_counts, s_obj, s_rows, s_rm, s_cnt, s_ahi, s_alo, s_lplan, s_scan, s_packed, s_qsplit, s_bstage;
+    // per-call scratch lives in slots (struct Scratch below): searches take any free slot under the shared side of the
+    // lock, so kSlots of them run at once on different streams; everything else runs alone on slot 0
+    Scratch scr[kSlots];
     int64_t scratch_budget = (int64_t)8 << 30;  // search scratch ceiling (candidates dominate); sc_index_set_param("scratch_bytes")
     int scan_variant = 0;
     int lists_cfg = 0;  // list-major tile items: 0 = tcgen05 where it applies (scan_lists_ts.cu: list rows from tensor memory), 1 = FFMA tiles, 2 = FFMA tiles with 32-float stages, 3 / 5 = the shared-memory-operand tcgen05 kernels (scan_lists_tc.cu v1 / v2), 4 = 0 with the 8-query page scan on mma.sync
     int scan_mode = 0;  // 0 = auto, 1 = query-major (scan.cu), 2 = list-major (scan_lists.cu)
-    cudaEvent_t ev_done = nullptr;
-    cudaStream_t side[2] = {nullptr, nullptr};  // fork/join streams of the list-major scan
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
-    uint32_t plan_epoch = 0;  // launch counter of the pair plan's look-back words (s_scan)
     int lists_fork = 0;  // measured slower on C2 (tile CTAs pin shared memory the page scan needs): off by default
 
-    // profiling of the last search
-    bool profiling = false;
-    std::vector<cudaEvent_t> prof_ev;  // 6 events per chunk: t0 coarse | select | plan | scan | topk t5
-    unsigned long long *prof_rows = nullptr;  // device counter
-    int64_t prof_pages = 0;
-    int prof_scan_launches = 0, prof_total_launches = 0;
+    bool profiling = false;  // per-phase events of searches (kept in the slot the search ran in)
+    unsigned long long use_clock = 0;
+    int last_slot = 0;       // slot of the search that finished last: what sc_index_last_search_times reports
 
+    // reader / writer lock with slot hand-out (host side); the device side is ordered by events: a search waits for its
+    // slot's previous user and for the last writer, a writer waits for every slot and the last writer
+    std::condition_variable cv;
+    int readers = 0, writers_waiting = 0;
+    bool writer = false;
+    cudaEvent_t ev_write = nullptr;
     std::mutex mu;
+};
+
+// Host-side entry discipline of the C ABI.  WriteGuard: alone on the handle (waits for running searches, blocks new ones),
+// slot 0.  ReadGuard: shared with other searches, each on its own free slot (waits while kSlots searches are in the library).
+// Both only cover the time the call spends ENQUEUEING work; on the device the slots and the writers are ordered by events
+// (begin_call / end_call).
+struct WriteGuard {
+    sc_index *ix;
+    explicit WriteGuard(sc_index *i) : ix(i) {
+        std::unique_lock<std::mutex> lk(ix->mu);
+        ++ix->writers_waiting;
+        ix->cv.wait(lk, [&] { return !ix->writer && ix->readers == 0; });
+        --ix->writers_waiting;
+        ix->writer = true;
+        tl_scr = &ix->scr[0];
+        tl_writer = true;
+    }
+    ~WriteGuard() {
+        {
+            std::lock_guard<std::mutex> lk(ix->mu);
+            ix->writer = false;
+        }
+        tl_scr = nullptr;
+        tl_writer = false;
+        ix->cv.notify_all();
+    }
+    WriteGuard(const WriteGuard &) = delete;
+    WriteGuard &operator=(const WriteGuard &) = delete;
+};
+
+struct ReadGuard {
+    sc_index *ix;
+    int slot = -1;
+    ReadGuard(sc_index *i, void *stream) : ix(i) {
+        std::unique_lock<std::mutex> lk(ix->mu);
+        ix->cv.wait(lk, [&] {
+            if (ix->writer || ix->writers_waiting > 0) return false;  // writers first: a stream of searches cannot starve an insert
+            for (int k = 0; k < kSlots; ++k)
+                if (!ix->scr[k].busy) return true;
+            return false;
+        });
+        // A caller keeps the slot its stream used last (one stream: one slot, no second set of scratch buffers; one host
+        // thread alternating between two streams: two slots, so its searches overlap on the device); otherwise the free
+        // slot that has rested longest.
+        int same = -1, oldest = -1;
+        for (int k = 0; k < kSlots; ++k) {
+            const Scratch &c = ix->scr[k];
+            if (c.busy) continue;
+            if (same < 0 && c.used && c.last_stream == stream) same = k;
+            if (oldest < 0 || c.last_use < ix->scr[oldest].last_use) oldest = k;
+        }
+        slot = same >= 0 ? same : oldest;
+        Scratch &sl = ix->scr[slot];
+        sl.busy = true;
+        sl.used = true;
+        sl.last_stream = stream;
+        sl.last_use = ++ix->use_clock;
+        ++ix->readers;
+        tl_scr = &sl;
+        tl_writer = false;
+    }
+    ~ReadGuard() {
+        {
+            std::lock_guard<std::mutex> lk(ix->mu);
+            ix->scr[slot].busy = false;
+            --ix->readers;
+            ix->last_slot = slot;
+        }
+        tl_scr = nullptr;
+        ix->cv.notify_all();
+    }
+    ReadGuard(const ReadGuard &) = delete;
+    ReadGuard &operator=(const ReadGuard &) = delete;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -365,14 +471,20 @@ int stage_rows(sc_index *ix, const float *x, int64_t n, DevBuf &raw, DevBuf &pad
 }
 
 int begin_call(sc_index *ix, cudaStream_t st) {
-    // scratch is shared by all calls on the handle: order this call after the previous one even
-    // when the caller switched streams
-    CU(cudaStreamWaitEvent(st, ix->ev_done, 0));
+    // order this call on the device after the previous user of its slot and after the last writer (a writer: after every
+    // slot), even when the caller switched streams
+    if (tl_writer) {
+        for (int k = 0; k < kSlots; ++k) CU(cudaStreamWaitEvent(st, ix->scr[k].ev_done, 0));
+    } else {
+        CU(cudaStreamWaitEvent(st, tl_scr->ev_done, 0));
+    }
+    CU(cudaStreamWaitEvent(st, ix->ev_write, 0));
     return SC_OK;
 }
 
 int end_call(sc_index *ix, cudaStream_t st) {
-    CU(cudaEventRecord(ix->ev_done, st));
+    CU(cudaEventRecord(tl_scr->ev_done, st));
+    if (tl_writer) CU(cudaEventRecord(ix->ev_write, st));
     return SC_OK;
 }
 
@@ -404,10 +516,10 @@ int coarse_scores(sc_index *ix, const float *xd, int64_t m, float *scores, cudaS
         CU(launch_gemm_nt(xd, m, ix->centroids, ix->nlist, ix->ds, l2 ? ix->cnorm : nullptr, scores, st));
         return SC_OK;
     }
-    CU(ix->s_ahi.reserve((size_t)m * ix->ds * 4));
-    CU(ix->s_alo.reserve((size_t)m * ix->ds * 4));
-    CU(launch_split_tf32(xd, m * ix->ds, ix->s_ahi.as<float>(), ix->s_alo.as<float>(), st));
-    CU(launch_gemm_tc_scores(ix->s_ahi.as<float>(), ix->s_alo.as<float>(), m, ix->cent_hi, ix->cent_lo, ix->nlist, ix->ds,
+    CU(tl_scr->s_ahi.reserve((size_t)m * ix->ds * 4));
+    CU(tl_scr->s_alo.reserve((size_t)m * ix->ds * 4));
+    CU(launch_split_tf32(xd, m * ix->ds, tl_scr->s_ahi.as<float>(), tl_scr->s_alo.as<float>(), st));
+    CU(launch_gemm_tc_scores(tl_scr->s_ahi.as<float>(), tl_scr->s_alo.as<float>(), m, ix->cent_hi, ix->cent_lo, ix->nlist, ix->ds,
                              l2 ? 2.f : 1.f, l2 ? ix->cnorm : nullptr, scores, ix->num_sms, st));
     return SC_OK;
 }
@@ -427,25 +539,25 @@ int coarse_assign(sc_index *ix, const float *xd, int64_t n, int32_t *assign, flo
         // Centroids are swept in slabs whose hi/lo copies (~48 MB) stay L2-resident while every row
         // tile passes; the running best is carried across slabs in best/assign.
         const bool l2 = ix->metric == SC_METRIC_L2;
-        CU(ix->s_ahi.reserve((size_t)n * ix->ds * 4));
-        CU(ix->s_alo.reserve((size_t)n * ix->ds * 4));
-        CU(launch_split_tf32(xd, n * ix->ds, ix->s_ahi.as<float>(), ix->s_alo.as<float>(), st));
+        CU(tl_scr->s_ahi.reserve((size_t)n * ix->ds * 4));
+        CU(tl_scr->s_alo.reserve((size_t)n * ix->ds * 4));
+        CU(launch_split_tf32(xd, n * ix->ds, tl_scr->s_ahi.as<float>(), tl_scr->s_alo.as<float>(), st));
         float *bv = best;
         if (!bv) {
-            CU(ix->s_best.reserve((size_t)n * 4));
-            bv = ix->s_best.as<float>();
+            CU(tl_scr->s_best.reserve((size_t)n * 4));
+            bv = tl_scr->s_best.as<float>();
         }
         int64_t slab = (((int64_t)48 << 20) / ((int64_t)ix->ds * 8)) / 256 * 256;
         slab = std::max<int64_t>(256, std::min<int64_t>(slab, ix->nlist));
         unsigned long long *packed = nullptr;
         if (ix->tc_variant == 0) {  // 256x256 tiles: per-row best merged across CTAs and slabs with atomicMax
-            CU(ix->s_packed.reserve((size_t)n * 8));
-            packed = ix->s_packed.as<unsigned long long>();
+            CU(tl_scr->s_packed.reserve((size_t)n * 8));
+            packed = tl_scr->s_packed.as<unsigned long long>();
             CU(cudaMemsetAsync(packed, 0, (size_t)n * 8, st));
         }
         for (int64_t c0 = 0; c0 < ix->nlist; c0 += slab) {
             const int nc = (int)std::min<int64_t>(slab, ix->nlist - c0);
-            CU(launch_gemm_tc_argmax(ix->s_ahi.as<float>(), ix->s_alo.as<float>(), n, ix->cent_hi + c0 * ix->ds,
+            CU(launch_gemm_tc_argmax(tl_scr->s_ahi.as<float>(), tl_scr->s_alo.as<float>(), n, ix->cent_hi + c0 * ix->ds,
                                      ix->cent_lo + c0 * ix->ds, nc, ix->ds, l2 ? 2.f : 1.f, l2 ? ix->cnorm + c0 : nullptr, bv,
                                      assign, (int)c0, c0 > 0 ? 1 : 0, ix->num_sms, packed, st));
         }
@@ -453,11 +565,11 @@ int coarse_assign(sc_index *ix, const float *xd, int64_t n, int32_t *assign, flo
         return SC_OK;
     }
     const int64_t ch = coarse_chunk_rows(ix, n);
-    CU(ix->s_scores.reserve((size_t)ch * ix->nlist * sizeof(float)));
+    CU(tl_scr->s_scores.reserve((size_t)ch * ix->nlist * sizeof(float)));
     for (int64_t s = 0; s < n; s += ch) {
         const int64_t m = std::min(ch, n - s);
-        SC(coarse_scores(ix, xd + s * ix->ds, m, ix->s_scores.as<float>(), st));
-        CU(launch_argmax_rows(ix->s_scores.as<float>(), m, ix->nlist, assign + s, best ? best + s : nullptr, st));
+        SC(coarse_scores(ix, xd + s * ix->ds, m, tl_scr->s_scores.as<float>(), st));
+        CU(launch_argmax_rows(tl_scr->s_scores.as<float>(), m, ix->nlist, assign + s, best ? best + s : nullptr, st));
     }
     return SC_OK;
 }
@@ -466,24 +578,24 @@ int coarse_assign(sc_index *ix, const float *xd, int64_t n, int32_t *assign, flo
 int add_device_rows_unguarded(sc_index *ix, const float *xd, const int64_t *ids_d, const uint32_t *repo_d, const uint8_t *lang_d,
                               const int32_t *lists_d, int64_t n, cudaStream_t st, bool *bumped) {
     const int nlist = ix->nlist;
-    CU(ix->s_pos.reserve((size_t)n * 4));
-    CU(ix->s_lenold.reserve((size_t)nlist * 4));
-    CU(ix->s_need.reserve((size_t)nlist * 4));
-    CU(ix->s_npg.reserve((size_t)nlist * 4));
-    CU(ix->s_needoff.reserve((size_t)(nlist + 1) * 4));
-    CU(ix->s_bad.reserve(16));
-    CU(cudaMemcpyAsync(ix->s_lenold.p, ix->list_len, (size_t)nlist * 4, cudaMemcpyDeviceToDevice, st));
-    CU(cudaMemsetAsync(ix->s_bad.p, 0, 16, st));
+    CU(tl_scr->s_pos.reserve((size_t)n * 4));
+    CU(tl_scr->s_lenold.reserve((size_t)nlist * 4));
+    CU(tl_scr->s_need.reserve((size_t)nlist * 4));
+    CU(tl_scr->s_npg.reserve((size_t)nlist * 4));
+    CU(tl_scr->s_needoff.reserve((size_t)(nlist + 1) * 4));
+    CU(tl_scr->s_bad.reserve(16));
+    CU(cudaMemcpyAsync(tl_scr->s_lenold.p, ix->list_len, (size_t)nlist * 4, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemsetAsync(tl_scr->s_bad.p, 0, 16, st));
     *bumped = true;  // from here on the device list lengths are ahead of the page table until the scatter is queued
-    CU(launch_count_positions(lists_d, repo_d, n, nlist, ix->list_len, ix->s_pos.as<int32_t>(), ix->s_bad.as<int32_t>(), st));
-    CU(launch_page_need(ix->s_lenold.as<int32_t>(), ix->list_len, nlist, ix->s_need.as<int32_t>(),
-                        ix->s_npg.as<int32_t>(), st));
-    CU(launch_exclusive_scan_i32(ix->s_need.as<int32_t>(), nlist, ix->s_needoff.as<int32_t>(), st));
-    CU(launch_exclusive_scan_i32(ix->s_npg.as<int32_t>(), nlist, ix->pt_off_alt, st));
+    CU(launch_count_positions(lists_d, repo_d, n, nlist, ix->list_len, tl_scr->s_pos.as<int32_t>(), tl_scr->s_bad.as<int32_t>(), st));
+    CU(launch_page_need(tl_scr->s_lenold.as<int32_t>(), ix->list_len, nlist, tl_scr->s_need.as<int32_t>(),
+                        tl_scr->s_npg.as<int32_t>(), st));
+    CU(launch_exclusive_scan_i32(tl_scr->s_need.as<int32_t>(), nlist, tl_scr->s_needoff.as<int32_t>(), st));
+    CU(launch_exclusive_scan_i32(tl_scr->s_npg.as<int32_t>(), nlist, ix->pt_off_alt, st));
     int32_t h_new = 0, h_total = 0, h_bad[2] = {0, 0};
-    CU(cudaMemcpyAsync(&h_new, ix->s_needoff.as<int32_t>() + nlist, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&h_new, tl_scr->s_needoff.as<int32_t>() + nlist, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&h_total, ix->pt_off_alt + nlist, 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(h_bad, ix->s_bad.p, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_bad, tl_scr->s_bad.p, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (h_bad[0] != 0) return fail(SC_ERR_INVALID, "%d rows carry a list id outside [0, %d)", h_bad[0], nlist);
     if (h_bad[1] != 0) return fail(SC_ERR_INVALID, "%d rows carry a repo tag above %u", h_bad[1], kTagRepoMax);
@@ -502,9 +614,9 @@ int add_device_rows_unguarded(sc_index *ix, const float *xd, const int64_t *ids_
         CU(cudaMalloc(&ix->pt_alt, (size_t)want * 4));
         ix->pt_alt_cap = want;
     }
-    CU(launch_rebuild_pt(ix->pt_off, ix->pt, ix->pt_off_alt, ix->pt_alt, ix->s_needoff.as<int32_t>(), ix->pool_top,
+    CU(launch_rebuild_pt(ix->pt_off, ix->pt, ix->pt_off_alt, ix->pt_alt, tl_scr->s_needoff.as<int32_t>(), ix->pool_top,
                          ix->free_pages ? ix->free_pages + (ix->nfree - from_free) : nullptr, from_free, nlist, st));
-    CU(launch_scatter_rows(xd, ids_d, repo_d, lang_d, lists_d, ix->s_pos.as<int32_t>(), n, ix->ds, ix->pt_off_alt, ix->pt_alt,
+    CU(launch_scatter_rows(xd, ids_d, repo_d, lang_d, lists_d, tl_scr->s_pos.as<int32_t>(), n, ix->ds, ix->pt_off_alt, ix->pt_alt,
                            ix->d_tab, ix->slab_shift, st));
     // committed: every launch is queued, only now does the host state move
     std::swap(ix->pt, ix->pt_alt);
@@ -527,7 +639,7 @@ int add_device_rows(sc_index *ix, const float *xd, const int64_t *ids_d, const u
     if (rc != SC_OK && bumped) {
         const std::string why = g_err;
         cudaGetLastError();
-        if (cudaMemcpyAsync(ix->list_len, ix->s_lenold.p, (size_t)ix->nlist * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
+        if (cudaMemcpyAsync(ix->list_len, tl_scr->s_lenold.p, (size_t)ix->nlist * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
             cudaStreamSynchronize(st) != cudaSuccess) {
             cudaGetLastError();
             return fail(rc, "%s; AND the list lengths could not be restored: reset the index", why.c_str());
@@ -558,16 +670,16 @@ int add_chunks(sc_index *ix, const float *x, const int64_t *ids, const uint32_t 
         const uint32_t *repo_d = nullptr;
         const uint8_t *lang_d = nullptr;
         const int32_t *lists_d = nullptr;
-        SC(stage_rows(ix, x + s * ix->dim, m, ix->s_x, ix->s_xpad, st, &xd));
-        SC(stage(ix, ids + s, (size_t)m, ix->s_ids, st, &ids_d));
-        SC(stage(ix, repo ? repo + s : nullptr, (size_t)m, ix->s_repo, st, &repo_d));
-        SC(stage(ix, lang ? lang + s : nullptr, (size_t)m, ix->s_lang, st, &lang_d));
+        SC(stage_rows(ix, x + s * ix->dim, m, tl_scr->s_x, tl_scr->s_xpad, st, &xd));
+        SC(stage(ix, ids + s, (size_t)m, tl_scr->s_ids, st, &ids_d));
+        SC(stage(ix, repo ? repo + s : nullptr, (size_t)m, tl_scr->s_repo, st, &repo_d));
+        SC(stage(ix, lang ? lang + s : nullptr, (size_t)m, tl_scr->s_lang, st, &lang_d));
         if (lists) {
-            SC(stage(ix, lists + s, (size_t)m, ix->s_assign, st, &lists_d));
+            SC(stage(ix, lists + s, (size_t)m, tl_scr->s_assign, st, &lists_d));
         } else {
-            CU(ix->s_assign.reserve((size_t)m * 4));
-            SC(coarse_assign(ix, xd, m, ix->s_assign.as<int32_t>(), nullptr, st));
-            lists_d = ix->s_assign.as<int32_t>();
+            CU(tl_scr->s_assign.reserve((size_t)m * 4));
+            SC(coarse_assign(ix, xd, m, tl_scr->s_assign.as<int32_t>(), nullptr, st));
+            lists_d = tl_scr->s_assign.as<int32_t>();
         }
         SC(add_device_rows(ix, xd, ids_d, repo_d, lang_d, lists_d, m, st));
     }
@@ -614,10 +726,10 @@ int build_filter(sc_index *ix, const sc_filter_t *filt, cudaStream_t st, FilterD
             const uint32_t nbits = mx + 1;
             std::vector<uint32_t> bits((nbits + 31) / 32, 0u);
             for (int i = 0; i < filt->n_repos; ++i) bits[filt->repo_tags[i] >> 5] |= 1u << (filt->repo_tags[i] & 31);
-            CU(ix->s_repobits.reserve(bits.size() * 4));
-            CU(cudaMemcpyAsync(ix->s_repobits.p, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, st));
+            CU(tl_scr->s_repobits.reserve(bits.size() * 4));
+            CU(cudaMemcpyAsync(tl_scr->s_repobits.p, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, st));
             CU(cudaStreamSynchronize(st));  // `bits` dies at scope exit
-            f.repo_bits = ix->s_repobits.as<uint32_t>();
+            f.repo_bits = tl_scr->s_repobits.as<uint32_t>();
             f.n_repo_bits = nbits;
         }
     }
@@ -625,11 +737,11 @@ int build_filter(sc_index *ix, const sc_filter_t *filt, cudaStream_t st, FilterD
     return SC_OK;
 }
 
-void clear_prof(sc_index *ix) {
-    for (auto e : ix->prof_ev) cudaEventDestroy(e);
-    ix->prof_ev.clear();
-    ix->prof_scan_launches = 0;
-    ix->prof_total_launches = 0;
+void clear_prof(Scratch *sl) {
+    for (auto e : sl->prof_ev) cudaEventDestroy(e);
+    sl->prof_ev.clear();
+    sl->prof_scan_launches = 0;
+    sl->prof_total_launches = 0;
 }
 
 int prof_mark(sc_index *ix, cudaStream_t st) {
@@ -637,7 +749,7 @@ int prof_mark(sc_index *ix, cudaStream_t st) {
     cudaEvent_t e;
     CU(cudaEventCreate(&e));
     CU(cudaEventRecord(e, st));
-    ix->prof_ev.push_back(e);
+    tl_scr->prof_ev.push_back(e);
     return SC_OK;
 }
 
@@ -662,12 +774,12 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
     SC(begin_call(ix, st));
     FilterDev fdev;
     SC(build_filter(ix, filt, st, &fdev));
-    ix->prof_scan_launches = 0;  // launch counts describe the last call, profiled or not
-    ix->prof_total_launches = 0;
+    tl_scr->prof_scan_launches = 0;  // launch counts describe the last call, profiled or not
+    tl_scr->prof_total_launches = 0;
     if (ix->profiling) {
-        clear_prof(ix);
-        if (!ix->prof_rows) CU(cudaMalloc(&ix->prof_rows, 16));
-        CU(cudaMemsetAsync(ix->prof_rows, 0, 16, st));
+        clear_prof(tl_scr);
+        if (!tl_scr->prof_rows) CU(cudaMalloc(&tl_scr->prof_rows, 16));
+        CU(cudaMemsetAsync(tl_scr->prof_rows, 0, 16, st));
     }
 
     // worst-case pages one query can touch -> candidate scratch per query
@@ -697,20 +809,20 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
     }
 
     const int64_t npairs_max = nqc * np;
-    if (!lists && !all_lists) CU(ix->s_scores.reserve((size_t)nqc * ix->nlist * 4));
-    if (!lists) CU(ix->s_probe.reserve((size_t)npairs_max * 4));
-    CU(ix->s_pageoff.reserve((size_t)(npairs_max + 1) * 8));
+    if (!lists && !all_lists) CU(tl_scr->s_scores.reserve((size_t)nqc * ix->nlist * 4));
+    if (!lists) CU(tl_scr->s_probe.reserve((size_t)npairs_max * 4));
+    CU(tl_scr->s_pageoff.reserve((size_t)(npairs_max + 1) * 8));
     {   // look-back words of the pair plan: zero when (re)allocated and when the 22-bit epoch wraps
-        const void *before = ix->s_scan.p;
-        CU(ix->s_scan.reserve(plan_pairs_look_words(npairs_max) * 8));
-        if (ix->s_scan.p != before) {
-            CU(cudaMemsetAsync(ix->s_scan.p, 0, ix->s_scan.cap, st));
-            ix->plan_epoch = 0;
+        const void *before = tl_scr->s_scan.p;
+        CU(tl_scr->s_scan.reserve(plan_pairs_look_words(npairs_max) * 8));
+        if (tl_scr->s_scan.p != before) {
+            CU(cudaMemsetAsync(tl_scr->s_scan.p, 0, tl_scr->s_scan.cap, st));
+            tl_scr->plan_epoch = 0;
         }
     }
-    CU(ix->s_cand.reserve((size_t)nqc * pb * kPageRows * 4));
-    if (!outd_dev) CU(ix->s_outd.reserve((size_t)nqc * k * 4));
-    if (!outi_dev) CU(ix->s_outi.reserve((size_t)nqc * k * 8));
+    CU(tl_scr->s_cand.reserve((size_t)nqc * pb * kPageRows * 4));
+    if (!outd_dev) CU(tl_scr->s_outd.reserve((size_t)nqc * k * 4));
+    if (!outi_dev) CU(tl_scr->s_outi.reserve((size_t)nqc * k * 8));
     if (ex) {
         // The step's epoch moves only now, after the large scratch reservations: a rank that fails above (out of memory)
         // has not published anything and its peers time out cleanly.  A failure further down leaves this rank's epoch ahead
@@ -723,46 +835,46 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
         const int64_t m = std::min(nqc, nq - s);
         const int64_t npairs = m * np;
         const float *qd = nullptr;
-        SC(stage_rows(ix, q + s * ix->dim, m, ix->s_q, ix->s_xpad, st, &qd));
+        SC(stage_rows(ix, q + s * ix->dim, m, tl_scr->s_q, tl_scr->s_xpad, st, &qd));
         const int32_t *probe = nullptr;
         SC(prof_mark(ix, st));
         if (lists) {
-            SC(stage(ix, lists + s * np, (size_t)npairs, ix->s_probe, st, &probe));
+            SC(stage(ix, lists + s * np, (size_t)npairs, tl_scr->s_probe, st, &probe));
             SC(prof_mark(ix, st));
         } else if (all_lists) {
             SC(prof_mark(ix, st));
-            iota_rows_kernel<<<ix->num_sms * 4, 256, 0, st>>>(ix->s_probe.as<int32_t>(), m, np);
+            iota_rows_kernel<<<ix->num_sms * 4, 256, 0, st>>>(tl_scr->s_probe.as<int32_t>(), m, np);
             CU(cudaGetLastError());
-            probe = ix->s_probe.as<int32_t>();
-            ix->prof_total_launches += 1;
+            probe = tl_scr->s_probe.as<int32_t>();
+            tl_scr->prof_total_launches += 1;
         } else if (ex) {
             // this rank ranks the centroids for its 1/world of the batch and stores the rows into every peer's table
             const int64_t per = (m + ex->world - 1) / ex->world;
             const int64_t lo = std::min<int64_t>(m, (int64_t)ex->rank * per), hi = std::min<int64_t>(m, lo + per);
-            if (hi > lo) SC(coarse_scores(ix, qd + lo * ix->ds, hi - lo, ix->s_scores.as<float>(), st));
+            if (hi > lo) SC(coarse_scores(ix, qd + lo * ix->ds, hi - lo, tl_scr->s_scores.as<float>(), st));
             SC(prof_mark(ix, st));
             PeerRows rows;
             memset(&rows, 0, sizeof(rows));
             for (int p = 0; p < ex->world; ++p) rows.p[p] = reinterpret_cast<int32_t *>(ex->peer[p] + exl.probes);
             rows.row0 = lo;
-            CU(launch_select_rows_peers(ix->s_scores.as<float>(), hi - lo, ix->nlist, np, rows, make_signal(ex, 0), st));
+            CU(launch_select_rows_peers(tl_scr->s_scores.as<float>(), hi - lo, ix->nlist, np, rows, make_signal(ex, 0), st));
             CU(launch_peer_wait(make_wait(ex, 0), st));
             probe = reinterpret_cast<const int32_t *>(ex->peer[ex->rank] + exl.probes);
-            ix->prof_total_launches += (use_tc(ix) ? 3 : 2) + 1;
+            tl_scr->prof_total_launches += (use_tc(ix) ? 3 : 2) + 1;
         } else {
-            SC(coarse_scores(ix, qd, m, ix->s_scores.as<float>(), st));
+            SC(coarse_scores(ix, qd, m, tl_scr->s_scores.as<float>(), st));
             SC(prof_mark(ix, st));
-            CU(launch_select_rows(ix->s_scores.as<float>(), m, ix->nlist, np, ix->s_probe.as<int32_t>(), nullptr, st));
-            probe = ix->s_probe.as<int32_t>();
-            ix->prof_total_launches += use_tc(ix) ? 3 : 2;
+            CU(launch_select_rows(tl_scr->s_scores.as<float>(), m, ix->nlist, np, tl_scr->s_probe.as<int32_t>(), nullptr, st));
+            probe = tl_scr->s_probe.as<int32_t>();
+            tl_scr->prof_total_launches += use_tc(ix) ? 3 : 2;
         }
         SC(prof_mark(ix, st));
-        if (((ix->plan_epoch + 1) & 0x3fffffu) == 0) {  // epochs 1 .. 2^22 - 2, then start over on zeroed words
-            CU(cudaMemsetAsync(ix->s_scan.p, 0, ix->s_scan.cap, st));
-            ix->plan_epoch = 0;
+        if (((tl_scr->plan_epoch + 1) & 0x3fffffu) == 0) {  // epochs 1 .. 2^22 - 2, then start over on zeroed words
+            CU(cudaMemsetAsync(tl_scr->s_scan.p, 0, tl_scr->s_scan.cap, st));
+            tl_scr->plan_epoch = 0;
         }
-        CU(launch_plan_pairs(probe, npairs, ix->list_len, ix->nlist, ix->s_pageoff.as<int64_t>(),
-                             ix->s_scan.as<unsigned long long>(), ++ix->plan_epoch, ix->profiling ? ix->prof_rows : nullptr, st));
+        CU(launch_plan_pairs(probe, npairs, ix->list_len, ix->nlist, tl_scr->s_pageoff.as<int64_t>(),
+                             tl_scr->s_scan.as<unsigned long long>(), ++tl_scr->plan_epoch, ix->profiling ? tl_scr->prof_rows : nullptr, st));
         SC(prof_mark(ix, st));
         ScanArgs a;
         memset(&a, 0, sizeof(a));
@@ -772,13 +884,13 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
         a.nprobe = np;
         a.npairs = npairs;
         a.probe = probe;
-        a.page_off = ix->s_pageoff.as<int64_t>();
+        a.page_off = tl_scr->s_pageoff.as<int64_t>();
         a.list_len = ix->list_len;
         a.pt_off = ix->pt_off;
         a.pt = ix->pt;
         a.slabs = ix->d_tab;
         a.slab_shift = ix->slab_shift;
-        a.cand = ix->s_cand.as<float>();
+        a.cand = tl_scr->s_cand.as<float>();
         a.filt = fdev;
         a.slab_maps = ix->d_maps;
         // large batches re-probe the same lists: read each list once and score it against all its queries
@@ -797,8 +909,8 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
             const size_t nl = (size_t)ix->nlist;
             const size_t agg_words = (size_t)list_plan_ctas(ix->nlist) * 8;  // 4 x u64 per plan CTA
             const size_t words = 3 * nl + 4 + agg_words + 4 * (nl + 1) + (size_t)npairs + 16;
-            CU(ix->s_lplan.reserve(words * 4));
-            int32_t *w = ix->s_lplan.as<int32_t>();
+            CU(tl_scr->s_lplan.reserve(words * 4));
+            int32_t *w = tl_scr->s_lplan.as<int32_t>();
             ListPlan lp;
             lp.nlist = ix->nlist;
             // tile items on the tensor cores (scan_lists_tc.cu): inner product and whole 32-float k-blocks only;
@@ -811,14 +923,14 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
                 const bool ts = ix->lists_cfg != 5 && ix->lists_cfg != 3 && ix->d_maps != nullptr &&
                                 npairs * (int64_t)(ix->ds / 32) < ((int64_t)1 << 30);
                 if (!ts) {
-                    CU(ix->s_qsplit.reserve((size_t)m * ix->ds * 4 * 2));
-                    lp.qsplit = ix->s_qsplit.as<float>();
+                    CU(tl_scr->s_qsplit.reserve((size_t)m * ix->ds * 4 * 2));
+                    lp.qsplit = tl_scr->s_qsplit.as<float>();
                 }
                 if (ts) {
-                    const void *before = ix->s_bstage.p;
-                    CU(ix->s_bstage.reserve(scan_lists_ts_stage_bytes(ix->ds, ix->num_sms)));
-                    if (ix->s_bstage.p != before) CU(cudaMemsetAsync(ix->s_bstage.p, 0, ix->s_bstage.cap, st));  // padded rows are read (never stored): keep them finite
-                    lp.bstage = ix->s_bstage.as<float>();
+                    const void *before = tl_scr->s_bstage.p;
+                    CU(tl_scr->s_bstage.reserve(scan_lists_ts_stage_bytes(ix->ds, ix->num_sms)));
+                    if (tl_scr->s_bstage.p != before) CU(cudaMemsetAsync(tl_scr->s_bstage.p, 0, tl_scr->s_bstage.cap, st));  // padded rows are read (never stored): keep them finite
+                    lp.bstage = tl_scr->s_bstage.as<float>();
                 }
             }
             lp.cnt = w;
@@ -831,19 +943,19 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
             lp.pg8off = lp.off32 + nl + 1;
             lp.pg4off = lp.pg8off + nl + 1;
             lp.lq = lp.pg4off + nl + 1;
-            lp.unique_rows = ix->profiling ? ix->prof_rows + 1 : nullptr;
+            lp.unique_rows = ix->profiling ? tl_scr->prof_rows + 1 : nullptr;
             for (int i = 0; i < 2; ++i) {
-                lp.side[i] = ix->lists_fork ? ix->side[i] : nullptr;
-                lp.ev_join[i] = ix->ev_join[i];
+                lp.side[i] = ix->lists_fork ? tl_scr->side[i] : nullptr;
+                lp.ev_join[i] = tl_scr->ev_join[i];
             }
-            lp.ev_fork = ix->ev_fork;
-            CU(launch_scan_lists(a, lp, ix->lists_cfg, ix->num_sms, &ix->prof_scan_launches, st));
+            lp.ev_fork = tl_scr->ev_fork;
+            CU(launch_scan_lists(a, lp, ix->lists_cfg, ix->num_sms, &tl_scr->prof_scan_launches, st));
         } else {
-            CU(launch_scan_pages(a, ix->scan_variant, ix->num_sms, &ix->prof_scan_launches, st));
+            CU(launch_scan_pages(a, ix->scan_variant, ix->num_sms, &tl_scr->prof_scan_launches, st));
         }
         SC(prof_mark(ix, st));
-        float *od = outd_dev ? out_dist + s * k : ix->s_outd.as<float>();
-        int64_t *oi = outi_dev ? out_ids + s * k : ix->s_outi.as<int64_t>();
+        float *od = outd_dev ? out_dist + s * k : tl_scr->s_outd.as<float>();
+        int64_t *oi = outi_dev ? out_ids + s * k : tl_scr->s_outi.as<int64_t>();
         if (ex) {
             PeerTopk pk;
             memset(&pk, 0, sizeof(pk));
@@ -854,15 +966,18 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
             }
             CU(launch_select_candidates_peers(a, m, k, pk, make_signal(ex, 1), st));
             char *mine = ex->peer[ex->rank];
-            CU(launch_merge_topk_wait(reinterpret_cast<const float *>(mine + exl.part_d),
-                                      reinterpret_cast<const int64_t *>(mine + exl.part_i), ex->world, m, k, k, ix->metric,
-                                      od, oi, make_wait(ex, 1), st));
-            ix->prof_total_launches += 1;
+            // The wait is its own one-warp kernel: a merge whose every CTA spins would fill the SMs while it waits, and with two
+            // steps in flight per rank (two streams, two exchanges) the peers' producers of the OTHER step could then be
+            // locked out on every rank at once.
+            CU(launch_peer_wait(make_wait(ex, 1), st));
+            CU(launch_merge_topk(reinterpret_cast<const float *>(mine + exl.part_d),
+                                 reinterpret_cast<const int64_t *>(mine + exl.part_i), ex->world, m, k, k, ix->metric, od, oi, st));
+            tl_scr->prof_total_launches += 2;
         } else {
             CU(launch_select_candidates(a, m, k, od, oi, st));
         }
         SC(prof_mark(ix, st));
-        ix->prof_total_launches += 2;  // pair plan, top-k (the scan launchers count their own)
+        tl_scr->prof_total_launches += 2;  // pair plan, top-k (the scan launchers count their own)
         if (!outd_dev) CU(cudaMemcpyAsync(out_dist + s * k, od, (size_t)m * k * 4, cudaMemcpyDeviceToHost, st));
         if (!outi_dev) CU(cudaMemcpyAsync(out_ids + s * k, oi, (size_t)m * k * 8, cudaMemcpyDeviceToHost, st));
     }
@@ -948,17 +1063,22 @@ int sc_index_create(int32_t dim, int32_t metric, int32_t nlist, int32_t device, 
     if (e == cudaSuccess) e = cudaMalloc(&ix->pt_off, (size_t)(nlist + 1) * 4);
     if (e == cudaSuccess) e = cudaMalloc(&ix->pt_off_alt, (size_t)(nlist + 1) * 4);
     if (e == cudaSuccess) e = cudaMalloc(&ix->pt, 1024 * 4);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->ev_done, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->ev_fork, cudaEventDisableTiming);
-    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
-        e = cudaStreamCreateWithFlags(&ix->side[i], cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->ev_join[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->ev_write, cudaEventDisableTiming);
+    for (int k = 0; k < kSlots && e == cudaSuccess; ++k) {
+        Scratch &sl = ix->scr[k];
+        e = cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.ev_fork, cudaEventDisableTiming);
+        for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+            e = cudaStreamCreateWithFlags(&sl.side[i], cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.ev_join[i], cudaEventDisableTiming);
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(sl.ev_done, 0);
     }
+    if (e == cudaSuccess) e = cudaEventRecord(ix->ev_write, 0);
     if (e == cudaSuccess) e = cudaMemset(ix->list_len, 0, (size_t)nlist * 4);
     if (e == cudaSuccess) e = cudaMemset(ix->pt_off, 0, (size_t)(nlist + 1) * 4);
     if (e == cudaSuccess) e = cudaMemset(ix->d_tab, 0, sizeof(SlabTable));
     if (e == cudaSuccess) e = cudaMemset(ix->centroids, 0, (size_t)nlist * ix->ds * 4);
-    if (e == cudaSuccess) e = cudaEventRecord(ix->ev_done, 0);
     if (e != cudaSuccess) {
         cudaGetLastError();
         return cleanup(fail(e == cudaErrorMemoryAllocation ? SC_ERR_OOM : SC_ERR_CUDA, "index allocation failed: %s",
@@ -974,21 +1094,22 @@ int sc_index_destroy(sc_index_t *ix) {
     DeviceGuard g(ix->device);
     cudaDeviceSynchronize();
     free_lists(ix);
-    clear_prof(ix);
-    for (DevBuf *b : {&ix->s_q, &ix->s_scores, &ix->s_probe, &ix->s_pageoff, &ix->s_cand, &ix->s_outd,
-                      &ix->s_outi, &ix->s_repobits, &ix->s_x, &ix->s_xpad, &ix->s_ids, &ix->s_repo, &ix->s_lang,
-                      &ix->s_assign, &ix->s_best, &ix->s_pos, &ix->s_lenold, &ix->s_need, &ix->s_npg, &ix->s_needoff,
-                      &ix->s_bad, &ix->s_sums, &ix->s_counts, &ix->s_obj, &ix->s_rows, &ix->s_rm, &ix->s_cnt, &ix->s_ahi, &ix->s_alo, &ix->s_lplan, &ix->s_scan, &ix->s_packed, &ix->s_qsplit, &ix->s_bstage})
-        b->release();
-    for (void *p : {(void *)ix->centroids, (void *)ix->cnorm, (void *)ix->cent_hi, (void *)ix->cent_lo, (void *)ix->d_tab, (void *)ix->d_maps, (void *)ix->list_len, (void *)ix->pt_off,
-                    (void *)ix->pt_off_alt, (void *)ix->pt, (void *)ix->pt_alt, (void *)ix->prof_rows, (void *)ix->free_pages})
-        if (p) cudaFree(p);
-    if (ix->ev_done) cudaEventDestroy(ix->ev_done);
-    if (ix->ev_fork) cudaEventDestroy(ix->ev_fork);
-    for (int i = 0; i < 2; ++i) {
-        if (ix->ev_join[i]) cudaEventDestroy(ix->ev_join[i]);
-        if (ix->side[i]) cudaStreamDestroy(ix->side[i]);
+    for (int k = 0; k < kSlots; ++k) {
+        Scratch &sl = ix->scr[k];
+        clear_prof(&sl);
+        sl.each_buf([](DevBuf *b) { b->release(); });
+        if (sl.prof_rows) cudaFree(sl.prof_rows);
+        if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+        if (sl.ev_fork) cudaEventDestroy(sl.ev_fork);
+        for (int i = 0; i < 2; ++i) {
+            if (sl.ev_join[i]) cudaEventDestroy(sl.ev_join[i]);
+            if (sl.side[i]) cudaStreamDestroy(sl.side[i]);
+        }
     }
+    if (ix->ev_write) cudaEventDestroy(ix->ev_write);
+    for (void *p : {(void *)ix->centroids, (void *)ix->cnorm, (void *)ix->cent_hi, (void *)ix->cent_lo, (void *)ix->d_tab, (void *)ix->d_maps, (void *)ix->list_len, (void *)ix->pt_off,
+                    (void *)ix->pt_off_alt, (void *)ix->pt, (void *)ix->pt_alt, (void *)ix->free_pages})
+        if (p) cudaFree(p);
     delete ix->h_tab;
     cudaGetLastError();
     delete ix;
@@ -997,7 +1118,7 @@ int sc_index_destroy(sc_index_t *ix) {
 
 int sc_index_reset(sc_index_t *ix) {
     if (!ix) return fail(SC_ERR_INVALID, "idx is NULL");
-    std::lock_guard<std::mutex> lk(ix->mu);
+    WriteGuard lk(ix);
     DeviceGuard g(ix->device);
     CU(cudaDeviceSynchronize());
     free_lists(ix);
@@ -1012,13 +1133,13 @@ int sc_index_reset(sc_index_t *ix) {
 int sc_index_set_centroids(sc_index_t *ix, const float *centroids, int32_t nlist, void *stream) {
     if (!ix || !centroids) return fail(SC_ERR_INVALID, "NULL argument");
     if (nlist != ix->nlist) return fail(SC_ERR_INVALID, "nlist %d does not match the index (%d)", nlist, ix->nlist);
-    std::lock_guard<std::mutex> lk(ix->mu);
+    WriteGuard lk(ix);
     DeviceGuard g(ix->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (ix->ntotal > 0) return fail(SC_ERR_STATE, "cannot replace centroids of a non-empty index (reset it first)");
     CU(cudaDeviceSynchronize());
     const float *cd = nullptr;
-    SC(stage(ix, centroids, (size_t)nlist * ix->dim, ix->s_x, st, &cd));
+    SC(stage(ix, centroids, (size_t)nlist * ix->dim, tl_scr->s_x, st, &cd));
     CU(launch_pad_rows(cd, nlist, ix->dim, ix->ds, ix->centroids, st));
     SC(update_cnorm(ix, st));
     CU(cudaStreamSynchronize(st));
@@ -1028,7 +1149,7 @@ int sc_index_set_centroids(sc_index_t *ix, const float *centroids, int32_t nlist
 
 int sc_index_get_centroids(sc_index_t *ix, float *out, void *stream) {
     if (!ix || !out) return fail(SC_ERR_INVALID, "NULL argument");
-    std::lock_guard<std::mutex> lk(ix->mu);
+    WriteGuard lk(ix);
     DeviceGuard g(ix->device);
     cudaStream_t st = (cudaStream_t)stream;
     SC(require_trained(ix));
@@ -1045,7 +1166,7 @@ int sc_index_get_centroids(sc_index_t *ix, float *out, void *stream) {
 int sc_index_kmeans_init(sc_index_t *ix, const float *x, int64_t n, const int64_t *init_rows, void *stream) {
     if (!ix || !x || !init_rows) return fail(SC_ERR_INVALID, "NULL argument");
     if (n < ix->nlist) return fail(SC_ERR_INVALID, "need at least nlist=%d training rows, got %lld", ix->nlist, (long long)n);
-    std::lock_guard<std::mutex> lk(ix->mu);
+    WriteGuard lk(ix);
     DeviceGuard g(ix->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (ix->ntotal > 0) return fail(SC_ERR_STATE, "cannot retrain a non-empty index (reset it first)");
@@ -1060,9 +1181,9 @@ int sc_index_kmeans_init(sc_index_t *ix, const float *x, int64_t n, const int64_
         if (rows[i] < 0 || rows[i] >= n) return fail(SC_ERR_INVALID, "init_rows[%d]=%lld outside [0,%lld)", i, (long long)rows[i], (long long)n);
     if (is_device_ptr(x, ix->device)) {
         if (ix->ds == ix->dim && ((uintptr_t)x & 15) == 0) {
-            CU(ix->s_rows.reserve((size_t)ix->nlist * 8));
-            CU(cudaMemcpyAsync(ix->s_rows.p, rows.data(), (size_t)ix->nlist * 8, cudaMemcpyHostToDevice, st));
-            CU(launch_gather_rows(x, ix->s_rows.as<int64_t>(), ix->nlist, ix->ds, ix->centroids, st));
+            CU(tl_scr->s_rows.reserve((size_t)ix->nlist * 8));
+            CU(cudaMemcpyAsync(tl_scr->s_rows.p, rows.data(), (size_t)ix->nlist * 8, cudaMemcpyHostToDevice, st));
+            CU(launch_gather_rows(x, tl_scr->s_rows.as<int64_t>(), ix->nlist, ix->ds, ix->centroids, st));
         } else {
             for (int i = 0; i < ix->nlist; ++i)
                 CU(launch_pad_rows(x + rows[i] * ix->dim, 1, ix->dim, ix->ds, ix->centroids + (int64_t)i * ix->ds, st));
@@ -1085,7 +1206,7 @@ int sc_index_kmeans_step(sc_index_t *ix, const float *x, int64_t n, double *sums
                          void *stream) {
     if (!ix || !sums || !counts || !objective) return fail(SC_ERR_INVALID, "NULL argument");
     if (n < 0) return fail(SC_ERR_INVALID, "n < 0");
-    std::lock_guard<std::mutex> lk(ix->mu);
+    WriteGuard lk(ix);
     DeviceGuard g(ix->device);
     cudaStream_t st = (cudaStream_t)stream;
     SC(require_trained(ix));
@@ -1099,14 +1220,14 @@ int sc_index_kmeans_step(sc_index_t *ix, const float *x, int64_t n, double *sums
     int64_t chunk = std::max<int64_t>(1024, ((int64_t)256 << 20) / ((int64_t)ix->ds * 4));
     if (is_device_ptr(x, ix->device)) chunk = std::max<int64_t>(chunk, (int64_t)1 << 18);
     chunk = std::min(chunk, n);
-    CU(ix->s_assign.reserve((size_t)chunk * 4));
-    CU(ix->s_best.reserve((size_t)chunk * 4));
+    CU(tl_scr->s_assign.reserve((size_t)chunk * 4));
+    CU(tl_scr->s_best.reserve((size_t)chunk * 4));
     for (int64_t s = 0; s < n; s += chunk) {
         const int64_t m = std::min(chunk, n - s);
         const float *xd = nullptr;
-        SC(stage_rows(ix, x + s * ix->dim, m, ix->s_x, ix->s_xpad, st, &xd));
-        SC(coarse_assign(ix, xd, m, ix->s_assign.as<int32_t>(), ix->s_best.as<float>(), st));
-        CU(launch_kmeans_accumulate(xd, m, ix->ds, ix->s_assign.as<int32_t>(), ix->s_best.as<float>(), ix->metric, sums,
+        SC(stage_rows(ix, x + s * ix->dim, m, tl_scr->s_x, tl_scr->s_xpad, st, &xd));
+        SC(coarse_assign(ix, xd, m, tl_scr->s_assign.as<int32_t>(), tl_scr->s_best.as<float>(), st));
+        CU(launch_kmeans_accumulate(xd, m, ix->ds, tl_scr->s_assign.as<int32_t>(), tl_scr->s_best.as<float>(), ix->metric, sums,
                                     counts, objective, st));
     }
     SC(end_call(ix, st));
@@ -1118,7 +1239,7 @@ int sc_index_kmeans_step(sc_index_t *ix, const float *x, int64_t n, double *sums
 int sc_index_kmeans_update(sc_index_t *ix, const double *sums, const int32_t *counts, int32_t *nsplit_out,
                            void *stream) {
     if (!ix || !sums || !counts) return fail(SC_ERR_INVALID, "NULL argument");
-    std::lock_guard<std::mutex> lk(ix->mu);
+    WriteGuard lk(ix);
     DeviceGuard g(ix->device);
     cudaStream_t st = (cudaStream_t)stream;
     SC(require_trained(ix));
@@ -1228,7 +1349,7 @@ int sc_index_train(sc_index_t *ix, const float *x, int64_t n, int32_t niter, con
 int sc_index_assign(sc_index_t *ix, const float *x, int64_t n, int32_t *out_list, void *stream) {
     if (!ix || !out_list) return fail(SC_ERR_INVALID, "NULL argument");
     if (n < 0) return fail(SC_ERR_INVALID, "n < 0");
-    std::lock_guard<std::mutex> lk(ix->mu);
+    ReadGuard lk(ix, stream);
     DeviceGuard g(ix->device);
     cudaStream_t st = (cudaStream_t)stream;
     SC(require_trained(ix));
@@ -1238,12 +1359,12 @@ int sc_index_assign(sc_index_t *ix, const float *x, int64_t n, int32_t *out_list
     const bool dev = is_device_ptr(out_list, ix->device);
     int64_t chunk = std::max<int64_t>(1024, ((int64_t)256 << 20) / ((int64_t)ix->ds * 4));
     chunk = std::min(chunk, n);
-    if (!dev) CU(ix->s_assign.reserve((size_t)chunk * 4));
+    if (!dev) CU(tl_scr->s_assign.reserve((size_t)chunk * 4));
     for (int64_t s = 0; s < n; s += chunk) {
         const int64_t m = std::min(chunk, n - s);
         const float *xd = nullptr;
-        SC(stage_rows(ix, x + s * ix->dim, m, ix->s_x, ix->s_xpad, st, &xd));
-        int32_t *dst = dev ? out_list + s : ix->s_assign.as<int32_t>();
+        SC(stage_rows(ix, x + s * ix->dim, m, tl_scr->s_x, tl_scr->s_xpad, st, &xd));
+        int32_t *dst = dev ? out_list + s : tl_scr->s_assign.as<int32_t>();
         SC(coarse_assign(ix, xd, m, dst, nullptr, st));
         if (!dev) CU(cudaMemcpyAsync(out_list + s, dst, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
     }
@@ -1256,7 +1377,7 @@ int sc_index_probe(sc_index_t *ix, const float *q, int64_t nq, int32_t nprobe, i
                    void *stream) {
     if (!ix || !out_lists) return fail(SC_ERR_INVALID, "NULL argument");
     if (nq < 0 || nprobe < 1) return fail(SC_ERR_INVALID, "bad nq / nprobe");
-    std::lock_guard<std::mutex> lk(ix->mu);
+    ReadGuard lk(ix, stream);
     DeviceGuard g(ix->device);
     cudaStream_t st = (cudaStream_t)stream;
     SC(require_trained(ix));
@@ -1268,17 +1389,17 @@ int sc_index_probe(sc_index_t *ix, const float *q, int64_t nq, int32_t nprobe, i
     const bool ldev = is_device_ptr(out_lists, ix->device);
     const bool sdev = out_scores ? is_device_ptr(out_scores, ix->device) : true;
     const int64_t ch = coarse_chunk_rows(ix, nq);
-    CU(ix->s_scores.reserve((size_t)ch * ix->nlist * 4));
-    if (!ldev) CU(ix->s_probe.reserve((size_t)ch * nprobe * 4));
-    if (out_scores && !sdev) CU(ix->s_best.reserve((size_t)ch * nprobe * 4));
+    CU(tl_scr->s_scores.reserve((size_t)ch * ix->nlist * 4));
+    if (!ldev) CU(tl_scr->s_probe.reserve((size_t)ch * nprobe * 4));
+    if (out_scores && !sdev) CU(tl_scr->s_best.reserve((size_t)ch * nprobe * 4));
     for (int64_t s = 0; s < nq; s += ch) {
         const int64_t m = std::min(ch, nq - s);
         const float *qd = nullptr;
-        SC(stage_rows(ix, q + s * ix->dim, m, ix->s_q, ix->s_xpad, st, &qd));
-        SC(coarse_scores(ix, qd, m, ix->s_scores.as<float>(), st));
-        int32_t *ol = ldev ? out_lists + s * nprobe : ix->s_probe.as<int32_t>();
-        float *os = out_scores ? (sdev ? out_scores + s * nprobe : ix->s_best.as<float>()) : nullptr;
-        CU(launch_select_rows(ix->s_scores.as<float>(), m, ix->nlist, nprobe, ol, os, st));
+        SC(stage_rows(ix, q + s * ix->dim, m, tl_scr->s_q, tl_scr->s_xpad, st, &qd));
+        SC(coarse_scores(ix, qd, m, tl_scr->s_scores.as<float>(), st));
+        int32_t *ol = ldev ? out_lists + s * nprobe : tl_scr->s_probe.as<int32_t>();
+        float *os = out_scores ? (sdev ? out_scores + s * nprobe : tl_scr->s_best.as<float>()) : nullptr;
+        CU(launch_select_rows(tl_scr->s_scores.as<float>(), m, ix->nlist, nprobe, ol, os, st));
         if (!ldev) CU(cudaMemcpyAsync(out_lists + s * nprobe, ol, (size_t)m * nprobe * 4, cudaMemcpyDeviceToHost, st));
         if (out_scores && !sdev)
             CU(cudaMemcpyAsync(out_scores + s * nprobe, os, (size_t)m * nprobe * 4, cudaMemcpyDeviceToHost, st));
@@ -1292,7 +1413,7 @@ int sc_index_probe(sc_index_t *ix, const float *q, int64_t nq, int32_t nprobe, i
 int sc_index_add(sc_index_t *ix, const float *x, const int64_t *ids, const uint32_t *repo_tags,
                  const uint8_t *lang_tags, int64_t n, void *stream) {
     if (!ix) return fail(SC_ERR_INVALID, "idx is NULL");
-    std::lock_guard<std::mutex> lk(ix->mu);
+    WriteGuard lk(ix);
     DeviceGuard g(ix->device);
     return add_impl(ix, x, ids, repo_tags, lang_tags, nullptr, n, (cudaStream_t)stream);
 }
@@ -1301,7 +1422,7 @@ int sc_index_add_preassigned(sc_index_t *ix, const float *x, const int64_t *ids,
                              const uint8_t *lang_tags, const int32_t *lists, int64_t n, void *stream) {
     if (!ix) return fail(SC_ERR_INVALID, "idx is NULL");
     if (!lists && n > 0) return fail(SC_ERR_INVALID, "lists is NULL");
-    std::lock_guard<std::mutex> lk(ix->mu);
+    WriteGuard lk(ix);
     DeviceGuard g(ix->device);
     return add_impl(ix, x, ids, repo_tags, lang_tags, lists, n, (cudaStream_t)stream);
 }
@@ -1312,7 +1433,7 @@ int sc_index_remove_ids(sc_index_t *ix, const int64_t *ids, int64_t n, int64_t *
     if (n_removed_out) *n_removed_out = 0;
     if (n == 0) return SC_OK;
     if (!ids) return fail(SC_ERR_INVALID, "ids is NULL");
-    std::lock_guard<std::mutex> lk(ix->mu);
+    WriteGuard lk(ix);
     DeviceGuard g(ix->device);
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaDeviceSynchronize());
@@ -1324,14 +1445,14 @@ int sc_index_remove_ids(sc_index_t *ix, const int64_t *ids, int64_t n, int64_t *
     }
     std::sort(h.begin(), h.end());
     h.erase(std::unique(h.begin(), h.end()), h.end());
-    CU(ix->s_rm.reserve(h.size() * 8));
-    CU(ix->s_cnt.reserve(8));
-    CU(cudaMemcpyAsync(ix->s_rm.p, h.data(), h.size() * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemsetAsync(ix->s_cnt.p, 0, 8, st));
-    CU(launch_remove_ids(ix->s_rm.as<int64_t>(), (int64_t)h.size(), ix->d_tab, ix->slab_shift, ix->pool_top,
-                         ix->s_cnt.as<unsigned long long>(), st));
+    CU(tl_scr->s_rm.reserve(h.size() * 8));
+    CU(tl_scr->s_cnt.reserve(8));
+    CU(cudaMemcpyAsync(tl_scr->s_rm.p, h.data(), h.size() * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(tl_scr->s_cnt.p, 0, 8, st));
+    CU(launch_remove_ids(tl_scr->s_rm.as<int64_t>(), (int64_t)h.size(), ix->d_tab, ix->slab_shift, ix->pool_top,
+                         tl_scr->s_cnt.as<unsigned long long>(), st));
     unsigned long long cnt = 0;
-    CU(cudaMemcpyAsync(&cnt, ix->s_cnt.p, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&cnt, tl_scr->s_cnt.p, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     ix->ntotal -= (int64_t)cnt;
     ix->nremoved += (int64_t)cnt;
@@ -1343,7 +1464,7 @@ int sc_index_remove_ids(sc_index_t *ix, const int64_t *ids, int64_t n, int64_t *
 int sc_index_search(sc_index_t *ix, const float *q, int64_t nq, int32_t k, int32_t nprobe, const sc_filter_t *filter,
                     float *out_dist, int64_t *out_ids, void *stream) {
     if (!ix) return fail(SC_ERR_INVALID, "idx is NULL");
-    std::lock_guard<std::mutex> lk(ix->mu);
+    ReadGuard lk(ix, stream);
     DeviceGuard g(ix->device);
     return search_impl(ix, q, nq, k, nprobe, nullptr, filter, out_dist, out_ids, (cudaStream_t)stream);
 }
@@ -1353,7 +1474,7 @@ int sc_index_search_preassigned(sc_index_t *ix, const float *q, int64_t nq, int3
                                 void *stream) {
     if (!ix) return fail(SC_ERR_INVALID, "idx is NULL");
     if (!lists && nq > 0) return fail(SC_ERR_INVALID, "lists is NULL");
-    std::lock_guard<std::mutex> lk(ix->mu);
+    ReadGuard lk(ix, stream);
     DeviceGuard g(ix->device);
     return search_impl(ix, q, nq, k, nprobe, lists, filter, out_dist, out_ids, (cudaStream_t)stream);
 }
@@ -1434,7 +1555,7 @@ int sc_index_search_sharded(sc_index_t *ix, sc_exchange_t *ex, const float *q, i
                             const int32_t *lists, const sc_filter_t *filter, float *out_dist, int64_t *out_ids, void *stream) {
     if (!ix) return fail(SC_ERR_INVALID, "idx is NULL");
     if (!ex) return fail(SC_ERR_INVALID, "exchange is NULL");
-    std::lock_guard<std::mutex> lk(ix->mu);
+    ReadGuard lk(ix, stream);
     DeviceGuard g(ix->device);
     if (ex->broken || *(volatile unsigned int *)ex->h_status != 0)
         return fail(SC_ERR_STATE, "the exchange is unusable: %s.  Results since then are invalid; destroy the exchange on every "
@@ -1468,7 +1589,7 @@ int sc_merge_topk(const float *part_dist, const int64_t *part_ids, int32_t parts
 int sc_index_compact(sc_index_t *ix, int64_t *pages_freed_out, void *stream) {
     if (!ix) return fail(SC_ERR_INVALID, "idx is NULL");
     if (pages_freed_out) *pages_freed_out = 0;
-    std::lock_guard<std::mutex> lk(ix->mu);
+    WriteGuard lk(ix);
     DeviceGuard g(ix->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (ix->nremoved == 0) return SC_OK;
@@ -1493,15 +1614,15 @@ int sc_index_compact(sc_index_t *ix, int64_t *pages_freed_out, void *stream) {
         CU(cudaMalloc(&ix->pt_alt, (size_t)std::max<int32_t>(h_old, 1024) * 4));
         ix->pt_alt_cap = std::max<int32_t>(h_old, 1024);
     }
-    CU(ix->s_npg.reserve((size_t)nlist * 4));
-    CU(ix->s_bad.reserve(16));
+    CU(tl_scr->s_npg.reserve((size_t)nlist * 4));
+    CU(tl_scr->s_bad.reserve(16));
     CU(launch_compact_lists(nlist, ix->list_len, ix->pt_off, ix->pt, ix->d_tab, ix->slab_shift, ix->ds, ix->num_sms, st));
-    CU(launch_pages_of_len(ix->list_len, nlist, ix->s_npg.as<int32_t>(), st));
-    CU(launch_exclusive_scan_i32(ix->s_npg.as<int32_t>(), nlist, ix->pt_off_alt, st));
-    CU(cudaMemcpyAsync(ix->s_bad.p, &ix->nfree, 4, cudaMemcpyHostToDevice, st));  // cursor starts behind the current entries
-    CU(launch_compact_pt(ix->pt_off, ix->pt, ix->pt_off_alt, ix->pt_alt, nlist, ix->free_pages, ix->s_bad.as<int32_t>(), st));
+    CU(launch_pages_of_len(ix->list_len, nlist, tl_scr->s_npg.as<int32_t>(), st));
+    CU(launch_exclusive_scan_i32(tl_scr->s_npg.as<int32_t>(), nlist, ix->pt_off_alt, st));
+    CU(cudaMemcpyAsync(tl_scr->s_bad.p, &ix->nfree, 4, cudaMemcpyHostToDevice, st));  // cursor starts behind the current entries
+    CU(launch_compact_pt(ix->pt_off, ix->pt, ix->pt_off_alt, ix->pt_alt, nlist, ix->free_pages, tl_scr->s_bad.as<int32_t>(), st));
     int32_t h_free = 0;
-    CU(cudaMemcpyAsync(&h_free, ix->s_bad.p, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&h_free, tl_scr->s_bad.p, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     std::swap(ix->pt, ix->pt_alt);
     std::swap(ix->pt_cap, ix->pt_alt_cap);
@@ -1516,7 +1637,7 @@ int sc_index_compact(sc_index_t *ix, int64_t *pages_freed_out, void *stream) {
 // ---- introspection ----------------------------------------------------------------------------------
 int sc_index_stats(sc_index_t *ix, sc_stats_t *out) {
     if (!ix || !out) return fail(SC_ERR_INVALID, "NULL argument");
-    std::lock_guard<std::mutex> lk(ix->mu);
+    WriteGuard lk(ix);
     memset(out, 0, sizeof(*out));
     out->dim = ix->dim;
     out->dim_padded = ix->ds;
@@ -1531,11 +1652,11 @@ int sc_index_stats(sc_index_t *ix, sc_stats_t *out) {
     const int64_t rows = ((int64_t)ix->slabs.size() << ix->slab_shift) * kPageRows;
     out->bytes_lists = rows * ((int64_t)ix->ds * 4 + 12);
     int64_t sb = 0;
-    for (const DevBuf *b : {&ix->s_q, &ix->s_scores, &ix->s_probe, &ix->s_pageoff, &ix->s_cand,
-                            &ix->s_outd, &ix->s_outi, &ix->s_repobits, &ix->s_x, &ix->s_xpad, &ix->s_ids, &ix->s_repo,
-                            &ix->s_lang, &ix->s_assign, &ix->s_best, &ix->s_pos, &ix->s_lenold, &ix->s_need, &ix->s_npg,
-                            &ix->s_needoff, &ix->s_bad, &ix->s_sums, &ix->s_counts, &ix->s_obj, &ix->s_rows, &ix->s_rm,
-                            &ix->s_cnt, &ix->s_ahi, &ix->s_alo, &ix->s_lplan, &ix->s_scan, &ix->s_packed, &ix->s_qsplit, &ix->s_bstage})
+    for (const DevBuf *b : {&tl_scr->s_q, &tl_scr->s_scores, &tl_scr->s_probe, &tl_scr->s_pageoff, &tl_scr->s_cand,
+                            &tl_scr->s_outd, &tl_scr->s_outi, &tl_scr->s_repobits, &tl_scr->s_x, &tl_scr->s_xpad, &tl_scr->s_ids, &tl_scr->s_repo,
+                            &tl_scr->s_lang, &tl_scr->s_assign, &tl_scr->s_best, &tl_scr->s_pos, &tl_scr->s_lenold, &tl_scr->s_need, &tl_scr->s_npg,
+                            &tl_scr->s_needoff, &tl_scr->s_bad, &tl_scr->s_sums, &tl_scr->s_counts, &tl_scr->s_obj, &tl_scr->s_rows, &tl_scr->s_rm,
+                            &tl_scr->s_cnt, &tl_scr->s_ahi, &tl_scr->s_alo, &tl_scr->s_lplan, &tl_scr->s_scan, &tl_scr->s_packed, &tl_scr->s_qsplit, &tl_scr->s_bstage})
         sb += (int64_t)b->cap;
     out->bytes_scratch = sb;
     int32_t mx = 0, mn = ix->nlist > 0 ? INT32_MAX : 0;
@@ -1550,7 +1671,7 @@ int sc_index_stats(sc_index_t *ix, sc_stats_t *out) {
 
 int sc_index_list_sizes(sc_index_t *ix, int32_t *out_host) {
     if (!ix || !out_host) return fail(SC_ERR_INVALID, "NULL argument");
-    std::lock_guard<std::mutex> lk(ix->mu);
+    WriteGuard lk(ix);
     memcpy(out_host, ix->h_len.data(), (size_t)ix->nlist * 4);
     return SC_OK;
 }
@@ -1559,7 +1680,7 @@ int sc_index_export_list(sc_index_t *ix, int32_t list, int64_t cap, float *vecs,
                          int64_t *len_out, void *stream) {
     if (!ix) return fail(SC_ERR_INVALID, "idx is NULL");
     if (list < 0 || list >= ix->nlist) return fail(SC_ERR_INVALID, "list %d outside [0,%d)", list, ix->nlist);
-    std::lock_guard<std::mutex> lk(ix->mu);
+    WriteGuard lk(ix);
     DeviceGuard g(ix->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int32_t len = ix->h_len[list];
@@ -1577,16 +1698,16 @@ int sc_index_export_list(sc_index_t *ix, int32_t list, int64_t cap, float *vecs,
     int64_t *idd = ids;
     uint32_t *td = tags;
     if (vecs && !vdev) {
-        CU(ix->s_x.reserve((size_t)len * ix->dim * 4));
-        vd = ix->s_x.as<float>();
+        CU(tl_scr->s_x.reserve((size_t)len * ix->dim * 4));
+        vd = tl_scr->s_x.as<float>();
     }
     if (ids && !idev) {
-        CU(ix->s_ids.reserve((size_t)len * 8));
-        idd = ix->s_ids.as<int64_t>();
+        CU(tl_scr->s_ids.reserve((size_t)len * 8));
+        idd = tl_scr->s_ids.as<int64_t>();
     }
     if (tags && !tdev) {
-        CU(ix->s_repo.reserve((size_t)len * 4));
-        td = ix->s_repo.as<uint32_t>();
+        CU(tl_scr->s_repo.reserve((size_t)len * 4));
+        td = tl_scr->s_repo.as<uint32_t>();
     }
     CU(launch_export_list(ix->pt, pt_begin, len, ix->ds, ix->dim, ix->d_tab, ix->slab_shift, vd, idd, td, st));
     if (vecs && !vdev) CU(cudaMemcpyAsync(vecs, vd, (size_t)len * ix->dim * 4, cudaMemcpyDeviceToHost, st));
@@ -1604,7 +1725,7 @@ int sc_index_export_lists(sc_index_t *ix, int32_t list_begin, int32_t list_end, 
     if (!ix) return fail(SC_ERR_INVALID, "idx is NULL");
     if (list_begin < 0 || list_end > ix->nlist || list_begin > list_end)
         return fail(SC_ERR_INVALID, "list range [%d, %d) outside [0, %d]", list_begin, list_end, ix->nlist);
-    std::lock_guard<std::mutex> lk(ix->mu);
+    WriteGuard lk(ix);
     DeviceGuard g(ix->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int32_t nl = list_end - list_begin;
@@ -1622,20 +1743,20 @@ int sc_index_export_lists(sc_index_t *ix, int32_t list_begin, int32_t list_end, 
     int64_t *idd = ids;
     uint32_t *td = tags;
     if (vecs && !vdev) {
-        CU(ix->s_x.reserve((size_t)rows * ix->dim * 4));
-        vd = ix->s_x.as<float>();
+        CU(tl_scr->s_x.reserve((size_t)rows * ix->dim * 4));
+        vd = tl_scr->s_x.as<float>();
     }
     if (ids && !idev) {
-        CU(ix->s_ids.reserve((size_t)rows * 8));
-        idd = ix->s_ids.as<int64_t>();
+        CU(tl_scr->s_ids.reserve((size_t)rows * 8));
+        idd = tl_scr->s_ids.as<int64_t>();
     }
     if (tags && !tdev) {
-        CU(ix->s_repo.reserve((size_t)rows * 4));
-        td = ix->s_repo.as<uint32_t>();
+        CU(tl_scr->s_repo.reserve((size_t)rows * 4));
+        td = tl_scr->s_repo.as<uint32_t>();
     }
-    CU(ix->s_rows.reserve(off.size() * 8));
-    CU(cudaMemcpyAsync(ix->s_rows.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, st));
-    CU(launch_export_range(ix->pt_off, ix->pt, list_begin, nl, ix->s_rows.as<int64_t>(), rows, ix->ds, ix->dim, ix->d_tab, ix->slab_shift,
+    CU(tl_scr->s_rows.reserve(off.size() * 8));
+    CU(cudaMemcpyAsync(tl_scr->s_rows.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, st));
+    CU(launch_export_range(ix->pt_off, ix->pt, list_begin, nl, tl_scr->s_rows.as<int64_t>(), rows, ix->ds, ix->dim, ix->d_tab, ix->slab_shift,
                            vd, idd, td, ix->num_sms, st));
     if (vecs && !vdev) CU(cudaMemcpyAsync(vecs, vd, (size_t)rows * ix->dim * 4, cudaMemcpyDeviceToHost, st));
     if (ids && !idev) CU(cudaMemcpyAsync(ids, idd, (size_t)rows * 8, cudaMemcpyDeviceToHost, st));
@@ -1647,26 +1768,27 @@ int sc_index_export_lists(sc_index_t *ix, int32_t list_begin, int32_t list_end, 
 
 int sc_index_set_profiling(sc_index_t *ix, int32_t enabled) {
     if (!ix) return fail(SC_ERR_INVALID, "idx is NULL");
-    std::lock_guard<std::mutex> lk(ix->mu);
+    WriteGuard lk(ix);
     ix->profiling = enabled != 0;
     if (!ix->profiling) {
         DeviceGuard g(ix->device);
-        clear_prof(ix);
+        for (int k = 0; k < kSlots; ++k) clear_prof(&ix->scr[k]);
     }
     return SC_OK;
 }
 
 int sc_index_last_search_times(sc_index_t *ix, sc_search_times_t *out) {
     if (!ix || !out) return fail(SC_ERR_INVALID, "NULL argument");
-    std::lock_guard<std::mutex> lk(ix->mu);
+    WriteGuard lk(ix);
+    tl_scr = &ix->scr[ix->last_slot];  // the search that finished last
     DeviceGuard g(ix->device);
     memset(out, 0, sizeof(*out));
-    if (!ix->profiling || ix->prof_ev.empty()) return fail(SC_ERR_STATE, "profiling is off or no search has run");
-    if (ix->prof_ev.size() % 6 != 0) return fail(SC_ERR_STATE, "incomplete profile (a search failed midway)");
-    CU(cudaEventSynchronize(ix->prof_ev.back()));
-    for (size_t c = 0; c < ix->prof_ev.size(); c += 6) {
+    if (!ix->profiling || tl_scr->prof_ev.empty()) return fail(SC_ERR_STATE, "profiling is off or no search has run");
+    if (tl_scr->prof_ev.size() % 6 != 0) return fail(SC_ERR_STATE, "incomplete profile (a search failed midway)");
+    CU(cudaEventSynchronize(tl_scr->prof_ev.back()));
+    for (size_t c = 0; c < tl_scr->prof_ev.size(); c += 6) {
         float ms[5];
-        for (int i = 0; i < 5; ++i) CU(cudaEventElapsedTime(&ms[i], ix->prof_ev[c + i], ix->prof_ev[c + i + 1]));
+        for (int i = 0; i < 5; ++i) CU(cudaEventElapsedTime(&ms[i], tl_scr->prof_ev[c + i], tl_scr->prof_ev[c + i + 1]));
         out->coarse_ms += ms[0];
         out->probe_select_ms += ms[1];
         out->plan_ms += ms[2];
@@ -1674,20 +1796,20 @@ int sc_index_last_search_times(sc_index_t *ix, sc_search_times_t *out) {
         out->topk_ms += ms[4];
     }
     float tot = 0.f;
-    CU(cudaEventElapsedTime(&tot, ix->prof_ev.front(), ix->prof_ev.back()));
+    CU(cudaEventElapsedTime(&tot, tl_scr->prof_ev.front(), tl_scr->prof_ev.back()));
     out->total_ms = tot;
     unsigned long long rows[2] = {0, 0};
-    if (ix->prof_rows) CU(cudaMemcpy(rows, ix->prof_rows, 16, cudaMemcpyDeviceToHost));
+    if (tl_scr->prof_rows) CU(cudaMemcpy(rows, tl_scr->prof_rows, 16, cudaMemcpyDeviceToHost));
     out->scanned_rows = (int64_t)rows[0];
     out->unique_rows = (int64_t)rows[1];
-    out->scan_launches = ix->prof_scan_launches;
-    out->total_launches = ix->prof_total_launches + ix->prof_scan_launches;
+    out->scan_launches = tl_scr->prof_scan_launches;
+    out->total_launches = tl_scr->prof_total_launches + tl_scr->prof_scan_launches;
     return SC_OK;
 }
 
 int sc_index_set_param(sc_index_t *ix, const char *name, int64_t value) {
     if (!ix || !name) return fail(SC_ERR_INVALID, "NULL argument");
-    std::lock_guard<std::mutex> lk(ix->mu);
+    WriteGuard lk(ix);
     if (strcmp(name, "scratch_bytes") == 0) {
         if (value < ((int64_t)1 << 20)) return fail(SC_ERR_INVALID, "scratch_bytes must be >= 1 MiB");
         ix->scratch_budget = value;
@@ -1714,7 +1836,7 @@ int sc_index_set_param(sc_index_t *ix, const char *name, int64_t value) {
     }
     if (strcmp(name, "plan_epoch") == 0) {  // tests: put the pair plan's launch counter next to its 22-bit wrap
         if (value < 0 || value >= (1 << 22)) return fail(SC_ERR_INVALID, "plan_epoch must be in [0, 2^22)");
-        ix->plan_epoch = (uint32_t)value;
+        for (int k = 0; k < kSlots; ++k) ix->scr[k].plan_epoch = (uint32_t)value;
         return SC_OK;
     }
     if (strcmp(name, "add_chunk_rows") == 0) {  // tests: rows per add chunk (0 = automatic)

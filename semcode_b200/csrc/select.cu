@@ -1,10 +1,14 @@
 // K6: per-query top-k selection, one CTA per query.
-//   k <= 128: ONE pass over the candidates.  Every thread keeps the 4 best (key, index) pairs it meets in
-//   registers; the k-th best of the 512 per-thread maxima is a bound T with at least k candidates >= T; the kept
-//   pairs >= T (a few more than k) are gathered in shared memory and sorted.  A thread whose 4th pair is >= T may
-//   have dropped a winner -- then (rarely: candidates of a query are dealt round-robin to the threads) the CTA
-//   falls back to the radix select.  (The first version always ran the radix select: 4 reads of the candidates,
-//   1.4 of 14 ms at nq 4096 / nprobe 128.)
+//   k <= 128: ONE pass over the candidates with a threshold.  Every thread takes the maximum of the values dealt to it
+//   (16-byte loads, the first 32 values stay in registers); the warp's ceil(k / 16)-th best thread maximum, minimised
+//   over the 16 warps, is a bound T with at least k candidates >= T and -- candidates being dealt round-robin -- only a
+//   few more (54 .. 130 of 16 384 for k = 10 .. 32).  The threads whose maximum reaches T put their values >= T into
+//   shared memory; up to 128 gathered pairs are ranked by counting (no sort, no barrier ladder), more by a bitonic
+//   sort.  More than 2048 values >= T (never seen outside the tests) falls back to the radix select.
+//   (v1 always ran the radix select -- 4 reads of the candidates, 1.4 of 14 ms at nq 4096 / nprobe 128; v2 kept 4 pairs
+//   per thread and sorted the 512 thread maxima: one CTA took 20 us for 16 384 scores -- 41 k cycles for 2 900
+//   instructions per warp, a chain of 8 load rounds, 45 sort stages and 32 insertion networks -- which was 45 of the
+//   72 us of an nq = 1 search and the second wave of every N = 8 step.)
 //   Otherwise: 3-pass radix select (11/11/10 bits) over an order-preserving key finds the k-th best similarity
 //   exactly, the winners are compacted into shared memory.
 // Either way the winners are bitonic-sorted (key descending, candidate index ascending) and translated to ids.  Replaces FAISS HeapResultHandler / the Milvus segment reduce behind
@@ -32,9 +36,9 @@ struct SelShared {
     uint32_t sel_bin, need, eq_total, cnt_gt, cnt_eq, base;
     uint32_t fast_cnt, fast_overflow;
 };
-constexpr int SEL_FAST_K = 128;  // largest k of the one-pass selection
-constexpr int SEL_KEEP = 4;      // pairs kept per thread
-constexpr int SEL_FAST_MIN_N = 8192;
+constexpr int SEL_FAST_K = 128;   // largest k of the one-pass selection
+constexpr int SEL_RV = 8;         // 16-byte chunks per thread that stay in registers between the two phases
+constexpr int SEL_RANK_MAX = 128; // gathered pairs ranked by counting; more are sorted
 
 __device__ __forceinline__ unsigned long long pack_pair(uint32_t key, uint32_t idx) {
     return ((unsigned long long)key << 32) | (unsigned long long)(0xffffffffu - idx);
@@ -104,6 +108,8 @@ struct RowsSrc {
         const float *p;
         uint32_t n;
         __device__ __forceinline__ float load(uint32_t i) const { return __ldg(p + i); }
+        __device__ __forceinline__ bool vec() const { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+        __device__ __forceinline__ float4 load4(uint32_t i4) const { return __ldg(reinterpret_cast<const float4 *>(p) + i4); }
     };
     __device__ __forceinline__ View view(int64_t q) const { return View{s + q * (int64_t)N, (uint32_t)N}; }
     __device__ __forceinline__ void emit(int64_t q, int j, bool valid, float score, uint32_t idx) const {
@@ -139,6 +145,8 @@ struct CandSrc {
         const float *p;
         uint32_t n;
         __device__ __forceinline__ float load(uint32_t i) const { return __ldg(p + i); }
+        __device__ __forceinline__ bool vec() const { return true; }  // whole pages of 32 floats
+        __device__ __forceinline__ float4 load4(uint32_t i4) const { return __ldg(reinterpret_cast<const float4 *>(p) + i4); }
     };
     __device__ __forceinline__ View view(int64_t q) const {
         const int64_t b = a.page_off[q * a.nprobe], e = a.page_off[(q + 1) * a.nprobe];
@@ -193,6 +201,8 @@ struct MergeSrc {
             const float d = __ldcg(m->pd + o);
             return m->metric == 0 ? d : -d;
         }
+        __device__ __forceinline__ bool vec() const { return false; }
+        __device__ __forceinline__ float4 load4(uint32_t) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
     };
     __device__ __forceinline__ View view(int64_t q) const { return View{this, q, (uint32_t)(parts * kin)}; }
     __device__ __forceinline__ void emit(int64_t q, int j, bool valid, float, uint32_t idx) const {
@@ -218,7 +228,7 @@ __device__ __forceinline__ T warp_incl_scan(T v, int lane) {
     return v;
 }
 
-static_assert(SEL_KEEP * SEL_T <= kMaxK && SEL_FAST_K <= SEL_T, "one-pass selection: gathered pairs must fit sh.pairs");
+static_assert(SEL_FAST_K <= SEL_T && SEL_RANK_MAX <= SEL_T, "one-pass selection: one gathered pair per thread in the ranking step");
 
 // bitonic sort (descending) of pairs[0, P), P a power of two, by the whole CTA
 __device__ __forceinline__ void bitonic_sort_desc(unsigned long long *pairs, uint32_t P) {
@@ -240,81 +250,100 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned long long *pairs, uin
     }
 }
 
-// One pass over the view.  Returns true with the winners (possibly a few more than kk, unsorted) in sh.pairs[0, *count);
-// false (uniformly for the CTA) when a thread may have dropped a winner.
+// One pass over the view.  Returns true with every candidate >= T (at least kk of them when the view holds that many,
+// unsorted) in sh.pairs[0, *count); false (uniformly for the CTA) when more than kMaxK candidates reached T.
 template <class View>
 __device__ __forceinline__ bool select_one_pass(const View &view, uint32_t n, uint32_t kk, SelShared &sh, uint32_t *count) {
-    const uint32_t tid = threadIdx.x;
-    unsigned long long kept[SEL_KEEP];
-#pragma unroll
-    for (int i = 0; i < SEL_KEEP; ++i) kept[i] = 0ull;  // 0 = empty (a real pair has key > kKeyNegInf)
-    auto offer = [&](float v, uint32_t idx) {
-        const uint32_t key = f2key(v);
-        if (key <= kKeyNegInf) return;
-        const unsigned long long pr = pack_pair(key, idx);
-        if (pr > kept[SEL_KEEP - 1]) {
-            kept[SEL_KEEP - 1] = pr;
-#pragma unroll
-            for (int i = SEL_KEEP - 1; i > 0; --i) {
-                if (kept[i] > kept[i - 1]) {
-                    const unsigned long long t = kept[i];
-                    kept[i] = kept[i - 1];
-                    kept[i - 1] = t;
-                }
-            }
-        }
-    };
-    uint32_t i = tid;
-    for (; i + 3 * SEL_T < n; i += 4 * SEL_T) {  // four loads in flight per thread
-        const float v0 = view.load(i), v1 = view.load(i + SEL_T), v2 = view.load(i + 2 * SEL_T), v3 = view.load(i + 3 * SEL_T);
-        offer(v0, i);
-        offer(v1, i + SEL_T);
-        offer(v2, i + 2 * SEL_T);
-        offer(v3, i + 3 * SEL_T);
-    }
-    for (; i < n; i += SEL_T) offer(view.load(i), i);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float NEG = -INFINITY;
+    const bool vec = view.vec();
+    const uint32_t n4 = vec ? (n >> 2) : 0u;  // 16-byte chunks; the tail (and a view without vector loads) goes scalar
+    if (tid == 0) sh.fast_cnt = 0;
 
-    // T = the kk-th best of the per-thread maxima: at least kk candidates are >= T (0: fewer than kk threads saw one).
-    // Bitonic sort of one value per thread: strides below 32 are shuffles, the ten stages with strides >= 32 exchange
-    // through shared memory (two alternating buffers: one barrier per stage; 45 barriers when sorted in place)
-    if (tid == 0) {
-        sh.fast_cnt = 0;
-        sh.fast_overflow = 0;
-    }
-    unsigned long long v = kept[0];
-    int flip = 0;
-#pragma unroll 1
-    for (uint32_t size = 2; size <= (uint32_t)SEL_T; size <<= 1) {
-        const bool desc = (tid & size) == 0;
-#pragma unroll 1
-        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-            unsigned long long other;
-            if (stride >= 32) {
-                unsigned long long *buf = sh.pairs + flip * SEL_T;
-                flip ^= 1;
-                buf[tid] = v;
-                __syncthreads();
-                other = buf[tid ^ stride];
-            } else {
-                other = __shfl_xor_sync(0xffffffffu, v, stride);
-            }
-            const bool take_max = ((tid & stride) == 0) == desc;
-            v = take_max ? (v > other ? v : other) : (v < other ? v : other);
-        }
-    }
-    __syncthreads();  // the exchange buffers are free
-    if (tid == kk - 1) sh.pairs[0] = v;  // position kk - 1 of the descending order (kk <= SEL_FAST_K <= SEL_T)
-    __syncthreads();
-    const unsigned long long T = sh.pairs[0];
-    __syncthreads();
-    if (kept[SEL_KEEP - 1] != 0ull && kept[SEL_KEEP - 1] >= T) sh.fast_overflow = 1;  // may have dropped a pair >= T
+    // phase 1: the maximum key of the values dealt to this thread
+    float4 r[SEL_RV];
 #pragma unroll
-    for (int j = 0; j < SEL_KEEP; ++j) {
-        if (kept[j] != 0ull && kept[j] >= T) sh.pairs[atomicAdd(&sh.fast_cnt, 1u)] = kept[j];  // <= SEL_KEEP * SEL_T = kMaxK
+    for (int j = 0; j < SEL_RV; ++j) {
+        const uint32_t i4 = tid + (uint32_t)j * SEL_T;
+        r[j] = i4 < n4 ? view.load4(i4) : make_float4(NEG, NEG, NEG, NEG);
+    }
+    uint32_t mx = 0;
+#pragma unroll
+    for (int j = 0; j < SEL_RV; ++j)
+        mx = max(max(mx, max(f2key(r[j].x), f2key(r[j].y))), max(f2key(r[j].z), f2key(r[j].w)));
+    {
+        uint32_t i4 = tid + (uint32_t)SEL_RV * SEL_T;
+        for (; i4 + 3 * SEL_T < n4; i4 += 4 * SEL_T) {  // four loads in flight per thread
+            const float4 v0 = view.load4(i4), v1 = view.load4(i4 + SEL_T), v2 = view.load4(i4 + 2 * SEL_T), v3 = view.load4(i4 + 3 * SEL_T);
+            mx = max(max(mx, max(f2key(v0.x), f2key(v0.y))), max(f2key(v0.z), f2key(v0.w)));
+            mx = max(max(mx, max(f2key(v1.x), f2key(v1.y))), max(f2key(v1.z), f2key(v1.w)));
+            mx = max(max(mx, max(f2key(v2.x), f2key(v2.y))), max(f2key(v2.z), f2key(v2.w)));
+            mx = max(max(mx, max(f2key(v3.x), f2key(v3.y))), max(f2key(v3.z), f2key(v3.w)));
+        }
+        for (; i4 < n4; i4 += SEL_T) {
+            const float4 v = view.load4(i4);
+            mx = max(max(mx, max(f2key(v.x), f2key(v.y))), max(f2key(v.z), f2key(v.w)));
+        }
+        uint32_t i = 4 * n4 + tid;
+        for (; i + 3 * SEL_T < n; i += 4 * SEL_T) {
+            const float v0 = view.load(i), v1 = view.load(i + SEL_T), v2 = view.load(i + 2 * SEL_T), v3 = view.load(i + 3 * SEL_T);
+            mx = max(max(mx, max(f2key(v0), f2key(v1))), max(f2key(v2), f2key(v3)));
+        }
+        for (; i < n; i += SEL_T) mx = max(mx, f2key(view.load(i)));
+    }
+
+    // T: every warp holds at least jstar thread maxima >= its jstar-th best one, so the minimum of those over the warps
+    // has at least (SEL_T / 32) * jstar >= kk candidates at or above it.  A view that fits the gather buffer needs no bound.
+    uint32_t T = kKeyNegInf + 1u;
+    if (n > (uint32_t)kMaxK) {
+        const uint32_t jstar = (kk + SEL_T / 32 - 1) / (SEL_T / 32);
+        uint32_t v = mx, tw = 0;
+        for (uint32_t j = 0; j < jstar; ++j) {
+            tw = __reduce_max_sync(0xffffffffu, v);
+            const uint32_t holders = __ballot_sync(0xffffffffu, v == tw);
+            if (lane == (uint32_t)(__ffs(holders) - 1)) v = 0;  // one holder leaves the pool per round
+        }
+        if (lane == 0) sh.warp_tot[warp] = tw;
+        __syncthreads();
+        uint32_t t = sh.warp_tot[0];
+#pragma unroll
+        for (int w = 1; w < SEL_T / 32; ++w) t = min(t, sh.warp_tot[w]);
+        T = max(T, t);
+    } else {
+        __syncthreads();  // fast_cnt is zero
+    }
+
+    // phase 2: the threads that hold a value >= T gather them (most threads skip this)
+    if (mx >= T) {
+        auto put = [&](float f, uint32_t idx) {
+            const uint32_t key = f2key(f);
+            if (key >= T) {
+                const uint32_t s = atomicAdd(&sh.fast_cnt, 1u);
+                if (s < (uint32_t)kMaxK) sh.pairs[s] = pack_pair(key, idx);
+            }
+        };
+#pragma unroll
+        for (int j = 0; j < SEL_RV; ++j) {
+            const uint32_t i4 = tid + (uint32_t)j * SEL_T;
+            if (i4 < n4) {
+                put(r[j].x, 4 * i4);
+                put(r[j].y, 4 * i4 + 1);
+                put(r[j].z, 4 * i4 + 2);
+                put(r[j].w, 4 * i4 + 3);
+            }
+        }
+        for (uint32_t i4 = tid + (uint32_t)SEL_RV * SEL_T; i4 < n4; i4 += SEL_T) {
+            const float4 v = view.load4(i4);
+            put(v.x, 4 * i4);
+            put(v.y, 4 * i4 + 1);
+            put(v.z, 4 * i4 + 2);
+            put(v.w, 4 * i4 + 3);
+        }
+        for (uint32_t i = 4 * n4 + tid; i < n; i += SEL_T) put(view.load(i), i);
     }
     __syncthreads();
     *count = sh.fast_cnt;
-    return sh.fast_overflow == 0;
+    return sh.fast_cnt <= (uint32_t)kMaxK;
 }
 
 template <class Src>
@@ -332,8 +361,7 @@ __device__ __forceinline__ void select_topk_body(const Src &src, int k, SelShare
 
     uint32_t n_sort = 0;  // pairs in sh.pairs to sort; the first min(n_sort, kk) are the result
     bool selected = false;
-    // (below ~8k candidates the radix passes hit L2 and cost less than the one-pass bookkeeping: measured at n = 3072)
-    if (kk <= (uint32_t)SEL_FAST_K && n >= (uint32_t)SEL_FAST_MIN_N) {
+    if (kk <= (uint32_t)SEL_FAST_K) {
         selected = select_one_pass(view, n, kk, sh, &n_sort);
         __syncthreads();  // everybody has read the verdict before the radix path reuses the shared fields
     }
@@ -432,6 +460,18 @@ __device__ __forceinline__ void select_topk_body(const Src &src, int k, SelShare
 
     }
     const uint32_t n_valid = n_sort < kk ? n_sort : kk;
+
+    if (n_sort <= (uint32_t)SEL_RANK_MAX) {
+        // few winners: the rank of a pair is the number of pairs above it (pairs are distinct: the index is part of them)
+        if ((uint32_t)tid < n_sort) {
+            const unsigned long long mine = sh.pairs[tid];
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < n_sort; ++j) rank += sh.pairs[j] > mine ? 1u : 0u;
+            if (rank < n_valid) src.emit(q, (int)rank, true, key2f((uint32_t)(mine >> 32)), 0xffffffffu - (uint32_t)mine);
+        }
+        for (int j = (int)n_valid + tid; j < k; j += SEL_T) src.emit(q, j, false, 0.f, 0);
+        return;
+    }
 
     // bitonic sort (descending) of the winners
     uint32_t P = 1;
@@ -546,14 +586,6 @@ cudaError_t launch_merge_topk(const float *part_dist, const int64_t *part_ids, i
     if (nq <= 0) return cudaSuccess;
     MergeSrc src{part_dist, part_ids, parts, nq, kin, k, metric, out_dist, out_ids};
     select_topk_kernel<MergeSrc><<<(unsigned)nq, SEL_T, 0, st>>>(src, k, PeerWait{}, PeerSignal{});
-    return cudaGetLastError();
-}
-
-cudaError_t launch_merge_topk_wait(const float *part_dist, const int64_t *part_ids, int parts, int64_t nq, int kin, int k,
-                                   int metric, float *out_dist, int64_t *out_ids, const PeerWait &wait, cudaStream_t st) {
-    if (nq <= 0) return cudaSuccess;
-    MergeSrc src{part_dist, part_ids, parts, nq, kin, k, metric, out_dist, out_ids};
-    select_topk_kernel<MergeSrc><<<(unsigned)nq, SEL_T, 0, st>>>(src, k, wait, PeerSignal{});
     return cudaGetLastError();
 }
 

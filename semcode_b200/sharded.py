@@ -26,7 +26,7 @@ from .index import KMEANS_NITER, KMEANS_SEED, metric_code
 class ShardedIVFFlat:
     def __init__(self, dim: int, nlist: int, metric="IP", device: Optional[int] = None, group=None,
                  engine=None, merge: Optional[Callable] = None, shard_by: str = "rows", exchange: str = "auto",
-                 exchange_bytes: int = 64 << 20):
+                 exchange_bytes: int = 64 << 20, inflight: int = 1):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialised (one process per GPU)")
         self.group = group
@@ -56,22 +56,29 @@ class ShardedIVFFlat:
         # over peer-mapped memory (PeerExchange); "nccl": all-gather + merge kernel; "auto": p2p when it can be set up
         if exchange not in ("auto", "p2p", "nccl"):
             raise ValueError("exchange must be 'auto', 'p2p' or 'nccl'")
+        # inflight > 1: that many exchanges ("lanes"), so that many fused steps can be in flight per rank, each on its own
+        # stream (search(..., lane=j) / search_batches): while one step waits for the slowest peer's partial top-k the next
+        # step's coarse pass and scan run.  The engine hands each lane its own scratch slot (two slots per handle).
         self.exchange = None
+        self.exchanges = []
+        self._lane_streams = None
         self.exchange_error: Optional[str] = None
         if exchange != "nccl" and self.world > 1 and hasattr(engine, "_h"):
             ok = torch.zeros(1, dtype=torch.int32, device=engine.tensor_device())
             try:
                 from .index import PeerExchange
 
-                self.exchange = PeerExchange(engine.device, group, exchange_bytes)
+                self.exchanges = [PeerExchange(engine.device, group, exchange_bytes) for _ in range(max(1, int(inflight)))]
                 ok += 1
             except Exception as e:  # symmetric memory unavailable on this box / build
                 self.exchange_error = f"{type(e).__name__}: {e}"
             dist.all_reduce(ok, group=group)  # all ranks or none
             if int(ok.item()) != self.world:
-                self.exchange = None
+                self.exchanges = []
                 if exchange == "p2p":
                     raise RuntimeError(f"peer-memory exchange unavailable: {self.exchange_error}")
+            if self.exchanges:
+                self.exchange = self.exchanges[0]
 
     # -- coarse quantizer -------------------------------------------------------------------------
     def set_centroids(self, centroids=None, src: int = 0) -> None:
@@ -154,7 +161,7 @@ class ShardedIVFFlat:
 
     def check_exchange(self) -> None:
         """Synchronise and raise if any fused step issued so far timed out waiting for a peer."""
-        if self.exchange is not None and self.exchange.status()[0]:
+        if any(ex.status()[0] for ex in self.exchanges):
             raise RuntimeError("sharded search: a peer did not arrive within the exchange timeout; the results of that step "
                                "and the ones after it are invalid -- rebuild the exchange after a barrier")
 
@@ -180,27 +187,49 @@ class ShardedIVFFlat:
         dist.all_gather_into_tensor(full, mine, group=self.group)
         return full[:nq]
 
-    def search(self, q, k: int, nprobe: int = 16, repos=None, langs=None, shard_coarse: bool = True):
-        """Every rank passes the same queries and receives the same merged (dist, ids) tensors."""
+    def search_batches(self, batches, k: int, nprobe: int = 16, repos=None, langs=None):
+        """Several query batches, `inflight` of them in flight at a time (one stream and one exchange per lane; every rank
+        passes the same batches in the same order).  Returns the list of (dist, ids), complete on the current stream."""
+        dev = self.local.tensor_device()
+        lanes = max(1, len(self.exchanges))
+        if lanes == 1 or self.world == 1:
+            return [self.search(q, k, nprobe, repos, langs) for q in batches]
+        if self._lane_streams is None:
+            self._lane_streams = [torch.cuda.Stream(device=dev) for _ in range(lanes)]
+        cur = torch.cuda.current_stream(dev)
+        for st in self._lane_streams:
+            st.wait_stream(cur)
+        outs = []
+        for i, q in enumerate(batches):
+            with torch.cuda.stream(self._lane_streams[i % lanes]):
+                outs.append(self.search(q, k, nprobe, repos, langs, lane=i % lanes))
+        for st in self._lane_streams:
+            cur.wait_stream(st)
+        return outs
+
+    def search(self, q, k: int, nprobe: int = 16, repos=None, langs=None, shard_coarse: bool = True, lane: int = 0):
+        """Every rank passes the same queries and receives the same merged (dist, ids) tensors.  `lane` picks the exchange
+        of a fused step (see `inflight`); steps of one lane are ordered by the caller's stream."""
         dev = self.local.tensor_device()
         if not torch.is_tensor(q):
             q = torch.from_numpy(np.ascontiguousarray(q, dtype=np.float32))
         q = q.to(dev, torch.float32)
         if self.world == 1:
             return self.local.search(q, k, nprobe=nprobe, repos=repos, langs=langs)
-        if self.exchange is not None and self.shard_by == "rows" and q.shape[0] >= 1:
+        if self.exchanges and self.shard_by == "rows" and q.shape[0] >= 1:
+            ex = self.exchanges[lane]
             # A step whose merge gave up waiting for a peer returned garbage, and the late peer now writes into buffers
             # of later steps: never continue silently.  (The C ABI refuses as well; this gives the Python-level reason.)
-            if self.exchange.poll():
+            if ex.poll():
                 raise RuntimeError("sharded search: a peer did not arrive within the exchange timeout (or a step failed "
                                    "midway); results since then are invalid -- rebuild the exchange after a barrier")
             # fused steps of at most 8192 queries: split coarse pass, probe rows and partial top-k stored into the
             # peers' buffers by the kernels that produce them, merge kernel waiting on the peers' flags
             np_ = min(int(nprobe), self.nlist)
             step = 8192
-            while step > 1 and 2 * (step * np_ * 4 + self.world * step * k * 12 + 1024) + 4096 > self.exchange.nbytes:
+            while step > 1 and 2 * (step * np_ * 4 + self.world * step * k * 12 + 1024) + 4096 > ex.nbytes:
                 step //= 2  # same arithmetic on every rank
-            outs = [self.local.search(q[s:s + step], k, nprobe=nprobe, repos=repos, langs=langs, exchange=self.exchange)
+            outs = [self.local.search(q[s:s + step], k, nprobe=nprobe, repos=repos, langs=langs, exchange=ex)
                     for s in range(0, q.shape[0], step)]
             if len(outs) == 1:
                 return outs[0]

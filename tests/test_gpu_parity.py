@@ -103,9 +103,13 @@ def test_probe_and_assign_match_oracle(sb, orc, metric, d):
         if not np.array_equal(got[r], want[r]):
             # only near-ties (fp32 rounding of the contraction) may reorder
             assert sorted(got[r]) == sorted(want[r]) or np.allclose(
-                np.sort(sim[r][got[r]]), np.sort(sim[r][want[r]]), rtol=1e-5, atol=2e-7
+                np.sort(sim[r][got[r]]), np.sort(sim[r][want[r]]), rtol=1e-5, atol=5e-7
             ), f"query {r}: probes differ beyond rounding"
-        assert close(sc[r], sim[r][got[r]].astype(np.float32)).all()
+        # coarse similarities only rank the lists (they are not returned distances): the 3xTF32 contraction drops the
+        # lo x lo term, 2^-22 of |x||c|, which the L2 form 2 x.c - |c|^2 doubles and then cancels against (0.0011 +- 5.5e-7
+        # seen at d = 30) -- so they get 1e-6 absolute on top of the relative bound, the final distances do not
+        ref = sim[r][got[r]].astype(np.float32)
+        assert (np.abs(sc[r].astype(np.float64) - ref) <= 1e-5 * np.abs(ref) + 1e-6).all()
     a = g.assign(x)
     a_ref = np.argmax(orc.coarse_similarity(x, cent, metric, dtype=np.float64), axis=1)
     diff = np.flatnonzero(a != a_ref)
@@ -342,7 +346,7 @@ def test_one_pass_selection_of_probes(sb, orc):
             assert close(sc[r], sim[r][got[r]].astype(np.float32)).all()
             assert (np.diff(sc[r]) <= 0).all()
             if not np.array_equal(got[r], want[r]):  # only near-ties (fp32 rounding of the contraction) may reorder
-                assert np.allclose(np.sort(sim[r][got[r]]), np.sort(sim[r][want[r]]), rtol=1e-5, atol=2e-7), (nprobe, r)
+                assert np.allclose(np.sort(sim[r][got[r]]), np.sort(sim[r][want[r]]), rtol=1e-5, atol=5e-7), (nprobe, r)
 
 
 def test_chunked_search_equals_single_pass(sb, orc):
@@ -394,7 +398,7 @@ def test_kmeans_tracks_oracle(sb, orc, metric):
     g2 = sb.IVFFlatIndex(40, nlist=24, metric=metric)
     obj2 = g2.train(x, niter=8, init_centroids=x[orc.kmeans_init_rows(6000, 24, 5)])
     np.testing.assert_allclose(obj2, obj, rtol=1e-6)
-    np.testing.assert_allclose(g2.get_centroids(), g.get_centroids(), rtol=1e-5, atol=2e-7)
+    np.testing.assert_allclose(g2.get_centroids(), g.get_centroids(), rtol=1e-5, atol=5e-7)
 
 
 def test_kmeans_empty_cluster_split(sb, orc):
@@ -764,7 +768,7 @@ def test_small_batch_path(sb, orc, metric, d, nq):
     want = orc.top_desc(exact, 11)
     for r in range(nq):
         if not np.array_equal(lists[r], want[r]):
-            assert np.allclose(np.sort(exact[r][lists[r]]), np.sort(exact[r][want[r]]), rtol=1e-5, atol=2e-7)
+            assert np.allclose(np.sort(exact[r][lists[r]]), np.sort(exact[r][want[r]]), rtol=1e-5, atol=5e-7)
         assert close(sc[r], exact[r][lists[r]].astype(np.float32)).all()
     g.set_param("small_coarse", 0)
     lists_tc = g.probe(q, 11)
@@ -994,4 +998,58 @@ def test_headline_regime_list_major_against_oracle(sb, orc_c, metric):
     ids = np.concatenate([p[1] for p in parts])
     od, oi = orc_c.scan_search(qs, g.metric, remap[probes], off, vecs, ids, k)
     assert_topk_parity(d0[pick], i0[pick], od, oi, "list-major vs C oracle")
+    g.close()
+
+
+def test_two_searches_in_flight_on_one_handle(sb, orc):
+    """Two host threads, each on its own CUDA stream, search the same handle at once (the handle keeps two scratch slots;
+    searches share the lock, writers take it alone) while a third thread inserts rows.  Every result equals the result of
+    the same search made alone, and the inserted rows are all there afterwards."""
+    import threading
+
+    import torch
+
+    x, q, cent, ids = make_case(orc, 60000, 256, 64, 600, "IP", seed=21)
+    g, _, _ = build_pair(sb, orc, x[:50000], ids[:50000], cent, "IP")
+    dev = torch.device("cuda", 0)
+    qd = torch.from_numpy(q).to(dev)
+    batches = [qd[i * 100:(i + 1) * 100].contiguous() for i in range(6)]
+    # (list-major for the 100-query batches at nprobe 12, query-major at nprobe 2: both routes run concurrently)
+    want = {(b, npb): tuple(t.cpu().numpy() for t in g.search(batches[b], 10, nprobe=npb)) for b in range(6) for npb in (2, 12)}
+    errors, results = [], {}
+
+    def searcher(tid):
+        try:
+            st = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(st):
+                for rep in range(8):
+                    for b in range(tid, 6, 2):
+                        for npb in (2, 12):
+                            d, i = g.search(batches[b], 10, nprobe=npb)
+                            results[(tid, rep, b, npb)] = (d, i)
+            st.synchronize()
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    def writer():
+        try:
+            far = np.zeros((1, 256), dtype=np.float32)
+            far[0, 0] = -1.0  # rows nobody retrieves: the searches' expected results do not change
+            for j in range(20):
+                g.add(np.repeat(far, 50, axis=0), np.arange(10**9 + 50 * j, 10**9 + 50 * (j + 1), dtype=np.int64))
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    ts = [threading.Thread(target=searcher, args=(0,)), threading.Thread(target=searcher, args=(1,)), threading.Thread(target=writer)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
+    torch.cuda.synchronize()
+    assert g.ntotal == 50000 + 1000
+    for (tid, rep, b, npb), (d, i) in results.items():
+        wd, wi = want[(b, npb)]
+        np.testing.assert_array_equal(i.cpu().numpy(), wi, err_msg=f"thread {tid} rep {rep} batch {b} nprobe {npb}")
+        np.testing.assert_array_equal(d.cpu().numpy(), wd)
     g.close()

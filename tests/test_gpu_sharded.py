@@ -66,6 +66,23 @@ def _worker(rank, world, port, ret):
             if sh.exchange is not None:
                 timed_out, steps = sh.exchange.status()
                 assert not timed_out and steps == 8
+        # two fused steps in flight per rank (two lanes: stream + exchange + scratch slot each): same results as one at a time
+        sh2 = ShardedIVFFlat(d, nlist, "IP", device=rank, exchange="auto", inflight=2)
+        sh2.set_centroids(torch.from_numpy(x[:nlist].copy()).cuda() if rank == 0 else None, src=0)
+        sh2.add(x, ids)
+        one3 = sb.IVFFlatIndex(d, nlist=nlist, metric="IP", device=rank)
+        one3.set_centroids(sh2.local.get_centroids())
+        one3.add(x, ids)
+        qd = torch.from_numpy(q).cuda()
+        batches = [qd[a:b].contiguous() for a, b in ((0, 100), (100, 101), (101, 300), (0, 300), (50, 250), (7, 9), (0, 128))]
+        for rep in range(3):
+            outs = sh2.search_batches(batches, 10, nprobe=9)
+            torch.cuda.synchronize()
+            for (gd, gi), qb in zip(outs, batches):
+                rd, ri = one3.search(qb, 10, nprobe=9)
+                assert_topk_parity(gd.cpu().numpy(), gi.cpu().numpy(), rd.cpu().numpy(), ri.cpu().numpy(), f"two in flight, round {rep}")
+        sh2.check_exchange()
+        kinds.append(f"inflight {len(sh2.exchanges)}")
         ret[rank] = "ok " + "; ".join(kinds)
     except Exception:
         import traceback
