@@ -86,8 +86,10 @@ def parse_args():
     p.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
                    help="N > 1: p2p = probe rows and partial top-k stored straight into the peers' buffers by the kernels "
                         "that produce them (NVLink peer memory), merge kernel waits on flags; nccl = all-gathers + merge")
-    p.add_argument("--inflight", type=int, default=2,
-                   help="N > 1, p2p exchange: fused steps in flight per rank (one stream + one exchange + one scratch slot each)")
+    p.add_argument("--inflight", type=int, default=0,
+                   help="N > 1, p2p exchange: fused steps in flight per rank (one stream + one exchange + one scratch slot each); "
+                        "0 = automatic: 2 from 4 ranks on (measured at N = 8: 1.36M vs 1.26M QPS -- the second step fills the waits for "
+                        "the slowest peer), 1 below (N = 2: 423k vs 438k -- little to hide, and the interleaved scans share L2)")
     p.add_argument("--shard-by", default="rows", choices=["rows", "lists"],
                    help="N > 1: deal every list's rows round-robin (rows) or whole lists (list l on rank l %% N)")
     return p.parse_args()
@@ -556,19 +558,23 @@ def extra_clustered(c, peaks, peak_src):
                 "roofline": scan_roofline(c, prof, ms, d, list_major_name(args, d) if c.last_list_major else "scan_pages_kernel (query-major)",
                                           peaks, peak_src),
                 "parity": {kk: v for kk, v in check_parity(c, g, q, k, args.nprobe, od, oi, min(32, args.cpu_queries)).items() if kk != "_cpu"}})
+    # recall@10 depends on nprobe only: measured once per nprobe on a fixed set of queries against exhaustive search
+    rq = max(args.recall_queries, 256)
+    qr = gen_rows(torch, 0, rq, d, 99991, c.dev, "clustered")
+    exact = g.search(qr, k, nprobe=nlist)[1].cpu().numpy()
+    recall_by_nprobe = {}
+    for np_ in [int(v) for v in args.sweep_nprobe.split(",")]:
+        ia = g.search(qr, k, nprobe=np_)[1].cpu().numpy()
+        recall_by_nprobe[np_] = float(np.mean([len(np.intersect1d(ia[r][ia[r] >= 0], exact[r])) / k for r in range(rq)]))
+    out["recall_at_10_by_nprobe"] = {str(kk): v for kk, v in recall_by_nprobe.items()}
     sweep = []
     for nq_ in [int(v) for v in args.sweep_nq.split(",")]:
         qs = gen_rows(torch, 0, nq_, d, 777 + nq_, c.dev, "clustered")
-        rq = min(nq_, args.recall_queries)
-        _, ei = g.search(qs[:rq], k, nprobe=nlist)
-        exact = ei.cpu().numpy()
         for np_ in [int(v) for v in args.sweep_nprobe.split(",")]:
-            ms_, (_, ii) = time_search(c, g, qs, k, np_, 20 if nq_ <= 256 else 3)
+            ms_, _ = time_search(c, g, qs, k, np_, 50 if nq_ <= 16 else (20 if nq_ <= 256 else 3))
             p = profiled(c, g, qs, k, np_, reps=1)
-            ia = ii[:rq].cpu().numpy()
-            rec = float(np.mean([len(np.intersect1d(ia[r][ia[r] >= 0], exact[r])) / k for r in range(rq)]))
             lm = p["unique_rows"] > 0
-            sweep.append({"nq": nq_, "nprobe": np_, "ms": ms_, "qps": nq_ / ms_ * 1e3, "recall_at_10": rec,
+            sweep.append({"nq": nq_, "nprobe": np_, "ms": ms_, "qps": nq_ / ms_ * 1e3, "recall_at_10": recall_by_nprobe[np_],
                           "scan": "list-major" if lm else "query-major",
                           "scan_GBps": (p["unique_rows"] if lm else p["scanned_rows"]) * 4 * d / max(p["scan_ms"], 1e-6) / 1e6,
                           "logical_GBps": p["scanned_rows"] * 4 * d / ms_ / 1e6})
@@ -742,7 +748,7 @@ def run_ours(args):
         try:
             from semcode_b200.index import PeerExchange
 
-            exs = [PeerExchange(local, None, 64 << 20) for _ in range(max(1, args.inflight))]
+            exs = [PeerExchange(local, None, 64 << 20) for _ in range(args.inflight if args.inflight > 0 else (2 if world >= 4 else 1))]
             ok += 1
         except Exception as e:
             ex_err = f"{type(e).__name__}: {e}"

@@ -12,6 +12,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace sc {
 
@@ -49,6 +50,13 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Programmatic dependent launch (small-batch path): a kernel launched with launch_pdl(..., true) may become resident while
+// its predecessor in the stream still runs; pdl_wait() blocks until that predecessor has completed and its stores are
+// visible, so every global access of the kernel must come after it.  pdl_launch_dependents() lets the NEXT kernel in the
+// stream do the same with respect to this one.  Both are no-ops for kernels launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 // order-preserving float -> uint key (larger float => larger key). NaN -> 0 (below -inf).
 constexpr uint32_t kKeyNegInf = 0x007fffffu;  // key of -inf; keys <= this are "no result"
 __device__ __forceinline__ uint32_t f2key(float f) {
@@ -62,6 +70,22 @@ __device__ __forceinline__ float key2f(uint32_t k) {
 }
 
 #endif  // __CUDACC__
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // ---- kernel launchers (host API, defined in the .cu files) ---------------------------------
 
@@ -169,6 +193,14 @@ struct PeerRows {
     int64_t row0;                            // first row of THIS rank's slice
 };
 
+// small batches (M <= kPlanTailMaxQ, k <= 128): launch_select_rows and launch_plan_pairs in ONE launch (select.cu).
+// ws: kPlanTailWords 64-bit words of scratch, zero when first used (the kernel leaves them ready for the next launch)
+constexpr int kPlanTailMaxQ = 16;
+constexpr int kPlanTailWords = 1 + kPlanTailMaxQ;
+cudaError_t launch_select_rows_plan(const float *scores, int64_t M, int N, int k, int32_t *out_idx, const int32_t *list_len,
+                                    int32_t nlist, int64_t *page_off, unsigned long long *ws, unsigned long long *rows_total,
+                                    cudaStream_t st, bool pdl);
+
 // pair plan (scan.cu): page_off [npairs + 1] = exclusive prefix of the pages of every (query, list) pair, one launch
 // (single-pass scan, decoupled look-back).  look: plan_pairs_look_words(npairs) 64-bit words of scratch, zero when
 // first used; epoch: differs from the recent launches on the same scratch (22 bits are used: the caller counts up and
@@ -179,7 +211,7 @@ cudaError_t launch_plan_pairs(const int32_t *probe, int64_t npairs, const int32_
                               unsigned long long *rows_total, cudaStream_t st);
 // exclusive prefix sum of in[n] -> out[n+1] (out[n] = total), one CTA (inputs are nlist long)
 cudaError_t launch_exclusive_scan_i32(const int32_t *in, int64_t n, int32_t *out, cudaStream_t st);
-cudaError_t launch_scan_pages(const ScanArgs &a, int variant, int num_sms, int *launches, cudaStream_t st);
+cudaError_t launch_scan_pages(const ScanArgs &a, int variant, int num_sms, int *launches, cudaStream_t st, bool pdl = false);
 
 // list-major scan (scan_lists.cu, scan_mq.cu): the probed lists are read ONCE per batch and scored against every
 // query that probes them.  Scratch (all device, caller-sized): cnt | cursor | counters | agg adjacent (one memset;
@@ -217,7 +249,7 @@ cudaError_t launch_split_queries(const float *q, int64_t n4, float *out, int num
 cudaError_t encode_slab_map(void *map128, const float *base, int64_t rows, int ds);
 // final top-k over the candidates of each query + id translation
 cudaError_t launch_select_candidates(const ScanArgs &a, int64_t nq, int k, float *out_dist, int64_t *out_ids,
-                                     cudaStream_t st);
+                                     cudaStream_t st, bool pdl = false);
 cudaError_t launch_merge_topk(const float *part_dist, const int64_t *part_ids, int parts, int64_t nq, int kin, int k,
                               int metric, float *out_dist, int64_t *out_ids, cudaStream_t st);
 // exchange variants (select.cu): the same selections, writing into every peer / waiting for every peer

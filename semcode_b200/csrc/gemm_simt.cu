@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(256) coarse_small_kernel(const float *__restri
                                                            float *__restrict__ scores) {
     extern __shared__ __align__(16) float4 qs4[];  // [nq][ds4]
     const int ds4 = ds >> 2;
+    pdl_launch_dependents();  // the probe selection may take its place on an SM while the table streams
     for (int i = threadIdx.x; i < nq * ds4; i += blockDim.x) qs4[i] = __ldg(reinterpret_cast<const float4 *>(q) + i);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -145,7 +145,7 @@ constexpr int kSlots = 2;
 struct Scratch {
     DevBuf s_q, s_scores, s_probe, s_pageoff, s_cand, s_outd, s_outi, s_repobits;
     DevBuf s_x, s_xpad, s_ids, s_repo, s_lang, s_assign, s_best, s_pos, s_lenold, s_need, s_npg, s_needoff, s_bad;
-    DevBuf s_sums, s_counts, s_obj, s_rows, s_rm, s_cnt, s_ahi, s_alo, s_lplan, s_scan, s_packed, s_qsplit, s_bstage;
+    DevBuf s_sums, s_counts, s_obj, s_rows, s_rm, s_cnt, s_ahi, s_alo, s_lplan, s_scan, s_packed, s_qsplit, s_bstage, s_ptail;
     cudaEvent_t ev_done = nullptr;
     cudaStream_t side[2] = {nullptr, nullptr};  // fork/join streams of the list-major scan
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
@@ -164,7 +164,7 @@ struct Scratch {
     void each_buf(F f) {
         for (DevBuf *b : {&s_q, &s_scores, &s_probe, &s_pageoff, &s_cand, &s_outd, &s_outi, &s_repobits, &s_x, &s_xpad, &s_ids, &s_repo,
                           &s_lang, &s_assign, &s_best, &s_pos, &s_lenold, &s_need, &s_npg, &s_needoff, &s_bad, &s_sums, &s_counts, &s_obj,
-                          &s_rows, &s_rm, &s_cnt, &s_ahi, &s_alo, &s_lplan, &s_scan, &s_packed, &s_qsplit, &s_bstage})
+                          &s_rows, &s_rm, &s_cnt, &s_ahi, &s_alo, &s_lplan, &s_scan, &s_packed, &s_qsplit, &s_bstage, &s_ptail})
             f(b);
     }
 };
@@ -185,6 +185,8 @@ struct sc_index {
     float *cent_lo = nullptr;    // [nlist, ds] tf32(c - cent_hi) } coarse contraction (gemm_tc.cu)
     int coarse_impl = 0;         // 0 = tcgen05 3xTF32, 1 = fp32 SIMT (exact-fp32 reference kernel)
     int small_coarse = 1;        // batches of <= 16 rows use coarse_small_kernel
+    int fuse_plan = 1;           // batches of <= 16 rows: probe selection + pair plan in one launch
+    int pdl = 1;                 // ... and the step's kernels chained by programmatic dependent launch
     int tc_variant = 0;          // fused argmax tile: 0 = 256x256 (64 B swizzle), 1 = 128x256 (128 B swizzle)
 
     // paged lists
@@ -501,6 +503,8 @@ int update_cnorm(sc_index *ix, cudaStream_t st) {
 }
 
 bool use_tc(const sc_index *ix) { return ix->coarse_impl == 0 && ix->ds >= 32; }
+// kernels coarse_scores launches for m rows (the launch count reported with the search times)
+int coarse_launches(const sc_index *ix, int64_t m) { return (m <= 16 && ix->small_coarse) ? 1 : (use_tc(ix) ? 2 : 1); }
 
 // scores[m, nlist] = similarity to maximise (IP: x.c ; L2: 2 x.c - |c|^2) of device rows xd[m, ds]
 int coarse_scores(sc_index *ix, const float *xd, int64_t m, float *scores, cudaStream_t st) {
@@ -837,6 +841,10 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
         const float *qd = nullptr;
         SC(stage_rows(ix, q + s * ix->dim, m, tl_scr->s_q, tl_scr->s_xpad, st, &qd));
         const int32_t *probe = nullptr;
+        bool planned = false;  // the pair plan came with the probe selection
+        // small batches without per-phase events: each kernel of the step is launched as a programmatic dependent of the one
+        // before it (resident early, blocked in griddepcontrol.wait), which hides the launch latency of the 4-kernel chain
+        const bool pdl = ix->pdl && !ix->profiling;
         SC(prof_mark(ix, st));
         if (lists) {
             SC(stage(ix, lists + s * np, (size_t)npairs, tl_scr->s_probe, st, &probe));
@@ -860,21 +868,37 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
             CU(launch_select_rows_peers(tl_scr->s_scores.as<float>(), hi - lo, ix->nlist, np, rows, make_signal(ex, 0), st));
             CU(launch_peer_wait(make_wait(ex, 0), st));
             probe = reinterpret_cast<const int32_t *>(ex->peer[ex->rank] + exl.probes);
-            tl_scr->prof_total_launches += (use_tc(ix) ? 3 : 2) + 1;
+            tl_scr->prof_total_launches += (hi > lo ? coarse_launches(ix, hi - lo) : 0) + 1 + 1;  // coarse, select + scatter, wait
+        } else if (m <= kPlanTailMaxQ && np <= 128 && ix->fuse_plan) {
+            // small batches: probe selection and pair plan share one launch
+            SC(coarse_scores(ix, qd, m, tl_scr->s_scores.as<float>(), st));
+            SC(prof_mark(ix, st));
+            if (!tl_scr->s_ptail.p) {
+                CU(tl_scr->s_ptail.reserve((size_t)kPlanTailWords * 8));
+                CU(cudaMemsetAsync(tl_scr->s_ptail.p, 0, tl_scr->s_ptail.cap, st));
+            }
+            CU(launch_select_rows_plan(tl_scr->s_scores.as<float>(), m, ix->nlist, np, tl_scr->s_probe.as<int32_t>(), ix->list_len, ix->nlist,
+                                       tl_scr->s_pageoff.as<int64_t>(), tl_scr->s_ptail.as<unsigned long long>(),
+                                       ix->profiling ? tl_scr->prof_rows : nullptr, st, pdl));
+            probe = tl_scr->s_probe.as<int32_t>();
+            tl_scr->prof_total_launches += coarse_launches(ix, m) + 1 - 1;  // select + plan in one; no separate plan launch below
+            planned = true;
         } else {
             SC(coarse_scores(ix, qd, m, tl_scr->s_scores.as<float>(), st));
             SC(prof_mark(ix, st));
             CU(launch_select_rows(tl_scr->s_scores.as<float>(), m, ix->nlist, np, tl_scr->s_probe.as<int32_t>(), nullptr, st));
             probe = tl_scr->s_probe.as<int32_t>();
-            tl_scr->prof_total_launches += use_tc(ix) ? 3 : 2;
+            tl_scr->prof_total_launches += coarse_launches(ix, m) + 1;
         }
         SC(prof_mark(ix, st));
-        if (((tl_scr->plan_epoch + 1) & 0x3fffffu) == 0) {  // epochs 1 .. 2^22 - 2, then start over on zeroed words
-            CU(cudaMemsetAsync(tl_scr->s_scan.p, 0, tl_scr->s_scan.cap, st));
-            tl_scr->plan_epoch = 0;
+        if (!planned) {
+            if (((tl_scr->plan_epoch + 1) & 0x3fffffu) == 0) {  // epochs 1 .. 2^22 - 2, then start over on zeroed words
+                CU(cudaMemsetAsync(tl_scr->s_scan.p, 0, tl_scr->s_scan.cap, st));
+                tl_scr->plan_epoch = 0;
+            }
+            CU(launch_plan_pairs(probe, npairs, ix->list_len, ix->nlist, tl_scr->s_pageoff.as<int64_t>(),
+                                 tl_scr->s_scan.as<unsigned long long>(), ++tl_scr->plan_epoch, ix->profiling ? tl_scr->prof_rows : nullptr, st));
         }
-        CU(launch_plan_pairs(probe, npairs, ix->list_len, ix->nlist, tl_scr->s_pageoff.as<int64_t>(),
-                             tl_scr->s_scan.as<unsigned long long>(), ++tl_scr->plan_epoch, ix->profiling ? tl_scr->prof_rows : nullptr, st));
         SC(prof_mark(ix, st));
         ScanArgs a;
         memset(&a, 0, sizeof(a));
@@ -951,7 +975,7 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
             lp.ev_fork = tl_scr->ev_fork;
             CU(launch_scan_lists(a, lp, ix->lists_cfg, ix->num_sms, &tl_scr->prof_scan_launches, st));
         } else {
-            CU(launch_scan_pages(a, ix->scan_variant, ix->num_sms, &tl_scr->prof_scan_launches, st));
+            CU(launch_scan_pages(a, ix->scan_variant, ix->num_sms, &tl_scr->prof_scan_launches, st, pdl && planned));
         }
         SC(prof_mark(ix, st));
         float *od = outd_dev ? out_dist + s * k : tl_scr->s_outd.as<float>();
@@ -974,7 +998,7 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
                                  reinterpret_cast<const int64_t *>(mine + exl.part_i), ex->world, m, k, k, ix->metric, od, oi, st));
             tl_scr->prof_total_launches += 2;
         } else {
-            CU(launch_select_candidates(a, m, k, od, oi, st));
+            CU(launch_select_candidates(a, m, k, od, oi, st, pdl && planned && !list_major));
         }
         SC(prof_mark(ix, st));
         tl_scr->prof_total_launches += 2;  // pair plan, top-k (the scan launchers count their own)
@@ -1851,6 +1875,14 @@ int sc_index_set_param(sc_index_t *ix, const char *name, int64_t value) {
     }
     if (strcmp(name, "small_coarse") == 0) {
         ix->small_coarse = value != 0;
+        return SC_OK;
+    }
+    if (strcmp(name, "pdl") == 0) {  // small batches: programmatic dependent launch of the step's kernels (default on)
+        ix->pdl = value != 0;
+        return SC_OK;
+    }
+    if (strcmp(name, "fuse_plan") == 0) {  // batches of <= 16 queries: probe selection + pair plan in one launch (default on)
+        ix->fuse_plan = value != 0;
         return SC_OK;
     }
     if (strcmp(name, "tc_variant") == 0) {

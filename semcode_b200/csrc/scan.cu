@@ -162,6 +162,8 @@ __global__ void __launch_bounds__(256, MINB) scan_pages_kernel(const ScanArgs a)
     const int wpb = blockDim.x >> 5;
     const int ds4 = a.ds >> 2;
     float4 *qs = qsmem + (size_t)warp * ds4;
+    pdl_launch_dependents();
+    pdl_wait();
 
     const int64_t W = a.page_off[a.npairs];
     const int64_t nwarps = (int64_t)gridDim.x * wpb;
@@ -270,7 +272,7 @@ __global__ void __launch_bounds__(256, MINB) scan_pages_kernel(const ScanArgs a)
 }
 
 template <int R, int U, bool L2, bool EXACT, int MINB>
-cudaError_t launch_variant(const ScanArgs &a, int num_sms, cudaStream_t st) {
+cudaError_t launch_variant(const ScanArgs &a, int num_sms, cudaStream_t st, bool pdl) {
     auto kern = scan_pages_kernel<R, U, L2, EXACT, MINB>;
     // shared memory: one query copy per warp; shrink the CTA when the query is large
     const size_t per_warp = (size_t)a.ds * sizeof(float);
@@ -282,18 +284,17 @@ cudaError_t launch_variant(const ScanArgs &a, int num_sms, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int grid = num_sms * MINB;
-    kern<<<grid, wpb * 32, smem, st>>>(a);
-    return cudaGetLastError();
+    return launch_pdl(kern, dim3(grid), dim3(wpb * 32), smem, st, pdl, a);
 }
 
 template <int R, int U, int MINB>
-cudaError_t launch_rum(const ScanArgs &a, int num_sms, cudaStream_t st) {
+cudaError_t launch_rum(const ScanArgs &a, int num_sms, cudaStream_t st, bool pdl) {
     const bool exact = ((a.ds >> 2) % (32 * U)) == 0;
     if (a.metric == 1)
-        return exact ? launch_variant<R, U, true, true, MINB>(a, num_sms, st)
-                     : launch_variant<R, U, true, false, MINB>(a, num_sms, st);
-    return exact ? launch_variant<R, U, false, true, MINB>(a, num_sms, st)
-                 : launch_variant<R, U, false, false, MINB>(a, num_sms, st);
+        return exact ? launch_variant<R, U, true, true, MINB>(a, num_sms, st, pdl)
+                     : launch_variant<R, U, true, false, MINB>(a, num_sms, st, pdl);
+    return exact ? launch_variant<R, U, false, true, MINB>(a, num_sms, st, pdl)
+                 : launch_variant<R, U, false, false, MINB>(a, num_sms, st, pdl);
 }
 
 }  // namespace
@@ -313,20 +314,20 @@ cudaError_t launch_plan_pairs(const int32_t *probe, int64_t npairs, const int32_
 }
 
 // variant: 0 = auto, 1 = R2/U6 x2 CTAs, 2 = R4/U6 x1 CTA, 3 = R2/U4 x2 CTAs, 4 = R4/U4 x2 CTAs
-cudaError_t launch_scan_pages(const ScanArgs &a, int variant, int num_sms, int *launches, cudaStream_t st) {
+cudaError_t launch_scan_pages(const ScanArgs &a, int variant, int num_sms, int *launches, cudaStream_t st, bool pdl) {
     if (a.npairs <= 0) return cudaSuccess;
     if (launches) *launches += 1;
     const int ds4 = a.ds >> 2;
     if (variant == 0) variant = (ds4 % 192 == 0) ? 1 : 3;
     switch (variant) {
         case 1:
-            return launch_rum<2, 6, 2>(a, num_sms, st);
+            return launch_rum<2, 6, 2>(a, num_sms, st, pdl);
         case 2:
-            return launch_rum<4, 6, 1>(a, num_sms, st);
+            return launch_rum<4, 6, 1>(a, num_sms, st, pdl);
         case 3:
-            return launch_rum<2, 4, 2>(a, num_sms, st);
+            return launch_rum<2, 4, 2>(a, num_sms, st, pdl);
         case 4:
-            return launch_rum<4, 4, 2>(a, num_sms, st);
+            return launch_rum<4, 4, 2>(a, num_sms, st, pdl);
         default:
             return cudaErrorInvalidValue;
     }

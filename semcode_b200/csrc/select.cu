@@ -493,9 +493,86 @@ __device__ __forceinline__ void select_topk_body(const Src &src, int k, SelShare
 template <class Src>
 __global__ void __launch_bounds__(SEL_T) select_topk_kernel(Src src, int k, PeerWait wait, PeerSignal sig) {
     __shared__ SelShared sh;
+    pdl_launch_dependents();
+    pdl_wait();
     peer_wait(wait);
     select_topk_body(src, k, sh);
     peer_signal(sig);
+}
+
+// ---- small batches: probe selection and pair plan in one launch ------------------------------------------------------
+// One CTA per query ranks the centroids (as above), then turns its own probe row into page counts and their exclusive
+// prefix; the CTA that finishes last (a ticket) adds the per-query bases and writes the grand total -- what
+// plan_pairs_kernel (scan.cu) computes with its own launch and look-back chain.  For nq <= kPlanTailMaxQ a launch boundary
+// costs more than the plan itself (5.7 of the 53 us of an nq = 1 search).
+//   ws: [0] ticket (u32, zero between launches) | [1 ..] per-query page totals (i64), kPlanTailWords 64-bit words
+__global__ void __launch_bounds__(SEL_T) select_rows_plan_kernel(RowsSrc src, int k, const int32_t *__restrict__ list_len, int32_t nlist,
+                                                                  int64_t *__restrict__ page_off, unsigned long long *__restrict__ ws,
+                                                                  unsigned long long *__restrict__ rows_total) {
+    __shared__ SelShared sh;
+    __shared__ uint32_t s_last;
+    pdl_launch_dependents();
+    pdl_wait();
+    select_topk_body(src, k, sh);
+    __syncthreads();  // the CTA's own stores of the probe row are visible to the CTA
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t q = blockIdx.x, nq = gridDim.x;
+    int32_t pages = 0, len = 0;
+    if (tid < k) {
+        const int32_t l = __ldcg(src.out_idx + q * k + tid);
+        if (l >= 0 && l < nlist) {
+            len = __ldg(list_len + l);
+            pages = (len + kPageRows - 1) / kPageRows;
+        }
+    }
+    // exclusive prefix over the k <= 128 entries (warps 0..3)
+    int32_t incl = pages;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) sh.warp_tot[warp] = (uint32_t)incl;
+    if (rows_total != nullptr && warp < (k + 31) / 32) {
+        unsigned long long r = (unsigned long long)len;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+        if (lane == 0 && r) atomicAdd(rows_total, r);
+    }
+    __syncthreads();
+    int64_t wpre = 0, total = 0;
+    for (int w = 0; w < (k + 31) / 32; ++w) {
+        const int64_t t = sh.warp_tot[w];
+        if (w < warp) wpre += t;
+        total += t;
+    }
+    int64_t *qtot = reinterpret_cast<int64_t *>(ws + 1);
+    if (nq == 1) {
+        if (tid < k) page_off[tid] = wpre + incl - pages;
+        if (tid == 0) page_off[k] = total;
+        return;
+    }
+    if (tid < k) page_off[q * k + tid] = wpre + incl - pages;  // offsets inside this query's pairs; the base comes last
+    if (tid == 0) qtot[q] = total;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(reinterpret_cast<unsigned int *>(ws), 1u) == (unsigned int)(nq - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    int64_t base = 0;  // thread t serves entries t, t + SEL_T, ...: query = entry / k
+    for (int64_t e = tid; e < nq * k; e += SEL_T) {
+        const int64_t qq = e / k;
+        base = 0;
+        for (int64_t j = 0; j < qq; ++j) base += __ldcg(qtot + j);
+        if (qq > 0) page_off[e] = __ldcg(page_off + e) + base;
+    }
+    if (tid == 0) {
+        int64_t all = 0;
+        for (int64_t j = 0; j < nq; ++j) all += __ldcg(qtot + j);
+        page_off[nq * k] = all;
+        *reinterpret_cast<unsigned int *>(ws) = 0u;  // ready for the next launch on this scratch
+    }
 }
 
 // ---- exclusive prefix sums (single CTA; inputs are at most nq*nprobe or nlist long) -----------
@@ -547,6 +624,15 @@ cudaError_t launch_select_rows(const float *scores, int64_t M, int N, int k, int
     return cudaGetLastError();
 }
 
+cudaError_t launch_select_rows_plan(const float *scores, int64_t M, int N, int k, int32_t *out_idx, const int32_t *list_len,
+                                    int32_t nlist, int64_t *page_off, unsigned long long *ws, unsigned long long *rows_total,
+                                    cudaStream_t st, bool pdl) {
+    if (M <= 0 || M > kPlanTailMaxQ || k > SEL_FAST_K) return cudaErrorInvalidValue;
+    RowsSrc src{scores, N, k, out_idx, nullptr, 0, PeerRows{}};
+    return launch_pdl(select_rows_plan_kernel, dim3((unsigned)M), dim3(SEL_T), 0, st, pdl, src, k, list_len, nlist, page_off, ws,
+                      rows_total);
+}
+
 cudaError_t launch_select_rows_peers(const float *scores, int64_t M, int N, int k, const PeerRows &rows,
                                      const PeerSignal &sig, cudaStream_t st) {
     if (M <= 0) return launch_peer_signal(sig, st);
@@ -566,11 +652,10 @@ cudaError_t launch_peer_wait(const PeerWait &wait, cudaStream_t st) {
 }
 
 cudaError_t launch_select_candidates(const ScanArgs &a, int64_t nq, int k, float *out_dist, int64_t *out_ids,
-                                     cudaStream_t st) {
+                                     cudaStream_t st, bool pdl) {
     if (nq <= 0) return cudaSuccess;
     CandSrc src{a, k, out_dist, out_ids, 0, PeerTopk{}};
-    select_topk_kernel<CandSrc><<<(unsigned)nq, SEL_T, 0, st>>>(src, k, PeerWait{}, PeerSignal{});
-    return cudaGetLastError();
+    return launch_pdl(select_topk_kernel<CandSrc>, dim3((unsigned)nq), dim3(SEL_T), 0, st, pdl, src, k, PeerWait{}, PeerSignal{});
 }
 
 cudaError_t launch_select_candidates_peers(const ScanArgs &a, int64_t nq, int k, const PeerTopk &out, const PeerSignal &sig,
