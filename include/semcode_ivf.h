@@ -16,7 +16,13 @@
  *   - DEVICE outputs are valid once the caller synchronises `stream` (no hidden sync);
  *     HOST outputs are valid on return (the call synchronises `stream`).
  *   - the caller owns every input/output buffer; the library owns index storage and scratch.
- *   - a handle may be used from several threads: calls on one handle are serialised internally.
+ *   - a handle may be used from several threads.  Searches (sc_index_search*, sc_index_probe, sc_index_assign) share the
+ *     handle: two of them run in the library at a time, each on its own scratch slot, and overlap on the device when
+ *     their streams differ (one host thread alternating between two streams gets the same overlap: a stream keeps the
+ *     slot it used last).  Every other call runs alone: it waits for running searches and holds new ones back, on the
+ *     host and -- through events -- on the device, so a search never sees a half-applied insert.  This is the
+ *     concurrent-search contract of the reference's server.
+ *   - NVTX: every call and every search phase is an NVTX range (zero cost without a tool attached).
  *   - there is NO CPU fallback: every call fails with SC_ERR_CUDA when no sm_100 device is usable.
  */
 #ifndef SEMCODE_IVF_H
@@ -211,6 +217,11 @@ int sc_index_last_search_times(sc_index_t *idx, sc_search_times_t *out);
  *   "lists_fork"     1 = tile items on a side stream next to the page scans
  *   "coarse_impl"    0 = tcgen05 3xTF32 contraction, 1 = fp32 SIMT;  "tc_variant" 0 = 256x256, 1 = 128x256 tiles
  *   "small_coarse"   1 (default) = streamed fp32 coarse kernel for batches of <= 16 queries
+ *   "fuse_plan"      1 (default) = batches of <= 16 queries: probe selection and pair plan in one launch
+ *   "pdl"            1 (default) = ... and the step's kernels chained by programmatic dependent launch
+ *   "debug_canary"   1 = every scratch buffer allocated from now on (process-wide) sits between two 256-byte guards, without
+ *                    growth slack;  "check_canaries" (value = fewest guarded buffers expected) returns SC_ERR_STATE when a
+ *                    kernel wrote outside one -- the stand-in for compute-sanitizer memcheck where that is unavailable
  *   "plan_epoch"     tests: launch counter of the pair plan's look-back words (22-bit wrap)
  *   "add_chunk_rows" tests: rows per insert chunk (0 = automatic);  "fail_add_after" tests: the n-th insert chunk from
  *                    now fails after its slots were claimed (the index must stay consistent) */

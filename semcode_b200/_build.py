@@ -19,6 +19,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
+    "--threads", "0",  # the .cu files compile in parallel
+    "-ldl",            # NVTX v3 (header-only) resolves the tool's injection library with dlopen
 ]
 
 

@@ -18,6 +18,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/semcode_ivf.h"
 #include "common.cuh"
 
@@ -59,15 +61,40 @@ static int fail(int code, const char *fmt, ...) {
 // ------------------------------------------------------------------------------------------------
 namespace {
 
+// Debug guards (set_param "debug_canary"): every scratch buffer allocated while the switch is on gets a 256-byte guard in
+// front and one right behind the bytes that were asked for (no growth slack), filled with 0xA5; set_param "check_canaries"
+// verifies all of them.  compute-sanitizer is closed on the GPU pool this was developed on (profiles/
+// r2_sanitizer_closed_on_pool.log); this catches what memcheck would catch in the buffers the plan / scan / select kernels
+// index with computed offsets: writes before the start or past the end.
+static bool g_canary = false;
+constexpr size_t kGuardBytes = 256;
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    size_t guard = 0;  // bytes of guard in front of p (and behind p + cap); 0 = no guards
+    unsigned gen = 0;  // counts (re)allocations: "did the contents survive?" (a new block may come back at the old address)
     cudaError_t reserve(size_t bytes) {
         if (bytes == 0) bytes = 256;
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);  // cudaFree waits for in-flight work that may still use the buffer
-        p = nullptr;
-        cap = 0;
+        if (bytes <= cap && (guard != 0) == g_canary) return cudaSuccess;
+        release();  // cudaFree waits for in-flight work that may still use the buffer
+        ++gen;
+        if (g_canary) {
+            const size_t want = (bytes + 15) & ~(size_t)15;
+            char *base = nullptr;
+            cudaError_t e = cudaMalloc(&base, want + 2 * kGuardBytes);
+            if (e != cudaSuccess) return e;
+            e = cudaMemset(base, 0xA5, kGuardBytes);
+            if (e == cudaSuccess) e = cudaMemset(base + kGuardBytes + want, 0xA5, kGuardBytes);
+            if (e != cudaSuccess) {
+                cudaFree(base);
+                return e;
+            }
+            p = base + kGuardBytes;
+            cap = want;
+            guard = kGuardBytes;
+            return cudaSuccess;
+        }
         size_t want = bytes + bytes / 8;
         want = (want + 255) & ~(size_t)255;
         cudaError_t e = cudaMalloc(&p, want);
@@ -80,9 +107,10 @@ struct DevBuf {
         return e;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) cudaFree(static_cast<char *>(p) - guard);
         p = nullptr;
         cap = 0;
+        guard = 0;
     }
     template <typename T>
     T *as() const {
@@ -125,11 +153,39 @@ struct DeviceGuard {
     }
 };
 
+// NVTX ranges (tracing).  One range per C-ABI call and, inside a search, one per phase -- the host-side
+// enqueue of that phase, which a timeline tool (Nsight Systems) correlates with the kernels launched under it.  With no tool
+// attached a push/pop is a null function-pointer check.
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
+struct NvtxPhases {  // consecutive phases of one call: next() closes the running phase and opens another
+    bool open = false;
+    void next(const char *name) {
+        if (open) nvtxRangePop();
+        open = name != nullptr;
+        if (open) nvtxRangePushA(name);
+    }
+    ~NvtxPhases() {
+        if (open) nvtxRangePop();
+    }
+};
+
 // probe[q, j] = j : "every list", used when nprobe >= nlist (exhaustive search needs no ranking)
 __global__ void iota_rows_kernel(int32_t *p, int64_t rows, int32_t n) {
     const int64_t total = rows * n;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
         p[i] = (int32_t)(i % n);
+}
+
+// bad[0] += bytes of the two guards of one buffer that no longer hold 0xA5
+__global__ void check_guard_kernel(const unsigned char *front, const unsigned char *back, int n, unsigned int *bad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && front[i] != 0xA5) atomicAdd(bad, 1u);
+    if (i < n && back[i] != 0xA5) atomicAdd(bad + 1, 1u);
 }
 
 __global__ void fill_u32_kernel(uint32_t *p, int64_t n, uint32_t v) {
@@ -817,9 +873,9 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
     if (!lists) CU(tl_scr->s_probe.reserve((size_t)npairs_max * 4));
     CU(tl_scr->s_pageoff.reserve((size_t)(npairs_max + 1) * 8));
     {   // look-back words of the pair plan: zero when (re)allocated and when the 22-bit epoch wraps
-        const void *before = tl_scr->s_scan.p;
+        const unsigned before = tl_scr->s_scan.gen;
         CU(tl_scr->s_scan.reserve(plan_pairs_look_words(npairs_max) * 8));
-        if (tl_scr->s_scan.p != before) {
+        if (tl_scr->s_scan.gen != before) {
             CU(cudaMemsetAsync(tl_scr->s_scan.p, 0, tl_scr->s_scan.cap, st));
             tl_scr->plan_epoch = 0;
         }
@@ -841,6 +897,8 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
         const float *qd = nullptr;
         SC(stage_rows(ix, q + s * ix->dim, m, tl_scr->s_q, tl_scr->s_xpad, st, &qd));
         const int32_t *probe = nullptr;
+        NvtxPhases nv;
+        nv.next("search:coarse");
         bool planned = false;  // the pair plan came with the probe selection
         // small batches without per-phase events: each kernel of the step is launched as a programmatic dependent of the one
         // before it (resident early, blocked in griddepcontrol.wait), which hides the launch latency of the 4-kernel chain
@@ -861,6 +919,7 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
             const int64_t lo = std::min<int64_t>(m, (int64_t)ex->rank * per), hi = std::min<int64_t>(m, lo + per);
             if (hi > lo) SC(coarse_scores(ix, qd + lo * ix->ds, hi - lo, tl_scr->s_scores.as<float>(), st));
             SC(prof_mark(ix, st));
+            nv.next("search:select+exchange");
             PeerRows rows;
             memset(&rows, 0, sizeof(rows));
             for (int p = 0; p < ex->world; ++p) rows.p[p] = reinterpret_cast<int32_t *>(ex->peer[p] + exl.probes);
@@ -873,9 +932,11 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
             // small batches: probe selection and pair plan share one launch
             SC(coarse_scores(ix, qd, m, tl_scr->s_scores.as<float>(), st));
             SC(prof_mark(ix, st));
-            if (!tl_scr->s_ptail.p) {
+            nv.next("search:select+plan");
+            {
+                const unsigned before = tl_scr->s_ptail.gen;
                 CU(tl_scr->s_ptail.reserve((size_t)kPlanTailWords * 8));
-                CU(cudaMemsetAsync(tl_scr->s_ptail.p, 0, tl_scr->s_ptail.cap, st));
+                if (tl_scr->s_ptail.gen != before) CU(cudaMemsetAsync(tl_scr->s_ptail.p, 0, tl_scr->s_ptail.cap, st));
             }
             CU(launch_select_rows_plan(tl_scr->s_scores.as<float>(), m, ix->nlist, np, tl_scr->s_probe.as<int32_t>(), ix->list_len, ix->nlist,
                                        tl_scr->s_pageoff.as<int64_t>(), tl_scr->s_ptail.as<unsigned long long>(),
@@ -886,11 +947,13 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
         } else {
             SC(coarse_scores(ix, qd, m, tl_scr->s_scores.as<float>(), st));
             SC(prof_mark(ix, st));
+            nv.next("search:select");
             CU(launch_select_rows(tl_scr->s_scores.as<float>(), m, ix->nlist, np, tl_scr->s_probe.as<int32_t>(), nullptr, st));
             probe = tl_scr->s_probe.as<int32_t>();
             tl_scr->prof_total_launches += coarse_launches(ix, m) + 1;
         }
         SC(prof_mark(ix, st));
+        nv.next("search:plan");
         if (!planned) {
             if (((tl_scr->plan_epoch + 1) & 0x3fffffu) == 0) {  // epochs 1 .. 2^22 - 2, then start over on zeroed words
                 CU(cudaMemsetAsync(tl_scr->s_scan.p, 0, tl_scr->s_scan.cap, st));
@@ -900,6 +963,7 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
                                  tl_scr->s_scan.as<unsigned long long>(), ++tl_scr->plan_epoch, ix->profiling ? tl_scr->prof_rows : nullptr, st));
         }
         SC(prof_mark(ix, st));
+        nv.next("search:scan");
         ScanArgs a;
         memset(&a, 0, sizeof(a));
         a.q = qd;
@@ -951,9 +1015,9 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
                     lp.qsplit = tl_scr->s_qsplit.as<float>();
                 }
                 if (ts) {
-                    const void *before = tl_scr->s_bstage.p;
+                    const unsigned before = tl_scr->s_bstage.gen;
                     CU(tl_scr->s_bstage.reserve(scan_lists_ts_stage_bytes(ix->ds, ix->num_sms)));
-                    if (tl_scr->s_bstage.p != before) CU(cudaMemsetAsync(tl_scr->s_bstage.p, 0, tl_scr->s_bstage.cap, st));  // padded rows are read (never stored): keep them finite
+                    if (tl_scr->s_bstage.gen != before) CU(cudaMemsetAsync(tl_scr->s_bstage.p, 0, tl_scr->s_bstage.cap, st));  // padded rows are read (never stored): keep them finite
                     lp.bstage = tl_scr->s_bstage.as<float>();
                 }
             }
@@ -978,6 +1042,7 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
             CU(launch_scan_pages(a, ix->scan_variant, ix->num_sms, &tl_scr->prof_scan_launches, st, pdl && planned));
         }
         SC(prof_mark(ix, st));
+        nv.next(ex ? "search:topk+exchange+merge" : "search:topk");
         float *od = outd_dev ? out_dist + s * k : tl_scr->s_outd.as<float>();
         int64_t *oi = outi_dev ? out_ids + s * k : tl_scr->s_outi.as<int64_t>();
         if (ex) {
@@ -1228,6 +1293,7 @@ int sc_index_kmeans_init(sc_index_t *ix, const float *x, int64_t n, const int64_
 // ACCUMULATED into (device buffers owned by the caller, so that ranks can all-reduce them)
 int sc_index_kmeans_step(sc_index_t *ix, const float *x, int64_t n, double *sums, int32_t *counts, double *objective,
                          void *stream) {
+    NvtxRange nvtx_call("sc_index_kmeans_step");
     if (!ix || !sums || !counts || !objective) return fail(SC_ERR_INVALID, "NULL argument");
     if (n < 0) return fail(SC_ERR_INVALID, "n < 0");
     WriteGuard lk(ix);
@@ -1262,6 +1328,7 @@ int sc_index_kmeans_step(sc_index_t *ix, const float *x, int64_t n, double *sums
 // ties to the lowest index, +-1/1024 perturbation).  nsplit_out (host, nullable).
 int sc_index_kmeans_update(sc_index_t *ix, const double *sums, const int32_t *counts, int32_t *nsplit_out,
                            void *stream) {
+    NvtxRange nvtx_call("sc_index_kmeans_update");
     if (!ix || !sums || !counts) return fail(SC_ERR_INVALID, "NULL argument");
     WriteGuard lk(ix);
     DeviceGuard g(ix->device);
@@ -1307,6 +1374,7 @@ int sc_index_kmeans_update(sc_index_t *ix, const double *sums, const int32_t *co
 
 int sc_index_train(sc_index_t *ix, const float *x, int64_t n, int32_t niter, const int64_t *init_rows,
                    double *objective_out, void *stream) {
+    NvtxRange nvtx_call("sc_index_train");
     if (!ix || !x || !init_rows) return fail(SC_ERR_INVALID, "NULL argument");
     if (niter < 0) return fail(SC_ERR_INVALID, "niter < 0");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1371,6 +1439,7 @@ int sc_index_train(sc_index_t *ix, const float *x, int64_t n, int32_t niter, con
 
 // ---- coarse quantizer -----------------------------------------------------------------------------
 int sc_index_assign(sc_index_t *ix, const float *x, int64_t n, int32_t *out_list, void *stream) {
+    NvtxRange nvtx_call("sc_index_assign");
     if (!ix || !out_list) return fail(SC_ERR_INVALID, "NULL argument");
     if (n < 0) return fail(SC_ERR_INVALID, "n < 0");
     ReadGuard lk(ix, stream);
@@ -1399,6 +1468,7 @@ int sc_index_assign(sc_index_t *ix, const float *x, int64_t n, int32_t *out_list
 
 int sc_index_probe(sc_index_t *ix, const float *q, int64_t nq, int32_t nprobe, int32_t *out_lists, float *out_scores,
                    void *stream) {
+    NvtxRange nvtx_call("sc_index_probe");
     if (!ix || !out_lists) return fail(SC_ERR_INVALID, "NULL argument");
     if (nq < 0 || nprobe < 1) return fail(SC_ERR_INVALID, "bad nq / nprobe");
     ReadGuard lk(ix, stream);
@@ -1436,6 +1506,7 @@ int sc_index_probe(sc_index_t *ix, const float *q, int64_t nq, int32_t nprobe, i
 // ---- insert / remove ------------------------------------------------------------------------------
 int sc_index_add(sc_index_t *ix, const float *x, const int64_t *ids, const uint32_t *repo_tags,
                  const uint8_t *lang_tags, int64_t n, void *stream) {
+    NvtxRange nvtx_call("sc_index_add");
     if (!ix) return fail(SC_ERR_INVALID, "idx is NULL");
     WriteGuard lk(ix);
     DeviceGuard g(ix->device);
@@ -1444,6 +1515,7 @@ int sc_index_add(sc_index_t *ix, const float *x, const int64_t *ids, const uint3
 
 int sc_index_add_preassigned(sc_index_t *ix, const float *x, const int64_t *ids, const uint32_t *repo_tags,
                              const uint8_t *lang_tags, const int32_t *lists, int64_t n, void *stream) {
+    NvtxRange nvtx_call("sc_index_add_preassigned");
     if (!ix) return fail(SC_ERR_INVALID, "idx is NULL");
     if (!lists && n > 0) return fail(SC_ERR_INVALID, "lists is NULL");
     WriteGuard lk(ix);
@@ -1452,6 +1524,7 @@ int sc_index_add_preassigned(sc_index_t *ix, const float *x, const int64_t *ids,
 }
 
 int sc_index_remove_ids(sc_index_t *ix, const int64_t *ids, int64_t n, int64_t *n_removed_out, void *stream) {
+    NvtxRange nvtx_call("sc_index_remove_ids");
     if (!ix) return fail(SC_ERR_INVALID, "idx is NULL");
     if (n < 0) return fail(SC_ERR_INVALID, "n < 0");
     if (n_removed_out) *n_removed_out = 0;
@@ -1487,6 +1560,7 @@ int sc_index_remove_ids(sc_index_t *ix, const int64_t *ids, int64_t n, int64_t *
 // ---- search ---------------------------------------------------------------------------------------
 int sc_index_search(sc_index_t *ix, const float *q, int64_t nq, int32_t k, int32_t nprobe, const sc_filter_t *filter,
                     float *out_dist, int64_t *out_ids, void *stream) {
+    NvtxRange nvtx_call("sc_index_search");
     if (!ix) return fail(SC_ERR_INVALID, "idx is NULL");
     ReadGuard lk(ix, stream);
     DeviceGuard g(ix->device);
@@ -1496,6 +1570,7 @@ int sc_index_search(sc_index_t *ix, const float *q, int64_t nq, int32_t k, int32
 int sc_index_search_preassigned(sc_index_t *ix, const float *q, int64_t nq, int32_t k, int32_t nprobe,
                                 const int32_t *lists, const sc_filter_t *filter, float *out_dist, int64_t *out_ids,
                                 void *stream) {
+    NvtxRange nvtx_call("sc_index_search_preassigned");
     if (!ix) return fail(SC_ERR_INVALID, "idx is NULL");
     if (!lists && nq > 0) return fail(SC_ERR_INVALID, "lists is NULL");
     ReadGuard lk(ix, stream);
@@ -1577,6 +1652,7 @@ int sc_exchange_set_timeout_ms(sc_exchange_t *ex, int64_t ms) {
 
 int sc_index_search_sharded(sc_index_t *ix, sc_exchange_t *ex, const float *q, int64_t nq, int32_t k, int32_t nprobe,
                             const int32_t *lists, const sc_filter_t *filter, float *out_dist, int64_t *out_ids, void *stream) {
+    NvtxRange nvtx_call("sc_index_search_sharded");
     if (!ix) return fail(SC_ERR_INVALID, "idx is NULL");
     if (!ex) return fail(SC_ERR_INVALID, "exchange is NULL");
     ReadGuard lk(ix, stream);
@@ -1593,6 +1669,7 @@ int sc_index_search_sharded(sc_index_t *ix, sc_exchange_t *ex, const float *q, i
 
 int sc_merge_topk(const float *part_dist, const int64_t *part_ids, int32_t parts, int64_t nq, int32_t kin, int32_t k,
                   int32_t metric, float *out_dist, int64_t *out_ids, int32_t device, void *stream) {
+    NvtxRange nvtx_call("sc_merge_topk");
     if (!part_dist || !part_ids || !out_dist || !out_ids) return fail(SC_ERR_INVALID, "NULL argument");
     if (parts < 1 || kin < 1 || k < 1 || k > kMaxK || nq < 0) return fail(SC_ERR_INVALID, "bad parts / kin / k / nq");
     if (metric != SC_METRIC_IP && metric != SC_METRIC_L2) return fail(SC_ERR_INVALID, "unknown metric %d", metric);
@@ -1611,6 +1688,7 @@ int sc_merge_topk(const float *part_dist, const int64_t *part_ids, int32_t parts
 // calls this when nremoved / (ntotal + nremoved) passes its threshold.  Searches return the same rows before and after
 // (slot order inside a list is kept, so exact-tie order does not change either).
 int sc_index_compact(sc_index_t *ix, int64_t *pages_freed_out, void *stream) {
+    NvtxRange nvtx_call("sc_index_compact");
     if (!ix) return fail(SC_ERR_INVALID, "idx is NULL");
     if (pages_freed_out) *pages_freed_out = 0;
     WriteGuard lk(ix);
@@ -1746,6 +1824,7 @@ int sc_index_export_list(sc_index_t *ix, int32_t list, int64_t cap, float *vecs,
 // off_out [list_end - list_begin + 1] (host) = exclusive prefix of the slot counts; buffers host or device, nullable
 int sc_index_export_lists(sc_index_t *ix, int32_t list_begin, int32_t list_end, int64_t cap, float *vecs, int64_t *ids,
                           uint32_t *tags, int64_t *off_out, void *stream) {
+    NvtxRange nvtx_call("sc_index_export_lists");
     if (!ix) return fail(SC_ERR_INVALID, "idx is NULL");
     if (list_begin < 0 || list_end > ix->nlist || list_begin > list_end)
         return fail(SC_ERR_INVALID, "list range [%d, %d) outside [0, %d]", list_begin, list_end, ix->nlist);
@@ -1875,6 +1954,46 @@ int sc_index_set_param(sc_index_t *ix, const char *name, int64_t value) {
     }
     if (strcmp(name, "small_coarse") == 0) {
         ix->small_coarse = value != 0;
+        return SC_OK;
+    }
+    if (strcmp(name, "debug_canary") == 0) {  // guards around every scratch buffer allocated from now on (process-wide switch)
+        DeviceGuard g(ix->device);
+        CU(cudaDeviceSynchronize());
+        g_canary = value != 0;
+        for (int k = 0; k < kSlots; ++k) ix->scr[k].each_buf([](DevBuf *b) { b->release(); });  // re-allocated on next use
+        return SC_OK;
+    }
+    if (strcmp(name, "check_canaries") == 0) {  // SC_ERR_STATE when a kernel wrote outside a guarded scratch buffer
+        DeviceGuard g(ix->device);
+        CU(cudaDeviceSynchronize());
+        unsigned int *bad = nullptr;
+        CU(cudaMalloc(&bad, 8));
+        int checked = 0, which = -1, slot_bad = -1;
+        unsigned int hb[2] = {0, 0}, first[2] = {0, 0};
+        for (int k = 0; k < kSlots; ++k) {
+            int idx = 0;
+            ix->scr[k].each_buf([&](DevBuf *b) {
+                const int me = idx++;
+                if (!b->p || !b->guard) return;
+                cudaMemset(bad, 0, 8);
+                const unsigned char *base = static_cast<const unsigned char *>(b->p);
+                check_guard_kernel<<<1, (int)kGuardBytes>>>(base - b->guard, base + b->cap, (int)kGuardBytes, bad);
+                cudaMemcpy(hb, bad, 8, cudaMemcpyDeviceToHost);
+                ++checked;
+                if ((hb[0] || hb[1]) && which < 0) {
+                    which = me;
+                    slot_bad = k;
+                    first[0] = hb[0];
+                    first[1] = hb[1];
+                }
+            });
+        }
+        cudaFree(bad);
+        CU(cudaGetLastError());
+        if (which >= 0)
+            return fail(SC_ERR_STATE, "scratch buffer #%d of slot %d was written out of bounds: %u guard bytes in front, %u behind", which,
+                        slot_bad, first[0], first[1]);
+        if (value > 0 && checked < value) return fail(SC_ERR_STATE, "only %d guarded buffers exist (expected at least %lld)", checked, (long long)value);
         return SC_OK;
     }
     if (strcmp(name, "pdl") == 0) {  // small batches: programmatic dependent launch of the step's kernels (default on)

@@ -1053,3 +1053,50 @@ def test_two_searches_in_flight_on_one_handle(sb, orc):
         np.testing.assert_array_equal(i.cpu().numpy(), wi, err_msg=f"thread {tid} rep {rep} batch {b} nprobe {npb}")
         np.testing.assert_array_equal(d.cpu().numpy(), wd)
     g.close()
+
+
+def test_scratch_guards_stay_intact(sb, orc):
+    """Stand-in for compute-sanitizer memcheck (closed on the GPU pool, see profiles/): with `debug_canary` every scratch buffer
+    sits between two 256-byte guards and is allocated without slack; after a tour through every scan route, the pair plans, both
+    selection paths, filters, removal and insertion no guard byte may have changed."""
+    rng = np.random.default_rng(8)
+    x, q, cent, ids = make_case(orc, 40000, 768, 48, 700, "IP", seed=31)
+    repo = rng.integers(0, 20, x.shape[0]).astype(np.uint32)
+    lang = rng.integers(0, 3, x.shape[0]).astype(np.uint8)
+    g = sb.IVFFlatIndex(768, nlist=48, metric="IP")
+    try:
+        g.set_param("debug_canary", 1)
+        g.set_centroids(cent)
+        g.add(x[:30000], ids[:30000], repo[:30000], lang[:30000])
+        want = g.search(q[:64], 10, nprobe=6)
+        for nq, k, nprobe, kw in ((1, 10, 6, {}), (5, 10, 6, {}), (64, 10, 6, {}), (700, 10, 6, {}), (700, 10, 30, {}), (300, 200, 48, {}),
+                                  (700, 50, 12, {"repos": [1, 2, 3], "langs": [1]}), (16, 7, 3, {"langs": [0, 2]}), (129, 1, 1, {})):
+            g.search(q[:nq], k, nprobe=nprobe, **kw)
+            g.set_param("check_canaries", 0)
+        for mode in (1, 2):
+            g.set_param("scan_mode", mode)
+            g.search(q[:300], 10, nprobe=9)
+        g.set_param("scan_mode", 0)
+        for cfg in (1, 3, 5, 0):
+            g.set_param("lists_cfg", cfg)
+            g.search(q, 10, nprobe=24)
+        g.remove_ids(ids[:5000])
+        g.add(x[30000:], ids[30000:], repo[30000:], lang[30000:])
+        g.compact()
+        g.assign(x[:3000])
+        g.probe(q[:100], 9)
+        g.search(q, 33, nprobe=17)
+        g.set_param("check_canaries", 8)  # at least 8 guarded buffers were in play
+        # and the guarded run computes what the unguarded one does
+        g.set_param("lists_cfg", 0)
+        g2 = sb.IVFFlatIndex(768, nlist=48, metric="IP")
+        g.set_param("debug_canary", 0)
+        g2.set_centroids(cent)
+        g2.add(x[:30000], ids[:30000], repo[:30000], lang[:30000])
+        d2, i2 = g2.search(q[:64], 10, nprobe=6)
+        np.testing.assert_array_equal(want[1], i2)
+        np.testing.assert_array_equal(want[0], d2)
+        g2.close()
+    finally:
+        g.set_param("debug_canary", 0)
+        g.close()
