@@ -23,6 +23,12 @@ import torch.distributed as dist
 from .index import KMEANS_NITER, KMEANS_SEED, metric_code
 
 
+def _default_merge(metric: int, device):
+    from .index import merge_topk
+
+    return lambda pd, pi, k: merge_topk(pd, pi, k, metric, device)
+
+
 class ShardedIVFFlat:
     def __init__(self, dim: int, nlist: int, metric="IP", device: Optional[int] = None, group=None,
                  engine=None, merge: Optional[Callable] = None, shard_by: str = "rows", exchange: str = "auto",
@@ -170,6 +176,56 @@ class ShardedIVFFlat:
         t = torch.tensor([self.local.ntotal], dtype=torch.int64, device=self.local.tensor_device())
         dist.all_reduce(t, group=self.group)
         return int(t.item())
+
+    # -- persistence ----------------------------------------------------------------------------------
+    def save(self, path: str) -> None:
+        """Every rank writes its shard under `path/shard-RR/` (the engine's own snapshot: bulk list export underneath), rank 0
+        adds `sharded.json`, published last: a directory without it is not a snapshot.  `path` must be visible to every rank."""
+        import json
+        import os
+
+        os.makedirs(path, exist_ok=True)
+        if self.rank == 0 and os.path.exists(os.path.join(path, "sharded.json")):
+            os.remove(os.path.join(path, "sharded.json"))  # unpublish before the shards change
+        dist.barrier(group=self.group)
+        self.local.save(os.path.join(path, f"shard-{self.rank:02d}"))
+        dist.barrier(group=self.group)
+        if self.rank == 0:
+            tmp = os.path.join(path, "sharded.json.tmp")
+            with open(tmp, "w") as f:
+                json.dump({"format": 1, "world": self.world, "dim": self.dim, "nlist": self.nlist, "metric": self.metric,
+                           "shard_by": self.shard_by, "next_row": self._next_row}, f)
+            os.replace(tmp, os.path.join(path, "sharded.json"))
+        dist.barrier(group=self.group)
+
+    @classmethod
+    def load(cls, path: str, device: Optional[int] = None, group=None, exchange: str = "auto", exchange_bytes: int = 64 << 20,
+             inflight: int = 1, engine_loader: Optional[Callable] = None, merge: Optional[Callable] = None) -> "ShardedIVFFlat":
+        """Re-open a snapshot written by `save` with the SAME number of ranks (the deal of the rows is part of the data)."""
+        import json
+        import os
+
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed must be initialised (one process per GPU)")
+        with open(os.path.join(path, "sharded.json")) as f:
+            meta = json.load(f)
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if int(meta["world"]) != world:
+            raise ValueError(f"snapshot {path!r} was written by {meta['world']} ranks, this job has {world}")
+        shard = os.path.join(path, f"shard-{rank:02d}")
+        if engine_loader is None:
+            from .index import IVFFlatIndex
+
+            if device is None:
+                device = torch.cuda.current_device()
+            engine = IVFFlatIndex.load(shard, device=device)
+        else:
+            engine = engine_loader(shard)
+        self = cls(int(meta["dim"]), int(meta["nlist"]), int(meta["metric"]), device=device, group=group, engine=engine,
+                   merge=merge if merge is not None else (None if engine_loader is not None else _default_merge(int(meta["metric"]), device)),
+                   shard_by=meta.get("shard_by", "rows"), exchange=exchange, exchange_bytes=exchange_bytes, inflight=inflight)
+        self._next_row = int(meta.get("next_row", 0))
+        return self
 
     # -- search ---------------------------------------------------------------------------------------
     def probe(self, q, nprobe: int):

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, snap):
     import torch
     import torch.distributed as dist
 
@@ -83,6 +83,15 @@ def _worker(rank, world, port, ret):
                 assert_topk_parity(gd.cpu().numpy(), gi.cpu().numpy(), rd.cpu().numpy(), ri.cpu().numpy(), f"two in flight, round {rep}")
         sh2.check_exchange()
         kinds.append(f"inflight {len(sh2.exchanges)}")
+        # snapshot of the sharded index: one engine snapshot per rank + manifest; re-opened with the same ranks it answers alike
+        sh2.save(snap)
+        sh3 = ShardedIVFFlat.load(snap, device=rank)
+        assert sh3.ntotal == n
+        gd3, gi3 = sh3.search(qd, 10, nprobe=9)
+        gd2, gi2 = sh2.search(qd, 10, nprobe=9)
+        np.testing.assert_array_equal(gi3.cpu().numpy(), gi2.cpu().numpy())
+        np.testing.assert_array_equal(gd3.cpu().numpy(), gd2.cpu().numpy())
+        kinds.append("save/load")
         ret[rank] = "ok " + "; ".join(kinds)
     except Exception:
         import traceback
@@ -93,7 +102,7 @@ def _worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
-def test_sharded_nccl_equals_single_gpu(native_lib):
+def test_sharded_nccl_equals_single_gpu(native_lib, tmp_path):
     import torch
     import torch.multiprocessing as mp
 
@@ -106,7 +115,7 @@ def test_sharded_nccl_equals_single_gpu(native_lib):
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, ret, str(tmp_path / "sharded-snap")), nprocs=world, join=True)
     assert all(str(v).startswith("ok") for v in dict(ret).values()) and len(ret) == world, dict(ret)
     print(dict(ret))  # which exchange ran (p2p = fused peer-memory exchange, nccl = all-gather + merge)
 
