@@ -215,6 +215,8 @@ int sc_index_last_search_times(sc_index_t *idx, sc_search_times_t *out);
  *                    earlier tcgen05 tile kernels with both operands in shared memory (v1 / v2),
  *                    4 = 0 with the 8-query page scan on mma.sync (parity-green, measured slower)
  *   "lists_fork"     1 = tile items on a side stream next to the page scans
+ *   "mq_fused"       1 = the list-major page scans (lists probed by 1..4 / 5..16 queries) in one launch in which every
+ *                    warp works on both buckets (measured slower than the default two launches)
  *   "coarse_impl"    0 = tcgen05 3xTF32 contraction, 1 = fp32 SIMT;  "tc_variant" 0 = 256x256, 1 = 128x256 tiles
  *   "small_coarse"   1 (default) = streamed fp32 coarse kernel for batches of <= 16 queries
  *   "fuse_plan"      1 (default) = batches of <= 16 queries: probe selection and pair plan in one launch

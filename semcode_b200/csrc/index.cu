@@ -243,6 +243,7 @@ struct sc_index {
     int small_coarse = 1;        // batches of <= 16 rows use coarse_small_kernel
     int fuse_plan = 1;           // batches of <= 16 rows: probe selection + pair plan in one launch
     int pdl = 1;                 // ... and the step's kernels chained by programmatic dependent launch
+    int mq_fused = 0;            // 1 = list-major page scans (4-query and 8-query bucket) in ONE launch: measured slower, see scan_mq.cu
     int tc_variant = 0;          // fused argmax tile: 0 = 256x256 (64 B swizzle), 1 = 128x256 (128 B swizzle)
 
     // paged lists
@@ -1007,6 +1008,7 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
             lp.chunk = tc_tiles ? 64 : 32;
             lp.qsplit = nullptr;
             lp.bstage = nullptr;
+            lp.mq_fused = ix->mq_fused;
             if (tc_tiles) {
                 const bool ts = ix->lists_cfg != 5 && ix->lists_cfg != 3 && ix->d_maps != nullptr &&
                                 npairs * (int64_t)(ix->ds / 32) < ((int64_t)1 << 30);
@@ -1994,6 +1996,10 @@ int sc_index_set_param(sc_index_t *ix, const char *name, int64_t value) {
             return fail(SC_ERR_STATE, "scratch buffer #%d of slot %d was written out of bounds: %u guard bytes in front, %u behind", which,
                         slot_bad, first[0], first[1]);
         if (value > 0 && checked < value) return fail(SC_ERR_STATE, "only %d guarded buffers exist (expected at least %lld)", checked, (long long)value);
+        return SC_OK;
+    }
+    if (strcmp(name, "mq_fused") == 0) {  // list-major page scans: 1 = both buckets in one launch (measured slower), 0 = two launches
+        ix->mq_fused = value != 0;
         return SC_OK;
     }
     if (strcmp(name, "pdl") == 0) {  // small batches: programmatic dependent launch of the step's kernels (default on)

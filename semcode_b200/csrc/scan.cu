@@ -172,9 +172,8 @@ __global__ void __launch_bounds__(256, MINB) scan_pages_kernel(const ScanArgs a)
     const int sub_shift = (W * 4 <= nwarps) ? 2 : ((W * 2 <= nwarps) ? 1 : 0);
     const int part_rows = kPageRows >> sub_shift;
     const int64_t units = W << sub_shift;
-    const int64_t per = (units + nwarps - 1) / nwarps;
-    const int64_t u0 = gw * per;
-    const int64_t u1 = (u0 + per < units) ? (u0 + per) : units;
+    const int64_t u0 = gw * units / nwarps;  // balanced contiguous ranges (sizes differ by at most one unit)
+    const int64_t u1 = (gw + 1) * units / nwarps;
     if (u0 >= u1) return;
     const int64_t w0 = u0 >> sub_shift;
 

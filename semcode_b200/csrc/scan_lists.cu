@@ -473,6 +473,7 @@ cudaError_t launch_lists_variant(const ScanArgs &a, const ListPlan &p, int num_s
 }  // namespace
 
 cudaError_t launch_scan_mq(const ScanArgs &a, const ListPlan &p, int bucket, int cfg, const int32_t *pgoff, int num_sms, cudaStream_t st);
+cudaError_t launch_scan_mq_both(const ScanArgs &a, const ListPlan &p, int num_sms, cudaStream_t st);
 
 int list_plan_ctas(int32_t nlist) { return (nlist + PL_BLK - 1) / PL_BLK; }
 
@@ -514,10 +515,15 @@ cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int
         if ((e = launch_lists_variant<32, 64, 2, 128, 4>(a, p, num_sms, s32)) != cudaSuccess) return e;
     }
     if (fork && (e = cudaEventRecord(p.ev_join[0], s32)) != cudaSuccess) return e;
-    if ((e = launch_scan_mq(a, p, 1, cfg, p.pg8off, num_sms, st)) != cudaSuccess) return e;
-    if ((e = launch_scan_mq(a, p, 0, cfg, p.pg4off, num_sms, st)) != cudaSuccess) return e;
+    const bool both = cfg != 4 && p.mq_fused != 0;  // one launch for both page-scan buckets (an option: measured slower)
+    if (both) {
+        if ((e = launch_scan_mq_both(a, p, num_sms, st)) != cudaSuccess) return e;
+    } else {
+        if ((e = launch_scan_mq(a, p, 1, cfg, p.pg8off, num_sms, st)) != cudaSuccess) return e;
+        if ((e = launch_scan_mq(a, p, 0, cfg, p.pg4off, num_sms, st)) != cudaSuccess) return e;
+    }
     if (fork && (e = cudaStreamWaitEvent(st, p.ev_join[0], 0)) != cudaSuccess) return e;
-    if (launches) *launches += p.chunk == 64 && p.bstage == nullptr ? 7 : 6;  // the shared-memory-operand kernel splits the queries first
+    if (launches) *launches += (p.chunk == 64 && p.bstage == nullptr ? 7 : 6) - (both ? 1 : 0);  // the shared-memory-operand kernel splits the queries first
     return cudaSuccess;
 }
 

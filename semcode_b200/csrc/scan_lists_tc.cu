@@ -134,9 +134,8 @@ __global__ void __launch_bounds__(NT_TC2, 1) scan_lists_tc_kernel(const ScanArgs
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int32_t total = p.off32[p.nlist];
-    const int32_t per_cta = (int32_t)(((int64_t)total + gridDim.x - 1) / gridDim.x);
-    const int32_t u0 = (int32_t)min((int64_t)total, (int64_t)blockIdx.x * per_cta);
-    const int32_t u1 = (int32_t)min((int64_t)total, (int64_t)u0 + per_cta);
+    const int32_t u0 = (int32_t)((int64_t)blockIdx.x * total / gridDim.x);  // balanced contiguous ranges of units
+    const int32_t u1 = (int32_t)(((int64_t)blockIdx.x + 1) * total / gridDim.x);
     const int KB = a.ds / TK;  // launcher guarantees ds % 32 == 0
     const int slab_mask = (1 << a.slab_shift) - 1;
 

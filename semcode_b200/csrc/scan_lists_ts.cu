@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const __grid_co
     auto staged_bar = [&](int s) { return bar0 + 8u * (NR + NS + NB + ND + 4 + s); };
     auto bfree_bar = [&](int s) { return bar0 + 8u * (NR + NS + NB + ND + 6 + s); };
 
+    if (p.off32[p.nlist] == 0) return;  // no tile items in this batch (uniform: nothing has been set up yet)
     unsigned long long pw[3] = {0, 0, 0};
     const long long t_start = PROF ? clock64() : 0;
     auto pwait = [&](uint32_t bar, uint32_t parity, int which) {
@@ -170,9 +171,8 @@ __global__ void __launch_bounds__(NT_TS, 1) scan_lists_ts_kernel(const __grid_co
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int32_t total = p.off32[p.nlist];
-    const int32_t per_cta = (int32_t)(((int64_t)total + gridDim.x - 1) / gridDim.x);
-    const int32_t u0 = (int32_t)min((int64_t)total, (int64_t)blockIdx.x * per_cta);
-    const int32_t u1 = (int32_t)min((int64_t)total, (int64_t)u0 + per_cta);
+    const int32_t u0 = (int32_t)((int64_t)blockIdx.x * total / gridDim.x);  // balanced contiguous ranges of units
+    const int32_t u1 = (int32_t)(((int64_t)blockIdx.x + 1) * total / gridDim.x);
     const int KB = a.ds / TK;  // launcher guarantees ds % 32 == 0 and (u1 - u0) * KB < 2^31
     const int slab_mask = (1 << a.slab_shift) - 1;
 

@@ -80,10 +80,9 @@ __host__ __device__ constexpr size_t mq_warp_floats() {
 // candidate store per page): chosen when a scalar filter is active -- with 5 % of the rows live the streaming is
 // short and the per-(page, slice) read-modify-write of the candidates costs more than the restaging
 // (10M x 2048, 5 % selectivity, nprobe 64: 0.93 vs 1.15 ms).  With one slice the two orders coincide.
+// The work of ONE warp on ONE bucket: `qs` is the warp's own shared memory (mq_warp_floats<MQ, U>() floats).
 template <int MQ, int R, int U, bool L2, bool EXACT, bool SO>
-__global__ void __launch_bounds__(256, 2)
-    scan_mq_kernel(const ScanArgs a, const ListPlan p, const int32_t *__restrict__ pgoff) {
-    extern __shared__ __align__(16) float4 qsmem[];
+__device__ __forceinline__ void scan_mq_warp(const ScanArgs &a, const ListPlan &p, const int32_t *__restrict__ pgoff, float4 *qs) {
     constexpr int N = R * MQ;
     constexpr int SL4 = 32 * U;  // float4 per slice
     static_assert(N == 8 || N == 32, "reduce_transpose covers 8 or 32 partial sums");
@@ -93,8 +92,6 @@ __global__ void __launch_bounds__(256, 2)
     const int wpb = blockDim.x >> 5;
     const int ds4 = a.ds >> 2;
     const int nslices = (ds4 + SL4 - 1) / SL4;
-    constexpr size_t WF = mq_warp_floats<MQ, U>();  // floats per warp, 16-byte multiple
-    float4 *qs = qsmem + (size_t)warp * (WF / 4);                                 // [MQ][SL4]
     int64_t *cbs = reinterpret_cast<int64_t *>(qs + MQ * SL4);                    // [MQ] candidate base or -1
     const float4 **qgs = reinterpret_cast<const float4 **>(cbs + MQ);             // [MQ] query row or nullptr
     float *tot = reinterpret_cast<float *>(qgs + MQ);                             // [MQ][kTotLd]
@@ -102,11 +99,12 @@ __global__ void __launch_bounds__(256, 2)
     const int32_t W = pgoff[p.nlist];
     const int64_t nwarps = (int64_t)gridDim.x * wpb;
     const int64_t gw = (int64_t)blockIdx.x * wpb + warp;
-    const int32_t per = (int32_t)((W + nwarps - 1) / nwarps);
-    const int64_t w0l = gw * per;
-    if (w0l >= W) return;
-    const int32_t w0 = (int32_t)w0l;
-    const int32_t w1 = (w0 + per < W) ? (w0 + per) : W;
+    // balanced contiguous ranges: warp g takes units [g W / nwarps, (g + 1) W / nwarps) -- sizes differ by at most one and,
+    // when there are fewer units than warps, the busy warps are spread over all SMs (ranges of ceil(W / nwarps) units left
+    // half of the warps idle on an 8-way shard: `scan_mq<8>` 100 us for 0.26 GB)
+    const int32_t w0 = (int32_t)(gw * (int64_t)W / nwarps);
+    const int32_t w1 = (int32_t)((gw + 1) * (int64_t)W / nwarps);
+    if (w0 >= w1) return;
 
     // list that owns unit w0: last l with pgoff[l] <= w0 (lists without units are skipped)
     int32_t lo = 0, hi = p.nlist;
@@ -309,6 +307,40 @@ __global__ void __launch_bounds__(256, 2)
     }
 }
 
+template <int MQ, int R, int U, bool L2, bool EXACT, bool SO>
+__global__ void __launch_bounds__(256, 2)
+    scan_mq_kernel(const ScanArgs a, const ListPlan p, const int32_t *__restrict__ pgoff) {
+    extern __shared__ __align__(16) float4 qsmem[];
+    constexpr size_t WF = mq_warp_floats<MQ, U>();  // floats per warp, 16-byte multiple
+    scan_mq_warp<MQ, R, U, L2, EXACT, SO>(a, p, pgoff, qsmem + (size_t)(threadIdx.x >> 5) * (WF / 4));
+}
+
+// Both buckets in ONE launch (set_param "mq_fused" = 1; NOT the default).  Every warp takes its 1/nwarps of the 4-query bucket
+// AND of the 8-query bucket; odd warps start with the 8-query bucket, even warps end with it.  The idea: the 8-query scan is
+// issue-bound (47 % issue-active at 4.5 TB/s), the 4-query scan memory-bound (84 % of DRAM peak at 37 % issue-active), so side
+// by side on an SM they should fill each other's idle resource and save the tail + ramp between two launches.  Measured: it
+// loses -- headline scan 4.77 vs 4.10 ms, 8-way shard 0.671 vs 0.603 ms, clustered 4.98 vs 4.69 ms.  The shared per-warp
+// stage is the 8-query one (13.2 KB: 2 x 108 KB per SM -> the 228 KB carve-out and 28 KB of L1, the configuration in which the
+// 4-query scan alone already streamed 11 % slower), and the 8-query warps' shared-memory traffic now competes with the
+// 4-query warps' loads for the same L1 pipe for the whole launch instead of 10 % of the step.
+template <int U4, bool E4, int U8, bool E8, bool L2, bool SO>
+__global__ void __launch_bounds__(256, 2)
+    scan_mq_both_kernel(const ScanArgs a, const ListPlan p, const int32_t *__restrict__ pg4off, const int32_t *__restrict__ pg8off) {
+    extern __shared__ __align__(16) float4 qsmem[];
+    constexpr size_t WF4 = mq_warp_floats<4, U4>(), WF8 = mq_warp_floats<8, U8>();
+    constexpr size_t WF = WF4 > WF8 ? WF4 : WF8;
+    const int warp = threadIdx.x >> 5;
+    float4 *qs = qsmem + (size_t)warp * (WF / 4);
+#pragma unroll 1
+    for (int phase = 0; phase < 2; ++phase) {
+        if ((phase == 0) == ((warp & 1) != 0))
+            scan_mq_warp<8, 4, U8, L2, E8, SO>(a, p, pg8off, qs);
+        else
+            scan_mq_warp<4, 2, U4, L2, E4, SO>(a, p, pg4off, qs);
+        __syncwarp();
+    }
+}
+
 // ---- 8-query page scan on the (legacy) warp-level tensor cores (lists_cfg = 4; measured slower, see launch_scan_mq) ----
 // The scalar 8-query scan above is issue-bound (47 % issue-active at 4.3 TB/s: 384 FMAs, 24 LDS.128 and a 31-shuffle
 // butterfly per 6 KB).  Here a page is two 16-row MMA tiles and the 8 queries are exactly one n-tile of
@@ -351,11 +383,12 @@ __global__ void __launch_bounds__(256, 2)
     const int32_t W = pgoff[p.nlist];
     const int64_t nwarps = (int64_t)gridDim.x * wpb;
     const int64_t gw = (int64_t)blockIdx.x * wpb + warp;
-    const int32_t per = (int32_t)((W + nwarps - 1) / nwarps);
-    const int64_t w0l = gw * per;
-    if (w0l >= W) return;
-    const int32_t w0 = (int32_t)w0l;
-    const int32_t w1 = (w0 + per < W) ? (w0 + per) : W;
+    // balanced contiguous ranges: warp g takes units [g W / nwarps, (g + 1) W / nwarps) -- sizes differ by at most one and,
+    // when there are fewer units than warps, the busy warps are spread over all SMs (ranges of ceil(W / nwarps) units left
+    // half of the warps idle on an 8-way shard: `scan_mq<8>` 100 us for 0.26 GB)
+    const int32_t w0 = (int32_t)(gw * (int64_t)W / nwarps);
+    const int32_t w1 = (int32_t)((gw + 1) * (int64_t)W / nwarps);
+    if (w0 >= w1) return;
     int32_t lo = 0, hi = p.nlist;  // list that owns unit w0: last l with pgoff[l] <= w0
     while (hi - lo > 1) {
         const int32_t mid = (lo + hi) >> 1;
@@ -538,7 +571,35 @@ cudaError_t launch_mq_metric(const ScanArgs &a, const ListPlan &p, const int32_t
                          : launch_mq_variant<MQ, R, U, false, EXACT>(a, p, pgoff, num_sms, st);
 }
 
+template <int U4, bool E4, int U8, bool E8>
+cudaError_t launch_mq_both_cfg(const ScanArgs &a, const ListPlan &p, int num_sms, cudaStream_t st) {
+    constexpr size_t WF4 = mq_warp_floats<4, U4>(), WF8 = mq_warp_floats<8, U8>();
+    constexpr size_t per_warp = (WF4 > WF8 ? WF4 : WF8) * sizeof(float);
+    constexpr int wpb = 8;
+    constexpr size_t smem = per_warp * wpb;
+    static_assert(2 * (smem + 1024) <= 227 * 1024, "two CTAs per SM must fit");
+    auto go = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<num_sms * 2, wpb * 32, smem, st>>>(a, p, p.pg4off, p.pg8off);
+        return cudaGetLastError();
+    };
+    const bool so = a.filt.flags == 0;  // a scalar filter leaves few live rows per page: page-outer order (see SO above)
+    if (a.metric == 1) return so ? go(scan_mq_both_kernel<U4, E4, U8, E8, true, true>) : go(scan_mq_both_kernel<U4, E4, U8, E8, true, false>);
+    return so ? go(scan_mq_both_kernel<U4, E4, U8, E8, false, true>) : go(scan_mq_both_kernel<U4, E4, U8, E8, false, false>);
+}
+
 }  // namespace
+
+// Both page-scan buckets in one launch (same kernels' bodies, see scan_mq_both_kernel).
+cudaError_t launch_scan_mq_both(const ScanArgs &a, const ListPlan &p, int num_sms, cudaStream_t st) {
+    const int ds4 = a.ds >> 2;
+    if (ds4 % 192 == 0) return launch_mq_both_cfg<6, true, 3, true>(a, p, num_sms, st);  // 768, 1536, 2304, 3072, ...
+    if (ds4 % 128 == 0) return launch_mq_both_cfg<4, true, 2, true>(a, p, num_sms, st);  // 512, 1024, 2048, ...
+    if (ds4 % 96 == 0) return launch_mq_both_cfg<4, false, 3, true>(a, p, num_sms, st);
+    if (ds4 % 64 == 0) return launch_mq_both_cfg<4, false, 2, true>(a, p, num_sms, st);
+    return launch_mq_both_cfg<4, false, 3, false>(a, p, num_sms, st);
+}
 
 // bucket 0: remainders of 1..4 queries (one pass); bucket 1: remainders of 5..16 queries (passes of 8).
 // pgoff [nlist+1]: exclusive prefix of the bucket's page x pass units (plan_lists_kernel)

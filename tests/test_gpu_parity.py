@@ -649,6 +649,13 @@ def test_multi_query_page_scan_buckets_and_slices(sb, orc, metric, per_list):
             d3, i3 = g.search(q, 10, lists=probes)
             assert_topk_parity(d3, i3, d1, i1, f"mq cfg={cfg} {metric} d={d}")
             assert_topk_parity(d3, i3, rd, ri, f"mq cfg={cfg} vs oracle {metric} d={d}")
+        # both buckets in one launch (an option; same arithmetic, so the very same bits as the two launches)
+        g.set_param("lists_cfg", 0)
+        d3, i3 = g.search(q, 10, lists=probes)
+        g.set_param("mq_fused", 1)
+        d4, i4 = g.search(q, 10, lists=probes)
+        np.testing.assert_array_equal(i4, i3)
+        np.testing.assert_array_equal(d4, d3)
 
 
 @pytest.mark.parametrize("d,nlist,nq,nprobe,k", [(768, 6, 500, 3, 10), (128, 3, 200, 2, 50), (3072, 2, 150, 1, 10), (1024, 12, 900, 5, 7),
