@@ -983,15 +983,19 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
         a.filt = fdev;
         a.slab_maps = ix->d_maps;
         // large batches re-probe the same lists: read each list once and score it against all its queries
-        // (auto: when a list is probed 0.5x or more on average -- 79 % or fewer of the pair passes hit a distinct
-        //  list -- and lists hold at least a page.  Measured list-major / query-major step time at 0.125x / 0.25x /
+        // (auto: when a list is probed 0.5x or more on average (0.25x up to dim 1024) -- 79 % or fewer of the pair passes hit
+        //  a distinct list -- and lists hold at least a page.  Measured list-major / query-major step time at 0.125x / 0.25x /
         //  0.5x / 1x / 2x / 4x on C2 (dim 768): 1.01 / 0.95 / 0.85 / 0.69 / 0.48 / 0.32
         //  (profiles/r1_scan_mode_crossover.md); at dim 2048, where the 4-query page scan needs four slices, 0.25x is
         //  a loss (1.11) and 0.5x a gain (0.82).  With a scalar filter few rows per page are live and the scans are
         //  bound by per-page work rather than bytes: 10M x 2048, 5 % selectivity, whole step list-major / query-major
         //  at 0.5x: 0.92 / 0.70 ms, at 1x: 1.42 / 1.52 ms -> 0.75x, the threshold of the first version)
         const bool long_lists = ix->ntotal + ix->nremoved >= (int64_t)kPageRows * ix->nlist;
-        const int64_t lm_min_pairs = fdev.flags != 0 ? (3 * (int64_t)ix->nlist + 3) / 4 : ((int64_t)ix->nlist + 1) / 2;
+        // (round 2: 0.25x up to dim 1024 -- 0.95 on the iid set, and on clustered data, where the probes of a batch pile up on
+        //  the hot lists, far better: 10M x 768 clustered, nq 256 / nprobe 16 = 0.25x: 5.93 ms query-major, nprobe 32: 4.01 ms
+        //  list-major)
+        const int64_t lm_min_pairs = fdev.flags != 0 ? (3 * (int64_t)ix->nlist + 3) / 4
+                                                     : (ix->ds <= 1024 ? ((int64_t)ix->nlist + 3) / 4 : ((int64_t)ix->nlist + 1) / 2);
         const bool list_major = ix->ds >= 128 && npairs <= (int64_t)INT32_MAX &&
                                 (ix->scan_mode == 2 || (ix->scan_mode == 0 && long_lists && npairs >= lm_min_pairs));
         if (list_major) {
