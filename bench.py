@@ -751,7 +751,9 @@ def run_ours(args):
         try:
             from semcode_b200.index import PeerExchange
 
-            exs = [PeerExchange(local, None, 64 << 20) for _ in range(args.inflight if args.inflight > 0 else (2 if world >= 4 else 1))]
+            # two lanes exist at every N > 1: the end-to-end loop always pipelines two steps (the copies and the host's
+            # turn-around of one step hide behind the other); the device-resident loop uses `nlv` of them
+            exs = [PeerExchange(local, None, 64 << 20) for _ in range(max(2, args.inflight))]
             ok += 1
         except Exception as e:
             ex_err = f"{type(e).__name__}: {e}"
@@ -766,6 +768,7 @@ def run_ours(args):
             lane_out = [(torch.empty((nq, k), dtype=torch.float32, device=dev), torch.empty((nq, k), dtype=torch.int64, device=dev))
                         for _ in exs]
     nl = len(lanes)
+    nlv = min(nl, args.inflight if args.inflight > 0 else (2 if world >= 4 else 1))  # lanes of the device-resident loop
 
     def search_sharded(qs):
         if ex is not None:  # ONE C-ABI call: split coarse pass + probe scatter + scan + top-k scatter + waiting merge
@@ -792,8 +795,8 @@ def run_ours(args):
             sim_lists.append(torch.where(pl % args.shard_sim == 0, pl, torch.full_like(pl, -1)).contiguous())
 
     def step_device(i):
-        if nl > 1:  # lane i % nl: its own stream, exchange and (inside the library) scratch slot
-            j = i % nl
+        if nl > 0:  # lane i % nlv: its own stream, exchange and (inside the library) scratch slot
+            j = i % nlv
             with torch.cuda.stream(lanes[j]):
                 g.search(qb[i % nb], k, nprobe=nprobe, out=lane_out[j], exchange=exs[j])
             return lane_out[j]
@@ -812,7 +815,7 @@ def run_ours(args):
         if world == 1:
             g.search(qhost[i % nb], k, nprobe=nprobe, out=(host_d, host_i))  # C ABI, host buffers
             return host_d, host_i
-        if nl > 1:
+        if nl > 0:
             # the same pipeline end to end: lane j's previous step (i - nl) is read back to the host before the lane is reused
             j = i % nl
             lanes[j].synchronize()
@@ -991,7 +994,8 @@ def run_ours(args):
         "build_s": build_s,
     }
     if world > 1:
-        line["config"]["exchange"] = (f"p2p-fused (peer-memory stores + flags, no collective call), {nl} steps in flight per rank"
+        line["config"]["exchange"] = (f"p2p-fused (peer-memory stores + flags, no collective call), {nlv} steps in flight per rank "
+                                      f"({nl} in the end-to-end loop)"
                                       if ex is not None else f"nccl all-gather + merge ({ex_err or 'requested'})")
         if ex is not None:
             line["exchange_timed_out"] = any(e.status()[0] for e in exs)
