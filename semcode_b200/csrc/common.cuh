@@ -161,6 +161,7 @@ struct ScanArgs {
     const SlabTable *slabs;
     int slab_shift;
     float *cand;  // [page_off[npairs]*32] similarity to maximise, -inf for dead slots
+    int64_t max_cand;  // host-side upper bound of the candidate slots of ONE query (sizes the selection's CTAs)
     FilterDev filt;
     const void *slab_maps;  // one 128-byte TMA tensor map per slab (encode_slab_map), or nullptr
 };

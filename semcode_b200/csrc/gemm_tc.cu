@@ -23,6 +23,8 @@
 #include <cuda.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace sc {
@@ -159,24 +161,31 @@ __device__ __forceinline__ bool tile_of(const TcArgs &a, int i, int &mt, int &nt
     return true;
 }
 
-template <bool ARGMAX>
+// BN_: centroid rows per tile.  256 is the default; 128 (three stages of 64 KB) is used when 256-wide tiles would leave SMs
+// idle -- a 128-query coarse pass (one rank's share of a 1024-query batch on 8 GPUs) is ONE row tile: 64 tiles of 256 on
+// 148 SMs, each CTA pulling 2.3 MB through its own L2 -> SMEM path (42 us); 128 tiles of 128 pull 1.5 MB each.
+template <bool ARGMAX, int BN_>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
                const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo, const TcArgs a) {
+    constexpr int B_BYTES_ = BN_ * BK * 4;
+    constexpr int STAGE_BYTES_ = 2 * (A_BYTES + B_BYTES_);
+    constexpr int STAGES_ = BN_ == 256 ? STAGES : 3;
+    static_assert(BN_ == 256 || BN_ == 128, "tile widths: 256 or 128 centroid rows");
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES_ * STAGE_BYTES_);
     // bars: [0,S) full  [S,2S) empty  [2S,2S+2) accumulator full  [2S+2,2S+4) accumulator empty
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES_ + 4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
-    auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
-    auto tfull_bar = [&](int acc) { return bar0 + 8u * (2 * STAGES + acc); };
-    auto tempty_bar = [&](int acc) { return bar0 + 8u * (2 * STAGES + 2 + acc); };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES_ + s); };
+    auto tfull_bar = [&](int acc) { return bar0 + 8u * (2 * STAGES_ + acc); };
+    auto tempty_bar = [&](int acc) { return bar0 + 8u * (2 * STAGES_ + 2 + acc); };
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < STAGES_; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
@@ -206,13 +215,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
             for (int i = 0; tile_of<ARGMAX>(a, i, mt, nt); ++i) {
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
-                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                    mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES_);
+                    mbar_expect_tx(full_bar(stage), STAGE_BYTES_);
                     tma_load_2d(sa, &map_ahi, full_bar(stage), kb * BK, mt * BM);
                     tma_load_2d(sa + A_BYTES, &map_alo, full_bar(stage), kb * BK, mt * BM);
-                    tma_load_2d(sa + 2 * A_BYTES, &map_bhi, full_bar(stage), kb * BK, nt * BN);
-                    tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &map_blo, full_bar(stage), kb * BK, nt * BN);
-                    if (++stage == STAGES) {
+                    tma_load_2d(sa + 2 * A_BYTES, &map_bhi, full_bar(stage), kb * BK, nt * BN_);
+                    tma_load_2d(sa + 2 * A_BYTES + B_BYTES_, &map_blo, full_bar(stage), kb * BK, nt * BN_);
+                    if (++stage == STAGES_) {
                         stage = 0;
                         phase ^= 1u;
                     }
@@ -221,20 +230,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
         }
     } else if (warp == 1) {
         if (elect_one()) {  // ---- MMA issuer ----
-            constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
+            constexpr uint32_t idesc = umma_idesc_tf32(BM, BN_);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             int mt, nt;
             for (int i = 0; tile_of<ARGMAX>(a, i, mt, nt); ++i) {
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN_);
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES_);
                     const uint64_t d_ahi = umma_desc_sw128(sa), d_alo = umma_desc_sw128(sa + A_BYTES);
-                    const uint64_t d_bhi = umma_desc_sw128(sa + 2 * A_BYTES), d_blo = umma_desc_sw128(sa + 2 * A_BYTES + B_BYTES);
+                    const uint64_t d_bhi = umma_desc_sw128(sa + 2 * A_BYTES), d_blo = umma_desc_sw128(sa + 2 * A_BYTES + B_BYTES_);
 #pragma unroll
                     for (int ks = 0; ks < BK / 8; ++ks) {
                         const uint64_t off = (uint64_t)((ks * 8 * 4) >> 4);  // 32 bytes per k-step inside the swizzled row
@@ -243,7 +252,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                         umma_tf32(tmem_d, d_alo + off, d_bhi + off, idesc, 1u);
                     }
                     umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
-                    if (++stage == STAGES) {
+                    if (++stage == STAGES_) {
                         stage = 0;
                         phase ^= 1u;
                     }
@@ -268,7 +277,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const int64_t m = (int64_t)mt * BM + row;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN_);
             if (ARGMAX && nt == 0) {
                 best = -INFINITY;
                 best_i = 0;
@@ -278,10 +287,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constan
                 }
             }
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
+            for (int c = 0; c < BN_; c += 32) {
                 float v[32];
                 tmem_ld32(taddr + (uint32_t)c, v);
-                const int n0 = nt * BN + c;
+                const int n0 = nt * BN_ + c;
                 if (n0 >= a.N) continue;  // whole chunk is padding (loads above stay warp-uniform)
                 if (ARGMAX) {
 #pragma unroll
@@ -583,26 +592,42 @@ bool make_map(CUtensorMap *map, const float *base, int64_t rows, int K, int box_
               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <bool ARGMAX>
-cudaError_t launch_tc(const float *ahi, const float *alo, int64_t M, const float *bhi, const float *blo, int N, int K,
-                      TcArgs a, int num_sms, cudaStream_t st) {
-    if (M <= 0 || N <= 0) return cudaSuccess;
+template <bool ARGMAX, int BN_>
+cudaError_t launch_tc_bn(const float *ahi, const float *alo, int64_t M, const float *bhi, const float *blo, int N, int K,
+                         TcArgs a, int num_sms, cudaStream_t st) {
+    constexpr int stages = BN_ == 256 ? STAGES : 3;
+    constexpr int smem_bytes = stages * 2 * (A_BYTES + BN_ * BK * 4) + 1024 /*align*/ + 256 /*barriers*/;
     CUtensorMap mah, mal, mbh, mbl;
-    if (!make_map(&mah, ahi, M, K, BM) || !make_map(&mal, alo, M, K, BM) || !make_map(&mbh, bhi, N, K, BN) ||
-        !make_map(&mbl, blo, N, K, BN))
+    if (!make_map(&mah, ahi, M, K, BM) || !make_map(&mal, alo, M, K, BM) || !make_map(&mbh, bhi, N, K, BN_) ||
+        !make_map(&mbl, blo, N, K, BN_))
         return cudaErrorInvalidValue;
     a.M = M;
     a.N = N;
     a.K = K;
     a.m_tiles = (int)((M + BM - 1) / BM);
-    a.n_tiles = (N + BN - 1) / BN;
-    auto kern = gemm_tc_kernel<ARGMAX>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    a.n_tiles = (N + BN_ - 1) / BN_;
+    auto kern = gemm_tc_kernel<ARGMAX, BN_>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
     const int64_t work = ARGMAX ? a.m_tiles : (int64_t)a.m_tiles * a.n_tiles;
     const int grid = (int)(work < num_sms ? work : num_sms);
-    kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(mah, mal, mbh, mbl, a);
+    kern<<<grid, NTHREADS, smem_bytes, st>>>(mah, mal, mbh, mbl, a);
     return cudaGetLastError();
+}
+
+template <bool ARGMAX>
+cudaError_t launch_tc(const float *ahi, const float *alo, int64_t M, const float *bhi, const float *blo, int N, int K,
+                      TcArgs a, int num_sms, cudaStream_t st) {
+    if (M <= 0 || N <= 0) return cudaSuccess;
+    // score tiles of 128 centroid rows when tiles of 256 cannot occupy every SM (small batches)
+    const int64_t tiles256 = ((M + BM - 1) / BM) * (int64_t)((N + BN - 1) / BN);
+    static const bool bn128 = [] {  // SEMCODE_COARSE_BN128=0 keeps the 256-wide tiles (A/B measurements)
+        const char *e = getenv("SEMCODE_COARSE_BN128");
+        return !(e && e[0] == '0');
+    }();
+    if (!ARGMAX && tiles256 < num_sms && bn128)
+        return launch_tc_bn<ARGMAX, 128>(ahi, alo, M, bhi, blo, N, K, a, num_sms, st);
+    return launch_tc_bn<ARGMAX, 256>(ahi, alo, M, bhi, blo, N, K, a, num_sms, st);
 }
 
 }  // namespace

@@ -980,6 +980,7 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
         a.slabs = ix->d_tab;
         a.slab_shift = ix->slab_shift;
         a.cand = tl_scr->s_cand.as<float>();
+        a.max_cand = pb * kPageRows;
         a.filt = fdev;
         a.slab_maps = ix->d_maps;
         // large batches re-probe the same lists: read each list once and score it against all its queries

@@ -27,6 +27,10 @@ namespace sc {
 namespace {
 
 constexpr int SEL_T = 512;
+// Short candidate lists (an 8-way shard's 3072 candidates per query, a merge of 8 x k partials): a CTA's time is latency,
+// not work, so 128-thread CTAs -- 8 resident per SM instead of 2 -- finish 1024 queries in one wave instead of 3.5.
+constexpr int SEL_T_SMALL = 128;
+constexpr uint32_t SEL_SMALL_MAX_N = 8192;
 constexpr int SEL_BINS = 2048;
 
 struct SelShared {
@@ -228,14 +232,15 @@ __device__ __forceinline__ T warp_incl_scan(T v, int lane) {
     return v;
 }
 
-static_assert(SEL_FAST_K <= SEL_T && SEL_RANK_MAX <= SEL_T, "one-pass selection: one gathered pair per thread in the ranking step");
+static_assert(SEL_FAST_K <= SEL_T && SEL_RANK_MAX <= SEL_T_SMALL && SEL_BINS % SEL_T_SMALL == 0,
+              "one-pass selection: one gathered pair per thread in the ranking step; radix bins dealt evenly to the threads");
 
 // bitonic sort (descending) of pairs[0, P), P a power of two, by the whole CTA
 __device__ __forceinline__ void bitonic_sort_desc(unsigned long long *pairs, uint32_t P) {
     const uint32_t tid = threadIdx.x;
     for (uint32_t size = 2; size <= P; size <<= 1) {
         for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-            for (uint32_t t = tid; t < (P >> 1); t += SEL_T) {
+            for (uint32_t t = tid; t < (P >> 1); t += blockDim.x) {
                 const uint32_t lo = 2 * t - (t & (stride - 1));
                 const uint32_t hi = lo + stride;
                 const bool desc = (lo & size) == 0;
@@ -252,7 +257,7 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned long long *pairs, uin
 
 // One pass over the view.  Returns true with every candidate >= T (at least kk of them when the view holds that many,
 // unsorted) in sh.pairs[0, *count); false (uniformly for the CTA) when more than kMaxK candidates reached T.
-template <class View>
+template <int NT, class View>
 __device__ __forceinline__ bool select_one_pass(const View &view, uint32_t n, uint32_t kk, SelShared &sh, uint32_t *count) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float NEG = -INFINITY;
@@ -264,7 +269,7 @@ __device__ __forceinline__ bool select_one_pass(const View &view, uint32_t n, ui
     float4 r[SEL_RV];
 #pragma unroll
     for (int j = 0; j < SEL_RV; ++j) {
-        const uint32_t i4 = tid + (uint32_t)j * SEL_T;
+        const uint32_t i4 = tid + (uint32_t)j * NT;
         r[j] = i4 < n4 ? view.load4(i4) : make_float4(NEG, NEG, NEG, NEG);
     }
     uint32_t mx = 0;
@@ -272,31 +277,31 @@ __device__ __forceinline__ bool select_one_pass(const View &view, uint32_t n, ui
     for (int j = 0; j < SEL_RV; ++j)
         mx = max(max(mx, max(f2key(r[j].x), f2key(r[j].y))), max(f2key(r[j].z), f2key(r[j].w)));
     {
-        uint32_t i4 = tid + (uint32_t)SEL_RV * SEL_T;
-        for (; i4 + 3 * SEL_T < n4; i4 += 4 * SEL_T) {  // four loads in flight per thread
-            const float4 v0 = view.load4(i4), v1 = view.load4(i4 + SEL_T), v2 = view.load4(i4 + 2 * SEL_T), v3 = view.load4(i4 + 3 * SEL_T);
+        uint32_t i4 = tid + (uint32_t)SEL_RV * NT;
+        for (; i4 + 3 * NT < n4; i4 += 4 * NT) {  // four loads in flight per thread
+            const float4 v0 = view.load4(i4), v1 = view.load4(i4 + NT), v2 = view.load4(i4 + 2 * NT), v3 = view.load4(i4 + 3 * NT);
             mx = max(max(mx, max(f2key(v0.x), f2key(v0.y))), max(f2key(v0.z), f2key(v0.w)));
             mx = max(max(mx, max(f2key(v1.x), f2key(v1.y))), max(f2key(v1.z), f2key(v1.w)));
             mx = max(max(mx, max(f2key(v2.x), f2key(v2.y))), max(f2key(v2.z), f2key(v2.w)));
             mx = max(max(mx, max(f2key(v3.x), f2key(v3.y))), max(f2key(v3.z), f2key(v3.w)));
         }
-        for (; i4 < n4; i4 += SEL_T) {
+        for (; i4 < n4; i4 += NT) {
             const float4 v = view.load4(i4);
             mx = max(max(mx, max(f2key(v.x), f2key(v.y))), max(f2key(v.z), f2key(v.w)));
         }
         uint32_t i = 4 * n4 + tid;
-        for (; i + 3 * SEL_T < n; i += 4 * SEL_T) {
-            const float v0 = view.load(i), v1 = view.load(i + SEL_T), v2 = view.load(i + 2 * SEL_T), v3 = view.load(i + 3 * SEL_T);
+        for (; i + 3 * NT < n; i += 4 * NT) {
+            const float v0 = view.load(i), v1 = view.load(i + NT), v2 = view.load(i + 2 * NT), v3 = view.load(i + 3 * NT);
             mx = max(max(mx, max(f2key(v0), f2key(v1))), max(f2key(v2), f2key(v3)));
         }
-        for (; i < n; i += SEL_T) mx = max(mx, f2key(view.load(i)));
+        for (; i < n; i += NT) mx = max(mx, f2key(view.load(i)));
     }
 
     // T: every warp holds at least jstar thread maxima >= its jstar-th best one, so the minimum of those over the warps
-    // has at least (SEL_T / 32) * jstar >= kk candidates at or above it.  A view that fits the gather buffer needs no bound.
+    // has at least (NT / 32) * jstar >= kk candidates at or above it.  A view that fits the gather buffer needs no bound.
     uint32_t T = kKeyNegInf + 1u;
     if (n > (uint32_t)kMaxK) {
-        const uint32_t jstar = (kk + SEL_T / 32 - 1) / (SEL_T / 32);
+        const uint32_t jstar = (kk + NT / 32 - 1) / (NT / 32);
         uint32_t v = mx, tw = 0;
         for (uint32_t j = 0; j < jstar; ++j) {
             tw = __reduce_max_sync(0xffffffffu, v);
@@ -307,7 +312,7 @@ __device__ __forceinline__ bool select_one_pass(const View &view, uint32_t n, ui
         __syncthreads();
         uint32_t t = sh.warp_tot[0];
 #pragma unroll
-        for (int w = 1; w < SEL_T / 32; ++w) t = min(t, sh.warp_tot[w]);
+        for (int w = 1; w < NT / 32; ++w) t = min(t, sh.warp_tot[w]);
         T = max(T, t);
     } else {
         __syncthreads();  // fast_cnt is zero
@@ -324,7 +329,7 @@ __device__ __forceinline__ bool select_one_pass(const View &view, uint32_t n, ui
         };
 #pragma unroll
         for (int j = 0; j < SEL_RV; ++j) {
-            const uint32_t i4 = tid + (uint32_t)j * SEL_T;
+            const uint32_t i4 = tid + (uint32_t)j * NT;
             if (i4 < n4) {
                 put(r[j].x, 4 * i4);
                 put(r[j].y, 4 * i4 + 1);
@@ -332,21 +337,21 @@ __device__ __forceinline__ bool select_one_pass(const View &view, uint32_t n, ui
                 put(r[j].w, 4 * i4 + 3);
             }
         }
-        for (uint32_t i4 = tid + (uint32_t)SEL_RV * SEL_T; i4 < n4; i4 += SEL_T) {
+        for (uint32_t i4 = tid + (uint32_t)SEL_RV * NT; i4 < n4; i4 += NT) {
             const float4 v = view.load4(i4);
             put(v.x, 4 * i4);
             put(v.y, 4 * i4 + 1);
             put(v.z, 4 * i4 + 2);
             put(v.w, 4 * i4 + 3);
         }
-        for (uint32_t i = 4 * n4 + tid; i < n; i += SEL_T) put(view.load(i), i);
+        for (uint32_t i = 4 * n4 + tid; i < n; i += NT) put(view.load(i), i);
     }
     __syncthreads();
     *count = sh.fast_cnt;
     return sh.fast_cnt <= (uint32_t)kMaxK;
 }
 
-template <class Src>
+template <int NT, class Src>
 __device__ __forceinline__ void select_topk_body(const Src &src, int k, SelShared &sh) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t q = blockIdx.x;
@@ -355,14 +360,14 @@ __device__ __forceinline__ void select_topk_body(const Src &src, int k, SelShare
     const uint32_t kk = (uint32_t)k < n ? (uint32_t)k : n;
 
     if (kk == 0) {
-        for (int j = tid; j < k; j += SEL_T) src.emit(q, j, false, 0.f, 0);
+        for (int j = tid; j < k; j += NT) src.emit(q, j, false, 0.f, 0);
         return;
     }
 
     uint32_t n_sort = 0;  // pairs in sh.pairs to sort; the first min(n_sort, kk) are the result
     bool selected = false;
     if (kk <= (uint32_t)SEL_FAST_K) {
-        selected = select_one_pass(view, n, kk, sh, &n_sort);
+        selected = select_one_pass<NT>(view, n, kk, sh, &n_sort);
         __syncthreads();  // everybody has read the verdict before the radix path reuses the shared fields
     }
     if (!selected) {
@@ -371,33 +376,37 @@ __device__ __forceinline__ void select_topk_body(const Src &src, int k, SelShare
         for (int pass = 0; pass < 3; ++pass) {
             const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
             const uint32_t nb = pass == 2 ? 1024u : 2048u;
-            for (int b = tid; b < SEL_BINS; b += SEL_T) sh.hist[b] = 0;
+            for (int b = tid; b < SEL_BINS; b += NT) sh.hist[b] = 0;
             __syncthreads();
-            for (uint32_t i = tid; i < n; i += SEL_T) {
+            for (uint32_t i = tid; i < n; i += NT) {
                 const uint32_t key = f2key(view.load(i));
                 if ((key & mask) == prefix) atomicAdd(&sh.hist[(key >> shift) & (nb - 1)], 1u);
             }
             __syncthreads();
-            // thread t owns bins 4t..4t+3; find the bin (from the top) that holds the need-th element
-            uint32_t c[4];
+            // thread t owns bins BPT t .. BPT t + BPT - 1; find the bin (from the top) that holds the need-th element
+            constexpr int BPT = SEL_BINS / NT;
+            uint32_t c[BPT];
+            uint32_t local = 0;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) c[b] = sh.hist[4 * tid + b];
-            const uint32_t local = c[0] + c[1] + c[2] + c[3];
+            for (int b = 0; b < BPT; ++b) {
+                c[b] = sh.hist[BPT * tid + b];
+                local += c[b];
+            }
             const uint32_t incl = warp_incl_scan(local, lane);
             if (lane == 31) sh.warp_tot[warp] = incl;
             __syncthreads();
             uint32_t wprefix = 0, total = 0;
 #pragma unroll
-            for (int w = 0; w < SEL_T / 32; ++w) {
+            for (int w = 0; w < NT / 32; ++w) {
                 const uint32_t t = sh.warp_tot[w];
                 if (w < warp) wprefix += t;
                 total += t;
             }
             uint32_t running = total - (wprefix + incl);  // elements in bins above this thread's bins
 #pragma unroll
-            for (int b = 3; b >= 0; --b) {
+            for (int b = BPT - 1; b >= 0; --b) {
                 if (running < need && running + c[b] >= need) {
-                    sh.sel_bin = 4 * tid + b;
+                    sh.sel_bin = BPT * tid + b;
                     sh.need = need - running;
                     sh.eq_total = c[b];
                 }
@@ -421,7 +430,7 @@ __device__ __forceinline__ void select_topk_body(const Src &src, int k, SelShare
             sh.base = 0;
         }
         __syncthreads();
-        for (uint32_t i = tid; i < n; i += SEL_T) {
+        for (uint32_t i = tid; i < n; i += NT) {
             const uint32_t key = f2key(view.load(i));
             if (key > T) {
                 const uint32_t s = atomicAdd(&sh.cnt_gt, 1u);
@@ -434,7 +443,7 @@ __device__ __forceinline__ void select_topk_body(const Src &src, int k, SelShare
         __syncthreads();
         if (ordered) {
             // more candidates tie with the k-th than there is room for: keep the lowest indices
-            for (uint32_t c0 = 0; c0 < n; c0 += SEL_T) {
+            for (uint32_t c0 = 0; c0 < n; c0 += NT) {
                 const uint32_t base = sh.base;
                 if (base >= need) break;
                 const uint32_t i = c0 + tid;
@@ -444,7 +453,7 @@ __device__ __forceinline__ void select_topk_body(const Src &src, int k, SelShare
                 __syncthreads();
                 uint32_t wprefix = 0, total = 0;
 #pragma unroll
-                for (int w = 0; w < SEL_T / 32; ++w) {
+                for (int w = 0; w < NT / 32; ++w) {
                     const uint32_t t = sh.warp_tot[w];
                     if (w < warp) wprefix += t;
                     total += t;
@@ -469,17 +478,17 @@ __device__ __forceinline__ void select_topk_body(const Src &src, int k, SelShare
             for (uint32_t j = 0; j < n_sort; ++j) rank += sh.pairs[j] > mine ? 1u : 0u;
             if (rank < n_valid) src.emit(q, (int)rank, true, key2f((uint32_t)(mine >> 32)), 0xffffffffu - (uint32_t)mine);
         }
-        for (int j = (int)n_valid + tid; j < k; j += SEL_T) src.emit(q, j, false, 0.f, 0);
+        for (int j = (int)n_valid + tid; j < k; j += NT) src.emit(q, j, false, 0.f, 0);
         return;
     }
 
     // bitonic sort (descending) of the winners
     uint32_t P = 1;
     while (P < n_sort) P <<= 1;
-    for (uint32_t i = n_sort + tid; i < P; i += SEL_T) sh.pairs[i] = 0ull;
+    for (uint32_t i = n_sort + tid; i < P; i += NT) sh.pairs[i] = 0ull;
     __syncthreads();
     bitonic_sort_desc(sh.pairs, P);
-    for (int j = tid; j < k; j += SEL_T) {
+    for (int j = tid; j < k; j += NT) {
         if ((uint32_t)j < n_valid) {
             const unsigned long long p = sh.pairs[j];
             src.emit(q, j, true, key2f((uint32_t)(p >> 32)), 0xffffffffu - (uint32_t)p);
@@ -490,13 +499,14 @@ __device__ __forceinline__ void select_topk_body(const Src &src, int k, SelShare
 }
 
 // wait: peers whose stores this kernel consumes (merge); sig: peers that consume this kernel's stores
-template <class Src>
-__global__ void __launch_bounds__(SEL_T) select_topk_kernel(Src src, int k, PeerWait wait, PeerSignal sig) {
+// NT = threads per CTA: SEL_T, or SEL_T_SMALL for short candidate lists (see launch_select)
+template <class Src, int NT>
+__global__ void __launch_bounds__(NT) select_topk_kernel(Src src, int k, PeerWait wait, PeerSignal sig) {
     __shared__ SelShared sh;
     pdl_launch_dependents();
     pdl_wait();
     peer_wait(wait);
-    select_topk_body(src, k, sh);
+    select_topk_body<NT>(src, k, sh);
     peer_signal(sig);
 }
 
@@ -513,7 +523,7 @@ __global__ void __launch_bounds__(SEL_T) select_rows_plan_kernel(RowsSrc src, in
     __shared__ uint32_t s_last;
     pdl_launch_dependents();
     pdl_wait();
-    select_topk_body(src, k, sh);
+    select_topk_body<SEL_T>(src, k, sh);
     __syncthreads();  // the CTA's own stores of the probe row are visible to the CTA
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t q = blockIdx.x, nq = gridDim.x;
@@ -616,12 +626,20 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const T *__restric
 
 }  // namespace
 
+// n_max: an upper bound of the candidates per query (picks the CTA size)
+template <class Src>
+static cudaError_t launch_select(const Src &src, int64_t nq, int k, uint64_t n_max, const PeerWait &wait, const PeerSignal &sig,
+                                 cudaStream_t st, bool pdl) {
+    if (n_max <= SEL_SMALL_MAX_N && nq >= 64)
+        return launch_pdl(select_topk_kernel<Src, SEL_T_SMALL>, dim3((unsigned)nq), dim3(SEL_T_SMALL), 0, st, pdl, src, k, wait, sig);
+    return launch_pdl(select_topk_kernel<Src, SEL_T>, dim3((unsigned)nq), dim3(SEL_T), 0, st, pdl, src, k, wait, sig);
+}
+
 cudaError_t launch_select_rows(const float *scores, int64_t M, int N, int k, int32_t *out_idx, float *out_val,
                                cudaStream_t st) {
     if (M <= 0) return cudaSuccess;
     RowsSrc src{scores, N, k, out_idx, out_val, 0, PeerRows{}};
-    select_topk_kernel<RowsSrc><<<(unsigned)M, SEL_T, 0, st>>>(src, k, PeerWait{}, PeerSignal{});
-    return cudaGetLastError();
+    return launch_select(src, M, k, (uint64_t)N, PeerWait{}, PeerSignal{}, st, false);
 }
 
 cudaError_t launch_select_rows_plan(const float *scores, int64_t M, int N, int k, int32_t *out_idx, const int32_t *list_len,
@@ -637,8 +655,7 @@ cudaError_t launch_select_rows_peers(const float *scores, int64_t M, int N, int 
                                      const PeerSignal &sig, cudaStream_t st) {
     if (M <= 0) return launch_peer_signal(sig, st);
     RowsSrc src{scores, N, k, nullptr, nullptr, sig.world, rows};
-    select_topk_kernel<RowsSrc><<<(unsigned)M, SEL_T, 0, st>>>(src, k, PeerWait{}, sig);
-    return cudaGetLastError();
+    return launch_select(src, M, k, (uint64_t)N, PeerWait{}, sig, st, false);
 }
 
 cudaError_t launch_peer_signal(const PeerSignal &sig, cudaStream_t st) {
@@ -655,23 +672,21 @@ cudaError_t launch_select_candidates(const ScanArgs &a, int64_t nq, int k, float
                                      cudaStream_t st, bool pdl) {
     if (nq <= 0) return cudaSuccess;
     CandSrc src{a, k, out_dist, out_ids, 0, PeerTopk{}};
-    return launch_pdl(select_topk_kernel<CandSrc>, dim3((unsigned)nq), dim3(SEL_T), 0, st, pdl, src, k, PeerWait{}, PeerSignal{});
+    return launch_select(src, nq, k, (uint64_t)a.max_cand, PeerWait{}, PeerSignal{}, st, pdl);
 }
 
 cudaError_t launch_select_candidates_peers(const ScanArgs &a, int64_t nq, int k, const PeerTopk &out, const PeerSignal &sig,
                                            cudaStream_t st) {
     if (nq <= 0) return launch_peer_signal(sig, st);
     CandSrc src{a, k, nullptr, nullptr, sig.world, out};
-    select_topk_kernel<CandSrc><<<(unsigned)nq, SEL_T, 0, st>>>(src, k, PeerWait{}, sig);
-    return cudaGetLastError();
+    return launch_select(src, nq, k, (uint64_t)a.max_cand, PeerWait{}, sig, st, false);
 }
 
 cudaError_t launch_merge_topk(const float *part_dist, const int64_t *part_ids, int parts, int64_t nq, int kin, int k,
                               int metric, float *out_dist, int64_t *out_ids, cudaStream_t st) {
     if (nq <= 0) return cudaSuccess;
     MergeSrc src{part_dist, part_ids, parts, nq, kin, k, metric, out_dist, out_ids};
-    select_topk_kernel<MergeSrc><<<(unsigned)nq, SEL_T, 0, st>>>(src, k, PeerWait{}, PeerSignal{});
-    return cudaGetLastError();
+    return launch_select(src, nq, k, (uint64_t)parts * (uint64_t)kin, PeerWait{}, PeerSignal{}, st, false);
 }
 
 cudaError_t launch_exclusive_scan_i32(const int32_t *in, int64_t n, int32_t *out, cudaStream_t st) {
