@@ -23,6 +23,7 @@ import bench  # noqa: E402  (gen_rows, measured_peaks)
 def main():
     p = argparse.ArgumentParser()
     p.add_argument("--rows-per-gpu", type=int, default=6_250_000)
+    p.add_argument("--total-rows", type=int, default=0, help="rows of the whole job (C4: 50000000): rows per GPU = total / world")
     p.add_argument("--dim", type=int, default=768)
     p.add_argument("--nlist", type=int, default=65536)
     p.add_argument("--iters", type=int, default=3)
@@ -41,11 +42,13 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries the one JSON line: whatever libraries print on fd 1 (NCCL's banner / log) goes to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        if not os.environ.get("SEMCODE_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner would otherwise land on stdout
         dist.init_process_group("nccl", device_id=dev)
-    n, d, nlist = a.rows_per_gpu, a.dim, a.nlist
+    n, d, nlist = (a.total_rows // world if a.total_rows else a.rows_per_gpu), a.dim, a.nlist
     x = bench.gen_rows(torch, rank * n, (rank + 1) * n, d, 1234, dev, a.dataset)
     if world > 1:
         sh = ShardedIVFFlat(d, nlist, a.metric, device=local)
@@ -103,9 +106,10 @@ def main():
                                    "source": src},
             "mma_frac_of_tf32_stated": 3 * flop / world / it_s / 1e12 / (peaks.get("bf16_tflops", 1) / 2),
             "objective": objs,
+            "total_s_all_iterations": sum(times) / 1e3,
             "extrapolated_20_iterations_s": 20 * it_s,
         }
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
