@@ -1,12 +1,10 @@
-"""Diagnostic: how many distance VALUES differ between the list-major and query-major routes at full size."""
+"""How many distance VALUES differ between the list-major and query-major routes at full size."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench
 import semcode_b200 as sb
 
-class A: pass
-args = bench.parse_args.__wrapped__() if hasattr(bench.parse_args, "__wrapped__") else None
 sys.argv = [sys.argv[0]]
 args = bench.parse_args()
 c = bench.Ctx(); c.torch = torch; c.dist = None; c.sb = sb; c.args = args; c.world = 1; c.rank = 0; c.local = 0
