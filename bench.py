@@ -128,7 +128,8 @@ def gen_rows(torch, n0, n1, dim, seed, device, dataset="iid"):
             full = centres[c] + 0.3 * full
         out[lo - n0 : hi - n0] = full[lo - b * blk : hi - b * blk]
         b += 1
-    return torch.nn.functional.normalize(out, dim=1)
+    # in place (x / max(|x|, 1e-12), what F.normalize computes): a 50M x 768 k-means shard does not fit twice
+    return out.div_(out.norm(dim=1, keepdim=True).clamp_min_(1e-12))
 
 
 class ClockSampler:
