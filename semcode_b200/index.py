@@ -547,7 +547,6 @@ class PeerExchange:
 
     def __init__(self, device: int, group=None, nbytes: int = 64 << 20):
         import torch.distributed as dist
-        import torch.distributed._symmetric_memory as symm
 
         self.device = int(device)
         self.rank = dist.get_rank(group)
@@ -555,20 +554,62 @@ class PeerExchange:
         if self.world > 8:
             raise ValueError("PeerExchange covers the GPUs of one box (world <= 8)")
         dev = torch.device("cuda", self.device)
-        g = group if group is not None else dist.group.WORLD
-        self._buf = symm.empty(int(nbytes), dtype=torch.uint8, device=dev)
-        self._hdl = symm.rendezvous(self._buf, g)
-        self._buf.zero_()
+        # every rank must take the same route: agree on whether symmetric memory came up everywhere
+        ptrs, err = None, None
+        try:
+            ptrs = self._symmetric(dev, group, int(nbytes))
+        except Exception as e:  # noqa: BLE001
+            err = f"{type(e).__name__}: {e}"
+        oks = [None] * self.world
+        dist.all_gather_object(oks, ptrs is not None, group=group)
+        if not all(oks):
+            # CUDA IPC: each rank allocates its buffer and opens the peers' (cudaIpcOpenMemHandle underneath torch's tensor
+            # sharing).  This is what works when two ranks share one device -- torch's symmetric memory refuses that -- and on
+            # boxes without fabric handles; the C ABI only ever sees plain pointers.
+            self._hdl = None
+            try:
+                ptrs = self._ipc(dev, group, int(nbytes))
+            except Exception as e:  # noqa: BLE001
+                raise RuntimeError(f"no peer-mapped buffers: symmetric memory: {err}; CUDA IPC: {type(e).__name__}: {e}") from e
+            self.transport = "cuda-ipc"
+        else:
+            self.transport = "symmetric-memory"
         torch.cuda.synchronize(dev)
         dist.barrier(group=group)  # every rank's flags are zero before anybody stores into them
-        ptrs = [int(p) for p in self._hdl.buffer_ptrs]
         if len(ptrs) != self.world or any(p == 0 for p in ptrs):
-            raise RuntimeError("symmetric memory rendezvous returned no peer pointers")
+            raise RuntimeError("rendezvous returned no peer pointers")
         arr = (C.c_void_p * self.world)(*ptrs)
         h = C.c_void_p()
         _capi.check(_capi.lib().sc_exchange_create(self.rank, self.world, arr, int(nbytes), self.device, C.byref(h)))
         self.handle = h
         self.nbytes = int(nbytes)
+        self._group = group
+
+    def _symmetric(self, dev, group, nbytes: int):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        g = group if group is not None else dist.group.WORLD
+        self._buf = symm.empty(nbytes, dtype=torch.uint8, device=dev)
+        self._hdl = symm.rendezvous(self._buf, g)
+        self._buf.zero_()
+        return [int(p) for p in self._hdl.buffer_ptrs]
+
+    def _ipc(self, dev, group, nbytes: int):
+        import torch.distributed as dist
+        from torch.multiprocessing.reductions import reduce_tensor
+
+        self._buf = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize(dev)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, reduce_tensor(self._buf), group=group)
+        self._peers = []
+        ptrs = []
+        for r, (rebuild, args) in enumerate(handles):
+            t = self._buf if r == self.rank else rebuild(*args)
+            self._peers.append(t)  # keeps the mapping alive
+            ptrs.append(int(t.data_ptr()))
+        return ptrs
 
     def status(self) -> Tuple[bool, int]:
         """(timed_out, steps issued); synchronises the device."""
@@ -589,6 +630,7 @@ class PeerExchange:
         if getattr(self, "handle", None):
             _capi.lib().sc_exchange_destroy(self.handle)
             self.handle = None
+        self._peers = None  # drop the mappings of the peers' buffers before this rank's own buffer goes away
 
     def __del__(self):  # pragma: no cover
         try:

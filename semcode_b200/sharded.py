@@ -177,6 +177,16 @@ class ShardedIVFFlat:
         dist.all_reduce(t, group=self.group)
         return int(t.item())
 
+    def close(self) -> None:
+        """Collective: every rank drops its mappings of the peers' exchange buffers, then (after a barrier) its own buffer."""
+        for ex in self.exchanges:
+            ex.close()
+        if self.exchanges:
+            dist.barrier(group=self.group)
+            for ex in self.exchanges:
+                ex._buf = None
+        self.exchanges, self.exchange = [], None
+
     # -- persistence ----------------------------------------------------------------------------------
     def save(self, path: str) -> None:
         """Every rank writes its shard under `path/shard-RR/` (the engine's own snapshot: bulk list export underneath), rank 0

@@ -35,7 +35,7 @@ def _worker(rank, world, port, ret, snap):
         for metric, shard_by, exchange in (("IP", "rows", "auto"), ("L2", "rows", "auto"), ("IP", "rows", "nccl"),
                                            ("IP", "lists", "nccl"), ("L2", "lists", "nccl")):
             sh = ShardedIVFFlat(d, nlist, metric, device=rank, shard_by=shard_by, exchange=exchange)
-            kinds.append("p2p" if sh.exchange is not None else f"nccl ({sh.exchange_error})")
+            kinds.append(f"p2p/{sh.exchange.transport}" if sh.exchange is not None else f"nccl ({sh.exchange_error})")
             obj = sh.train(torch.from_numpy(x[rank::world]).cuda(), niter=4, seed=3)
             # single-GPU Lloyd from the same initial centroids over ALL rows gives the same centroids
             from semcode_b200.index import kmeans_init_rows
@@ -160,7 +160,8 @@ def _worker_one_gpu(rank, world, port, ret):
             assert_topk_parity(gd.cpu().numpy(), gi.cpu().numpy(), rd, ri, f"two ranks on one GPU, step {rep}")
         timed_out, steps = sh.exchange.status()
         assert not timed_out and steps == 5
-        ret[rank] = "ok p2p"
+        ret[rank] = f"ok p2p over {sh.exchange.transport}"
+        sh.close()
     except Exception:
         import traceback
 
@@ -170,6 +171,7 @@ def _worker_one_gpu(rank, world, port, ret):
         dist.destroy_process_group()
 
 
+@pytest.mark.timeout(240)
 def test_two_ranks_share_one_gpu(native_lib):
     import torch.multiprocessing as mp
 
