@@ -207,7 +207,7 @@ int sc_index_set_profiling(sc_index_t *idx, int32_t enabled);
 int sc_index_last_search_times(sc_index_t *idx, sc_search_times_t *out);
 /* tuning knobs (tests / bench; the defaults are the measured best):
  *   "scratch_bytes"  search scratch ceiling (>= 1 MiB, default 8 GiB): larger batches run in equal passes
- *   "scan_mode"      0 = automatic (list-major from nq*nprobe >= nlist/4 up to dim 1024, nlist/2 above, 3/4 nlist with a filter), 1 = query-major,
+ *   "scan_mode"      0 = automatic (list-major from nq*nprobe >= nlist/8 up to dim 1024 (nlist/4 for batches of <= 16), nlist/2 above, 3/4 nlist with a filter), 1 = query-major,
  *                    2 = list-major
  *   "scan_variant"   0..4 rows x loads in flight of the query-major scan
  *   "lists_cfg"      tile items of the list-major scan: 0 = tcgen05 where it applies (inner product, dim % 32 == 0; list
