@@ -278,6 +278,9 @@ class GpuCollection:
         self._growing.set_centroids(np.zeros((1, self.dim), dtype=np.float32))
         self._growing_rows = 0
         self._ivf = None  # IVFFlatIndex, or MultiDeviceIVFFlat when several devices are configured
+        # telemetry (`ivf_profile`): per-phase CUDA events of the sealed index's searches; last_search_stats() reports them
+        self.profile = False
+        self._last_stats: Optional[Dict[str, Any]] = None
         self._trained_rows = 0
         self.maintenance = {"compactions": 0, "retrains": 0}
 
@@ -676,7 +679,33 @@ class GpuCollection:
                             raise ValueError(f"unknown output field {name!r}")
                     hits.append(Hit(self._pk[r], float(d), f))
                 out.append(hits)
+            if self.profile:
+                self._record_stats(q.shape[0], nprobe)
             return out
+
+    def _record_stats(self, nq: int, nprobe: int) -> None:
+        """What the last search on the sealed index cost (telemetry; under concurrency it is SOME recent search)."""
+        ivf = self._ivf
+        if ivf is None or not hasattr(ivf, "last_search_times"):
+            return
+        try:
+            if not getattr(ivf, "_profiling_on", False):
+                ivf.set_profiling(True)  # takes effect from the next search on
+                ivf._profiling_on = True
+                return
+            t = ivf.last_search_times()
+        except Exception:  # no search on the sealed index yet
+            return
+        rows = t.unique_rows if t.unique_rows > 0 else t.scanned_rows
+        self._last_stats = {
+            "nq": int(nq), "nprobe": int(nprobe), "search_ms": float(t.total_ms), "scan_ms": float(t.scan_ms),
+            "scanned_rows": int(t.scanned_rows), "scanned_bytes": int(rows) * 4 * self.dim,
+            "scan_GBps": (int(rows) * 4 * self.dim / (t.scan_ms * 1e6)) if t.scan_ms > 0 else 0.0,
+            "scan": "list-major" if t.unique_rows > 0 else "query-major",
+        }
+
+    def last_search_stats(self) -> Optional[Dict[str, Any]]:
+        return dict(self._last_stats) if self._last_stats else None
 
 
 _REGISTRY: Dict[str, GpuCollection] = {}
@@ -820,6 +849,7 @@ class MilvusVectorStore:
                repos: Optional[Iterable[str]] = None, languages: Optional[Iterable[str]] = None) -> list:
         """Run a raw vector search (milvus_store.py:135-148); returns [Hits] for the one query."""
         collection = self._require()
+        collection.profile = bool(_setting("ivf_profile", False))
         return collection.search(
             data=[vector],
             anns_field="embedding",
@@ -867,3 +897,10 @@ class MilvusVectorStore:
     def flush(self) -> None:
         """Persist the collection when `ivf_persist_dir` (SEMCODE_IVF_PERSIST_DIR) is configured."""
         self._require().flush()
+
+    def last_search_stats(self) -> Optional[dict]:
+        """With `ivf_profile` set: what a recent search on the sealed index cost -- search / scan milliseconds, bytes of list
+        vectors it had to read and the scan's GB/s -- for the API's telemetry (api/telemetry.py:89-104 records per-query
+        metadata); None otherwise."""
+        collection = self._collection
+        return None if collection is None else collection.last_search_stats()

@@ -108,9 +108,24 @@ class OracleIVFFlat:
     def list_ranges(self, max_bytes=512 << 20):
         return [(0, self.nlist)]
 
+    # -- profiling hooks (what IVFFlatIndex.set_profiling / last_search_times report; here: row counts only)
+    def set_profiling(self, enabled):
+        self._prof = bool(enabled)
+
+    def last_search_times(self):
+        from types import SimpleNamespace
+
+        if not getattr(self, "_prof", False) or getattr(self, "_last", None) is None:
+            raise RuntimeError("profiling is off or no search has run")
+        nq, nprobe = self._last
+        rows = int(nq * nprobe * max(1, len(self._ids)) / self.nlist)
+        return SimpleNamespace(coarse_ms=0.01, probe_select_ms=0.01, plan_ms=0.01, scan_ms=0.1, topk_ms=0.01, total_ms=0.14,
+                               scanned_rows=rows, unique_rows=0, scan_launches=1, total_launches=5)
+
     # -- search
     def search(self, q, k, nprobe=16, repos=None, langs=None, lists=None, out=None, exchange=None):
         q = np.asarray(q, np.float32).reshape(-1, self.dim)
+        self._last = (q.shape[0], min(int(nprobe), self.nlist))
         idx = orc.build_index(self._x, self._ids, self.c, self.metric, self._repo, self._lang, assignment=self._list)
         mask = orc.row_mask(idx, repos=repos, langs=langs, removed_ids=self._ids[self._dead] if self._dead.any() else None)
         return orc.search(idx, q, int(k), min(int(nprobe), self.nlist), mask=mask, probes=lists)

@@ -429,3 +429,26 @@ def test_c3_shaped_collection_on_every_visible_gpu(real_store, monkeypatch, tmp_
     np.testing.assert_array_equal(r2.cpu().numpy() if torch.is_tensor(r2) else r2, r32)
     print(f"C3-shaped collection: {n} x {d} on devices {devices}: upserts {t_insert:.1f} s, seal {t_seal:.1f} s, "
           f"search(64 x nprobe 32) {t_search * 1e3:.1f} ms, recall@10 {recall:.3f}, reload {t_load:.1f} s")
+
+
+def test_search_stats_for_telemetry(real_store, monkeypatch):
+    """`ivf_profile`: the wrapper reports what a recent search on the sealed index cost (per-phase CUDA events of the engine),
+    which the optional caller patch records in the API's telemetry."""
+    ms = real_store
+    rng = np.random.default_rng(3)
+    n, d = 5000, 64
+    x = unit_rows(rng, n, d)
+    monkeypatch.setenv("SEMCODE_IVF_NLIST", "16")
+    monkeypatch.setenv("SEMCODE_IVF_SEAL_ROWS", "100000")
+    monkeypatch.setenv("SEMCODE_IVF_PROFILE", "1")
+    st = ms.MilvusVectorStore("stats_col", dim=d)
+    st.connect()
+    st.upsert_arrays([f"k{i}" for i in range(n)], x)
+    assert st.last_search_stats() is None
+    st.build_index(niter=2)
+    st.search(x[0].tolist(), top_k=5, nprobe=4)  # switches the events on
+    hits = st.search(x[1].tolist(), top_k=5, nprobe=4)[0]
+    assert hits[0].id == "k1"
+    s = st.last_search_stats()
+    assert s is not None and s["nq"] == 1 and s["nprobe"] == 4 and s["scan"] == "query-major"
+    assert s["scanned_rows"] > 0 and s["scanned_bytes"] == s["scanned_rows"] * 4 * d and s["scan_ms"] > 0 and s["scan_GBps"] > 0

@@ -205,7 +205,8 @@ def test_reference_integration_test_with_the_store_injected(ref, tmp_path, monke
 
 def test_optional_caller_patch_pushes_filters_down_and_batches(monkeypatch, tmp_path):
     """patches/semcode_filter_pushdown_and_batch.patch: QueryRequest.repos / languages reach the
-    index scan through SemanticSearchPipeline.query, and retrieve_batch issues ONE store call for many questions."""
+    index scan through SemanticSearchPipeline.query, retrieve_batch issues ONE store call for many questions, and the API's
+    telemetry records the scan's bytes and GB/s."""
     src = tmp_path / "patched" / "src"
     shutil.copytree(REF_SRC, src)
     patch = os.path.join(ROOT, "patches", "semcode_filter_pushdown_and_batch.patch")
@@ -245,6 +246,21 @@ def test_optional_caller_patch_pushes_filters_down_and_batches(monkeypatch, tmp_
         seen = {}
         monkeypatch.setattr(api.pipeline, "query", lambda question, **kw: seen.update(kw) or {"answer": "a", "sources": []})
         assert api.query(req).answer == "a" and seen == {"repos": ["other"], "languages": None}
+        # telemetry: with `ivf_profile` the store reports what a search on the sealed index cost and the
+        # patched API records it next to the query's duration (api/telemetry.py)
+        monkeypatch.setattr(settings, "ivf_profile", True, raising=False)
+        monkeypatch.setattr(settings, "telemetry_enabled", True, raising=False)
+        store = api.pipeline.vector_store
+        store.connect()
+        store.build_index(niter=2)  # seal: searches now run on the IVF lists
+        vec = HashEmbedding().embed_query(q)
+        store.search(vec, top_k=3)  # switches the per-phase events on
+        store.search(vec, top_k=3)
+        stats = store.last_search_stats()
+        assert stats and stats["nq"] == 1 and stats["scanned_bytes"] > 0 and stats["scan_GBps"] > 0 and stats["scan"] in ("query-major", "list-major")
+        api.query(api.QueryRequest(question="q"))
+        event = api.telemetry.snapshot()["recent_events"][0]
+        assert event["kind"] == "query" and event["metadata"]["retrieval"]["scanned_bytes"] == stats["scanned_bytes"]
     finally:
         for name in list(ms._REGISTRY):
             ms.drop_collection(name)
