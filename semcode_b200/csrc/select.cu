@@ -501,7 +501,9 @@ __device__ __forceinline__ void select_topk_body(const Src &src, int k, SelShare
 // wait: peers whose stores this kernel consumes (merge); sig: peers that consume this kernel's stores
 // NT = threads per CTA: SEL_T, or SEL_T_SMALL for short candidate lists (see launch_select)
 template <class Src, int NT>
-__global__ void __launch_bounds__(NT) select_topk_kernel(Src src, int k, PeerWait wait, PeerSignal sig) {
+// (512 threads: no minimum -- 64 registers, two CTAs per SM; capping at 40 registers for three made the probe selection 44 -> 76 us.  128 threads:
+//  eight CTAs per SM at 64 registers: 8-way shard top-k 22 -> 16 us.)
+__global__ void __launch_bounds__(NT, NT == 512 ? 0 : 8) select_topk_kernel(Src src, int k, PeerWait wait, PeerSignal sig) {
     __shared__ SelShared sh;
     pdl_launch_dependents();
     pdl_wait();
