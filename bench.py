@@ -80,6 +80,7 @@ def parse_args():
     p.add_argument("--coarse-impl", type=int, default=0, help="0 = tcgen05 3xTF32, 1 = fp32 SIMT")
     p.add_argument("--scan-mode", type=int, default=0, help="0 = auto, 1 = query-major, 2 = list-major")
     p.add_argument("--lists-cfg", type=int, default=0, help="tile configuration of the list-major kernel")
+    p.add_argument("--tile-rem", type=int, default=0, help="4 = remainders of 5..16 queries become tcgen05 tile items")
     p.add_argument("--mq-fused", type=int, default=0, help="1 = the two list-major page-scan buckets in one launch (measured slower)")
     p.add_argument("--shard-sim", type=int, default=1,
                    help="single-GPU run over ONE rank's shard of a G-way row-sharded index (rows i with i %% G == 0 of the "
@@ -399,6 +400,8 @@ def build_index(c, n, d, nlist, dataset, metric="IP", tags=None):
         g.set_param("lists_cfg", args.lists_cfg)
     if args.mq_fused:
         g.set_param("mq_fused", 1)
+    if args.tile_rem:
+        g.set_param("tile_rem", args.tile_rem)
     cent = torch.empty((nlist, d), dtype=torch.float32, device=c.dev)
     if c.rank == 0:
         tr = gen_rows(torch, 0, min(args.train_rows, n), d, 1234, c.dev, dataset)

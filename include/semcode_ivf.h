@@ -215,6 +215,8 @@ int sc_index_last_search_times(sc_index_t *idx, sc_search_times_t *out);
  *                    earlier tcgen05 tile kernels with both operands in shared memory (v1 / v2),
  *                    4 = 0 with the 8-query page scan on mma.sync (parity-green, measured slower)
  *   "lists_fork"     1 = tile items on a side stream next to the page scans
+ *   "tile_rem"       4 = list-major: remainders of 5..16 queries per list become tcgen05 tile items as well (default 0: 9..16
+ *                    only, and only when enough lists have them): +5.6 % on the clustered headline, -3.5 % on the iid one
  *   "mq_fused"       1 = the list-major page scans (lists probed by 1..4 / 5..16 queries) in one launch in which every
  *                    warp works on both buckets (measured slower than the default two launches)
  *   "coarse_impl"    0 = tcgen05 3xTF32 contraction, 1 = fp32 SIMT;  "tc_variant" 0 = 256x256, 1 = 128x256 tiles

@@ -228,6 +228,7 @@ struct ListPlan {
     int32_t chunk;                     // queries per tile item: 32 (FFMA tiles) or 64 (tcgen05 tiles)
     float *qsplit;                     // tcgen05 tiles: 2 x [nq, ds] tf32 terms (hi, lo) of the queries (scratch)
     float *bstage;                     // scan_lists_ts.cu: per-CTA query staging slots (scan_lists_ts_stage_bytes), or nullptr
+    int32_t tile_rem;                  // 4 = remainders of 5..16 queries go to tile items (set_param "tile_rem"); 0 = 9..16 only
     int32_t mq_fused;                  // 1 = the two page-scan buckets in one launch (set_param "mq_fused"; measured slower: off)
     int32_t *n32;                      // [nlist] tile items (of `chunk` queries) per list
     int32_t *lq_off, *off32;           // [nlist+1] exclusive prefixes of cnt / n32 (chunk == 64: of n32 x 128-row tiles)

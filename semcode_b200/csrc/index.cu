@@ -243,6 +243,7 @@ struct sc_index {
     int small_coarse = 1;        // batches of <= 16 rows use coarse_small_kernel
     int fuse_plan = 1;           // batches of <= 16 rows: probe selection + pair plan in one launch
     int pdl = 1;                 // ... and the step's kernels chained by programmatic dependent launch
+    int tile_rem = 0;            // 4 = list-major: remainders of 5..16 queries become tcgen05 tile items (0: 9..16 only)
     int mq_fused = 0;            // 1 = list-major page scans (4-query and 8-query bucket) in ONE launch: measured slower, see scan_mq.cu
     int tc_variant = 0;          // fused argmax tile: 0 = 256x256 (64 B swizzle), 1 = 128x256 (128 B swizzle)
 
@@ -1016,6 +1017,7 @@ int search_impl(sc_index *ix, const float *q, int64_t nq, int k, int nprobe, con
             lp.qsplit = nullptr;
             lp.bstage = nullptr;
             lp.mq_fused = ix->mq_fused;
+            lp.tile_rem = ix->tile_rem;
             if (tc_tiles) {
                 const bool ts = ix->lists_cfg != 5 && ix->lists_cfg != 3 && ix->d_maps != nullptr &&
                                 npairs * (int64_t)(ix->ds / 32) < ((int64_t)1 << 30);
@@ -2003,6 +2005,11 @@ int sc_index_set_param(sc_index_t *ix, const char *name, int64_t value) {
             return fail(SC_ERR_STATE, "scratch buffer #%d of slot %d was written out of bounds: %u guard bytes in front, %u behind", which,
                         slot_bad, first[0], first[1]);
         if (value > 0 && checked < value) return fail(SC_ERR_STATE, "only %d guarded buffers exist (expected at least %lld)", checked, (long long)value);
+        return SC_OK;
+    }
+    if (strcmp(name, "tile_rem") == 0) {
+        if (value != 0 && value != 4) return fail(SC_ERR_INVALID, "tile_rem: 0 (remainders of 9..16 queries may become tile items) or 4 (5..16)");
+        ix->tile_rem = (int)value;
         return SC_OK;
     }
     if (strcmp(name, "mq_fused") == 0) {  // list-major page scans: 1 = both buckets in one launch (measured slower), 0 = two launches

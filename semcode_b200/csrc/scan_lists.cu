@@ -40,7 +40,9 @@ __global__ void count_list_pairs_kernel(const int32_t *__restrict__ probe, int64
     if (i >= npairs) return;
     const int32_t l = probe[i];
     if (l >= 0 && l < nlist && list_len[l] > 0) {
-        if (atomicAdd(cnt + l, 1) == 8) atomicAdd(over8, 1);
+        const int32_t before = atomicAdd(cnt + l, 1);
+        if (before == 8) atomicAdd(over8, 1);
+        if (before == 4) atomicAdd(over8 + 2, 1);  // counters[3]: lists probed by more than 4 queries
     }
 }
 
@@ -66,7 +68,7 @@ __device__ __forceinline__ unsigned long long pl_ld(const unsigned long long *p)
 }
 
 __global__ void __launch_bounds__(PL_T) plan_lists_kernel(const int32_t *__restrict__ cnt, const int32_t *__restrict__ list_len,
-                                                          int32_t nlist, int32_t chunk, int32_t min_items,
+                                                          int32_t nlist, int32_t chunk, int32_t min_items, int32_t tile_rem,
                                                           int32_t *__restrict__ counters, unsigned long long *__restrict__ agg,
                                                           int32_t *__restrict__ n32, int32_t *__restrict__ lq_off,
                                                           int32_t *__restrict__ off32, int32_t *__restrict__ pg8off,
@@ -82,7 +84,8 @@ __global__ void __launch_bounds__(PL_T) plan_lists_kernel(const int32_t *__restr
     // a ragged tile item costs ~2.8 list reads of time on the FFMA tiles (two passes of 8 are cheaper up to 16
     // queries) but about 1.6 on the tcgen05 tiles (cheaper than two passes from 9 queries on) -- provided there are
     // enough items to fill the GPU: an item is walked by ONE CTA (~100 us), so a handful of them is a pure tail
-    const int32_t rem_tile = (chunk == 64 && counters[1] >= min_items) ? 8 : 16;
+    // tile_rem = 4 (set_param "tile_rem"): remainders of 5..16 queries become tile items too when enough lists have them
+    const int32_t rem_tile = chunk != 64 ? 16 : ((tile_rem == 4 && counters[3] >= min_items) ? 4 : (counters[1] >= min_items ? 8 : 16));
     const int32_t i0 = b * PL_BLK + tid * PL_IPT;
     int32_t v[4][PL_IPT];
     int32_t local[4] = {0, 0, 0, 0};
@@ -487,7 +490,7 @@ cudaError_t launch_scan_lists(const ScanArgs &a, const ListPlan &p, int cfg, int
     const unsigned plan_ctas = (unsigned)list_plan_ctas(p.nlist);
     if ((e = cudaMemsetAsync(p.cnt, 0, (size_t)(2 * p.nlist + 4) * 4 + (size_t)plan_ctas * 32, st)) != cudaSuccess) return e;
     count_list_pairs_kernel<<<pb, 256, 0, st>>>(a.probe, a.npairs, a.list_len, p.nlist, p.cnt, p.counters + 1);
-    plan_lists_kernel<<<plan_ctas, PL_T, 0, st>>>(p.cnt, a.list_len, p.nlist, p.chunk, 2 * num_sms, p.counters, p.agg, p.n32, p.lq_off, p.off32,
+    plan_lists_kernel<<<plan_ctas, PL_T, 0, st>>>(p.cnt, a.list_len, p.nlist, p.chunk, 2 * num_sms, p.tile_rem, p.counters, p.agg, p.n32, p.lq_off, p.off32,
                                                   p.pg8off, p.pg4off, p.unique_rows);
     fill_list_pairs_kernel<<<pb, 256, 0, st>>>(a.probe, a.npairs, a.list_len, p.nlist, p.lq_off, p.cursor, p.lq);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
