@@ -1005,6 +1005,12 @@ def test_headline_regime_list_major_against_oracle(sb, orc_c, metric):
     ids = np.concatenate([p[1] for p in parts])
     od, oi = orc_c.scan_search(qs, g.metric, remap[probes], off, vecs, ids, k)
     assert_topk_parity(d0[pick], i0[pick], od, oi, "list-major vs C oracle")
+    if metric == "IP":
+        # the option that sends remainders of 5..16 queries to the tensor-core tiles as well: same results
+        g.set_param("tile_rem", 4)
+        d2, i2 = g.search(q, k, nprobe=nprobe)
+        g.set_param("tile_rem", 0)
+        assert_topk_parity(d2.cpu().numpy(), i2.cpu().numpy(), d1, i1, "tile_rem = 4 vs query-major")
     g.close()
 
 
