@@ -592,6 +592,20 @@ def extra_clustered(c, peaks, peak_src):
     return out
 
 
+def lookup_traffic(args, nq, nprobe, dataset, scan):
+    """DRAM bytes per launch of the scan kernels from the committed ncu captures (profiles/scan_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "scan_traffic.json")) as f:
+            for ent in json.load(f)["captures"]:
+                mm = ent["match"]
+                if ent.get("scan", "query-major") == scan and all(mm[key] == val for key, val in (
+                        ("n", args.n), ("dim", args.dim), ("nlist", args.nlist), ("nprobe", nprobe), ("nq", nq), ("dataset", dataset))):
+                    return ent["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def extra_tiles(c, g, peaks, peak_src):
     """nq 4096 / nprobe 128 on the headline index: every list probed ~32x -> the tcgen05 tile kernel carries the scan."""
     torch, args = c.torch, c.args
@@ -600,7 +614,8 @@ def extra_tiles(c, g, peaks, peak_src):
     ms, (od, oi) = time_search(c, g, q, k, 128, 5)
     prof = profiled(c, g, q, k, 128)
     c.last_list_major = prof["unique_rows"] > 0
-    roof = scan_roofline(c, prof, ms, d, list_major_name(args, d), peaks, peak_src)
+    roof = scan_roofline(c, prof, ms, d, list_major_name(args, d), peaks, peak_src,
+                         lookup_traffic(args, 4096, 128, args.dataset, "list-major") if args.shard_sim == 1 else None)
     # parity of this batch: the same 4096 queries through the query-major kernel
     g.set_param("scan_mode", 1)
     qd, qi = g.search(q, k, nprobe=128)
