@@ -38,7 +38,7 @@ struct SelShared {
     unsigned long long pairs[kMaxK];
     uint32_t warp_tot[SEL_T / 32];
     uint32_t sel_bin, need, eq_total, cnt_gt, cnt_eq, base;
-    uint32_t fast_cnt, fast_overflow;
+    uint32_t fast_cnt, fast_nq;
 };
 constexpr int SEL_FAST_K = 128;   // largest k of the one-pass selection
 constexpr int SEL_RV = 8;         // 16-byte chunks per thread that stay in registers between the two phases
@@ -263,7 +263,10 @@ __device__ __forceinline__ bool select_one_pass(const View &view, uint32_t n, ui
     const float NEG = -INFINITY;
     const bool vec = view.vec();
     const uint32_t n4 = vec ? (n >> 2) : 0u;  // 16-byte chunks; the tail (and a view without vector loads) goes scalar
-    if (tid == 0) sh.fast_cnt = 0;
+    if (tid == 0) {
+        sh.fast_cnt = 0;
+        sh.fast_nq = 0;
+    }
 
     // phase 1: the maximum key of the values dealt to this thread
     float4 r[SEL_RV];
@@ -318,15 +321,20 @@ __device__ __forceinline__ bool select_one_pass(const View &view, uint32_t n, ui
         __syncthreads();  // fast_cnt is zero
     }
 
-    // phase 2: the threads that hold a value >= T gather them (most threads skip this)
+    // phase 2: gather the values >= T.  Only the few threads whose maximum reached T can hold one.  Their first SEL_RV chunks are
+    // still in registers; what they were dealt beyond that is re-read -- by the WHOLE CTA, one (qualifying thread, chunk) pair per
+    // thread, so it is one round trip.  (First version: each qualifying thread re-read its own chunks one after the other:
+    // 31 dependent loads at 82k candidates -- 30 of a CTA's 42 us, half of the warp lanes idle over the whole kernel by ncu.)
+    auto put = [&](float f, uint32_t idx) {
+        const uint32_t key = f2key(f);
+        if (key >= T) {
+            const uint32_t s = atomicAdd(&sh.fast_cnt, 1u);
+            if (s < (uint32_t)kMaxK) sh.pairs[s] = pack_pair(key, idx);
+        }
+    };
+    const uint32_t chunks_per_thread = (n4 + NT - 1) / NT;  // chunks dealt to a thread (the last one may fall off the end)
+    const bool reread = chunks_per_thread > (uint32_t)SEL_RV;
     if (mx >= T) {
-        auto put = [&](float f, uint32_t idx) {
-            const uint32_t key = f2key(f);
-            if (key >= T) {
-                const uint32_t s = atomicAdd(&sh.fast_cnt, 1u);
-                if (s < (uint32_t)kMaxK) sh.pairs[s] = pack_pair(key, idx);
-            }
-        };
 #pragma unroll
         for (int j = 0; j < SEL_RV; ++j) {
             const uint32_t i4 = tid + (uint32_t)j * NT;
@@ -337,14 +345,41 @@ __device__ __forceinline__ bool select_one_pass(const View &view, uint32_t n, ui
                 put(r[j].w, 4 * i4 + 3);
             }
         }
-        for (uint32_t i4 = tid + (uint32_t)SEL_RV * NT; i4 < n4; i4 += NT) {
-            const float4 v = view.load4(i4);
-            put(v.x, 4 * i4);
-            put(v.y, 4 * i4 + 1);
-            put(v.z, 4 * i4 + 2);
-            put(v.w, 4 * i4 + 3);
+        if (reread) {
+            const uint32_t slot = atomicAdd(&sh.fast_nq, 1u);
+            if (slot < (uint32_t)SEL_BINS) sh.hist[slot] = tid;  // the histogram is idle on this path
         }
-        for (uint32_t i = 4 * n4 + tid; i < n; i += NT) put(view.load(i), i);
+    }
+    if (reread) {
+        __syncthreads();
+        const uint32_t nqual = sh.fast_nq;
+        if (nqual > (uint32_t)SEL_BINS) {  // (cannot happen with NT <= SEL_BINS threads; kept as the overflow rule)
+            *count = kMaxK + 1;
+            return false;
+        }
+        const uint32_t per = chunks_per_thread - (uint32_t)SEL_RV;  // chunks to re-read per qualifying thread
+        for (uint32_t w = tid; w < nqual * per; w += NT) {
+            const uint32_t i4 = sh.hist[w / per] + ((uint32_t)SEL_RV + w % per) * NT;
+            if (i4 < n4) {
+                const float4 v = view.load4(i4);
+                put(v.x, 4 * i4);
+                put(v.y, 4 * i4 + 1);
+                put(v.z, 4 * i4 + 2);
+                put(v.w, 4 * i4 + 3);
+            }
+        }
+    }
+    // values outside the 16-byte chunks (the tail; everything, for a view without vector loads): every thread checks its own
+    {
+        uint32_t i = 4 * n4 + tid;
+        for (; i + 3 * NT < n; i += 4 * NT) {
+            const float v0 = view.load(i), v1 = view.load(i + NT), v2 = view.load(i + 2 * NT), v3 = view.load(i + 3 * NT);
+            put(v0, i);
+            put(v1, i + NT);
+            put(v2, i + 2 * NT);
+            put(v3, i + 3 * NT);
+        }
+        for (; i < n; i += NT) put(view.load(i), i);
     }
     __syncthreads();
     *count = sh.fast_cnt;
