@@ -262,6 +262,18 @@ class GpuCollection:
         self.persist_dir: Optional[str] = None
         self._generation = 0
         self._dirty = False
+        # Incremental persistence: between full snapshots ("generations") the logical operations -- upserted rows, deleted
+        # keys -- are appended to the published generation as journal files and replayed by from_snapshot(), so an ingest of a
+        # few hundred rows into a large collection does not rewrite the collection.  A full snapshot follows once the journal
+        # has grown to journal_ratio x the snapshot's size, after a structural change (seal, re-train), or on request.
+        self.journal_ratio = 0.5
+        self._pending: List[tuple] = []
+        self._pending_bytes = 0
+        self._needs_full = True  # no generation yet
+        self._journal_bytes = 0
+        self._journal_files = 0
+        self._snapshot_bytes = 0
+        self._replaying = False
         self._lock = _RWLock()
         # host scalar columns, indexed by row number (== the int64 id stored next to the vector)
         self._pk: List[Optional[str]] = []
@@ -302,10 +314,68 @@ class GpuCollection:
     def load(self) -> None:
         return None
 
-    def flush(self) -> None:
-        """Collection.flush(): with a persist directory configured, write the snapshot."""
-        if self.persist_dir:
-            self.save(self.persist_dir)
+    def flush(self, full: bool = False) -> None:
+        """Collection.flush(): with a persist directory configured, make everything ingested so far durable -- as a journal
+        file next to the published snapshot while the changes are small, as a new snapshot generation otherwise (`full`)."""
+        if not self.persist_dir:
+            return
+        with self._lock.write():
+            grown = self._journal_bytes + self._pending_bytes > self.journal_ratio * max(self._snapshot_bytes, 1)
+            if full or self._needs_full or self._generation == 0 or self.journal_ratio <= 0 or grown:
+                self.save(self.persist_dir)
+            elif self._pending:
+                self._write_journal()
+            self._dirty = False
+
+    _PENDING_MAX = 256 << 20  # bytes of un-flushed vectors kept for the journal; beyond that the next flush is a full snapshot
+
+    def _record(self, op: tuple, nbytes: int) -> None:
+        if not self.persist_dir or self._replaying or self._needs_full:
+            return
+        if self._pending_bytes + nbytes > self._PENDING_MAX:
+            self._pending, self._pending_bytes, self._needs_full = [], 0, True
+            return
+        self._pending.append(op)
+        self._pending_bytes += nbytes
+
+    def _write_journal(self) -> None:
+        gen_dir = os.path.join(self.persist_dir, f"gen-{self._generation:08d}")
+        ops, arrays = [], {}
+        for i, op in enumerate(self._pending):
+            if op[0] == "upsert":
+                _, ids, vec, repos, paths, languages, texts, metadata = op
+                ops.append({"op": "upsert", "ids": ids, "repos": repos, "paths": paths, "languages": languages, "texts": texts,
+                            "metadata": metadata, "vec": f"v{i}"})
+                arrays[f"v{i}"] = vec
+            else:
+                ops.append({"op": "delete", "ids": op[1]})
+        arrays["ops"] = np.frombuffer(json.dumps(ops).encode("utf-8"), dtype=np.uint8)
+        name = os.path.join(gen_dir, f"journal-{self._journal_files + 1:06d}.npz")
+        with open(name + ".tmp", "wb") as f:
+            np.savez(f, **arrays)
+            f.flush()
+            os.fsync(f.fileno())
+        os.replace(name + ".tmp", name)  # the publication point of this batch of operations
+        self._journal_files += 1
+        self._journal_bytes += os.path.getsize(name)
+        self._pending, self._pending_bytes = [], 0
+
+    def _replay_journal(self, snap: str) -> None:
+        files = sorted(f for f in os.listdir(snap) if f.startswith("journal-") and f.endswith(".npz"))
+        self._replaying = True
+        try:
+            for fname in files:
+                with np.load(os.path.join(snap, fname)) as z:
+                    for op in json.loads(bytes(z["ops"]).decode("utf-8")):
+                        if op["op"] == "upsert":
+                            self.upsert_columns(op["ids"], z[op["vec"]], op["repos"], op["paths"], op["languages"], op["texts"],
+                                                op["metadata"])
+                        else:
+                            self.delete(op["ids"])
+                self._journal_bytes += os.path.getsize(os.path.join(snap, fname))
+            self._journal_files = len(files)
+        finally:
+            self._replaying = False
 
     # -- persistence (SURVEY.md section 8f rank 1: connect() on an existing collection just loads,
     #    milvus_store.py:51-54; Milvus keeps its data in a volume, docker-compose.yml:13-14) -----------
@@ -344,6 +414,9 @@ class GpuCollection:
             os.replace(os.path.join(path, "CURRENT.tmp"), os.path.join(path, "CURRENT"))  # the publication point
             self._generation = gen
             self._dirty = False
+            self._pending, self._pending_bytes, self._needs_full = [], 0, False
+            self._journal_bytes, self._journal_files = 0, 0
+            self._snapshot_bytes = sum(os.path.getsize(os.path.join(dp, fn)) for dp, _, fns in os.walk(final) for fn in fns)
             for old in os.listdir(path):
                 if old.startswith("gen-") and old != name:
                     shutil.rmtree(os.path.join(path, old), ignore_errors=True)
@@ -395,6 +468,11 @@ class GpuCollection:
         if "rows" in meta and len(col._pk) != int(meta["rows"]) or live != len(col._row_of):
             raise ValueError(f"snapshot {snap!r} is inconsistent: {len(col._pk)} column rows, {len(col._row_of)} live keys, "
                              f"{live} live vectors")
+        col._needs_full = False
+        col._snapshot_bytes = sum(os.path.getsize(os.path.join(dp, fn)) for dp, _, fns in os.walk(snap) for fn in fns
+                                  if not fn.startswith("journal-"))
+        col._replay_journal(snap)  # what was ingested after that generation was written
+        col._dirty = False
         return col
 
     @property
@@ -483,6 +561,12 @@ class GpuCollection:
             if len(keep) != n:
                 vec = vec[torch.as_tensor(keep, device=vec.device)] if not isinstance(vec, np.ndarray) else vec[keep]
             self._dirty = True
+            if self.persist_dir and not self._replaying and not self._needs_full:
+                host = vec if isinstance(vec, np.ndarray) else vec.detach().cpu().numpy()
+                self._record(("upsert", [str(ids[i]) for i in keep], np.array(host, dtype=np.float32, copy=True),
+                              [str(repos[i] or "") for i in keep], [str(paths[i] or "") for i in keep],
+                              [str(languages[i] or "") for i in keep], [texts[i] for i in keep], [metadata[i] for i in keep]),
+                             int(host.nbytes) + sum(len(str(texts[i])) for i in keep) + 96 * len(keep))
             if self._ivf is not None:
                 self._ivf.add(vec, row_ids, rtags, ltags)
                 self._maintain()
@@ -513,6 +597,7 @@ class GpuCollection:
             rows = [self._row_of[str(pk)] for pk in ids if str(pk) in self._row_of]
             if rows:
                 self._remove_rows(rows)
+                self._record(("delete", [str(pk) for pk in ids]), 64 * len(rows))
                 self._maintain()
             return len(rows)
 
@@ -567,6 +652,7 @@ class GpuCollection:
             old.close()
             self._trained_rows = n
             self._dirty = True
+            self._needs_full = True  # the lists were rebuilt: replaying a journal on the old snapshot would not reproduce them
             self.maintenance["retrains"] += 1
             log.info("index_retrained", collection=self.name, nlist=nlist, rows=n)
 
@@ -600,6 +686,8 @@ class GpuCollection:
             self._growing.reset()
             self._growing_rows = 0
             self._dirty = True
+            if not self._replaying:
+                self._needs_full = True  # sealed: the next flush writes a generation instead of a journal file
             return self._ivf
 
     # -- search ---------------------------------------------------------------------------------------
@@ -785,6 +873,7 @@ class MilvusVectorStore:
                     collection.close()
                     raise ValueError(f"snapshot {snap!r} has dim {collection.dim}, requested {self.dim}")
                 collection.persist_dir = snap
+                collection.journal_ratio = float(_setting("ivf_journal_ratio", 0.5))
                 _REGISTRY[self.collection_name] = collection
                 return collection
             log.info("creating_milvus_collection", collection=self.collection_name, dim=self.dim)
@@ -806,6 +895,7 @@ class MilvusVectorStore:
                 retrain_factor=_setting("ivf_retrain_factor", 0.0),
             )
             collection.persist_dir = snap or None
+            collection.journal_ratio = float(_setting("ivf_journal_ratio", 0.5))
             collection.load()
             _REGISTRY[self.collection_name] = collection
             return collection
@@ -895,8 +985,9 @@ class MilvusVectorStore:
         self._require().retrain(niter=niter)
 
     def flush(self) -> None:
-        """Persist the collection when `ivf_persist_dir` (SEMCODE_IVF_PERSIST_DIR) is configured."""
-        self._require().flush()
+        """Persist the collection when `ivf_persist_dir` (SEMCODE_IVF_PERSIST_DIR) is configured: an explicit flush writes a
+        complete snapshot generation (the implicit ones after upsert_embeddings journal small changes instead)."""
+        self._require().flush(full=True)
 
     def last_search_stats(self) -> Optional[dict]:
         """With `ivf_profile` set: what a recent search on the sealed index cost -- search / scan milliseconds, bytes of list

@@ -231,6 +231,12 @@ def test_persist_without_flush_on_the_gpu(real_store, monkeypatch, tmp_path):
     scenario_persist_without_flush(real_store, monkeypatch, tmp_path)
 
 
+def test_journal_on_the_gpu(real_store, monkeypatch, tmp_path):
+    from test_store_host import scenario_journal
+
+    scenario_journal(real_store, monkeypatch, tmp_path)
+
+
 def test_compaction_and_retrain_on_the_gpu(real_store, monkeypatch):
     from test_store_host import scenario_compaction_and_retrain
 

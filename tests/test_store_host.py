@@ -61,10 +61,18 @@ def scenario_persist_without_flush(ms, monkeypatch, tmp_path):
     assert [h.id for h in after] == [h.id for h in before]
     assert [round(h.distance, 5) for h in after] == [round(h.distance, 5) for h in before]
     assert after[0].entity.get("text") == pay[5].text and after[0].entity.get("metadata")["path"] == pay[5].metadata["path"]
-    # a crash in the middle of the next snapshot leaves the published generation loadable
+    # a small ingest is journalled next to the published generation, not a rewrite of the collection ...
     again.upsert_embeddings(make_payloads(rng, 20, 16, repo="s")[0])
+    assert (snap / "CURRENT").read_text() == cur and sorted(f for f in os.listdir(snap / cur) if f.startswith("journal-")) == ["journal-000001.npz"]
+    ms._REGISTRY.pop("persisted").close()
+    again = ms.MilvusVectorStore("persisted", dim=16)
+    again.connect()  # ... and replayed by the next process
+    assert again._collection.num_entities == 320
+    assert [h.id for h in again.search(x[5].tolist(), top_k=3)[0]] == [h.id for h in before]
+    # an explicit flush writes a new generation; a crash in the middle of a snapshot leaves the published one loadable
+    again.flush()
     cur2 = (snap / "CURRENT").read_text()
-    assert cur2 != cur and not (snap / cur).exists()
+    assert cur2 != cur and not (snap / cur).exists() and not [f for f in os.listdir(snap / cur2) if f.startswith("journal-")]
     os.makedirs(snap / "gen-99999999.tmp" / "ivf")  # debris of an interrupted save
     ms._REGISTRY.pop("persisted").close()
     third = ms.MilvusVectorStore("persisted", dim=16)
@@ -76,6 +84,62 @@ def scenario_persist_without_flush(ms, monkeypatch, tmp_path):
     (snap / cur2 / "columns.jsonl").write_text("\n".join(lines[:-5]) + "\n")
     with pytest.raises(ValueError, match="inconsistent"):
         ms.MilvusVectorStore("persisted", dim=16).connect()
+
+
+def scenario_journal(ms, monkeypatch, tmp_path):
+    """Incremental persistence: upserts, replacements and deletes after a snapshot are appended to it as journal files and
+    replayed on connect(); the journal turns into a new generation once it has grown to `ivf_journal_ratio` of the snapshot;
+    a half-written journal file (crash) is ignored."""
+    monkeypatch.setenv("SEMCODE_IVF_PERSIST_DIR", str(tmp_path / "persist"))
+    monkeypatch.setenv("SEMCODE_IVF_NLIST", "4")
+    monkeypatch.setenv("SEMCODE_IVF_SEAL_ROWS", "200")
+    monkeypatch.setenv("SEMCODE_IVF_JOURNAL_RATIO", "0.5")
+    rng = np.random.default_rng(9)
+    name = "journalled"
+    snap = tmp_path / "persist" / name
+
+    def reopen():
+        ms._REGISTRY.pop(name).close()
+        st = ms.MilvusVectorStore(name, dim=16)
+        st.connect()
+        return st
+
+    st = ms.MilvusVectorStore(name, dim=16)
+    st.connect()
+    pay, x = make_payloads(rng, 400, 16)
+    st.upsert_embeddings(pay)  # seals at 200 rows -> a generation
+    gen = (snap / "CURRENT").read_text()
+    journals = lambda: sorted(f for f in os.listdir(snap / (snap / "CURRENT").read_text()) if f.startswith("journal-"))  # noqa: E731
+    assert journals() == []
+    # three small changes: new rows, replacements of existing keys (new vectors), a delete
+    new, xn = make_payloads(rng, 30, 16, repo="late")
+    st.upsert_embeddings(new)
+    repl, xr = make_payloads(rng, 10, 16)  # same ids as pay[:10]
+    st.upsert_embeddings(repl)
+    st._collection.delete([pay[20].id, new[3].id])
+    st._collection.flush()
+    assert (snap / "CURRENT").read_text() == gen and journals() == ["journal-000001.npz", "journal-000002.npz", "journal-000003.npz"]
+    want = {kk: [h.id for h in st.search(v.tolist(), top_k=4, nprobe=4)[0]] for kk, v in (("old", x[77]), ("new", xn[5]), ("repl", xr[2]))}
+    (snap / gen / "journal-000004.npz.tmp").write_bytes(b"half a file")  # crash while journalling
+    st = reopen()
+    col = st._collection
+    assert col.num_entities == 400 + 30 - 2 and col._journal_files == 3
+    for kk, v in (("old", x[77]), ("new", xn[5]), ("repl", xr[2])):
+        assert [h.id for h in st.search(v.tolist(), top_k=4, nprobe=4)[0]] == want[kk]
+    top = st.search(xr[2].tolist(), top_k=1, nprobe=4)[0][0]
+    assert top.id == repl[2].id and abs(top.distance - 1.0) < 1e-5  # the replacement's vector answers for that key
+    assert pay[20].id not in col._row_of and new[3].id not in col._row_of
+    # the journal continues where it stopped ...
+    st.upsert_embeddings(make_payloads(rng, 5, 16, repo="later")[0])
+    assert journals()[-1] == "journal-000004.npz" and (snap / "CURRENT").read_text() == gen
+    # ... until it has grown to half the snapshot: then the next implicit flush writes a generation and the journal is gone
+    big, _ = make_payloads(rng, 600, 16, repo="bulk")
+    st.upsert_embeddings(big)
+    gen2 = (snap / "CURRENT").read_text()
+    col = st._collection
+    assert gen2 != gen and journals() == [] and not (snap / gen).exists(), (col._snapshot_bytes, col._journal_bytes, col._pending_bytes)
+    st = reopen()
+    assert st._collection.num_entities == 400 + 30 - 2 + 5 + 600 and st._collection._journal_files == 0
 
 
 def scenario_compaction_and_retrain(ms, monkeypatch):
@@ -160,6 +224,10 @@ def scenario_concurrent_searches(ms, monkeypatch):
 
 def test_persist_without_flush(double_engine, monkeypatch, tmp_path):
     scenario_persist_without_flush(double_engine, monkeypatch, tmp_path)
+
+
+def test_journal(double_engine, monkeypatch, tmp_path):
+    scenario_journal(double_engine, monkeypatch, tmp_path)
 
 
 def test_compaction_and_retrain(double_engine, monkeypatch):
