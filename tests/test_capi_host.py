@@ -109,3 +109,14 @@ def test_kmeans_row_selection_matches_oracle():
     np.testing.assert_array_equal(index.kmeans_init_rows(5000, 64, 9), orc.kmeans_init_rows(5000, 64, 9))
     np.testing.assert_array_equal(index.kmeans_subsample_rows(50000, 16, 256, 9), orc.kmeans_subsample_rows(50000, 16, 256, 9))
     assert index.kmeans_subsample_rows(100, 16, 256, 9) is None
+
+
+def test_every_tuning_knob_is_documented_in_the_header():
+    """sc_index_set_param takes names, not enums: every name index.cu accepts must be described in include/semcode_ivf.h."""
+    import re
+
+    src = open(os.path.join(ROOT, "semcode_b200", "csrc", "index.cu")).read()
+    names = sorted(set(re.findall(r'strcmp\(name, "([a-z_0-9]+)"\)', src)))
+    header = open(os.path.join(ROOT, "include", "semcode_ivf.h")).read()
+    assert len(names) >= 15
+    assert [n for n in names if f'"{n}"' not in header] == []
