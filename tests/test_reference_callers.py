@@ -203,6 +203,68 @@ def test_reference_integration_test_with_the_store_injected(ref, tmp_path, monke
     assert ref.has_collection("test_semcode_chunks") and ref._REGISTRY["test_semcode_chunks"].num_entities > 0
 
 
+def test_reference_api_app_ingests_and_answers_from_the_drop_in(ref, tmp_path, monkeypatch):
+    """The reference's FastAPI application (api/main.py), unmodified, over HTTP (fastapi.testclient): POST /ingest runs the
+    real IndexerService into the drop-in store, POST /query runs the real SemanticSearchPipeline out of it -- the module
+    constructs both at import time (api/main.py:24-29) with whatever `semcode.storage.MilvusVectorStore` is.  Embeddings and
+    the LLM are the only stand-ins (they are network services)."""
+    from fastapi.testclient import TestClient
+    from semcode.settings import settings
+
+    workspace = tmp_path / "workspace"
+    monkeypatch.setattr(settings, "workspace_root", workspace)
+    monkeypatch.setattr(settings, "embedding_dimension", DIM, raising=False)
+    monkeypatch.setattr(settings, "api_key", "secret", raising=False)
+    monkeypatch.setattr(settings, "telemetry_enabled", True, raising=False)
+    monkeypatch.setattr(settings, "rag_max_context_sources", 3, raising=False)
+    monkeypatch.setattr("semcode.services.indexer.EmbeddingProviderFactory.create", lambda provider=None, model=None: HashEmbedding())
+    api = importlib.import_module("semcode.api.main")
+    assert type(api.indexer.vector_store) is ref.MilvusVectorStore and type(api.pipeline.vector_store) is ref.MilvusVectorStore
+    api.pipeline._embedding = HashEmbedding()
+
+    class _LLM:
+        def invoke(self, messages):
+            return type("R", (), {"content": "an answer"})()
+
+    monkeypatch.setattr(api.pipeline, "_create_llm", lambda: _LLM())
+    root = tmp_path / "checkout"
+    root.mkdir()
+    _make_repo(root / "src")
+    client = TestClient(api.app)
+    hdr = {"X-API-Key": "secret"}
+    assert client.post("/query", json={"question": "x"}).status_code == 401  # the app's own auth still guards the route
+    r = client.post("/ingest", headers=hdr, json={"name": "demo", "root": str(root), "include": ["src"]})
+    assert r.status_code == 200, r.text
+    body = r.json()
+    assert body["name"] == "demo" and body["chunk_count"] > 3 and set(body["languages"]) == {"python", "cpp"}
+    col = ref._REGISTRY["semcode_chunks"]  # ONE collection behind both the indexer's and the pipeline's store objects
+    assert col.num_entities == body["chunk_count"]
+    assert [rp["name"] for rp in client.get("/repos", headers=hdr).json()] == ["demo"]
+    text = col._text[next(rr for rr in col._row_of.values() if col._language[rr] == "cpp")]
+    r = client.post("/query", headers=hdr, json={"question": text})
+    assert r.status_code == 200, r.text
+    out = r.json()
+    assert out["answer"] == "an answer" and len(out["sources"]) == 3 and out["meta"] == {"fallback_used": False}
+    assert out["sources"][0]["snippet"] == text and out["sources"][0]["language"] == "cpp" and abs(out["sources"][0]["score"] - 1.0) < 1e-5
+    tele = client.get("/telemetry", headers=hdr).json()
+    assert tele["ingest"]["count"] == 1 and tele["query"]["count"] == 1 and tele["query"]["failures"] == 0
+
+
+def test_reference_api_endpoint_test_runs_with_the_store_swapped(ref, tmp_path, monkeypatch):
+    """reference tests/integration/test_api_endpoints.py, body unchanged: importing semcode.api.main constructs the indexer and
+    the pipeline on top of the drop-in store."""
+    path = os.path.join(REF_ROOT, "tests", "integration", "test_api_endpoints.py")
+    spec = importlib.util.spec_from_file_location("ref_test_api_endpoints", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert type(mod.api_main.indexer.vector_store) is ref.MilvusVectorStore
+    keep = mod.api_main.pipeline
+    try:
+        mod.test_api_endpoints_with_stubs(tmp_path, monkeypatch)
+    finally:
+        mod.api_main.pipeline = keep  # the reference test assigns its stub without monkeypatch
+
+
 def test_optional_caller_patch_pushes_filters_down_and_batches(monkeypatch, tmp_path):
     """patches/semcode_filter_pushdown_and_batch.patch: QueryRequest.repos / languages reach the
     index scan through SemanticSearchPipeline.query, retrieve_batch issues ONE store call for many questions, and the API's
