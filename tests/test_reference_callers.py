@@ -265,6 +265,43 @@ def test_reference_api_endpoint_test_runs_with_the_store_swapped(ref, tmp_path, 
         mod.api_main.pipeline = keep  # the reference test assigns its stub without monkeypatch
 
 
+def test_reference_cli_ingests_and_a_later_process_answers(ref, tmp_path, monkeypatch):
+    """`semcode ingest` (cli.py:118-301, unmodified, through typer's CliRunner) fills the collection in one process; with
+    `ivf_persist_dir` set the rows are there for the NEXT process -- here the reference's API app -- although the reference
+    never calls flush() (its Milvus server persisted for it): the one-process limitation ADVICE round 1 pointed at."""
+    from fastapi.testclient import TestClient
+    from semcode.settings import settings
+    from typer.testing import CliRunner
+
+    workspace = tmp_path / "workspace"
+    monkeypatch.setattr(settings, "workspace_root", workspace)
+    monkeypatch.setattr(settings, "embedding_dimension", DIM, raising=False)
+    monkeypatch.setattr(settings, "ivf_persist_dir", str(tmp_path / "persist"), raising=False)
+    monkeypatch.setattr(settings, "api_key", "", raising=False)
+    monkeypatch.setattr(settings, "rag_max_context_sources", 2, raising=False)
+    monkeypatch.setattr("semcode.services.indexer.EmbeddingProviderFactory.create", lambda provider=None, model=None: HashEmbedding())
+    root = tmp_path / "checkout"
+    root.mkdir()
+    _make_repo(root / "src")
+    cli = importlib.import_module("semcode.cli")
+    res = CliRunner().invoke(cli.app, ["ingest", "--name", "demo", "--include", "src", "--root", str(root), "--yes"])
+    assert res.exit_code == 0, res.output
+    assert "Ingested demo" in res.output and "chunks=" in res.output
+    n = ref._REGISTRY["semcode_chunks"].num_entities
+    assert n > 3 and os.path.exists(tmp_path / "persist" / "semcode_chunks" / "CURRENT")
+    ref._REGISTRY.pop("semcode_chunks").close()  # the CLI process is gone
+
+    api = importlib.import_module("semcode.api.main")  # a new process: the API server
+    api.pipeline._embedding = HashEmbedding()
+    monkeypatch.setattr(api.pipeline, "_create_llm", lambda: type("L", (), {"invoke": lambda self, m: type("R", (), {"content": "ok"})()})())
+    client = TestClient(api.app)
+    r = client.post("/query", json={"question": "int add(int a, int b) {\n  return a + b;\n}"})
+    assert r.status_code == 200, r.text
+    out = r.json()
+    assert ref._REGISTRY["semcode_chunks"].num_entities == n  # loaded from the snapshot the CLI's upsert left behind
+    assert out["answer"] == "ok" and len(out["sources"]) == 2 and out["sources"][0]["repo"] == "demo"
+
+
 def test_optional_caller_patch_pushes_filters_down_and_batches(monkeypatch, tmp_path):
     """patches/semcode_filter_pushdown_and_batch.patch: QueryRequest.repos / languages reach the
     index scan through SemanticSearchPipeline.query, retrieve_batch issues ONE store call for many questions, and the API's
