@@ -360,6 +360,14 @@ def test_optional_caller_patch_pushes_filters_down_and_batches(monkeypatch, tmp_
         api.query(api.QueryRequest(question="q"))
         event = api.telemetry.snapshot()["recent_events"][0]
         assert event["kind"] == "query" and event["metadata"]["retrieval"]["scanned_bytes"] == stats["scanned_bytes"]
+        # the Streamlit front end sends a narrowed repo / language selection along instead of only post-filtering the answer
+        # (streamlit is not in the image: a bare stand-in module lets the patched file import)
+        monkeypatch.setitem(sys.modules, "streamlit", type(sys)("streamlit"))
+        fe = importlib.import_module("semcode.frontend.app")
+        sent = {}
+        monkeypatch.setattr(fe, "_request", lambda method, url, api_key=None, **kw: sent.update(kw["json"]) or type("R", (), {"json": lambda self: {}})())
+        fe._run_query("http://x", None, "q", repos=["other"], languages=None)
+        assert sent == {"question": "q", "repos": ["other"]}
     finally:
         for name in list(ms._REGISTRY):
             ms.drop_collection(name)
